@@ -1,0 +1,199 @@
+/* -*- c++ -*- ---------------------------------------------------------------
+   minilmp engine -- TEST INFRASTRUCTURE (oracle side).
+
+   A small restatement of the LAMMPS-core services a Pair plugin lives in
+   (stable_2Aug2023 semantics): Domain (orthogonal +
+   triclinic), Lattice, create_box/create_atoms/replicate, Atom::sort,
+   CommBrick (exchange/borders/forward/reverse, incl. Pair hooks),
+   NBinStandard + NStencilFull[Ghost]Bin3d + NPairFullBin[Ghost], Verlet,
+   fix nve, thermo (temp/press/pe/ke), velocity create, set type/fraction,
+   plugin load, and an input-line interpreter for the subset of commands
+   the two shipped inputs use.  MPI ranks are threads of one process.
+
+   It hosts (a) the reference pair styles compiled verbatim (oracle/_ref),
+   (b) the plain restatement (oracle/port) and (c) the B200 plugins, which is
+   how parity is asserted on identical inputs.  Only tests/, smoke() and
+   bench.py's CPU-baseline legs may use it; no product path links it.
+---------------------------------------------------------------------------- */
+#ifndef MINILMP_ENGINE_H
+#define MINILMP_ENGINE_H
+
+#include "lmpshim.h"
+
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct lmpshim_rankctx {
+  LAMMPS_NS::Universe *universe;
+  int rank;
+};
+
+namespace LAMMPS_NS {
+
+// ------------------------------------------------------------ thread-rank "MPI"
+class Universe {
+ public:
+  int nprocs;
+  std::vector<lmpshim_rankctx> ctx;
+  explicit Universe(int n);
+  void barrier();
+  void abort_all();
+  // blocking exchange: every rank calls it once per swap
+  int sendrecv(int me, int src, const double *sbuf, int nsend, std::vector<double> &rbuf);
+  void allreduce_sum(int me, double *v, int n);
+  void allreduce_max(int me, double *v, int n);
+  bigint scan_exclusive(int me, bigint v, bigint &total);
+  void bcast(int me, void *buf, size_t nbytes, int root);
+
+ private:
+  std::mutex mtx;
+  std::condition_variable cv;
+  int count, generation;
+  bool aborted;
+  std::vector<const void *> slot_ptr;
+  std::vector<size_t> slot_n;
+  std::vector<std::vector<double>> red;
+};
+
+// ------------------------------------------------------------ lattice / region
+class Lattice {
+ public:
+  double xlattice, ylattice, zlattice;
+  double a1[3], a2[3], a3[3], origin[3], scale;
+  std::vector<std::vector<double>> basis;
+  Lattice();
+  void setup();
+  void lattice2box(double &x, double &y, double &z) const;
+  void box2lattice(double &x, double &y, double &z) const;
+  void bbox(int flag, double x, double y, double z, double &xmin, double &ymin, double &zmin,
+            double &xmax, double &ymax, double &zmax) const;
+
+ private:
+  double primitive[3][3], priminv[3][3];
+};
+
+struct Region {
+  std::string id, style;
+  double xlo, xhi, ylo, yhi, zlo, zhi, xy, xz, yz;
+};
+
+// ------------------------------------------------------------ domain
+class Domain : protected Pointers {
+ public:
+  int box_exist, box_change, dimension, triclinic;
+  int periodicity[3], xperiodic, yperiodic, zperiodic;
+  double boxlo[3], boxhi[3], xy, xz, yz;
+  double prd[3], prd_half[3], xprd, yprd, zprd;
+  double h[6], h_inv[6];
+  double boxlo_lamda[3], boxhi_lamda[3], prd_lamda[3];
+  double boxlo_bound[3], boxhi_bound[3];
+  double sublo[3], subhi[3], sublo_lamda[3], subhi_lamda[3];
+  Lattice *lattice;
+  std::vector<Region> regions;
+
+  explicit Domain(LAMMPS *lmp);
+  ~Domain() override;
+  void set_global_box();
+  void set_local_box();
+  void x2lamda(int n);
+  void lamda2x(int n);
+  void x2lamda(const double *x, double *lamda) const;
+  void lamda2x(const double *lamda, double *x) const;
+  void bbox(const double *lo, const double *hi, double *bboxlo, double *bboxhi) const;
+  void pbc();
+  void remap(double *x) const;
+  double volume() const { return xprd * yprd * zprd; }
+};
+
+// ------------------------------------------------------------ update / integrate / modify / output
+struct ThermoRow {
+  bigint step;
+  double temp, press, pe, ke, etotal, vol;
+  double virial[6];    // pair virial (global sum), energy units
+};
+
+class Update : protected Pointers {
+ public:
+  bigint ntimestep, firststep, laststep;
+  double dt;
+  std::string unit_style;
+  int eflag_global, vflag_global;    // last ev_set result
+  bigint nbuild, ndanger;
+  double time_pair, time_neigh, time_comm, time_modify, time_loop;
+
+  explicit Update(LAMMPS *lmp);
+  void set_units(const std::string &style);
+  void setup_run();           // Verlet::setup
+  void run(int nsteps);       // Verlet::run
+  void force_clear();
+  void ev_set(bigint step, int &eflag, int &vflag);
+};
+
+class Modify : protected Pointers {
+ public:
+  int nve;    // 1 if "fix nve" on group all is defined
+  explicit Modify(LAMMPS *lmp) : Pointers(lmp), nve(0) {}
+  void initial_integrate();
+  void final_integrate();
+};
+
+class Output : protected Pointers {
+ public:
+  int thermo_every;
+  std::vector<ThermoRow> rows;
+  explicit Output(LAMMPS *lmp) : Pointers(lmp), thermo_every(0) {}
+  bigint next_thermo;
+  void compute_thermo(ThermoRow &row);    // collective
+  void write_thermo(bigint step);         // collective
+  double compute_temp();                  // collective
+};
+
+// ------------------------------------------------------------ input
+class Input : protected Pointers {
+ public:
+  explicit Input(LAMMPS *lmp) : Pointers(lmp) {}
+  void one(const std::string &line);    // collective over ranks
+  void file(const std::string &path);
+
+ private:
+  std::string substitute(const std::string &line);
+  void lattice(std::vector<std::string> &a);
+  void region(std::vector<std::string> &a);
+  void create_box(std::vector<std::string> &a);
+  void create_atoms(std::vector<std::string> &a);
+  void replicate(std::vector<std::string> &a);
+  void mass(std::vector<std::string> &a);
+  void pair_style(std::vector<std::string> &a);
+  void pair_coeff(std::vector<std::string> &a);
+  void neighbor_cmd(std::vector<std::string> &a);
+  void neigh_modify(std::vector<std::string> &a);
+  void velocity(std::vector<std::string> &a);
+  void set_cmd(std::vector<std::string> &a);
+  void fix(std::vector<std::string> &a);
+  void run(std::vector<std::string> &a);
+  void plugin(std::vector<std::string> &a);
+  void displace_atoms(std::vector<std::string> &a);
+};
+
+// Park-Miller RNG as used by LAMMPS' velocity/set commands (RanPark)
+class RanPark {
+ public:
+  explicit RanPark(int seed_init) : seed(seed_init), save(0), second(0.0) {}
+  double uniform();
+  double gaussian();
+  void reset(int ibase, const double *coord);
+
+ private:
+  int seed, save;
+  double second;
+};
+
+// one rank's full instance
+LAMMPS *create_instance(Universe *u, int rank, const int *procgrid);
+void destroy_instance(LAMMPS *lmp);
+
+}    // namespace LAMMPS_NS
+
+#endif

@@ -1,0 +1,211 @@
+/* b200md.h -- C ABI of the B200-native force path for the LAMMPS pair styles
+ * `rebomos` (REBO Mo/S + tapered LJ) and `aeam` (angular EAM).
+ *
+ * Plain C, plain pointers and sizes, no C++/torch types.  The library behind it
+ * (lammps_plugins_b200/libb200md.so) is hand-written CUDA for sm_100a; there is
+ * no CPU fallback: every entry point returns B200MD_ERR_CUDA when no device or
+ * kernel image is usable, and the host pair classes turn that into error->one().
+ *
+ * What each entry point replaces in the reference (lammps/lammps-plugins):
+ *
+ *   b200md_rebomos_init        PairREBOMoS::read_file/init_one parameter block
+ *                              USER-REBOMOS/pair_rebomos.cpp:857-1107, 244-274
+ *   b200md_set_neighbor_list   the NeighList handed to Pair::init_list / used at
+ *                              pair_rebomos.cpp:304-307, 476-479; pair_aeam.cpp:150-153
+ *   b200md_rebomos_compute     PairREBOMoS::compute           pair_rebomos.cpp:102-111
+ *                                = REBO_neigh :281-352 + FREBO :358-447
+ *                                + bondorder :571-847 + FLJ :453-558
+ *                                + Pair::virial_fdotr_compute (LAMMPS-core)
+ *   b200md_rebomos_neigh       PairREBOMoS::REBO_neigh output (REBO_numneigh,
+ *                              REBO_firstneigh, nM, nS)        pair_rebomos.cpp:281-352
+ *   b200md_aeam_init           PairAEAM::file2array/array2spline tables
+ *                              USER-AEAM/pair_aeam.cpp:752-942
+ *   b200md_aeam_compute        PairAEAM::compute               pair_aeam.cpp:110-479
+ *   b200md_aeam_get_rho_fp     per-atom rho/fp (the data of pack/unpack_*_comm,
+ *                              pair_aeam.cpp:946-990)
+ *   b200md_neigh_build         LAMMPS-core NBinStandard + NPairFullBin[Ghost]
+ *                              ("pair build: full/bin/ghost", log.rebomos-bulk.1:49)
+ *   b200md_system_*            the LAMMPS run loop around compute(): Verlet::run,
+ *                              fix nve, Neighbor::decide, CommBrick forward/reverse/
+ *                              borders/exchange, thermo (GPU-resident driver)
+ *
+ * Conventions: positions/forces are AoS double[n][3] exactly like atom->x /
+ * atom->f; `type` is the 1-based LAMMPS atom type; `tag` the int32 atom ID;
+ * neighbor indices are local indices (owned first, then ghosts), the top 3 bits
+ * are masked with NEIGHMASK as the reference does.  All functions return 0 on
+ * success, a negative B200MD_ERR_* otherwise; b200md_last_error() gives the text.
+ */
+#ifndef B200MD_H
+#define B200MD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MD_VERSION 100
+
+#define B200MD_OK 0
+#define B200MD_ERR_CUDA (-1)      /* no device / kernel launch or runtime failure */
+#define B200MD_ERR_ARG (-2)       /* bad argument or call order */
+#define B200MD_ERR_OVERFLOW (-3)  /* a per-atom row exceeded its capacity */
+#define B200MD_ERR_NCCL (-4)
+
+#define B200MD_ENERGY_GLOBAL 1    /* == Pair::ENERGY_GLOBAL */
+#define B200MD_VIRIAL_PAIR 1      /* == Pair::VIRIAL_PAIR   */
+#define B200MD_VIRIAL_FDOTR 2     /* == Pair::VIRIAL_FDOTR  */
+
+typedef struct b200md_ctx b200md_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int b200md_create(int device, b200md_ctx **out);
+void b200md_destroy(b200md_ctx *ctx);
+/* text of the last error on this context (ctx may be NULL: last create error) */
+const char *b200md_last_error(const b200md_ctx *ctx);
+int b200md_version(void);
+
+/* ---- REBOMoS parameters (MoS.REBO.set5b after PairREBOMoS::read_file) ----
+ * 2x2 tables are row-major [itype][jtype] with 0 = Mo, 1 = S, exactly the
+ * member arrays of pair_rebomos.h:54-60.                                      */
+typedef struct {
+  double rcmin[4], rcmax[4];
+  double Q[4], alpha[4], A[4], BIJc[4], Beta[4];
+  double b[7][2];  /* b0..b6  [order][elem]   pair_rebomos.h:56 */
+  double bg[7][2]; /* bg0..bg6                pair_rebomos.h:57 */
+  double a[4][2];  /* a0..a3                  pair_rebomos.h:58 */
+  double rcLJmin[4], rcLJmax[4];
+  double epsilon[4], sigma[4];
+} b200md_rebomos_params;
+
+/* map[1..ntypes] = 0 (Mo), 1 (S) or -1 (NULL), as PairREBOMoS::coeff builds it */
+int b200md_rebomos_init(b200md_ctx *ctx, const b200md_rebomos_params *p, int ntypes, const int *map);
+
+/* ---- AEAM tables (AlSi.aeam after PairAEAM::read_file + file2array) -------
+ * Raw tabulated values, 0-based, as stored in the file; the library builds the
+ * 7-coefficient splines itself (PairAEAM::interpolate, pair_aeam.cpp:915-942),
+ * bit-identically, and keeps them on the device.                              */
+typedef struct {
+  int nelements;        /* == ntypes (the reference requires it, pair_aeam.cpp:568-572) */
+  int nnonangular;      /* types 1..nnonangular are plain EAM, the rest angular */
+  const int *nrho;      /* [nelements]                         */
+  const double *drho;   /* [nelements]                         */
+  const int *nr;        /* [nelements*nelements] row-major i,j */
+  const double *dr;     /* [nelements*nelements]               */
+  const double *cut;    /* [nelements*nelements]               */
+  const double *const *frho; /* [nelements] -> nrho[i] values               */
+  const double *const *rhor; /* [nelements*nelements] -> nr[i][j] values    */
+  const double *const *z2r;  /* [nelements*nelements] -> nr[i][j] values; only j<=i read */
+} b200md_aeam_tables;
+
+int b200md_aeam_init(b200md_ctx *ctx, const b200md_aeam_tables *t);
+/* read back one built spline table (testing: bit-parity with array2spline).
+ * kind: 0 = frho[i], 1 = rhor[i*nel+j], 2 = z2r[type2z2r]; out[(n+1)*7]      */
+int b200md_aeam_get_spline(b200md_ctx *ctx, int kind, int index, double *out, int nrows);
+
+/* ---- neighbor list hand-over (host CSR, LAMMPS NeighList layout) ----------
+ * inum owned rows + gnum ghost rows (gnum = 0 for AEAM); row i has numneigh[i]
+ * entries at firstneigh[i].  `skin` is neighbor->skin: the list is valid until
+ * some atom has moved more than skin/2 (LAMMPS' rebuild rule).  Call again
+ * whenever LAMMPS rebuilt the list (neighbor->ago == 0).                      */
+int b200md_set_neighbor_list(b200md_ctx *ctx, int inum, int gnum, const int *numneigh,
+                             const int *const *firstneigh, double skin);
+/* same, from a flat CSR (offsets[inum+gnum+1], values) */
+int b200md_set_neighbor_csr(b200md_ctx *ctx, int inum, int gnum, const int64_t *offsets,
+                            const int *values, double skin);
+
+/* ---- GPU neighbor build (replaces the host-built list) --------------------
+ * Builds the full list (and ghost rows if ghost_rows) on the device from host
+ * positions, reproducing LAMMPS' bin/stencil traversal order bit-for-bit.
+ * cutneighsq / cutneighghostsq are (ntypes+1)^2 row-major like Neighbor's.
+ * box: boxlo[3], boxhi[3], tilt xy xz yz, sub-domain lo/hi (lamda if triclinic),
+ * cutghost[3] (Comm::cutghost).                                               */
+typedef struct {
+  int triclinic;
+  double boxlo[3], boxhi[3];
+  double xy, xz, yz;
+  double sublo[3], subhi[3];
+  double cutghost[3];
+  double cutneighmax;
+} b200md_box;
+
+int b200md_neigh_build(b200md_ctx *ctx, const b200md_box *box, int ntypes, const double *cutneighsq,
+                       const double *cutneighghostsq, int nlocal, int nghost, const double *x,
+                       const int *type, int ghost_rows, double skin);
+/* size / download of the device-resident list (testing and plugin hand-back) */
+int b200md_neigh_size(b200md_ctx *ctx, int *nrows, int64_t *nentries);
+int b200md_neigh_download(b200md_ctx *ctx, int *numneigh, int64_t *offsets, int *values);
+
+/* ---- REBOMoS compute (host buffers in, host buffers out) ------------------
+ * f is ACCUMULATED into (like atom->f after force_clear()); eng_vdwl and
+ * virial[6] are overwritten with this call's contribution (caller adds).
+ * Forces are complete after LAMMPS' reverse_comm; the split of a pair's force
+ * between an owner and its ghost image differs from the reference. */
+int b200md_rebomos_compute(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                           const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
+                           double *virial);
+
+/* REBO short-range sub-list for owned AND ghost atoms from the current list and
+ * positions: numneigh[nall], rows packed with stride `stride`, nM[nall], nS[nall] */
+int b200md_rebomos_neigh(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                         int stride, int *rebo_numneigh, int *rebo_rows, double *nM, double *nS);
+
+/* ---- AEAM compute ---------------------------------------------------------- */
+int b200md_aeam_compute(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                        int eflag, int vflag, double *f, double *eng_vdwl, double *virial);
+/* rho[nlocal], fp[nlocal] of the last compute */
+int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
+
+/* ---- tuning / introspection ------------------------------------------------ */
+/* option names: "deterministic" (0/1), "margin" (inner-list skin in 1e-3 A, 0 = use skin),
+ * "sync_timing" (0/1) */
+int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
+/* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
+ * "rebo_bonds", "lj_entries", "short_entries" */
+long long b200md_get_counter(b200md_ctx *ctx, const char *name);
+/* device time of the kernels of the last compute call, ms, by name
+ * ("rebo_neigh","bondorder_p","bondorder_f","lj","fdotr","aeam_density","aeam_force",...) */
+double b200md_last_kernel_ms(b200md_ctx *ctx, const char *name);
+/* raw CUDA stream the context launches on (cudaStream_t), for external event timing */
+void *b200md_stream(b200md_ctx *ctx);
+
+/* =============================================================================
+ * GPU-resident MD system (the benchmark driver's run loop; one per GPU/rank)
+ * ============================================================================ */
+typedef struct {
+  int style;             /* 0 = rebomos, 1 = aeam (potential set with *_init before) */
+  int ntypes;
+  const double *mass;    /* [ntypes+1], 1-based */
+  b200md_box box;        /* global box; sublo/subhi/cutghost are computed by the library */
+  int procgrid[3];       /* brick decomposition; product = number of ranks */
+  int rank;
+  double skin;           /* neighbor skin */
+  double dt;             /* timestep (ps) */
+  double ftm2v, mvv2e, boltz, nktv2p; /* unit constants (metal: Update::set_units) */
+  int sort_every;        /* atom_modify sort frequency (0 = never) */
+} b200md_system_desc;
+
+/* upload this rank's owned atoms; builds ghosts + lists + initial forces (Verlet::setup) */
+int b200md_system_create(b200md_ctx *ctx, const b200md_system_desc *d, int nlocal, const double *x,
+                         const double *v, const int *type, const int *tag);
+/* multi-GPU: 128-byte NCCL unique id from rank 0, then every rank joins */
+int b200md_nccl_unique_id(void *id128);
+int b200md_system_comm_init(b200md_ctx *ctx, const void *id128, int nranks, int rank);
+/* advance n NVE steps entirely on the device; thermo quantities are evaluated on the last step
+ * (and every thermo_every steps, retrievable with b200md_system_thermo) */
+int b200md_system_run(b200md_ctx *ctx, int nsteps, int thermo_every);
+/* thermo of the most recent evaluation: out[0..11] = step, temp, press, pe, ke, vol, virial[6]
+ * (global sums over ranks) */
+int b200md_system_thermo(b200md_ctx *ctx, double *out);
+int b200md_system_thermo_count(b200md_ctx *ctx);
+int b200md_system_thermo_row(b200md_ctx *ctx, int i, double *out);
+/* sizes: out[0]=nlocal, out[1]=nghost, out[2]=neighbor builds, out[3]=dangerous builds */
+int b200md_system_sizes(b200md_ctx *ctx, long long *out);
+/* download owned+ghost state (any pointer may be NULL) */
+int b200md_system_download(b200md_ctx *ctx, double *x, double *v, double *f, int *type, int *tag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

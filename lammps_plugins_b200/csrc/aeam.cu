@@ -1,0 +1,899 @@
+// b200md -- angular EAM (pair_style aeam) force path on sm_100a.
+//
+// Reference semantics: lammps-plugins USER-AEAM/pair_aeam.cpp
+//   density pass :164-253, embedding :264-303, force pass :309-476,
+//   file2array :752-872, array2spline :876-911, interpolate :915-942.
+//
+// Formulation (DESIGN.md "AEAM kernels"):
+//   A1 aeam_density      8 lanes / owned non-angular atom: rho_i = sum_j f_ij(r), row streamed as sectors
+//   A2 aeam_density_ang  warp / owned angular atom: rho_i = sum_{j<k} 2 f_ij f_ik (cos+1/3)^2
+//   A3 aeam_embed        thread / owned atom: fp_i = F'(rho^ni), energy F
+//   (fp of ghosts: halo exchange -- live here, numerically dead in the reference)
+//   B1 aeam_force        8 lanes / owned atom, GATHER form: both directed visits (i->j and j->i) of a
+//                        pair are evaluated from i's side using fp_j, so the pair term needs no atomics
+//   B2 aeam_force_ang    warp / owned angular atom: 3-body forces, FP64 atomics on j,k (0.75 % of atoms)
+// Spline rows live on the device as {c3,c4,c5,c6} (32 B = one sector per lookup); the derivative
+// coefficients c0..c2 of the reference are exactly 3c3/d, 2c4/d, c5/d (pair_aeam.cpp:937-941).
+
+#include "common.cuh"
+
+#define BLOCK 256
+#define ANG_CAP 96    // staged neighbors per angular center
+
+// ================================================================== host: tables
+// PairAEAM::interpolate (pair_aeam.cpp:915-942), 1-based rows, 7 coefficients
+static void interpolate7(int n, double delta, const double *f /*1-based*/, double *spline /*(n+1)*7*/)
+{
+  auto S = [&](int m, int k) -> double & { return spline[(size_t) m * 7 + k]; };
+  for (int m = 1; m <= n; m++) S(m, 6) = f[m];
+  S(1, 5) = S(2, 6) - S(1, 6);
+  S(2, 5) = 0.5 * (S(3, 6) - S(1, 6));
+  S(n - 1, 5) = 0.5 * (S(n, 6) - S(n - 2, 6));
+  S(n, 5) = S(n, 6) - S(n - 1, 6);
+  for (int m = 3; m <= n - 2; m++)
+    S(m, 5) = ((S(m - 2, 6) - S(m + 2, 6)) + 8.0 * (S(m + 1, 6) - S(m - 1, 6))) / 12.0;
+  for (int m = 1; m <= n - 1; m++) {
+    S(m, 4) = 3.0 * (S(m + 1, 6) - S(m, 6)) - 2.0 * S(m, 5) - S(m + 1, 5);
+    S(m, 3) = S(m, 5) + S(m + 1, 5) - 2.0 * (S(m + 1, 6) - S(m, 6));
+  }
+  S(n, 4) = 0.0;
+  S(n, 3) = 0.0;
+  for (int m = 1; m <= n; m++) {
+    S(m, 2) = S(m, 5) / delta;
+    S(m, 1) = 2.0 * S(m, 4) / delta;
+    S(m, 0) = 3.0 * S(m, 3) / delta;
+  }
+  for (int k = 0; k < 7; k++) S(0, k) = 0.0;
+}
+
+struct AeamHost {
+  int nel = 0;
+  std::vector<std::vector<double>> frho7, rhor7, z2r7;    // 7-coefficient tables (reference layout)
+  std::vector<int> frho_n, rhor_n, z2r_n;
+};
+static std::map<b200md_ctx *, AeamHost> g_aeam_host;
+
+static int pack4(const std::vector<double> &s7, int n, std::vector<double> &out)
+{
+  int off = (int) (out.size() / 4);
+  for (int m = 0; m <= n; m++)
+    for (int k = 3; k <= 6; k++) out.push_back(s7[(size_t) m * 7 + k]);
+  return off;
+}
+
+extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, t && t->nelements >= 1 && t->nelements <= 4, "aeam_init: nelements must be 1..4");
+  ARG_CHECK(c, t->nnonangular >= 0 && t->nnonangular <= t->nelements, "aeam_init: bad nnonangular");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int nel = t->nelements;
+  AeamHost &H = g_aeam_host[c];
+  H = AeamHost();
+  H.nel = nel;
+  AeamDev &d = c->ap;
+  memset(&d, 0, sizeof(d));
+  d.nel = nel;
+  d.nnonangular = t->nnonangular;
+
+  std::vector<double> p_frho, p_rhor, p_z2r;
+  // frho: one table per element (the reference's extra all-zero table serves pair hybrid only)
+  for (int i = 0; i < nel; i++) {
+    const int n = t->nrho[i];
+    ARG_CHECK(c, n >= 5 && t->drho[i] > 0.0, "aeam_init: need nrho >= 5 and drho > 0");
+    std::vector<double> f1((size_t) n + 1, 0.0);
+    for (int m = 1; m <= n; m++) f1[m] = t->frho[i][m - 1];
+    std::vector<double> s7((size_t) (n + 1) * 7);
+    interpolate7(n, t->drho[i], f1.data(), s7.data());
+    d.nrho[i] = n;
+    d.rdrho[i] = 1.0 / t->drho[i];
+    d.frho_off[i] = pack4(s7, n, p_frho);
+    H.frho7.push_back(std::move(s7));
+    H.frho_n.push_back(n);
+  }
+  // rhor: full matrix, table index i*nel+j (type2rhor, pair_aeam.cpp:816-821)
+  for (int i = 0; i < nel; i++)
+    for (int j = 0; j < nel; j++) {
+      const int ij = i * nel + j;
+      const int n = t->nr[ij];
+      ARG_CHECK(c, n >= 5 && t->dr[ij] > 0.0 && t->cut[ij] > 0.0, "aeam_init: need nr >= 5, dr > 0, cut > 0");
+      std::vector<double> f1((size_t) n + 1, 0.0);
+      for (int m = 1; m <= n; m++) f1[m] = t->rhor[ij][m - 1];
+      std::vector<double> s7((size_t) (n + 1) * 7);
+      interpolate7(n, t->dr[ij], f1.data(), s7.data());
+      d.nr[ij] = n;
+      d.rdr[ij] = 1.0 / t->dr[ij];
+      d.cut[ij] = t->cut[ij];
+      d.rhor_off[ij] = pack4(s7, n, p_rhor);
+      H.rhor7.push_back(std::move(s7));
+      H.rhor_n.push_back(n);
+    }
+  // z2r: lower triangle (j <= i), interpolated with nr/dr of [i][j] (file2array :836-843);
+  // pair (a,b) uses table (max,min) (type2z2r :853-871)
+  std::vector<int> tri_off((size_t) nel * nel, 0);
+  for (int i = 0; i < nel; i++)
+    for (int j = 0; j <= i; j++) {
+      const int ij = i * nel + j;
+      const int n = t->nr[ij];
+      std::vector<double> f1((size_t) n + 1, 0.0);
+      for (int m = 1; m <= n; m++) f1[m] = t->z2r[ij][m - 1];
+      std::vector<double> s7((size_t) (n + 1) * 7);
+      interpolate7(n, t->dr[ij], f1.data(), s7.data());
+      tri_off[ij] = pack4(s7, n, p_z2r);
+      H.z2r7.push_back(std::move(s7));
+      H.z2r_n.push_back(n);
+    }
+  for (int i = 0; i < nel; i++)
+    for (int j = 0; j < nel; j++) {
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      d.z2r_off[i * nel + j] = tri_off[hi * nel + lo];
+    }
+
+  CUDA_TRY(c, c->spl_frho.reserve(p_frho.size() + 8));
+  CUDA_TRY(c, c->spl_rhor.reserve(p_rhor.size() + 8));
+  CUDA_TRY(c, c->spl_z2r.reserve(p_z2r.size() + 8));
+  CUDA_TRY(c, cudaMemcpyAsync(c->spl_frho.p, p_frho.data(), p_frho.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->spl_rhor.p, p_rhor.data(), p_rhor.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->spl_z2r.p, p_z2r.data(), p_z2r.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->ntypes = nel;
+  c->aeam_ready = true;
+  c->rebomos_ready = false;
+  c->inner_valid = false;
+  return B200MD_OK;
+}
+
+extern "C" int b200md_aeam_get_spline(b200md_ctx *c, int kind, int index, double *out, int nrows)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->aeam_ready && out, "aeam_get_spline: call b200md_aeam_init first");
+  AeamHost &H = g_aeam_host[c];
+  const std::vector<std::vector<double>> *tab = kind == 0 ? &H.frho7 : kind == 1 ? &H.rhor7 : kind == 2 ? &H.z2r7 : nullptr;
+  const std::vector<int> *ns = kind == 0 ? &H.frho_n : kind == 1 ? &H.rhor_n : &H.z2r_n;
+  ARG_CHECK(c, tab && index >= 0 && index < (int) tab->size(), "aeam_get_spline: bad table");
+  ARG_CHECK(c, nrows == (*ns)[index], "aeam_get_spline: nrows must equal the table length");
+  memcpy(out, (*tab)[index].data(), (size_t) (nrows + 1) * 7 * sizeof(double));
+  return B200MD_OK;
+}
+
+void b200md_aeam_forget(b200md_ctx *c) { g_aeam_host.erase(c); }
+
+// ================================================================== device helpers
+__device__ __forceinline__ int etype(const double4 &q) { return __double2int_rn(q.w); }
+
+__device__ __forceinline__ void spl_index(double x, double rdx, int n, int &m, double &p)
+{
+  p = x * rdx + 1.0;
+  m = (int) p;
+  m = min(m, n - 1);
+  p -= m;
+  p = fmin(p, 1.0);
+}
+__device__ __forceinline__ double spl_val(const double4 &c, double p)
+{
+  return ((c.x * p + c.y) * p + c.z) * p + c.w;
+}
+__device__ __forceinline__ double spl_der(const double4 &c, double p, double rdx)
+{
+  return ((3.0 * c.x * p + 2.0 * c.y) * p + c.z) * rdx;
+}
+
+// positions + 0-based element packed into one 32-byte sector
+__global__ void __launch_bounds__(BLOCK) aeam_pack_kernel(const double *__restrict__ x,
+                                                          const int *__restrict__ type, int nel, int nall,
+                                                          double4 *__restrict__ xq, int *__restrict__ flags)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nall) return;
+  int t = type[i];
+  if (t < 1 || t > nel) {
+    flags[3] = 1;
+    t = 1;
+  }
+  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (double) (t - 1));
+}
+
+// inner rows: master row filtered to r <= max(cut_ij, cut_ji) + margin, 8-aligned, order preserved
+__global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq,
+    const int64_t *__restrict__ list_off, const int *__restrict__ list_num,
+    const int *__restrict__ list_val, int inum, const int64_t *__restrict__ ea_off,
+    int *__restrict__ ea_num, int *__restrict__ ea_val, int *__restrict__ ang_list, int *__restrict__ flags)
+{
+  const int lane = threadIdx.x & 31;
+  const int i = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
+  if (i >= inum) return;
+  const double4 xi = xq[i];
+  const int ti = etype(xi);
+  const int n = list_num[i];
+  const int64_t base = list_off[i], obase = ea_off[i];
+  const unsigned lt = (1u << lane) - 1u;
+  int no = 0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    bool keep = false;
+    int j = 0;
+    if (e < n) {
+      j = ld_stream_int(list_val + base + e) & B200MD_NEIGHMASK;
+      const double4 xj = xq[j];
+      const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+      keep = dx * dx + dy * dy + dz * dz <= par.cutsq_list[ti * par.nel + etype(xj)];
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (keep) ea_val[obase + no + __popc(mk & lt)] = j;
+    no += __popc(mk);
+  }
+  if (lane == 0) {
+    ea_num[i] = no;
+    atomicAdd(&flags[5], no);
+    if (ti >= par.nnonangular) ang_list[atomicAdd(&flags[6], 1)] = i;
+  }
+}
+
+// ================================================================== A1: density of non-angular atoms
+__global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
+    int inum, double *__restrict__ rho)
+{
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int i = tid >> 3, sub = tid & 7;
+  double acc = 0.0;
+  bool mine = false;
+  if (i < inum) {
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    mine = ti < par.nnonangular;
+    if (mine) {
+      const int n = ea_num[i];
+      const int *row = ea_val + ea_off[i];
+      for (int e0 = 0; e0 < n; e0 += 32) {
+        int jj[4];
+        double4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u * 8 + sub;
+          jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (jj[u] >= 0) xj[u] = xq[jj[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (jj[u] < 0) continue;
+          const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
+          const double r1 = sqrt(dx * dx + dy * dy + dz * dz);
+          const int pt = ti * par.nel + etype(xj[u]);
+          if (r1 > par.cut[pt]) continue;    // i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
+          int m;
+          double p;
+          spl_index(r1, par.rdr[pt], par.nr[pt], m, p);
+          acc += spl_val(rhor[par.rhor_off[pt] + m], p);
+        }
+      }
+    }
+  }
+  acc = group_sum<8>(acc);
+  if (mine && sub == 0) rho[i] = acc;
+}
+
+// ================================================================== A2 / B2: angular atoms (warp per atom)
+struct AngStage {
+  double dx[ANG_CAP], dy[ANG_CAP], dz[ANG_CAP], r[ANG_CAP], f[ANG_CAP], df[ANG_CAP];
+  int j[ANG_CAP];
+  unsigned char inD[ANG_CAP];    // passes the density-pass cutoff (cut - CutDec)
+};
+
+// stage the in-range neighbors of angular center i in row order; returns count (uniform over the warp)
+__device__ __forceinline__ int ang_stage(const AeamDev &par, const double4 *__restrict__ xq,
+                                         const double4 *__restrict__ rhor, const int *row, int n,
+                                         const double4 &xi, int ti, bool force_pass, AngStage &S, int lane,
+                                         int *flags)
+{
+  const unsigned lt = (1u << lane) - 1u;
+  int ns = 0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    bool keep = false, inD = false;
+    int j = 0;
+    double dx = 0, dy = 0, dz = 0, r1 = 0, fv = 0, dfv = 0;
+    if (e < n) {
+      j = row[e];
+      const double4 xj = xq[j];
+      dx = xj.x - xi.x;
+      dy = xj.y - xi.y;
+      dz = xj.z - xi.z;
+      r1 = sqrt(dx * dx + dy * dy + dz * dz);
+      const int tj = etype(xj);
+      const int pt = ti * par.nel + tj;
+      const double cutdec = (tj >= par.nnonangular) ? 1.5 : 0.0;    // i is angular here
+      inD = !(r1 > par.cut[pt] - cutdec);
+      // force pass: j-role uses the plain cutoff (pair_aeam.cpp:350), k-role the reduced one (:408-418)
+      keep = force_pass ? !(r1 > par.cut[pt]) : inD;
+      if (keep) {
+        int m;
+        double p;
+        spl_index(r1, par.rdr[pt], par.nr[pt], m, p);
+        const double4 cf = rhor[par.rhor_off[pt] + m];
+        fv = spl_val(cf, p);
+        dfv = spl_der(cf, p, par.rdr[pt]);
+      }
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = ns + __popc(mk & lt);
+      if (pos < ANG_CAP) {
+        S.dx[pos] = dx; S.dy[pos] = dy; S.dz[pos] = dz; S.r[pos] = r1; S.f[pos] = fv; S.df[pos] = dfv;
+        S.j[pos] = j;
+        S.inD[pos] = inD ? 1 : 0;
+      } else
+        flags[0] = 3;
+    }
+    ns += __popc(mk);
+  }
+  __syncwarp();
+  return min(ns, ANG_CAP);
+}
+
+__global__ void __launch_bounds__(128) aeam_density_ang_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
+    const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, double *__restrict__ rho,
+    int *__restrict__ flags)
+{
+  __shared__ AngStage stage[4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n_ang = *n_ang_ptr;
+  for (int a = blockIdx.x * 4 + wid; a < n_ang; a += gridDim.x * 4) {
+    const int i = ang_list[a];
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    AngStage &S = stage[wid];
+    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i], ea_num[i], xi, ti, false, S, lane, flags);
+    double acc = 0.0;
+    for (int p = 0; p < ns; p++) {
+      const double r1 = S.r[p], fij = S.f[p];
+      const double rsq1 = S.dx[p] * S.dx[p] + S.dy[p] * S.dy[p] + S.dz[p] * S.dz[p];
+      for (int q = p + 1 + lane; q < ns; q += 32) {
+        const double ex = S.dx[q] - S.dx[p], ey = S.dy[q] - S.dy[p], ez = S.dz[q] - S.dz[p];
+        const double rsq3 = ex * ex + ey * ey + ez * ez;
+        const double rsq2 = S.dx[q] * S.dx[q] + S.dy[q] * S.dy[q] + S.dz[q] * S.dz[q];
+        const double cs = (rsq1 + rsq2 - rsq3) / (2 * r1 * S.r[q]);
+        const double delcs = cs + (1.0 / 3.0);
+        acc += 2 * fij * S.f[q] * (delcs * delcs);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) rho[i] = acc;
+    __syncwarp();
+  }
+}
+
+// ================================================================== A3: embedding
+__global__ void __launch_bounds__(BLOCK) aeam_embed_kernel(const __grid_constant__ AeamDev par,
+                                                           const double4 *__restrict__ xq,
+                                                           const double4 *__restrict__ frho,
+                                                           const double *__restrict__ rho, int inum,
+                                                           double *__restrict__ fp, double *__restrict__ scal)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  double e[1] = {0.0};
+  if (i < inum) {
+    const int ti = etype(xq[i]);
+    const double rh = rho[i];
+    // p = pow(rho, ni)/drho + 1 with ni = 1 (non-angular) or 1/2 (angular)   pair_aeam.cpp:274-288
+    const double arg = (ti < par.nnonangular) ? rh : sqrt(rh);
+    double p = arg * par.rdrho[ti] + 1.0;
+    int m = (int) p;
+    m = max(1, min(m, par.nrho[ti] - 1));
+    p -= m;
+    p = fmin(p, 1.0);
+    const double4 cf = frho[par.frho_off[ti] + m];
+    fp[i] = spl_der(cf, p, par.rdrho[ti]);
+    e[0] = spl_val(cf, p);
+  }
+  block_accumulate<1, BLOCK>(e, scal);
+}
+
+// single-rank convenience: ghost fp/rho from the owner with the same atom ID
+__global__ void __launch_bounds__(BLOCK) aeam_tagmap_kernel(const int *__restrict__ tag, int nlocal,
+                                                            int *__restrict__ owner_of_tag, int maxtag)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i < nlocal) {
+    const int t = tag[i];
+    if (t >= 0 && t <= maxtag) owner_of_tag[t] = i;
+  }
+}
+__global__ void __launch_bounds__(BLOCK) aeam_ghost_fill_kernel(const int *__restrict__ tag, int nlocal,
+                                                                int nall, const int *__restrict__ owner_of_tag,
+                                                                int maxtag, double *__restrict__ fp,
+                                                                double *__restrict__ rho, int *__restrict__ flags)
+{
+  const int g = nlocal + blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= nall) return;
+  const int t = tag[g];
+  const int o = (t >= 0 && t <= maxtag) ? owner_of_tag[t] : -1;
+  if (o < 0) {
+    flags[7] = 1;
+    return;
+  }
+  fp[g] = fp[o];
+  rho[g] = rho[o];
+}
+
+// ================================================================== B1: pair + embedding forces (gather)
+template <bool EV>
+__global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
+    const double4 *__restrict__ z2r, const double *__restrict__ rho, const double *__restrict__ fp, int inum,
+    double *__restrict__ f, double *__restrict__ scal)
+{
+  const double minrho = 0.0000000000001;
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int i = tid >> 3, sub = tid & 7;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (i < inum) {
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    // (1-deli) * Fptmp * fp[i]: zero for angular i (deli = 1), fp[i] for non-angular i with rho > minrho
+    const double gi = (ti < par.nnonangular && rho[i] > minrho) ? fp[i] : 0.0;
+    const int n = ea_num[i];
+    const int *row = ea_val + ea_off[i];
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      int jj[4];
+      double4 xj[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * 8 + sub;
+        jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (jj[u] >= 0) xj[u] = xq[jj[u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (jj[u] < 0) continue;
+        const int j = jj[u];
+        const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
+        const double rsq = dx * dx + dy * dy + dz * dz;
+        const double r1 = sqrt(rsq);
+        const int tj = etype(xj[u]);
+        const int pij = ti * par.nel + tj, pji = tj * par.nel + ti;
+        const double recip = 1.0 / r1;
+        double coef = 0.0;    // fpair of visit (i,j) + fpair of visit (j,i)
+        if (!(r1 > par.cut[pij])) {
+          // visit (i,j): pair_aeam.cpp:350-393
+          int m;
+          double p;
+          spl_index(r1, par.rdr[pij], par.nr[pij], m, p);
+          const double dfij = spl_der(rhor[par.rhor_off[pij] + m], p, par.rdr[pij]);
+          const double4 cz = z2r[par.z2r_off[pij] + m];
+          const double phip = spl_der(cz, p, par.rdr[pij]);
+          const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
+          coef += fpair;
+          if (EV) {
+            ev[0] += 0.5 * spl_val(cz, p);
+            ev[1] += dx * dx * fpair;
+            ev[2] += dy * dy * fpair;
+            ev[3] += dz * dz * fpair;
+            ev[4] += dx * dy * fpair;
+            ev[5] += dx * dz * fpair;
+            ev[6] += dy * dz * fpair;
+          }
+        }
+        if (!(r1 > par.cut[pji])) {
+          // visit (j,i), evaluated here instead of scattering from j's row
+          int m;
+          double p;
+          spl_index(r1, par.rdr[pji], par.nr[pji], m, p);
+          const double gj = (tj < par.nnonangular && rho[j] > minrho) ? fp[j] : 0.0;
+          const double dfji = spl_der(rhor[par.rhor_off[pji] + m], p, par.rdr[pji]);
+          const double phip = spl_der(z2r[par.z2r_off[pji] + m], p, par.rdr[pji]);
+          coef += -gj * dfji * recip + 0.5 * (-phip * recip);
+        }
+        fx -= dx * coef;
+        fy -= dy * coef;
+        fz -= dz * coef;
+      }
+    }
+  }
+  fx = group_sum<8>(fx);
+  fy = group_sum<8>(fy);
+  fz = group_sum<8>(fz);
+  if (i < inum && sub == 0) {
+    atomicAdd(&f[3 * (size_t) i], fx);    // B2 may add to the same atom concurrently
+    atomicAdd(&f[3 * (size_t) i + 1], fy);
+    atomicAdd(&f[3 * (size_t) i + 2], fz);
+  }
+  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+}
+
+// ================================================================== B2: 3-body forces of angular atoms
+template <bool EV>
+__global__ void __launch_bounds__(128) aeam_force_ang_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
+    const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, const double *__restrict__ rho,
+    const double *__restrict__ fp, double *__restrict__ f, double *__restrict__ scal, int *__restrict__ flags)
+{
+  __shared__ AngStage stage[4];
+  const double minrho = 0.0000000000001;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n_ang = *n_ang_ptr;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int a = blockIdx.x * 4 + wid; a < n_ang; a += gridDim.x * 4) {
+    const int i = ang_list[a];
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    AngStage &S = stage[wid];
+    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i], ea_num[i], xi, ti, true, S, lane, flags);
+    // Fptmp*fp[i], Fptmp = ni*rho^(ni-1) = 0.5/sqrt(rho)   (pair_aeam.cpp:329-332)
+    const double rh = rho[i];
+    const double G = (rh > minrho) ? 0.5 / sqrt(rh) * fp[i] : 0.0;
+    const double ci = 2.0;
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    for (int p = 0; p < ns; p++) {
+      const double r1 = S.r[p], fij = S.f[p], dfij = S.df[p];
+      const double d1x = S.dx[p], d1y = S.dy[p], d1z = S.dz[p];
+      const double rsq1 = d1x * d1x + d1y * d1y + d1z * d1z;
+      double fjx = 0.0, fjy = 0.0, fjz = 0.0;
+      for (int q = p + 1 + lane; q < ns; q += 32) {
+        if (!S.inD[q]) continue;
+        const double r2 = S.r[q], fik = S.f[q], dfik = S.df[q];
+        const double d2x = S.dx[q], d2y = S.dy[q], d2z = S.dz[q];
+        const double d3x = d2x - d1x, d3y = d2y - d1y, d3z = d2z - d1z;
+        const double rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
+        const double rsq3 = d3x * d3x + d3y * d3y + d3z * d3z;
+        const double r3 = sqrt(rsq3);
+        const double cs = (rsq1 + rsq2 - rsq3) / (2 * r1 * r2);
+        const double dcosij = 1 / r2 - cs / r1;
+        const double dcosik = 1 / r1 - cs / r2;
+        const double dcosjk = -r3 / (r1 * r2);
+        const double delcs = cs + (1.0 / 3.0);
+        const double ftet = delcs * delcs;
+        const double delcs2 = 2 * delcs;
+        const double DFij = ci * (fik * dfij * ftet + fij * fik * delcs2 * dcosij);
+        const double DFik = ci * (fij * dfik * ftet + fij * fik * delcs2 * dcosik);
+        const double DFjk = ci * fij * fik * delcs2 * dcosjk;
+        const double FFij = -G * DFij / r1;
+        const double FFik = -G * DFik / r2;
+        const double FFjk = -G * DFjk / r3;
+        const double fj0 = d1x * FFij - d3x * FFjk, fj1 = d1y * FFij - d3y * FFjk, fj2 = d1z * FFij - d3z * FFjk;
+        const double fk0 = d2x * FFik + d3x * FFjk, fk1 = d2y * FFik + d3y * FFjk, fk2 = d2z * FFik + d3z * FFjk;
+        fjx += fj0; fjy += fj1; fjz += fj2;
+        fix -= fj0 + fk0; fiy -= fj1 + fk1; fiz -= fj2 + fk2;
+        const int k = S.j[q];
+        atomicAdd(&f[3 * (size_t) k], fk0);
+        atomicAdd(&f[3 * (size_t) k + 1], fk1);
+        atomicAdd(&f[3 * (size_t) k + 2], fk2);
+        if (EV) {    // ev_tally3 (delr1, delr2 are x_j - x_i, x_k - x_i)
+          v[0] += d1x * fj0 + d2x * fk0;
+          v[1] += d1y * fj1 + d2y * fk1;
+          v[2] += d1z * fj2 + d2z * fk2;
+          v[3] += d1x * fj1 + d2x * fk1;
+          v[4] += d1x * fj2 + d2x * fk2;
+          v[5] += d1y * fj2 + d2y * fk2;
+        }
+      }
+      fjx = warp_sum(fjx);
+      fjy = warp_sum(fjy);
+      fjz = warp_sum(fjz);
+      if (lane == 0 && (fjx != 0.0 || fjy != 0.0 || fjz != 0.0)) {
+        const int j = S.j[p];
+        atomicAdd(&f[3 * (size_t) j], fjx);
+        atomicAdd(&f[3 * (size_t) j + 1], fjy);
+        atomicAdd(&f[3 * (size_t) j + 2], fjz);
+      }
+    }
+    fix = warp_sum(fix);
+    fiy = warp_sum(fiy);
+    fiz = warp_sum(fiz);
+    if (lane == 0) {
+      atomicAdd(&f[3 * (size_t) i], fix);
+      atomicAdd(&f[3 * (size_t) i + 1], fiy);
+      atomicAdd(&f[3 * (size_t) i + 2], fiz);
+    }
+    __syncwarp();
+  }
+  if (EV) {
+    __shared__ double sh[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double s = warp_sum(v[k]);
+      if (lane == 0) sh[k][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) atomicAdd(&scal[1 + threadIdx.x], sh[threadIdx.x][0] + sh[threadIdx.x][1] +
+                                                                 sh[threadIdx.x][2] + sh[threadIdx.x][3]);
+  }
+}
+
+// ================================================================== host side
+static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
+
+int b200md_aeam_pack(b200md_ctx *c)
+{
+  if (c->nall == 0) return B200MD_OK;
+  LaunchScope ls(c, "pack");
+  aeam_pack_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, c->ap.nel, c->nall,
+                                                                     c->xq.p, c->flags.p);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+int b200md_aeam_build_inner(b200md_ctx *c)
+{
+  const int inum = c->list_inum;
+  double m = (c->margin_opt > 0.0) ? c->margin_opt : c->skin;
+  if (m > c->skin) m = c->skin;
+  c->margin = m;
+  const int nel = c->ap.nel;
+  for (int i = 0; i < nel; i++)
+    for (int j = 0; j < nel; j++) {
+      const double cc = fmax(c->ap.cut[i * nel + j], c->ap.cut[j * nel + i]) + m;
+      c->ap.cutsq_list[i * nel + j] = cc * cc;
+    }
+  CUDA_TRY(c, c->ea_off.reserve((size_t) inum + 2));
+  CUDA_TRY(c, c->ea_num.reserve((size_t) inum + 32));
+  CUDA_TRY(c, c->ang_list.reserve((size_t) inum + 32));
+  int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
+  if (rc) return rc;
+  CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
+  CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 4, 0, 3 * sizeof(int), c->stream));
+  if (inum > 0) {
+    LaunchScope ls(c, "build_inner");
+    aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(
+        c->ap, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, inum, c->ea_off.p, c->ea_num.p,
+        c->ea_val.p, c->ang_list.p, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->xhold.p, c->xq.p, (size_t) c->nall * sizeof(double4), cudaMemcpyDeviceToDevice,
+                              c->stream));
+  c->inner_valid = true;
+  c->n_inner_rebuild++;
+  return B200MD_OK;
+}
+
+__global__ void aeam_check_disp_kernel(const double4 *__restrict__ xq, const double4 *__restrict__ xhold,
+                                       int nall, double thresh_sq, int *__restrict__ flags)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nall) return;
+  double4 a = xq[i], b = xhold[i];
+  double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  if (dx * dx + dy * dy + dz * dz > thresh_sq) flags[1] = 1;
+}
+
+int b200md_aeam_refresh_inner(b200md_ctx *c)
+{
+  if (!c->inner_valid) return b200md_aeam_build_inner(c);
+  if (c->margin >= c->skin) return B200MD_OK;
+  const double half = 0.5 * c->margin;
+  {
+    LaunchScope ls(c, "check_disp");
+    aeam_check_disp_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(
+        c->xq.p, (const double4 *) c->xhold.p, c->nall, half * half, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  int flag = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (flag) {
+    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
+    return b200md_aeam_build_inner(c);
+  }
+  return B200MD_OK;
+}
+
+// density + embedding for owned atoms (rho, fp valid for [0,inum) afterwards)
+int b200md_aeam_density(b200md_ctx *c)
+{
+  const int inum = c->list_inum;
+  CUDA_TRY(c, c->rho.reserve((size_t) c->nall + 32));
+  CUDA_TRY(c, c->fp.reserve((size_t) c->nall + 32));
+  if (inum == 0) return B200MD_OK;
+  const double4 *rhor = (const double4 *) c->spl_rhor.p;
+  {
+    LaunchScope ls(c, "aeam_density");
+    aeam_density_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+        c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p);
+  }
+  if (c->ap.nnonangular < c->ap.nel) {
+    LaunchScope ls(c, "aeam_density_ang");
+    aeam_density_ang_kernel<<<c->num_sms * 2, 128, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p,
+                                                                  c->ea_val.p, rhor, c->ang_list.p,
+                                                                  c->flags.p + 6, c->rho.p, c->flags.p);
+  }
+  {
+    LaunchScope ls(c, "aeam_embed");
+    aeam_embed_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->ap, c->xq.p, (const double4 *) c->spl_frho.p,
+                                                                   c->rho.p, inum, c->fp.p, c->scal.p);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// ghost fp/rho from same-ID owners (valid when every ghost's owner is local: 1 rank, periodic images)
+int b200md_aeam_fill_ghosts_by_tag(b200md_ctx *c, int maxtag)
+{
+  if (c->nghost == 0) return B200MD_OK;
+  CUDA_TRY(c, c->scan_tmp.reserve((size_t) maxtag + 2));
+  CUDA_TRY(c, cudaMemsetAsync(c->scan_tmp.p, 0xff, ((size_t) maxtag + 1) * sizeof(int), c->stream));
+  {
+    LaunchScope ls(c, "aeam_tagmap");
+    aeam_tagmap_kernel<<<nblocks(c->nlocal, BLOCK), BLOCK, 0, c->stream>>>(c->tag.p, c->nlocal, c->scan_tmp.p, maxtag);
+  }
+  {
+    LaunchScope ls(c, "aeam_ghost_fill");
+    aeam_ghost_fill_kernel<<<nblocks(c->nghost, BLOCK), BLOCK, 0, c->stream>>>(
+        c->tag.p, c->nlocal, c->nall, c->scan_tmp.p, maxtag, c->fp.p, c->rho.p, c->flags.p);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// forces; needs rho/fp of owned AND ghost atoms
+int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
+{
+  const int inum = c->list_inum;
+  if (inum == 0) return B200MD_OK;
+  const double4 *rhor = (const double4 *) c->spl_rhor.p;
+  const double4 *z2r = (const double4 *) c->spl_z2r.p;
+  const bool ev = eflag || vflag;
+  {
+    LaunchScope ls(c, "aeam_force");
+    const int nb = nblocks((long long) inum * 8, BLOCK);
+    if (ev)
+      aeam_force_kernel<true><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
+                                                          rhor, z2r, c->rho.p, c->fp.p, inum, c->f.p, c->scal.p);
+    else
+      aeam_force_kernel<false><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
+                                                           rhor, z2r, c->rho.p, c->fp.p, inum, c->f.p, c->scal.p);
+  }
+  if (c->ap.nnonangular < c->ap.nel) {
+    LaunchScope ls(c, "aeam_force_ang");
+    if (ev)
+      aeam_force_ang_kernel<true><<<c->num_sms * 2, 128, 0, c->stream>>>(
+          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p,
+          c->fp.p, c->f.p, c->scal.p, c->flags.p);
+    else
+      aeam_force_ang_kernel<false><<<c->num_sms * 2, 128, 0, c->stream>>>(
+          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p,
+          c->fp.p, c->f.p, c->scal.p, c->flags.p);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int aeam_check_flags(b200md_ctx *c, const int *fl)
+{
+  if (fl[5]) c->n_lj_entries = fl[5];
+  c->n_ang = fl[6];
+  if (fl[3]) {
+    c->fail("atom type outside 1..nelements (pair_coeff must map every type, in file order)");
+    cudaMemsetAsync(c->flags.p + 3, 0, sizeof(int), c->stream);
+    return B200MD_ERR_ARG;
+  }
+  if (fl[7]) {
+    c->fail("aeam_compute: a ghost atom has no owner with the same ID on this rank; use the two-phase "
+            "API (b200md_aeam_density / halo exchange of fp / b200md_aeam_force)");
+    cudaMemsetAsync(c->flags.p + 7, 0, sizeof(int), c->stream);
+    return B200MD_ERR_ARG;
+  }
+  if (fl[0]) {
+    c->fail("AEAM angular-neighbor staging overflow (more than " + std::to_string(ANG_CAP) + " neighbors in range)");
+    cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream);
+    return B200MD_ERR_OVERFLOW;
+  }
+  return B200MD_OK;
+}
+
+static int aeam_begin(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type, const int *tag)
+{
+  ARG_CHECK(c, c->aeam_ready, "aeam: call b200md_aeam_init first");
+  ARG_CHECK(c, c->list_valid, "aeam: no neighbor list (b200md_set_neighbor_list / b200md_neigh_build)");
+  ARG_CHECK(c, c->list_inum == nlocal, "aeam: neighbor list was built for a different nlocal");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag);
+  if (rc) return rc;
+  const size_t n3 = 3 * (size_t) c->nall;
+  CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+  if ((rc = b200md_aeam_pack(c))) return rc;
+  return b200md_aeam_refresh_inner(c);
+}
+
+static int aeam_finish(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial)
+{
+  const size_t n3 = 3 * (size_t) c->nall;
+  CUDA_TRY(c, c->pin_f.reserve(n3 + 64));
+  int *pin_flags = (int *) (c->pin_scal.p + 32);
+  if (n3) CUDA_TRY(c, cudaMemcpyAsync(c->pin_f.p, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (long long) (n3 * sizeof(double) + 16 * sizeof(double) + 16 * sizeof(int));
+  b200md_collect_timers(c);
+  int rc = aeam_check_flags(c, pin_flags);
+  if (rc) return rc;
+  const double *src = c->pin_f.p;
+  for (size_t k = 0; k < n3; k++) f[k] += src[k];
+  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
+  if (virial)
+    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
+  return B200MD_OK;
+}
+
+// one-shot: ghosts are periodic images of owned atoms (single rank); ghost fp via atom IDs
+extern "C" int b200md_aeam_compute(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
+                                   const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
+                                   double *virial)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, f != nullptr, "aeam_compute: f is NULL");
+  ARG_CHECK(c, tag != nullptr || nghost == 0, "aeam_compute: atom IDs are needed to give ghosts their fp");
+  int rc = aeam_begin(c, nlocal, nghost, x, type, tag);
+  if (rc) return rc;
+  if ((rc = b200md_aeam_density(c))) return rc;
+  if (nghost) {
+    int maxtag = 0;
+    for (int i = 0; i < nlocal; i++) maxtag = tag[i] > maxtag ? tag[i] : maxtag;
+    if ((rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag))) return rc;
+  }
+  if ((rc = b200md_aeam_forces(c, eflag, vflag))) return rc;
+  return aeam_finish(c, eflag, vflag, f, eng_vdwl, virial);
+}
+
+// two-phase API for hosts that own the halo exchange (LAMMPS: comm->forward_comm(this) in between)
+extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, const double *x,
+                                         const int *type, double *rho_out, double *fp_out)
+{
+  if (!c) return B200MD_ERR_ARG;
+  int rc = aeam_begin(c, nlocal, nghost, x, type, nullptr);
+  if (rc) return rc;
+  if ((rc = b200md_aeam_density(c))) return rc;
+  if (nlocal) {
+    if (rho_out) CUDA_TRY(c, cudaMemcpyAsync(rho_out, c->rho.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (fp_out) CUDA_TRY(c, cudaMemcpyAsync(fp_out, c->fp.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  int fl[16];
+  CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += 2LL * nlocal * sizeof(double);
+  return aeam_check_flags(c, fl);
+}
+
+extern "C" int b200md_aeam_force_phase(b200md_ctx *c, const double *rho_all, const double *fp_all, int eflag,
+                                       int vflag, double *f, double *eng_vdwl, double *virial)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->aeam_ready && c->inner_valid && f && rho_all && fp_all, "aeam_force_phase: call the density phase first");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int ng = c->nghost;
+  if (ng) {
+    // owned entries are already on the device; ghosts come from the host's halo exchange
+    CUDA_TRY(c, cudaMemcpyAsync(c->rho.p + c->nlocal, rho_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->fp.p + c->nlocal, fp_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += 2LL * ng * sizeof(double);
+  }
+  int rc = b200md_aeam_forces(c, eflag, vflag);
+  if (rc) return rc;
+  return aeam_finish(c, eflag, vflag, f, eng_vdwl, virial);
+}
+
+extern "C" int b200md_aeam_get_rho_fp(b200md_ctx *c, int nlocal, double *rho, double *fp)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->aeam_ready && nlocal <= c->nlocal && c->rho.p, "aeam_get_rho_fp: nothing computed yet");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (nlocal) {
+    if (rho) CUDA_TRY(c, cudaMemcpyAsync(rho, c->rho.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (fp) CUDA_TRY(c, cudaMemcpyAsync(fp, c->fp.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200MD_OK;
+}

@@ -1,0 +1,290 @@
+// b200md -- common declarations for the sm_100a force-path library.
+// Context object, growable device buffers, error plumbing, warp helpers.
+#pragma once
+
+#include "b200md.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#define B200MD_NEIGHMASK 0x1FFFFFFF
+#define B200MD_SHORT_WIDTH 64      // max entries of a short (REBO-range + margin) row
+#define B200MD_MAX_REBO 16         // max REBO neighbors of one atom (bulk MoS2: 12)
+#define B200MD_MAX_TYPES 8
+
+// ---------------------------------------------------------------- errors
+#define CUDA_TRY(ctx, call)                                                                       \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (ctx)->fail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + " (" #call ")");                                     \
+      return B200MD_ERR_CUDA;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+#define ARG_CHECK(ctx, cond, msg)                                                                 \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      (ctx)->fail(std::string("argument error: ") + (msg));                                       \
+      return B200MD_ERR_ARG;                                                                      \
+    }                                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------- device buffer
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;    // elements
+  cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0)
+  {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = n + n / 8 + 256;
+    T *q = nullptr;
+    cudaError_t e = cudaMalloc((void **) &q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(st);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T> struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = n + n / 8 + 256;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void **) &p, ncap * sizeof(T));
+    if (e == cudaSuccess) cap = ncap;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---------------------------------------------------------------- potential parameter blocks
+// REBOMoS constants, passed BY VALUE to kernels (lives in the kernel-parameter constant bank).
+struct RebomosDev {
+  double rcmin[4], rcmax[4], rcmaxsq[4], rcw[4];    // rcw = rcmax-rcmin
+  double Q[4], alpha[4], A[4], BIJc[4], Beta[4];
+  double b[2][7], bg[2][7];    // [elem][order]
+  double a[2][4];
+  double rcLJmin[4], rcLJmax[4], sig95[4];    // sig95 = 0.95*sigma
+  double lj1[4], lj2[4], lj3[4], lj4[4];
+  double c2[4], c3[4];    // cubic taper coefficients (pair_rebomos.cpp:533-538)
+  double shortsq[4];      // (rcmax + margin)^2
+  double ljsq[4];         // (rcLJmax + margin)^2
+};
+
+struct AeamDev {
+  int nel, nnonangular;
+  // per type pair (row-major i*nel+j), nel <= 4
+  double cut[16], rdr[16];
+  int nr[16];
+  int rhor_off[16];    // row offset of table (i,j) in the packed rhor spline array
+  int z2r_off[16];     // row offset of the z2r table used by pair (i,j)
+  double rdrho[4];
+  int nrho[4];
+  int frho_off[4];
+  double cutsq_list[16];    // (cut+margin)^2 for the inner list
+};
+
+// ---------------------------------------------------------------- context
+struct KernelTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool used = false;
+};
+
+struct SystemState;    // resident MD system (system.cu)
+
+struct b200md_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int num_sms = 148;
+
+  // options
+  int deterministic = 0;
+  double margin_opt = 0.0;    // 0 -> use skin
+  int sync_timing = 0;
+
+  // counters
+  long long n_launch = 0, n_list_upload = 0, n_inner_rebuild = 0, h2d_bytes = 0, d2h_bytes = 0;
+  long long n_rebo_bonds = 0, n_lj_entries = 0, n_short_entries = 0;
+  std::map<std::string, KernelTimer> timers;
+  std::map<std::string, float> last_ms;
+
+  // ---- atoms (device)
+  int nlocal = 0, nghost = 0, nall = 0;
+  DevBuf<double> x_aos;      // [nall*3] staging of host x
+  DevBuf<double4> xq;        // packed {x,y,z,elem-as-double}
+  DevBuf<double> f;          // [nall*3]
+  DevBuf<int> type, tag;
+  PinBuf<double> pin_f;      // D2H staging
+  PinBuf<double> pin_scal;   // small scalar results
+  DevBuf<double> scal;       // [64] device accumulators: 0 = energy, 1..6 virial, 8.. misc
+  DevBuf<int> flags;         // [16] device flags: 0 = overflow, 1 = inner rebuild needed, 2.. counters
+
+  // ---- master neighbor list (dense CSR on device)
+  int list_inum = 0, list_gnum = 0;
+  int64_t list_entries = 0;
+  double skin = 0.0;
+  double margin = 0.0;       // margin actually used by the inner lists
+  bool list_valid = false, inner_valid = false;
+  DevBuf<int64_t> list_off;  // [rows+1]
+  DevBuf<int> list_num;      // [rows]
+  DevBuf<int> list_val;      // [entries]
+  DevBuf<double> xhold;      // [nall*3] positions at inner-list build
+
+  // ---- REBOMoS
+  bool rebomos_ready = false;
+  RebomosDev rp;
+  int ntypes = 0;
+  int map_h[B200MD_MAX_TYPES + 1];
+  DevBuf<int> map_d;
+  // inner lists
+  int short_pad = 0;         // padded row count (stride of the transposed short rows)
+  DevBuf<int> short_idx;     // [B200MD_SHORT_WIDTH * short_pad] transposed
+  DevBuf<int> short_num;     // [rows]
+  DevBuf<int64_t> lj_off;    // [inum+1] 8-aligned row offsets
+  DevBuf<int> lj_num;        // [inum]
+  DevBuf<int> lj_val;        // directed LJ-window rows
+  int64_t lj_capacity = 0;
+  // per-step bond table
+  DevBuf<int> bond_off, bond_num;    // per center
+  DevBuf<double> cen_P, cen_dP;      // per center P(N), P'(N)
+  DevBuf<double> nM, nS;
+  DevBuf<int> bond_center, bond_j;   // per directed bond slot
+  DevBuf<double> bond_geo;           // [slots*8]: dx,dy,dz,rinv,w,dw,r,pad
+  DevBuf<double> bond_pref, bond_frad;
+  size_t bond_cap = 0;
+
+  // ---- AEAM
+  bool aeam_ready = false;
+  AeamDev ap;
+  DevBuf<double> spl_frho, spl_rhor, spl_z2r;    // 7 coefficients per row (reference layout)
+  std::vector<int> frho_rows, rhor_rows, z2r_rows;
+  DevBuf<double> rho, fp;
+  DevBuf<int64_t> ea_off;
+  DevBuf<int> ea_num, ea_val;        // inner AEAM rows (filtered to cut+margin)
+  DevBuf<int> ang_list;              // owned angular atoms
+  int n_ang = 0;
+
+  // ---- device-built list scratch (neigh.cu)
+  DevBuf<int> bin_of, bin_count, bin_start, bin_atoms, stencil_d;
+  DevBuf<int> scan_tmp;
+  DevBuf<int64_t> scan_tmp64;
+
+  SystemState *sys = nullptr;
+
+  int fail(const std::string &m)
+  {
+    err = m;
+    return -1;
+  }
+};
+
+// launch bookkeeping + optional per-kernel timing
+struct LaunchScope {
+  b200md_ctx *c;
+  KernelTimer *t = nullptr;
+  LaunchScope(b200md_ctx *ctx, const char *name) : c(ctx)
+  {
+    c->n_launch++;
+    if (c->sync_timing) {
+      KernelTimer &kt = c->timers[name];
+      if (!kt.a) {
+        cudaEventCreate(&kt.a);
+        cudaEventCreate(&kt.b);
+      }
+      t = &kt;
+      t->used = true;
+      cudaEventRecord(t->a, c->stream);
+    }
+  }
+  ~LaunchScope()
+  {
+    if (t) cudaEventRecord(t->b, c->stream);
+  }
+};
+
+int b200md_collect_timers(b200md_ctx *c);    // after a stream sync: fills last_ms
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int W> __device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-level sum of `n` doubles per thread into global accumulators (one atomic per block per value)
+template <int N, int BLOCK> __device__ __forceinline__ void block_accumulate(double (&v)[N], double *out)
+{
+  __shared__ double sh[N][BLOCK / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) sh[k][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) s += sh[threadIdx.x][w];
+    atomicAdd(&out[threadIdx.x], s);
+  }
+}
+__device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
+{
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_stream_int(const int *p)
+{
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+#endif
+
+// shared internal entry points
+int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
+                        const int *tag);
+int b200md_exclusive_scan_i64(b200md_ctx *c, const int *in, int64_t *out, int n, int align);

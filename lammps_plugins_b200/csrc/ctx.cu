@@ -1,0 +1,403 @@
+// b200md -- context lifecycle, host<->device staging of atoms and neighbor lists,
+// device prefix scan, options/counters.  No CPU fallback anywhere: without a usable
+// sm_100a device every call fails with B200MD_ERR_CUDA.
+
+#include "common.cuh"
+
+#include <mutex>
+
+static std::string g_create_error;
+static std::mutex g_mutex;
+
+extern "C" int b200md_version(void) { return B200MD_VERSION; }
+
+extern "C" const char *b200md_last_error(const b200md_ctx *ctx)
+{
+  if (ctx) return ctx->err.c_str();
+  return g_create_error.c_str();
+}
+
+extern "C" int b200md_create(int device, b200md_ctx **out)
+{
+  std::lock_guard<std::mutex> lk(g_mutex);
+  if (!out) {
+    g_create_error = "b200md_create: out is NULL";
+    return B200MD_ERR_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("b200md_create: no CUDA device available (") +
+        (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+        "); this library has no CPU fallback";
+    return B200MD_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "b200md_create: device index out of range";
+    return B200MD_ERR_ARG;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return B200MD_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "b200md_create: device " + std::string(prop.name) + " is sm_" +
+        std::to_string(prop.major) + std::to_string(prop.minor) +
+        "; this library carries sm_100a code only";
+    return B200MD_ERR_CUDA;
+  }
+  b200md_ctx *c = new b200md_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete c;
+    return B200MD_ERR_CUDA;
+  }
+  if (c->scal.reserve(64) != cudaSuccess || c->flags.reserve(16) != cudaSuccess ||
+      c->pin_scal.reserve(64) != cudaSuccess) {
+    g_create_error = "b200md_create: device allocation failed";
+    delete c;
+    return B200MD_ERR_CUDA;
+  }
+  cudaMemsetAsync(c->scal.p, 0, 64 * sizeof(double), c->stream);
+  cudaMemsetAsync(c->flags.p, 0, 16 * sizeof(int), c->stream);
+  cudaStreamSynchronize(c->stream);
+  *out = c;
+  return B200MD_OK;
+}
+
+void b200md_system_free(b200md_ctx *c);    // system.cu
+
+extern "C" void b200md_destroy(b200md_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  b200md_system_free(c);
+  c->x_aos.release(); c->xq.release(); c->f.release(); c->type.release(); c->tag.release();
+  c->pin_f.release(); c->pin_scal.release(); c->scal.release(); c->flags.release();
+  c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
+  c->map_d.release(); c->short_idx.release(); c->short_num.release();
+  c->lj_off.release(); c->lj_num.release(); c->lj_val.release();
+  c->bond_off.release(); c->bond_num.release(); c->cen_P.release(); c->cen_dP.release();
+  c->nM.release(); c->nS.release(); c->bond_center.release(); c->bond_j.release();
+  c->bond_geo.release(); c->bond_pref.release(); c->bond_frad.release();
+  c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release();
+  c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
+  c->ang_list.release();
+  c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
+  c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();
+  for (auto &kv : c->timers) {
+    if (kv.second.a) cudaEventDestroy(kv.second.a);
+    if (kv.second.b) cudaEventDestroy(kv.second.b);
+  }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long value)
+{
+  if (!c || !name) return B200MD_ERR_ARG;
+  std::string n(name);
+  if (n == "deterministic") c->deterministic = value ? 1 : 0;
+  else if (n == "margin") {
+    c->margin_opt = 1.0e-3 * (double) value;
+    c->inner_valid = false;
+  } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
+  else {
+    c->fail("unknown option " + n);
+    return B200MD_ERR_ARG;
+  }
+  return B200MD_OK;
+}
+
+extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
+{
+  if (!c || !name) return -1;
+  std::string n(name);
+  if (n == "kernel_launches") return c->n_launch;
+  if (n == "list_uploads") return c->n_list_upload;
+  if (n == "inner_rebuilds") return c->n_inner_rebuild;
+  if (n == "h2d_bytes") return c->h2d_bytes;
+  if (n == "d2h_bytes") return c->d2h_bytes;
+  if (n == "rebo_bonds") return c->n_rebo_bonds;
+  if (n == "lj_entries") return c->n_lj_entries;
+  if (n == "short_entries") return c->n_short_entries;
+  if (n == "num_sms") return c->num_sms;
+  return -1;
+}
+
+extern "C" double b200md_last_kernel_ms(b200md_ctx *c, const char *name)
+{
+  if (!c || !name) return -1.0;
+  auto it = c->last_ms.find(name);
+  if (it == c->last_ms.end()) return -1.0;
+  return it->second;
+}
+
+extern "C" void *b200md_stream(b200md_ctx *c) { return c ? (void *) c->stream : nullptr; }
+
+int b200md_collect_timers(b200md_ctx *c)
+{
+  if (!c->sync_timing) return 0;
+  for (auto &kv : c->timers) {
+    if (!kv.second.used) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, kv.second.a, kv.second.b) == cudaSuccess) c->last_ms[kv.first] = ms;
+    kv.second.used = false;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- atoms
+int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
+                        const int *tag)
+{
+  ARG_CHECK(c, nlocal >= 0 && nghost >= 0 && x && type, "upload_atoms: bad sizes or NULL arrays");
+  int nall = nlocal + nghost;
+  c->nlocal = nlocal;
+  c->nghost = nghost;
+  c->nall = nall;
+  size_t n = (size_t) nall;
+  CUDA_TRY(c, c->x_aos.reserve(3 * n + 8));
+  CUDA_TRY(c, c->xq.reserve(n + 8));
+  CUDA_TRY(c, c->f.reserve(3 * n + 8));
+  CUDA_TRY(c, c->type.reserve(n + 8));
+  CUDA_TRY(c, c->tag.reserve(n + 8));
+  if (n) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->type.p, type, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long) (3 * n * sizeof(double) + n * sizeof(int));
+    if (tag) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->tag.p, tag, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      c->h2d_bytes += (long long) (n * sizeof(int));
+    }
+  }
+  return B200MD_OK;
+}
+
+// ---------------------------------------------------------------- exclusive scan (int -> int64, optional alignment)
+// Three-phase tile scan; only used when lists are (re)built, never per step.
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+
+__device__ __forceinline__ long long scan_elem(const int *in, int i, int n, int align)
+{
+  if (i >= n) return 0;
+  long long v = in[i];
+  if (align > 1) v = (v + align - 1) / align * align;
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums(const int *__restrict__ in, int n, int align,
+                                                            long long *__restrict__ tile_sum)
+{
+  __shared__ long long sh[SCAN_BLOCK / 32];
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) s += scan_elem(in, base + k, n, align);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < SCAN_BLOCK / 32; w++) t += sh[w];
+    tile_sum[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_tile_offsets(long long *tile_sum, int ntiles)
+{
+  // single thread: ntiles is small (n / 2048); runs once per list build
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < ntiles; t++) {
+      long long v = tile_sum[t];
+      tile_sum[t] = run;
+      run += v;
+    }
+    tile_sum[ntiles] = run;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_apply(const int *__restrict__ in, int n, int align,
+                                                             const long long *__restrict__ tile_off,
+                                                             long long *__restrict__ out)
+{
+  __shared__ long long sh[SCAN_BLOCK / 32];
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  long long v[SCAN_ITEMS];
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = scan_elem(in, base + k, n, align);
+    s += v[k];
+  }
+  // inclusive warp scan of per-thread sums
+  long long inc = s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sh[wid] = inc;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; w++) woff += sh[w];
+  long long run = tile_off[blockIdx.x] + woff + inc - s;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_off[gridDim.x];
+}
+
+int b200md_exclusive_scan_i64(b200md_ctx *c, const int *in, int64_t *out, int n, int align)
+{
+  if (n <= 0) {
+    CUDA_TRY(c, cudaMemsetAsync(out, 0, sizeof(int64_t), c->stream));
+    return B200MD_OK;
+  }
+  int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  CUDA_TRY(c, c->scan_tmp64.reserve((size_t) ntiles + 2));
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  {
+    LaunchScope ls(c, "scan");
+    scan_tile_sums<<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, align, (long long *) c->scan_tmp64.p);
+  }
+  {
+    LaunchScope ls(c, "scan");
+    scan_tile_offsets<<<1, 32, 0, c->stream>>>((long long *) c->scan_tmp64.p, ntiles);
+  }
+  {
+    LaunchScope ls(c, "scan");
+    scan_tile_apply<<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, align, (const long long *) c->scan_tmp64.p,
+                                                         (long long *) out);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// ---------------------------------------------------------------- neighbor list upload
+static int finish_list(b200md_ctx *c, int inum, int gnum, int64_t total, double skin)
+{
+  c->list_inum = inum;
+  c->list_gnum = gnum;
+  c->list_entries = total;
+  c->skin = skin;
+  c->list_valid = true;
+  c->inner_valid = false;
+  c->n_list_upload++;
+  return B200MD_OK;
+}
+
+extern "C" int b200md_set_neighbor_list(b200md_ctx *c, int inum, int gnum, const int *numneigh,
+                                        const int *const *firstneigh, double skin)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, inum >= 0 && gnum >= 0 && numneigh && firstneigh && skin >= 0.0, "set_neighbor_list");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rows = inum + gnum;
+  std::vector<int64_t> off((size_t) rows + 1);
+  int64_t total = 0;
+  for (int i = 0; i < rows; i++) {
+    off[i] = total;
+    total += numneigh[i];
+  }
+  off[rows] = total;
+  CUDA_TRY(c, c->list_off.reserve((size_t) rows + 1));
+  CUDA_TRY(c, c->list_num.reserve((size_t) rows + 8));
+  CUDA_TRY(c, c->list_val.reserve((size_t) total + 64));
+  CUDA_TRY(c, cudaMemcpyAsync(c->list_off.p, off.data(), (rows + 1) * sizeof(int64_t),
+                              cudaMemcpyHostToDevice, c->stream));
+  if (rows)
+    CUDA_TRY(c, cudaMemcpyAsync(c->list_num.p, numneigh, rows * sizeof(int), cudaMemcpyHostToDevice,
+                                c->stream));
+  // LAMMPS keeps rows in pages: copy every run of rows that is contiguous in host memory at once
+  int i = 0;
+  while (i < rows) {
+    int j = i;
+    const int *start = firstneigh[i];
+    int64_t len = numneigh[i];
+    while (j + 1 < rows && firstneigh[j + 1] == firstneigh[j] + numneigh[j]) {
+      j++;
+      len += numneigh[j];
+    }
+    if (len > 0)
+      CUDA_TRY(c, cudaMemcpyAsync(c->list_val.p + off[i], start, (size_t) len * sizeof(int),
+                                  cudaMemcpyHostToDevice, c->stream));
+    i = j + 1;
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // `off` is a stack-owned staging vector
+  c->h2d_bytes += (long long) (total * sizeof(int) + rows * (sizeof(int) + sizeof(int64_t)));
+  return finish_list(c, inum, gnum, total, skin);
+}
+
+extern "C" int b200md_set_neighbor_csr(b200md_ctx *c, int inum, int gnum, const int64_t *offsets,
+                                       const int *values, double skin)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, inum >= 0 && gnum >= 0 && offsets && skin >= 0.0, "set_neighbor_csr");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rows = inum + gnum;
+  int64_t total = offsets[rows];
+  ARG_CHECK(c, offsets[0] == 0 && total >= 0 && (values || total == 0), "set_neighbor_csr: bad offsets");
+  std::vector<int> num((size_t) rows + 1);
+  for (int i = 0; i < rows; i++) {
+    int64_t n = offsets[i + 1] - offsets[i];
+    ARG_CHECK(c, n >= 0 && n < (1 << 30), "set_neighbor_csr: offsets not monotone");
+    num[i] = (int) n;
+  }
+  CUDA_TRY(c, c->list_off.reserve((size_t) rows + 1));
+  CUDA_TRY(c, c->list_num.reserve((size_t) rows + 8));
+  CUDA_TRY(c, c->list_val.reserve((size_t) total + 64));
+  CUDA_TRY(c, cudaMemcpyAsync(c->list_off.p, offsets, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                              c->stream));
+  if (rows)
+    CUDA_TRY(c, cudaMemcpyAsync(c->list_num.p, num.data(), rows * sizeof(int), cudaMemcpyHostToDevice,
+                                c->stream));
+  if (total)
+    CUDA_TRY(c, cudaMemcpyAsync(c->list_val.p, values, (size_t) total * sizeof(int), cudaMemcpyHostToDevice,
+                                c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->h2d_bytes += (long long) (total * sizeof(int) + rows * (sizeof(int) + sizeof(int64_t)));
+  return finish_list(c, inum, gnum, total, skin);
+}
+
+extern "C" int b200md_neigh_size(b200md_ctx *c, int *nrows, int64_t *nentries)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->list_valid, "neigh_size: no neighbor list on the device");
+  if (nrows) *nrows = c->list_inum + c->list_gnum;
+  if (nentries) *nentries = c->list_entries;
+  return B200MD_OK;
+}
+
+extern "C" int b200md_neigh_download(b200md_ctx *c, int *numneigh, int64_t *offsets, int *values)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->list_valid, "neigh_download: no neighbor list on the device");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rows = c->list_inum + c->list_gnum;
+  if (numneigh && rows)
+    CUDA_TRY(c, cudaMemcpyAsync(numneigh, c->list_num.p, rows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (offsets)
+    CUDA_TRY(c, cudaMemcpyAsync(offsets, c->list_off.p, (rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                c->stream));
+  if (values && c->list_entries)
+    CUDA_TRY(c, cudaMemcpyAsync(values, c->list_val.p, (size_t) c->list_entries * sizeof(int),
+                                cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200MD_OK;
+}

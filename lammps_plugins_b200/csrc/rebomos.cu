@@ -1,0 +1,842 @@
+// b200md -- REBOMoS force path on sm_100a.
+//
+// Reference semantics: lammps-plugins USER-REBOMOS/pair_rebomos.cpp
+//   REBO_neigh :281-352, FREBO :358-447, bondorder :571-847, FLJ :453-558,
+//   gSpline/PijSpline/Sp pair_rebomos.h:68-211.
+//
+// Formulation (DESIGN.md "REBOMoS kernels"): the reference walks half-bonds (i,j) and
+// scatters 3 forces per (bond,k) triplet.  Here the energy is regrouped by CENTER atom,
+//   E = sum_i E_i,  E_i = sum_{j in R(i)} 1/2 [ VR_ij + p_ij VA_ij ],
+// p_ij depends only on i and its REBO neighbors, so all forces of E_i land on i and R(i):
+//   K3  rebo_neigh     thread / owned atom : ordered filter of the short row, N_i, bond table
+//   K4a bondorder_p    thread / directed bond (i->m): S = sum_k w_k G(cos), p, prefactors, energy
+//   K4b bondorder_f    thread / directed bond: F_m (all terms in which m takes part), F_i = -sum F_m
+//   K5  lj             8 lanes / owned atom over the directed LJ-window row, no atomics
+//   K8  fdotr          sum_{nall} x (x) f for the many-body part
+// FP64 throughout; neighbor-position gathers are one 32-byte sector (double4 {x,y,z,elem}).
+
+#include "common.cuh"
+
+#define TOL 1.0e-9
+#define BLOCK 256
+
+// ================================================================== device math
+__device__ __forceinline__ int elem_of(const double4 &q) { return __double2int_rn(q.w); }
+
+// Sp cutoff (pair_rebomos.h:195-211): value and derivative
+__device__ __forceinline__ double sp_switch(double r, double rmin, double rw, double &dS)
+{
+  const double t = (r - rmin) / rw;    // rw = rcmax - rcmin
+  if (t <= 0.0) {
+    dS = 0.0;
+    return 1.0;
+  }
+  if (t >= 1.0) {
+    dS = 0.0;
+    return 0.0;
+  }
+  double s, c;
+  sincospi(t, &s, &c);
+  dS = (-0.5 * 3.14159265358979323846 * s) / rw;
+  return 0.5 * (1.0 + c);
+}
+
+// G(cos) value only (pair_rebomos.h:68-167)
+__device__ __forceinline__ double gspline_val(const RebomosDev &par, double c, int t)
+{
+  const double *b = par.b[t];
+  double g = b[6];
+  g = fma(g, c, b[5]);
+  g = fma(g, c, b[4]);
+  g = fma(g, c, b[3]);
+  g = fma(g, c, b[2]);
+  g = fma(g, c, b[1]);
+  g = fma(g, c, b[0]);
+  if (c >= 0.5) {
+    const double *bg = par.bg[t];
+    double gam = bg[6];
+    gam = fma(gam, c, bg[5]);
+    gam = fma(gam, c, bg[4]);
+    gam = fma(gam, c, bg[3]);
+    gam = fma(gam, c, bg[2]);
+    gam = fma(gam, c, bg[1]);
+    gam = fma(gam, c, bg[0]);
+    const double psi = 0.5 * (1.0 - cospi(2.0 * (c - 0.5)));
+    g = g + psi * (gam - g);
+  }
+  return g;
+}
+
+// G(cos) and dG/dcos
+__device__ __forceinline__ double gspline(const RebomosDev &par, double c, int t, double &dgdc)
+{
+  const double *b = par.b[t];
+  double g = b[6];
+  double dg = 6.0 * b[6];
+  g = fma(g, c, b[5]);
+  dg = fma(dg, c, 5.0 * b[5]);
+  g = fma(g, c, b[4]);
+  dg = fma(dg, c, 4.0 * b[4]);
+  g = fma(g, c, b[3]);
+  dg = fma(dg, c, 3.0 * b[3]);
+  g = fma(g, c, b[2]);
+  dg = fma(dg, c, 2.0 * b[2]);
+  g = fma(g, c, b[1]);
+  dg = fma(dg, c, b[1]);
+  g = fma(g, c, b[0]);
+  if (c >= 0.5) {
+    const double *bg = par.bg[t];
+    double gam = bg[6];
+    double dgam = 6.0 * bg[6];
+    gam = fma(gam, c, bg[5]);
+    dgam = fma(dgam, c, 5.0 * bg[5]);
+    gam = fma(gam, c, bg[4]);
+    dgam = fma(dgam, c, 4.0 * bg[4]);
+    gam = fma(gam, c, bg[3]);
+    dgam = fma(dgam, c, 3.0 * bg[3]);
+    gam = fma(gam, c, bg[2]);
+    dgam = fma(dgam, c, 2.0 * bg[2]);
+    gam = fma(gam, c, bg[1]);
+    dgam = fma(dgam, c, bg[1]);
+    gam = fma(gam, c, bg[0]);
+    double sn, cs;
+    sincospi(2.0 * (c - 0.5), &sn, &cs);
+    const double psi = 0.5 * (1.0 - cs);
+    const double dpsi = 3.14159265358979323846 * sn;
+    dgdc = dg + dpsi * (gam - g) + psi * (dgam - dg);
+    return g + psi * (gam - g);
+  }
+  dgdc = dg;
+  return g;
+}
+
+// ================================================================== staging kernels
+__global__ void __launch_bounds__(BLOCK) pack_xq_kernel(const double *__restrict__ x,
+                                                        const int *__restrict__ type,
+                                                        const int *__restrict__ map, int ntypes, int nall,
+                                                        double4 *__restrict__ xq, int *__restrict__ flags)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nall) return;
+  int t = type[i];
+  int e = -1;
+  if (t >= 1 && t <= ntypes) e = map[t];
+  else flags[3] = 1;    // invalid atom type
+  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (double) e);
+}
+
+__global__ void __launch_bounds__(BLOCK) check_disp_kernel(const double4 *__restrict__ xq,
+                                                           const double4 *__restrict__ xhold, int nall,
+                                                           double thresh_sq, int *__restrict__ flags)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nall) return;
+  double4 a = xq[i], b = xhold[i];
+  double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  if (dx * dx + dy * dy + dz * dz > thresh_sq) flags[1] = 1;
+}
+
+// inner lists from the master rows: one warp per row, order-preserving ballot compaction
+__global__ void __launch_bounds__(BLOCK) build_inner_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
+    const int64_t *__restrict__ list_off, const int *__restrict__ list_num,
+    const int *__restrict__ list_val, int rows, int inum, int short_pad, int *__restrict__ short_idx,
+    int *__restrict__ short_num, const int64_t *__restrict__ lj_off, int *__restrict__ lj_num,
+    int *__restrict__ lj_val, int *__restrict__ flags)
+{
+  const int lane = threadIdx.x & 31;
+  const int i = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
+  if (i >= rows) return;
+  const double4 xi = xq[i];
+  const int ti = elem_of(xi);
+  const int n = list_num[i];
+  const int64_t base = list_off[i];
+  const int64_t ljbase = (i < inum) ? lj_off[i] : 0;
+  const unsigned lt = (1u << lane) - 1u;
+  int ns = 0, nl = 0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    bool ps = false, pl = false;
+    int j = 0;
+    if (e < n) {
+      j = ld_stream_int(list_val + base + e) & B200MD_NEIGHMASK;
+      const double4 xj = xq[j];
+      const int tj = elem_of(xj);
+      if (ti >= 0 && tj >= 0) {
+        const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        const double rsq = dx * dx + dy * dy + dz * dz;
+        const int pt = ti * 2 + tj;
+        ps = rsq <= par.shortsq[pt];
+        pl = (i < inum) && rsq <= par.ljsq[pt];
+      }
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, ps);
+    const unsigned ml = __ballot_sync(0xffffffffu, pl);
+    if (ps) {
+      const int pos = ns + __popc(ms & lt);
+      if (pos < B200MD_SHORT_WIDTH) short_idx[(size_t) pos * short_pad + i] = j;
+      else flags[0] = 1;
+    }
+    if (pl) {
+      const int pos = nl + __popc(ml & lt);
+      lj_val[ljbase + pos] = j;
+    }
+    ns += __popc(ms);
+    nl += __popc(ml);
+  }
+  if (lane == 0) {
+    short_num[i] = min(ns, B200MD_SHORT_WIDTH);
+    if (i < inum) lj_num[i] = nl;
+    atomicAdd(&flags[4], ns);    // statistics (low contention: one per row, only at rebuilds)
+    atomicAdd(&flags[5], nl);
+  }
+}
+
+// ================================================================== K3: REBO sub-list, N_i, bond table
+// One thread per center.  Scanning the short row sequentially keeps the reference's neighbor order
+// (lists bit-exact) and its nM/nS summation order (pair_rebomos.cpp:328-343; sums equal to rounding
+// of cos: sincospi(t) here vs cos(t*pi) there).
+__global__ void __launch_bounds__(BLOCK) rebo_neigh_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
+    const int *__restrict__ short_idx, const int *__restrict__ short_num, int short_pad, int ncenters,
+    int *__restrict__ bond_off, int *__restrict__ bond_num, double *__restrict__ cenP,
+    double *__restrict__ cendP, double *__restrict__ nM_out, double *__restrict__ nS_out,
+    int *__restrict__ bond_center, int *__restrict__ bond_j, double4 *__restrict__ bond_geo, int bond_cap,
+    int *__restrict__ flags)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int jb[B200MD_MAX_REBO];
+  int nb = 0;
+  double nM = 0.0, nS = 0.0;
+  double4 xi = make_double4(0, 0, 0, -1);
+  int ti = -1;
+  if (i < ncenters) {
+    xi = xq[i];
+    ti = elem_of(xi);
+    const int n = (ti >= 0) ? short_num[i] : 0;
+    for (int e = 0; e < n; e++) {
+      const int j = short_idx[(size_t) e * short_pad + i];
+      const double4 xj = xq[j];
+      const int tj = elem_of(xj);
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      // same operation order as the reference, no FMA contraction: membership must be bit-exact
+      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      const int pt = ti * 2 + tj;
+      if (rsq < par.rcmaxsq[pt]) {
+        if (nb < B200MD_MAX_REBO) jb[nb] = j;
+        else flags[0] = 1;
+        nb++;
+        double dS;
+        const double w = sp_switch(sqrt(rsq), par.rcmin[pt], par.rcw[pt], dS);
+        if (tj == 0) nM += w;
+        else nS += w;
+      }
+    }
+    nb = min(nb, B200MD_MAX_REBO);
+  }
+  // slot allocation: warp exclusive scan + one atomic per warp
+  int inc = nb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, inc, 31);
+  int wbase = 0;
+  if (lane == 31 && total > 0) wbase = atomicAdd(&flags[2], total);
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
+  int off = wbase + inc - nb;
+  if (i >= ncenters) return;
+  if (off + nb > bond_cap) {
+    flags[0] = 2;
+    nb = 0;
+    off = 0;
+  }
+  bond_off[i] = off;
+  bond_num[i] = nb;
+  nM_out[i] = nM;
+  nS_out[i] = nS;
+  if (ti >= 0) {
+    // PijSpline (pair_rebomos.h:173-179)
+    const double N = nM + nS;
+    const double *a = par.a[ti];
+    const double ex = exp(-a[2] * N);
+    cendP[i] = -a[0] + a[1] * a[2] * ex;
+    cenP[i] = -a[0] * (N - 1.0) - a[1] * ex + a[3];
+  } else {
+    cendP[i] = 0.0;
+    cenP[i] = 0.0;
+  }
+  for (int b = 0; b < nb; b++) {
+    const int j = jb[b];
+    const double4 xj = xq[j];
+    const int tj = elem_of(xj);
+    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const double rsq = dx * dx + dy * dy + dz * dz;
+    const double r = sqrt(rsq);
+    const int pt = ti * 2 + tj;
+    double dw;
+    const double w = sp_switch(r, par.rcmin[pt], par.rcw[pt], dw);
+    const int s = off + b;
+    bond_center[s] = i;
+    bond_j[s] = j;
+    bond_geo[2 * (size_t) s] = make_double4(dx, dy, dz, 1.0 / r);
+    bond_geo[2 * (size_t) s + 1] = make_double4(w, dw, r, (double) tj);
+  }
+}
+
+// parity/debug variant: REBO rows for owned AND ghost atoms written to caller-visible arrays
+__global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
+    const int *__restrict__ short_idx, const int *__restrict__ short_num, int short_pad, int nrows,
+    int stride, int *__restrict__ out_num, int *__restrict__ out_rows, double *__restrict__ nM_out,
+    double *__restrict__ nS_out, int *__restrict__ flags)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nrows) return;
+  const double4 xi = xq[i];
+  const int ti = elem_of(xi);
+  const int n = (ti >= 0) ? short_num[i] : 0;
+  int nb = 0;
+  double nM = 0.0, nS = 0.0;
+  for (int e = 0; e < n; e++) {
+    const int j = short_idx[(size_t) e * short_pad + i];
+    const double4 xj = xq[j];
+    const int tj = elem_of(xj);
+    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const int pt = ti * 2 + tj;
+    if (rsq < par.rcmaxsq[pt]) {
+      if (nb < stride) out_rows[(size_t) i * stride + nb] = j;
+      else flags[0] = 1;
+      nb++;
+      double dS;
+      const double w = sp_switch(sqrt(rsq), par.rcmin[pt], par.rcw[pt], dS);
+      if (tj == 0) nM += w;
+      else nS += w;
+    }
+  }
+  out_num[i] = nb;
+  nM_out[i] = nM;
+  nS_out[i] = nS;
+}
+
+// ================================================================== K4a: p_ij, prefactors, pair energy
+__global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
+    const int *__restrict__ nslots_ptr, const int *__restrict__ bond_center,
+    const int *__restrict__ bond_off, const int *__restrict__ bond_num, const double *__restrict__ cenP,
+    const double *__restrict__ cendP, const double4 *__restrict__ bond_geo, double *__restrict__ bond_pref,
+    double *__restrict__ bond_frad, double *__restrict__ scal)
+{
+  const int nslots = *nslots_ptr;
+  double acc[1] = {0.0};
+  for (int s = blockIdx.x * BLOCK + threadIdx.x; s < nslots; s += gridDim.x * BLOCK) {
+    const int i = bond_center[s];
+    const int off = bond_off[i], nb = bond_num[i];
+    const int ti = elem_of(xq[i]);
+    const double4 gm = bond_geo[2 * (size_t) s];
+    const double4 hm = bond_geo[2 * (size_t) s + 1];
+    const double wm = hm.x, dwm = hm.y, r = hm.z;
+    const int tj = __double2int_rn(hm.w);
+    double pref = 0.0, frad = 0.0;
+    if (wm > TOL) {
+      double S = 0.0;
+      for (int q = off; q < off + nb; q++) {
+        if (q == s) continue;
+        const double4 gn = bond_geo[2 * (size_t) q];
+        const double wn = bond_geo[2 * (size_t) q + 1].x;
+        double c = (gm.x * gn.x + gm.y * gn.y + gm.z * gn.z) * (gm.w * gn.w);
+        c = fmin(c, 1.0);
+        c = fmax(c, -1.0);
+        S += wn * gspline_val(par, c, ti);
+      }
+      const double p = 1.0 / sqrt(1.0 + S + cenP[i]);
+      const int pt = ti * 2 + tj;
+      const double rinv = gm.w;
+      const double Q = par.Q[pt], al = par.alpha[pt];
+      const double pre = wm * par.A[pt] * exp(-al * r);
+      const double VR = pre * (1.0 + Q * rinv);
+      const double dVR = pre * (-al - Q * rinv * rinv - Q * al * rinv) + VR / wm * dwm;
+      const double be = par.Beta[pt];
+      const double VA = -wm * par.BIJc[pt] * exp(-be * r);
+      const double dVA = -be * VA + VA / wm * dwm;
+      pref = VA * 0.5 * (-0.5 * p * p * p);
+      frad = 0.5 * (dVR + p * dVA) * rinv + pref * cendP[i] * dwm * rinv;
+      acc[0] += 0.5 * (VR + p * VA);
+    }
+    bond_pref[s] = pref;
+    bond_frad[s] = frad;
+  }
+  block_accumulate<1, BLOCK>(acc, scal);
+}
+
+// ================================================================== K4b: forces of the bond-order term
+__global__ void __launch_bounds__(BLOCK) bondorder_f_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
+    const int *__restrict__ nslots_ptr, const int *__restrict__ bond_center,
+    const int *__restrict__ bond_j, const int *__restrict__ bond_off, const int *__restrict__ bond_num,
+    const double *__restrict__ cendP, const double4 *__restrict__ bond_geo,
+    const double *__restrict__ bond_pref, const double *__restrict__ bond_frad, double *__restrict__ f)
+{
+  const int nslots = *nslots_ptr;
+  for (int s = blockIdx.x * BLOCK + threadIdx.x; s < nslots; s += gridDim.x * BLOCK) {
+    const int i = bond_center[s];
+    const int off = bond_off[i], nb = bond_num[i];
+    const int ti = elem_of(xq[i]);
+    const double4 gm = bond_geo[2 * (size_t) s];
+    const double4 hm = bond_geo[2 * (size_t) s + 1];
+    const double wm = hm.x, dwm = hm.y;
+    const double prefm = bond_pref[s];
+    const double dP = cendP[i];
+    const double rinvm = gm.w;
+    const double rinvm2 = rinvm * rinvm;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int q = off; q < off + nb; q++) {
+      if (q == s) continue;
+      const double prefn = bond_pref[q];
+      const double4 gn = bond_geo[2 * (size_t) q];
+      const double wn = bond_geo[2 * (size_t) q + 1].x;
+      const double ca = -(prefm * wn + prefn * wm);
+      const double cb = prefn * dwm;
+      if (ca == 0.0 && cb == 0.0) continue;
+      const double rr = rinvm * gn.w;
+      double c = (gm.x * gn.x + gm.y * gn.y + gm.z * gn.z) * rr;
+      c = fmin(c, 1.0);
+      c = fmax(c, -1.0);
+      double dg;
+      const double g = gspline(par, c, ti, dg);
+      const double A = ca * dg;
+      const double B = cb * (g + dP) * rinvm;
+      const double cm = A * c * rinvm2 + B;    // multiplies d_m
+      const double cn = -A * rr;               // multiplies d_n
+      fx += cm * gm.x + cn * gn.x;
+      fy += cm * gm.y + cn * gn.y;
+      fz += cm * gm.z + cn * gn.z;
+    }
+    const double fr = bond_frad[s];
+    fx += fr * gm.x;
+    fy += fr * gm.y;
+    fz += fr * gm.z;
+    const int j = bond_j[s];
+    atomicAdd(&f[3 * (size_t) j], fx);
+    atomicAdd(&f[3 * (size_t) j + 1], fy);
+    atomicAdd(&f[3 * (size_t) j + 2], fz);
+    atomicAdd(&f[3 * (size_t) i], -fx);
+    atomicAdd(&f[3 * (size_t) i + 1], -fy);
+    atomicAdd(&f[3 * (size_t) i + 2], -fz);
+  }
+}
+
+// ================================================================== K8: fdotr virial over owned + ghost
+__global__ void __launch_bounds__(BLOCK) fdotr_kernel(const double4 *__restrict__ xq,
+                                                      const double *__restrict__ f, int nall,
+                                                      double *__restrict__ scal)
+{
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < nall; i += gridDim.x * BLOCK) {
+    const double4 x = xq[i];
+    const double fx = f[3 * (size_t) i], fy = f[3 * (size_t) i + 1], fz = f[3 * (size_t) i + 2];
+    v[0] += fx * x.x;
+    v[1] += fy * x.y;
+    v[2] += fz * x.z;
+    v[3] += fy * x.x;
+    v[4] += fz * x.x;
+    v[5] += fz * x.y;
+  }
+  block_accumulate<6, BLOCK>(v, scal + 1);
+}
+
+// ================================================================== K5: tapered LJ, directed rows
+// 8 lanes per owned atom: each group streams its 32-byte-aligned row as full sectors, gathers one
+// double4 sector per neighbor, reduces with 3 shuffles.  Every directed pair is evaluated from both
+// ends, so nothing is scattered: f_i is complete, energy and virial carry a factor 1/2.
+template <bool EV>
+__global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ RebomosDev par,
+                                                   const double4 *__restrict__ xq,
+                                                   const int64_t *__restrict__ lj_off,
+                                                   const int *__restrict__ lj_num,
+                                                   const int *__restrict__ lj_val, int inum,
+                                                   double *__restrict__ f, double *__restrict__ scal)
+{
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int i = tid >> 3;
+  const int sub = tid & 7;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (i < inum) {
+    const double4 xi = xq[i];
+    const int ti = elem_of(xi);
+    const int n = (ti >= 0) ? lj_num[i] : 0;
+    const int *row = lj_val + lj_off[i];
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      int jj[4];
+      double4 xj[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * 8 + sub;
+        jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (jj[u] >= 0) xj[u] = xq[jj[u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (jj[u] < 0) continue;
+        const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+        const double rsq = dx * dx + dy * dy + dz * dz;
+        const int pt = ti * 2 + elem_of(xj[u]);
+        const double rmax = par.rcLJmax[pt];
+        if (rsq > rmax * rmax * (1.0 + 1.0e-14)) continue;    // certainly outside; exact test below
+        const double rij = sqrt(rsq);
+        // regimes exactly as pair_rebomos.cpp:518-543
+        if (rij > rmax || rij < par.rcLJmin[pt]) continue;
+        double VLJ, fpair;
+        if (rij >= par.sig95[pt]) {
+          const double r2inv = 1.0 / rsq;
+          const double r6inv = r2inv * r2inv * r2inv;
+          VLJ = r6inv * (par.lj3[pt] * r6inv - par.lj4[pt]);
+          fpair = r6inv * (par.lj1[pt] * r6inv - par.lj2[pt]) * r2inv;
+        } else {
+          const double drp = rij - par.rcLJmin[pt];
+          VLJ = drp * drp * (drp * par.c3[pt] + par.c2[pt]);
+          const double dVLJ = drp * (3.0 * drp * par.c3[pt] + 2.0 * par.c2[pt]);
+          fpair = -dVLJ / rij;
+        }
+        fx += dx * fpair;
+        fy += dy * fpair;
+        fz += dz * fpair;
+        if (EV) {
+          ev[0] += 0.5 * VLJ;
+          const double hf = 0.5 * fpair;
+          ev[1] += dx * dx * hf;
+          ev[2] += dy * dy * hf;
+          ev[3] += dz * dz * hf;
+          ev[4] += dx * dy * hf;
+          ev[5] += dx * dz * hf;
+          ev[6] += dy * dz * hf;
+        }
+      }
+    }
+  }
+  fx = group_sum<8>(fx);
+  fy = group_sum<8>(fy);
+  fz = group_sum<8>(fz);
+  if (i < inum && sub == 0) {
+    f[3 * (size_t) i] += fx;
+    f[3 * (size_t) i + 1] += fy;
+    f[3 * (size_t) i + 2] += fz;
+  }
+  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+}
+
+// ================================================================== host side
+static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
+
+static void derive_params(b200md_ctx *c, const b200md_rebomos_params *p)
+{
+  RebomosDev &d = c->rp;
+  for (int k = 0; k < 4; k++) {
+    d.rcmin[k] = p->rcmin[k];
+    d.rcmax[k] = p->rcmax[k];
+    d.rcmaxsq[k] = p->rcmax[k] * p->rcmax[k];                  // pair_rebomos.cpp:974-977
+    d.rcw[k] = p->rcmax[k] - p->rcmin[k];
+    d.Q[k] = p->Q[k];
+    d.alpha[k] = p->alpha[k];
+    d.A[k] = p->A[k];
+    d.BIJc[k] = p->BIJc[k];
+    d.Beta[k] = p->Beta[k];
+    d.rcLJmin[k] = p->rcLJmin[k];
+    d.rcLJmax[k] = p->rcLJmax[k];
+    const double eps = p->epsilon[k], sig = p->sigma[k];
+    d.sig95[k] = 0.95 * sig;
+    // init_one (pair_rebomos.cpp:262-265): powint(sigma,12), powint(sigma,6)
+    double s2 = sig * sig, s4 = s2 * s2, s8 = s4 * s4;
+    double s6 = s2 * s4, s12 = s4 * s8;
+    d.lj1[k] = 48.0 * eps * s12;
+    d.lj2[k] = 24.0 * eps * s6;
+    d.lj3[k] = 4.0 * eps * s12;
+    d.lj4[k] = 4.0 * eps * s6;
+    // cubic taper (pair_rebomos.cpp:533-538)
+    const double dr = 0.95 * sig - p->rcLJmin[k];
+    const double q = sig / (0.95 * sig);
+    const double q2 = q * q;
+    const double r6 = q2 * (q2 * q2);    // powint(q,6): yy = ww^2 * ww^4
+    const double vdw = 4 * eps * r6 * (r6 - 1.0);
+    const double dvdw = (-4 * eps / (0.95 * sig)) * r6 * (12.0 * r6 - 6.0);
+    d.c2[k] = ((3.0 / dr) * vdw - dvdw) / dr;
+    d.c3[k] = (vdw / (dr * dr) - d.c2[k]) / dr;
+  }
+  for (int e = 0; e < 2; e++) {
+    for (int o = 0; o < 7; o++) {
+      d.b[e][o] = p->b[o][e];
+      d.bg[e][o] = p->bg[o][e];
+    }
+    for (int o = 0; o < 4; o++) d.a[e][o] = p->a[o][e];
+  }
+}
+
+static void set_margin(b200md_ctx *c)
+{
+  double m = (c->margin_opt > 0.0) ? c->margin_opt : c->skin;
+  if (m > c->skin) m = c->skin;    // the master rows only cover cut + skin
+  c->margin = m;
+  for (int k = 0; k < 4; k++) {
+    const double s = c->rp.rcmax[k] + m;
+    const double l = c->rp.rcLJmax[k] + m;
+    c->rp.shortsq[k] = s * s;
+    c->rp.ljsq[k] = l * l;
+  }
+}
+
+extern "C" int b200md_rebomos_init(b200md_ctx *c, const b200md_rebomos_params *p, int ntypes,
+                                   const int *map)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, p && map && ntypes >= 1 && ntypes <= B200MD_MAX_TYPES, "rebomos_init: ntypes must be 1..8");
+  for (int k = 0; k < 4; k++)
+    ARG_CHECK(c, p->rcmax[k] > p->rcmin[k] && p->rcmin[k] > 0.0 && p->sigma[k] > 0.0,
+              "rebomos_init: need 0 < rcmin < rcmax and sigma > 0");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  derive_params(c, p);
+  c->ntypes = ntypes;
+  c->map_h[0] = -1;
+  for (int t = 1; t <= ntypes; t++) {
+    ARG_CHECK(c, map[t] >= -1 && map[t] <= 1, "rebomos_init: map entries must be -1, 0 (Mo) or 1 (S)");
+    c->map_h[t] = map[t];
+  }
+  CUDA_TRY(c, c->map_d.reserve(B200MD_MAX_TYPES + 1));
+  CUDA_TRY(c, cudaMemcpyAsync(c->map_d.p, c->map_h, (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                              c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->rebomos_ready = true;
+  c->aeam_ready = false;
+  c->inner_valid = false;
+  return B200MD_OK;
+}
+
+// pack positions (and fail on bad types)
+int b200md_rebomos_pack(b200md_ctx *c)
+{
+  if (c->nall == 0) return B200MD_OK;
+  LaunchScope ls(c, "pack");
+  pack_xq_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, c->map_d.p,
+                                                                   c->ntypes, c->nall, c->xq.p, c->flags.p);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// (re)build the inner lists (short rows + directed LJ rows) from the master list on the device
+int b200md_rebomos_build_inner(b200md_ctx *c)
+{
+  const int rows = c->list_inum + c->list_gnum;
+  const int inum = c->list_inum;
+  set_margin(c);
+  c->short_pad = (rows + 31) / 32 * 32;
+  CUDA_TRY(c, c->short_idx.reserve((size_t) B200MD_SHORT_WIDTH * c->short_pad + 32));
+  CUDA_TRY(c, c->short_num.reserve((size_t) rows + 32));
+  CUDA_TRY(c, c->lj_off.reserve((size_t) inum + 2));
+  CUDA_TRY(c, c->lj_num.reserve((size_t) inum + 32));
+  int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->lj_off.p, inum, 8);
+  if (rc) return rc;
+  // capacity bound without a host round trip: every row padded to a multiple of 8
+  const int64_t cap = c->list_entries + 8 * (int64_t) inum + 64;
+  CUDA_TRY(c, c->lj_val.reserve((size_t) cap));
+  c->lj_capacity = cap;
+  CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 4, 0, 2 * sizeof(int), c->stream));
+  if (rows > 0) {
+    LaunchScope ls(c, "build_inner");
+    build_inner_kernel<<<nblocks((long long) rows * 32, BLOCK), BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, rows, inum, c->short_pad,
+        c->short_idx.p, c->short_num.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->xhold.p, c->xq.p, (size_t) c->nall * sizeof(double4),
+                              cudaMemcpyDeviceToDevice, c->stream));
+  c->inner_valid = true;
+  c->n_inner_rebuild++;
+  return B200MD_OK;
+}
+
+// decide whether the inner lists are still valid for the positions now on the device
+int b200md_rebomos_refresh_inner(b200md_ctx *c)
+{
+  const int rows = c->list_inum + c->list_gnum;
+  ARG_CHECK(c, rows <= c->nall, "neighbor list has more rows than atoms");
+  if (!c->inner_valid) return b200md_rebomos_build_inner(c);
+  if (c->margin >= c->skin) return B200MD_OK;    // master-list owner (LAMMPS) enforces skin/2 itself
+  const double half = 0.5 * c->margin;
+  {
+    LaunchScope ls(c, "check_disp");
+    check_disp_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(
+        c->xq.p, (const double4 *) c->xhold.p, c->nall, half * half, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  int flag = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (flag) {
+    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
+    return b200md_rebomos_build_inner(c);
+  }
+  return B200MD_OK;
+}
+
+// force kernels on whatever is resident: xq, inner lists.  f and scal must be zeroed by the caller.
+int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
+{
+  const int ncen = c->list_inum;
+  const size_t cap = (size_t) 10 * ncen + 4096;
+  if (cap > c->bond_cap) {
+    CUDA_TRY(c, c->bond_center.reserve(cap));
+    CUDA_TRY(c, c->bond_j.reserve(cap));
+    CUDA_TRY(c, c->bond_geo.reserve(8 * cap));
+    CUDA_TRY(c, c->bond_pref.reserve(cap));
+    CUDA_TRY(c, c->bond_frad.reserve(cap));
+    c->bond_cap = cap;
+  }
+  CUDA_TRY(c, c->bond_off.reserve((size_t) ncen + 32));
+  CUDA_TRY(c, c->bond_num.reserve((size_t) ncen + 32));
+  CUDA_TRY(c, c->cen_P.reserve((size_t) ncen + 32));
+  CUDA_TRY(c, c->cen_dP.reserve((size_t) ncen + 32));
+  CUDA_TRY(c, c->nM.reserve((size_t) c->nall + 32));
+  CUDA_TRY(c, c->nS.reserve((size_t) c->nall + 32));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
+  if (ncen == 0) return B200MD_OK;
+  const int grid_bonds = c->num_sms * 8;
+  {
+    LaunchScope ls(c, "rebo_neigh");
+    rebo_neigh_kernel<<<nblocks(ncen, BLOCK), BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->short_idx.p, c->short_num.p, c->short_pad, ncen, c->bond_off.p, c->bond_num.p,
+        c->cen_P.p, c->cen_dP.p, c->nM.p, c->nS.p, c->bond_center.p, c->bond_j.p,
+        (double4 *) c->bond_geo.p, (int) c->bond_cap, c->flags.p);
+  }
+  {
+    LaunchScope ls(c, "bondorder_p");
+    bondorder_p_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->flags.p + 2, c->bond_center.p, c->bond_off.p, c->bond_num.p, c->cen_P.p,
+        c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->scal.p);
+  }
+  {
+    LaunchScope ls(c, "bondorder_f");
+    bondorder_f_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->flags.p + 2, c->bond_center.p, c->bond_j.p, c->bond_off.p, c->bond_num.p,
+        c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->f.p);
+  }
+  if (vflag) {
+    LaunchScope ls(c, "fdotr");
+    fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, c->scal.p);
+  }
+  {
+    LaunchScope ls(c, "lj");
+    const int nb = nblocks((long long) ncen * 8, BLOCK);
+    if (eflag || vflag)
+      lj_kernel<true><<<nb, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p,
+                                                  ncen, c->f.p, c->scal.p);
+    else
+      lj_kernel<false><<<nb, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p,
+                                                   ncen, c->f.p, c->scal.p);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int check_flags(b200md_ctx *c, const int *fl)
+{
+  c->n_rebo_bonds = fl[2];
+  if (fl[4] || fl[5]) {
+    c->n_short_entries = fl[4];
+    c->n_lj_entries = fl[5];
+  }
+  if (fl[3]) {
+    c->fail("atom type outside 1..ntypes");
+    return B200MD_ERR_ARG;
+  }
+  if (fl[0]) {
+    c->fail(fl[0] == 2 ? "REBO bond table overflow" : "REBO neighbor row overflow (more than " +
+                std::to_string(B200MD_MAX_REBO) + " REBO neighbors or " +
+                std::to_string(B200MD_SHORT_WIDTH) + " short-row entries on one atom)");
+    cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream);
+    return B200MD_ERR_OVERFLOW;
+  }
+  return B200MD_OK;
+}
+
+extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, const double *x,
+                                      const int *type, const int *tag, int eflag, int vflag, double *f,
+                                      double *eng_vdwl, double *virial)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->rebomos_ready, "rebomos_compute: call b200md_rebomos_init first");
+  ARG_CHECK(c, c->list_valid, "rebomos_compute: no neighbor list (b200md_set_neighbor_list / b200md_neigh_build)");
+  ARG_CHECK(c, c->list_inum == nlocal, "rebomos_compute: neighbor list was built for a different nlocal");
+  ARG_CHECK(c, f != nullptr, "rebomos_compute: f is NULL");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag);
+  if (rc) return rc;
+  const size_t n3 = 3 * (size_t) c->nall;
+  CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+  if ((rc = b200md_rebomos_pack(c))) return rc;
+  if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
+  if ((rc = b200md_rebomos_forces(c, eflag, vflag))) return rc;
+
+  CUDA_TRY(c, c->pin_f.reserve(n3 + 64));
+  int *pin_flags = (int *) (c->pin_scal.p + 32);
+  if (n3) CUDA_TRY(c, cudaMemcpyAsync(c->pin_f.p, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (long long) (n3 * sizeof(double) + 16 * sizeof(double) + 16 * sizeof(int));
+  b200md_collect_timers(c);
+  if ((rc = check_flags(c, pin_flags))) return rc;
+
+  const double *src = c->pin_f.p;
+  for (size_t k = 0; k < n3; k++) f[k] += src[k];
+  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
+  if (virial) {
+    // scal[1..6] = fdotr (xx,yy,zz,xy,xz,yz) of the many-body part + LJ pair virial in the same order
+    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
+  }
+  return B200MD_OK;
+}
+
+extern "C" int b200md_rebomos_neigh(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
+                                    int stride, int *rebo_numneigh, int *rebo_rows, double *nM, double *nS)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->rebomos_ready && c->list_valid, "rebomos_neigh: init and neighbor list required");
+  ARG_CHECK(c, c->list_inum == nlocal, "rebomos_neigh: neighbor list was built for a different nlocal");
+  ARG_CHECK(c, stride >= 1 && rebo_numneigh && rebo_rows && nM && nS, "rebomos_neigh: NULL output");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, nullptr);
+  if (rc) return rc;
+  if ((rc = b200md_rebomos_pack(c))) return rc;
+  if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
+  const int rows = c->list_inum + c->list_gnum;    // ghost rows exist only if the list carries them
+  DevBuf<int> d_num, d_rows;
+  CUDA_TRY(c, d_num.reserve((size_t) rows + 8));
+  CUDA_TRY(c, d_rows.reserve((size_t) rows * stride + 8));
+  CUDA_TRY(c, c->nM.reserve((size_t) c->nall + 32));
+  CUDA_TRY(c, c->nS.reserve((size_t) c->nall + 32));
+  if (rows) {
+    LaunchScope ls(c, "rebo_rows");
+    rebo_rows_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->short_idx.p, c->short_num.p, c->short_pad, rows, stride, d_num.p, d_rows.p,
+        c->nM.p, c->nS.p, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(rebo_numneigh, d_num.p, rows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(rebo_rows, d_rows.p, (size_t) rows * stride * sizeof(int),
+                                cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(nM, c->nM.p, rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(nS, c->nS.p, rows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  int fl[16];
+  CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  d_num.release();
+  d_rows.release();
+  return check_flags(c, fl);
+}

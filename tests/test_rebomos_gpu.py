@@ -1,0 +1,165 @@
+"""GPU parity of the REBOMoS force path against the oracle (reference sources compiled verbatim,
+oracle/_ref, or the port when _ref is absent) on identical inputs.  All calls go through the C ABI.
+
+Tolerance: forces 1e-10 relative to the largest force component (north star), energy 1e-12 relative,
+virial 1e-10 relative to the largest virial component.  Neighbor sub-lists: bit-exact."""
+import numpy as np
+import pytest
+
+import support as S
+
+pytestmark = pytest.mark.gpu
+
+FTOL = 1.0e-10
+ETOL = 1.0e-12
+
+
+def oracle_forces(lmp):
+    """owned-atom forces after reverse comm, energy, fdotr virial from the oracle engine"""
+    lmp.compute(1, 2, reverse=True)
+    nlocal = lmp.get_int("nlocal")
+    f = lmp.f()[:nlocal].copy()
+    return f, lmp.get_double("eng_vdwl"), np.array([lmp.get_double("virial%d" % k) for k in range(6)])
+
+
+def gpu_forces(ctx, snap, eflag=1, vflag=2):
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    f, e, v = ctx.rebomos_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], eflag, vflag)
+    return S.fold_ghost_forces(f, snap["swaps"], snap["nlocal"]), e, v
+
+
+def init_ctx(ctx):
+    ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+
+
+CASES = [
+    dict(id="bulk288", replicate=(1, 1, 1), displace=0.0),
+    dict(id="bulk288-d0.05", replicate=(1, 1, 1), displace=0.05),
+    dict(id="bulk288-d0.3", replicate=(1, 1, 1), displace=0.3),     # S-S pairs enter the switching window
+    dict(id="rep2x2x1-d0.15", replicate=(2, 2, 1), displace=0.15),
+    dict(id="rep2x1x2-d0.6", replicate=(2, 1, 2), displace=0.6),     # strongly disordered: LJ taper regime
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_forces_energy_virial(ctx, oracle_built, case):
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), case["replicate"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    init_ctx(ctx)
+    f, e, v = gpu_forces(ctx, snap)
+    ferr = S.rel_err(f, f_ref)
+    eerr = abs(e - e_ref) / abs(e_ref)
+    verr = S.rel_err(v, v_ref)
+    print("\n%s: nlocal %d nghost %d  max|f| %.4g  ferr %.3e  E %.10f eerr %.3e  verr %.3e  bonds %d lj %d"
+          % (case["id"], snap["nlocal"], snap["nghost"], np.abs(f_ref).max(), ferr, e, eerr, verr,
+             ctx.counter("rebo_bonds"), ctx.counter("lj_entries")))
+    assert ferr < FTOL
+    assert eerr < ETOL
+    assert verr < FTOL
+    lmp.close()
+
+
+def test_golden_step0_energy(ctx, oracle_built):
+    """PotEng of log.rebomos-bulk.1 step 0 straight from the CUDA path: -2061.6112 (8 digits)."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"))
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    init_ctx(ctx)
+    f, e, v = gpu_forces(ctx, snap)
+    assert S.fmt8(e) == "-2061.6112"
+    # Press(0) = trace(virial)/(3V) * nktv2p = 28799.53 bar
+    vol = 5922.4926
+    row = lmp.thermo()[0]
+    press = (v[0] + v[1] + v[2]) / 3.0 / row["vol"] * lmp.get_double("nktv2p")
+    assert S.fmt8(press) == "28799.53"
+    lmp.close()
+
+
+def test_no_energy_no_virial_flags(ctx, oracle_built):
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), displace=0.1)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, _, _ = oracle_forces(lmp)
+    init_ctx(ctx)
+    f, e, v = gpu_forces(ctx, snap, eflag=0, vflag=0)
+    assert e == 0.0 and not v.any()
+    assert S.rel_err(f, f_ref) < FTOL
+    lmp.close()
+
+
+def test_forces_accumulate(ctx, oracle_built):
+    """f is accumulated into, like atom->f (pair_rebomos.cpp:436-441 use +=)."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), displace=0.1)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    nall = snap["nlocal"] + snap["nghost"]
+    f0, _, _ = ctx.rebomos_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"])
+    pre = np.full((nall, 3), 1.5)
+    f1, _, _ = ctx.rebomos_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], f=pre.copy())
+    assert np.allclose(f1 - 1.5, f0, rtol=0, atol=1e-12)
+    lmp.close()
+
+
+def test_inner_list_margin(ctx, oracle_built):
+    """A smaller inner-list margin (two-level Verlet list) gives the same forces and rebuilds itself
+    when atoms have moved more than margin/2 since the inner build."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), displace=0.05)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    init_ctx(ctx)
+    ctx.set_option("margin", 500)    # 0.5 A
+    f, e, v = gpu_forces(ctx, snap)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    assert S.rel_err(f, f_ref) < FTOL
+    n0 = ctx.counter("inner_rebuilds")
+    # move owned atoms by up to 0.4 A (> margin/2, < skin/2) keeping the master list valid
+    rng = np.random.default_rng(7)
+    x = lmp.x()
+    nlocal = snap["nlocal"]
+    x[:nlocal] += rng.uniform(-0.4, 0.4, size=(nlocal, 3)) / np.sqrt(3.0)
+    lmp.forward_comm()
+    snap2 = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    f2, e2, v2 = ctx.rebomos_compute(snap2["nlocal"], snap2["nghost"], snap2["x"], snap2["type"], snap2["tag"])
+    f2 = S.fold_ghost_forces(f2, snap2["swaps"], nlocal)
+    assert ctx.counter("inner_rebuilds") == n0 + 1
+    assert S.rel_err(f2, f_ref) < FTOL
+    assert abs(e2 - e_ref) / abs(e_ref) < ETOL
+    ctx.set_option("margin", 0)
+    lmp.close()
+
+
+def test_rebo_sublist_bit_exact(ctx, oracle_built):
+    """REBO_neigh parity (pair_rebomos.cpp:281-352): sub-lists of owned AND ghost atoms identical in
+    content and order to a direct restatement of the filter over the oracle's full list; nM/nS to 1e-14."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), displace=0.3)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    num, rows, nM, nS = ctx.rebomos_neigh(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], stride=24)
+    P = S.rebomos_params_struct()
+    rcmin = np.array(P.rcmin[:]).reshape(2, 2)
+    rcmax = np.array(P.rcmax[:]).reshape(2, 2)
+    x, el = snap["x"], snap["type"] - 1
+    off, val = snap["off"], snap["val"]
+    nall = snap["nlocal"] + snap["nghost"]
+    worst = 0.0
+    for i in range(nall):
+        js = val[off[i]:off[i + 1]] & 0x1FFFFFFF
+        d = x[i] - x[js]
+        rsq = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        keep = rsq < (rcmax[el[i], el[js]] * rcmax[el[i], el[js]])
+        ref = js[keep]
+        assert num[i] == len(ref), i
+        assert np.array_equal(rows[i, :num[i]], ref), i
+        r = np.sqrt(rsq[keep])
+        t = (r - rcmin[el[i], el[ref]]) / (rcmax[el[i], el[ref]] - rcmin[el[i], el[ref]])
+        w = np.where(t <= 0, 1.0, np.where(t >= 1, 0.0, 0.5 * (1 + np.cos(t * np.pi))))
+        worst = max(worst, abs(nM[i] - w[el[ref] == 0].sum()), abs(nS[i] - w[el[ref] == 1].sum()))
+    assert worst < 1e-13
+    lmp.close()

@@ -151,9 +151,22 @@ int b200md_rebomos_compute(b200md_ctx *ctx, int nlocal, int nghost, const double
 int b200md_rebomos_neigh(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
                          int stride, int *rebo_numneigh, int *rebo_rows, double *nM, double *nS);
 
-/* ---- AEAM compute ---------------------------------------------------------- */
+/* ---- AEAM compute ----------------------------------------------------------
+ * The pair term is evaluated in gather form (both directed visits of a pair from the owned atom's
+ * side), which needs fp = F'(rho) of GHOST neighbors: the fp forward exchange that the reference
+ * declares (comm_forward = 1, pair_aeam.cpp:56,307,946-965) but never reads becomes live here.
+ *
+ * One-shot (single rank; every ghost is a periodic image of an owned atom, matched by atom ID): */
 int b200md_aeam_compute(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
-                        int eflag, int vflag, double *f, double *eng_vdwl, double *virial);
+                        const int *tag, int eflag, int vflag, double *f, double *eng_vdwl, double *virial);
+/* Two-phase, for hosts that own the halo exchange (PairAEAM::compute with LAMMPS' Comm):
+ *   density phase  = density pass + embedding  (pair_aeam.cpp:164-303): rho[nlocal], fp[nlocal] out
+ *   [host: comm->forward_comm(this) fills fp (and rho) of ghosts]
+ *   force phase    = force pass                (pair_aeam.cpp:309-478): rho/fp [nlocal+nghost] in     */
+int b200md_aeam_density_phase(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                              double *rho, double *fp);
+int b200md_aeam_force_phase(b200md_ctx *ctx, const double *rho_all, const double *fp_all, int eflag,
+                            int vflag, double *f, double *eng_vdwl, double *virial);
 /* rho[nlocal], fp[nlocal] of the last compute */
 int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
 

@@ -103,7 +103,9 @@ SYMBOLS = [
     ("b200md_neigh_download", c_int, [c_void_p, _PI, _PL, _PI]),
     ("b200md_rebomos_compute", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD]),
     ("b200md_rebomos_neigh", c_int, [c_void_p, c_int, c_int, _PD, _PI, c_int, _PI, _PI, _PD, _PD]),
-    ("b200md_aeam_compute", c_int, [c_void_p, c_int, c_int, _PD, _PI, c_int, c_int, _PD, _PD, _PD]),
+    ("b200md_aeam_compute", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD]),
+    ("b200md_aeam_density_phase", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PD, _PD]),
+    ("b200md_aeam_force_phase", c_int, [c_void_p, _PD, _PD, c_int, c_int, _PD, _PD, _PD]),
     ("b200md_aeam_get_rho_fp", c_int, [c_void_p, c_int, _PD, _PD]),
     ("b200md_set_option", c_int, [c_void_p, c_char_p, c_longlong]),
     ("b200md_get_counter", c_longlong, [c_void_p, c_char_p]),
@@ -270,16 +272,36 @@ class Context:
                                                 _ip(rows), _dp(nM), _dp(nS)))
         return num, rows, nM, nS
 
-    def aeam_compute(self, nlocal, nghost, x, type_, eflag=1, vflag=2, f=None):
+    def aeam_compute(self, nlocal, nghost, x, type_, tag, eflag=1, vflag=2, f=None):
         nall = nlocal + nghost
         x = np.ascontiguousarray(x, dtype=np.float64)
         type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
         if f is None:
             f = np.zeros((nall, 3))
         eng = c_double()
         vir = np.zeros(6)
-        self._check(self.L.b200md_aeam_compute(self.h, nlocal, nghost, _dp(x), _ip(type_), eflag, vflag, _dp(f),
-                                               ctypes.byref(eng), _dp(vir)))
+        self._check(self.L.b200md_aeam_compute(self.h, nlocal, nghost, _dp(x), _ip(type_), _ip(tag), eflag, vflag,
+                                               _dp(f), ctypes.byref(eng), _dp(vir)))
+        return f, eng.value, vir
+
+    def aeam_density_phase(self, nlocal, nghost, x, type_):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        rho = np.zeros(nlocal + nghost)
+        fp = np.zeros(nlocal + nghost)
+        self._check(self.L.b200md_aeam_density_phase(self.h, nlocal, nghost, _dp(x), _ip(type_), _dp(rho), _dp(fp)))
+        return rho, fp
+
+    def aeam_force_phase(self, rho_all, fp_all, eflag=1, vflag=2, f=None):
+        rho_all = np.ascontiguousarray(rho_all, dtype=np.float64)
+        fp_all = np.ascontiguousarray(fp_all, dtype=np.float64)
+        if f is None:
+            f = np.zeros((len(rho_all), 3))
+        eng = c_double()
+        vir = np.zeros(6)
+        self._check(self.L.b200md_aeam_force_phase(self.h, _dp(rho_all), _dp(fp_all), eflag, vflag, _dp(f),
+                                                   ctypes.byref(eng), _dp(vir)))
         return f, eng.value, vir
 
     def aeam_rho_fp(self, nlocal):

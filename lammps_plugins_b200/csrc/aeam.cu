@@ -504,9 +504,9 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
   fy = group_sum<8>(fy);
   fz = group_sum<8>(fz);
   if (i < inum && sub == 0) {
-    atomicAdd(&f[3 * (size_t) i], fx);    // B2 may add to the same atom concurrently
-    atomicAdd(&f[3 * (size_t) i + 1], fy);
-    atomicAdd(&f[3 * (size_t) i + 2], fz);
+    f[3 * (size_t) i] += fx;    // one group per atom; B2 (atomics) runs after this kernel
+    f[3 * (size_t) i + 1] += fy;
+    f[3 * (size_t) i + 2] += fz;
   }
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
 }

@@ -3,10 +3,6 @@
 #define NOTIMPL(c, name) do { if (c) (c)->fail(name ": not implemented yet"); return B200MD_ERR_ARG; } while (0)
 void b200md_system_free(b200md_ctx *) {}
 extern "C" {
-int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *) { NOTIMPL(c, "aeam_init"); }
-int b200md_aeam_get_spline(b200md_ctx *c, int, int, double *, int) { NOTIMPL(c, "aeam_get_spline"); }
-int b200md_aeam_compute(b200md_ctx *c, int, int, const double *, const int *, int, int, double *, double *, double *) { NOTIMPL(c, "aeam_compute"); }
-int b200md_aeam_get_rho_fp(b200md_ctx *c, int, double *, double *) { NOTIMPL(c, "aeam_get_rho_fp"); }
 int b200md_neigh_build(b200md_ctx *c, const b200md_box *, int, const double *, const double *, int, int, const double *, const int *, int, double) { NOTIMPL(c, "neigh_build"); }
 int b200md_system_create(b200md_ctx *c, const b200md_system_desc *, int, const double *, const double *, const int *, const int *) { NOTIMPL(c, "system_create"); }
 int b200md_nccl_unique_id(void *) { return B200MD_ERR_ARG; }

@@ -1,0 +1,152 @@
+"""GPU parity of the AEAM force path against the oracle (USER-AEAM/pair_aeam.cpp compiled verbatim,
+or the port) on identical inputs, through the C ABI.
+
+AEAM ships no golden output: parity is pinned to the reference SOURCE compiled
+verbatim; derived known answers (perfect fcc Al) are checked as well.
+Tolerances: forces 1e-10 of the largest force component, energy 1e-12, virial 1e-10 (relative)."""
+import numpy as np
+import pytest
+
+import support as S
+
+pytestmark = pytest.mark.gpu
+
+FTOL = 1.0e-10
+ETOL = 1.0e-12
+
+
+def aeam_tables():
+    t = S.load_aeam_fixture()
+    return dict(nelements=t["nelements"], nnonangular=t["nnonangular"], nrho=t["nrho"], drho=t["drho"],
+                nr=t["nr"], dr=t["dr"], cut=t["cut"], frho=t["frho"], rhor=t["rhor"], z2r=t["z2r"])
+
+
+def oracle_forces(lmp):
+    lmp.compute(1, 2, reverse=True)
+    nlocal = lmp.get_int("nlocal")
+    return (lmp.f()[:nlocal].copy(), lmp.get_double("eng_vdwl"),
+            np.array([lmp.get_double("virial%d" % k) for k in range(6)]))
+
+
+def gpu_forces(ctx, snap, eflag=1, vflag=2):
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    f, e, v = ctx.aeam_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], eflag, vflag)
+    return S.fold_ghost_forces(f, snap["swaps"], snap["nlocal"]), e, v
+
+
+CASES = [
+    dict(id="fcc-pure-d0.05", cells=(4, 4, 4), si=0.0, displace=0.05),
+    dict(id="al-0.75pctSi-d0.1", cells=(6, 6, 6), si=0.0075, displace=0.1),
+    dict(id="al-20pctSi-d0.2", cells=(5, 5, 5), si=0.2, displace=0.2),      # Si-Si pairs: CutDec paths
+    dict(id="si-rich-60pct-d0.3", cells=(4, 4, 4), si=0.6, displace=0.3),
+    dict(id="al-5pctSi-d0.5", cells=(5, 4, 6), si=0.05, displace=0.5),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_forces_energy_virial(ctx, oracle_built, case):
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), case["cells"], si_fraction=case["si"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    ctx.aeam_init(aeam_tables())
+    f, e, v = gpu_forces(ctx, snap)
+    ferr, eerr, verr = S.rel_err(f, f_ref), abs(e - e_ref) / abs(e_ref), S.rel_err(v, v_ref)
+    nsi = int((snap["type"][:snap["nlocal"]] == 2).sum())
+    print("\n%s: nlocal %d (Si %d) nghost %d max|f| %.4g ferr %.3e E %.10f eerr %.3e verr %.3e"
+          % (case["id"], snap["nlocal"], nsi, snap["nghost"], np.abs(f_ref).max(), ferr, e, eerr, verr))
+    assert ferr < FTOL
+    assert eerr < ETOL
+    assert verr < FTOL
+    lmp.close()
+
+
+def test_perfect_fcc_known_answer(ctx, oracle_built):
+    """Perfect fcc Al, a = 4.045: rho = 1.0404330586, E/atom = -3.4106573819 eV,
+    forces vanish by symmetry."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (4, 4, 4), si_fraction=0.0)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    ctx.aeam_init(aeam_tables())
+    f, e, v = gpu_forces(ctx, snap)
+    rho, fp = ctx.aeam_rho_fp(snap["nlocal"])
+    assert abs(e / snap["nlocal"] - (-3.4106573819)) < 1e-9
+    assert np.allclose(rho, 1.0404330586, rtol=0, atol=1e-9)
+    assert np.abs(f).max() < 1e-10
+    lmp.close()
+
+
+def test_two_phase_equals_one_shot(ctx, oracle_built):
+    """density phase -> (host halo exchange of fp, here by atom ID) -> force phase == one-shot compute."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.1, displace=0.15)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    ctx.aeam_init(aeam_tables())
+    f1, e1, v1 = gpu_forces(ctx, snap)
+    nl, ng = snap["nlocal"], snap["nghost"]
+    rho, fp = ctx.aeam_density_phase(nl, ng, snap["x"], snap["type"])
+    owner = np.zeros(snap["tag"].max() + 1, dtype=np.int64)
+    owner[snap["tag"][:nl]] = np.arange(nl)
+    rho[nl:] = rho[owner[snap["tag"][nl:]]]      # what comm->forward_comm(this) does on one rank
+    fp[nl:] = fp[owner[snap["tag"][nl:]]]
+    f2, e2, v2 = ctx.aeam_force_phase(rho, fp)
+    f2 = S.fold_ghost_forces(f2, snap["swaps"], nl)
+    assert S.rel_err(f2, f1) < 1e-13
+    assert abs(e2 - e1) < 1e-9 * abs(e1)
+    assert S.rel_err(v2, v1) < 1e-12
+    lmp.close()
+
+
+def _interpolate_np(n, delta, f):
+    """numpy restatement of PairAEAM::interpolate (pair_aeam.cpp:915-942); rows 1..n, elementwise IEEE ops"""
+    s = np.zeros((n + 1, 7))
+    s[1:, 6] = f
+    s[1, 5] = s[2, 6] - s[1, 6]
+    s[2, 5] = 0.5 * (s[3, 6] - s[1, 6])
+    s[n - 1, 5] = 0.5 * (s[n, 6] - s[n - 2, 6])
+    s[n, 5] = s[n, 6] - s[n - 1, 6]
+    m = np.arange(3, n - 1)
+    s[m, 5] = ((s[m - 2, 6] - s[m + 2, 6]) + 8.0 * (s[m + 1, 6] - s[m - 1, 6])) / 12.0
+    m = np.arange(1, n)
+    s[m, 4] = 3.0 * (s[m + 1, 6] - s[m, 6]) - 2.0 * s[m, 5] - s[m + 1, 5]
+    s[m, 3] = s[m, 5] + s[m + 1, 5] - 2.0 * (s[m + 1, 6] - s[m, 6])
+    s[n, 4] = 0.0
+    s[n, 3] = 0.0
+    s[1:, 2] = s[1:, 5] / delta
+    s[1:, 1] = 2.0 * s[1:, 4] / delta
+    s[1:, 0] = 3.0 * s[1:, 3] / delta
+    return s
+
+
+def test_spline_tables_bit_identical(ctx):
+    """The 7-coefficient tables built inside the library equal array2spline's bit for bit."""
+    t = S.load_aeam_fixture()
+    ctx.aeam_init(aeam_tables())
+    nel = t["nelements"]
+    for i in range(nel):
+        got = ctx.aeam_get_spline(0, i, t["nrho"][i])
+        assert np.array_equal(got, _interpolate_np(t["nrho"][i], t["drho"][i], t["frho"][i]))
+    for i in range(nel):
+        for j in range(nel):
+            got = ctx.aeam_get_spline(1, i * nel + j, int(t["nr"][i, j]))
+            assert np.array_equal(got, _interpolate_np(int(t["nr"][i, j]), float(t["dr"][i, j]), t["rhor"][i][j]))
+    k = 0
+    for i in range(nel):
+        for j in range(i + 1):
+            got = ctx.aeam_get_spline(2, k, int(t["nr"][i, j]))
+            assert np.array_equal(got, _interpolate_np(int(t["nr"][i, j]), float(t["dr"][i, j]), t["z2r"][i][j]))
+            k += 1
+
+
+def test_flags_and_accumulate(ctx, oracle_built):
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (4, 4, 4), si_fraction=0.05, displace=0.1)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    ctx.aeam_init(aeam_tables())
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    nl, ng = snap["nlocal"], snap["nghost"]
+    f0, e0, v0 = ctx.aeam_compute(nl, ng, snap["x"], snap["type"], snap["tag"], 0, 0)
+    assert e0 == 0.0 and not v0.any()
+    f1, _, _ = ctx.aeam_compute(nl, ng, snap["x"], snap["type"], snap["tag"], 1, 2, f=np.full((nl + ng, 3), 2.0))
+    assert np.allclose(f1 - 2.0, f0, rtol=0, atol=1e-12)
+    lmp.close()

@@ -309,3 +309,69 @@ class Context:
         fp = np.zeros(nlocal)
         self._check(self.L.b200md_aeam_get_rho_fp(self.h, nlocal, _dp(rho), _dp(fp)))
         return rho, fp
+
+    # -- GPU-resident system
+    def system_create(self, style, ntypes, mass, box: Box, x, v, type_, tag, skin, dt, units, procgrid=(1, 1, 1),
+                      rank=0, sort_every=1000):
+        """style: 'rebomos' | 'aeam'; mass: 1-based list (index 0 unused); units: dict ftm2v, mvv2e, boltz, nktv2p"""
+        mass = np.ascontiguousarray(mass, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
+        d = SystemDesc()
+        d.style = 0 if style == "rebomos" else 1
+        d.ntypes = ntypes
+        d.mass = _dp(mass)
+        d.box = box
+        d.procgrid[0], d.procgrid[1], d.procgrid[2] = procgrid
+        d.rank = rank
+        d.skin = skin
+        d.dt = dt
+        d.ftm2v, d.mvv2e, d.boltz, d.nktv2p = units["ftm2v"], units["mvv2e"], units["boltz"], units["nktv2p"]
+        d.sort_every = sort_every
+        vp = None
+        if v is not None:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            vp = _dp(v)
+        self._check(self.L.b200md_system_create(self.h, ctypes.byref(d), len(type_), _dp(x), vp, _ip(type_), _ip(tag)))
+
+    def system_run(self, nsteps, thermo_every=0):
+        self._check(self.L.b200md_system_run(self.h, int(nsteps), int(thermo_every)))
+
+    def system_thermo_rows(self):
+        rows = []
+        buf = np.zeros(12)
+        for i in range(self.L.b200md_system_thermo_count(self.h)):
+            self._check(self.L.b200md_system_thermo_row(self.h, i, _dp(buf)))
+            rows.append(dict(step=int(buf[0]), temp=buf[1], press=buf[2], pe=buf[3], ke=buf[4], vol=buf[5],
+                             virial=buf[6:12].copy()))
+        return rows
+
+    def system_sizes(self):
+        out = (c_longlong * 4)()
+        self._check(self.L.b200md_system_sizes(self.h, out))
+        return dict(nlocal=out[0], nghost=out[1], nbuild=out[2], ndanger=out[3])
+
+    def system_download(self):
+        sz = self.system_sizes()
+        nall = sz["nlocal"] + sz["nghost"]
+        x = np.zeros((nall, 3))
+        v = np.zeros((sz["nlocal"], 3))
+        f = np.zeros((nall, 3))
+        type_ = np.zeros(nall, dtype=np.int32)
+        tag = np.zeros(nall, dtype=np.int32)
+        self._check(self.L.b200md_system_download(self.h, _dp(x), _dp(v), _dp(f), _ip(type_), _ip(tag)))
+        return dict(x=x, v=v, f=f, type=type_, tag=tag, **sz)
+
+
+METAL_UNITS = dict(boltz=8.617343e-5, mvv2e=1.0364269e-4, ftm2v=1.0 / 1.0364269e-4, nktv2p=1.6021765e6)
+
+
+def make_box(boxlo, boxhi, xy=0.0, xz=0.0, yz=0.0, triclinic=None):
+    b = Box()
+    b.triclinic = int(triclinic if triclinic is not None else (xy != 0.0 or xz != 0.0 or yz != 0.0))
+    for d in range(3):
+        b.boxlo[d] = boxlo[d]
+        b.boxhi[d] = boxhi[d]
+    b.xy, b.xz, b.yz = xy, xz, yz
+    return b

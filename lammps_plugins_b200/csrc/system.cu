@@ -1,0 +1,1217 @@
+// b200md -- GPU-resident MD system: the run loop LAMMPS wraps around Pair::compute(), kept entirely
+// on the device for the benchmark driver (one instance per GPU / rank).
+//
+// Restates LAMMPS-core (stable_2Aug2023) semantics, SURVEY.md A.3-A.5:
+//   Verlet::setup / Verlet::run          setup() / b200md_system_run()
+//   FixNVE::initial/final_integrate      k_initial_integrate / k_final_integrate
+//   Neighbor::decide / check_distance    displacement flag fused into initial integrate
+//   Domain::x2lamda / lamda2x / pbc      k_x2lamda / k_lamda2x / k_pbc
+//   Atom::sort                           sort_atoms()
+//   CommBrick::setup/borders/forward_comm/reverse_comm  (+ Pair fp forward)   halo_*()
+//   CommBrick::exchange                  migrate()   (multi-GPU only)
+//   compute temp / pressure / thermo     thermo()
+// Halo swaps keep LAMMPS' staged x,y,z order and send-list order, so ghost ordering is identical to the
+// host engine; a swap whose partner is this rank is a device gather, otherwise an NCCL send/recv pair
+// over NVLink.  Arithmetic that decides membership (slab tests, lamda conversion) is written with
+// explicit non-contracted FP64 ops so the ghost set and its coordinates match the host bit for bit.
+
+#include "common.cuh"
+
+#include <nccl.h>
+
+#include <cmath>
+
+#define BLOCK 256
+#define BIGSLAB 1.0e20
+
+int b200md_rebomos_build_inner(b200md_ctx *c);
+int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag);
+int b200md_aeam_build_inner(b200md_ctx *c);
+int b200md_aeam_density(b200md_ctx *c);
+int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag);
+int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, const double *cutneighsq_h,
+                              const double *cutneighghostsq_h, int nlocal, int nghost, const double4 *xt,
+                              int ghost_rows, double skin);
+void b200md_neigh_forget(b200md_ctx *c);
+void b200md_aeam_forget(b200md_ctx *c);
+
+struct Swap {
+  int dim = 0, sendproc = 0, recvproc = 0;
+  double lo = 0, hi = 0;
+  int pbc_flag = 0, pbc[6] = {0, 0, 0, 0, 0, 0};
+  double bshift[3] = {0, 0, 0};    // shift applied in borders() (lamda units if triclinic)
+  double fshift[3] = {0, 0, 0};    // shift applied in forward_comm() (box units)
+  int nsend = 0, nrecv = 0, firstrecv = 0;
+  DevBuf<int> sendlist;
+};
+
+struct SystemState {
+  b200md_system_desc d;
+  std::vector<double> mass;
+  // geometry
+  int triclinic = 0;
+  double boxlo[3], boxhi[3], prd[3], h[6], h_inv[6];
+  double sublo[3], subhi[3];    // box coords, or lamda if triclinic
+  double cutghost[3];
+  double cutneighmax = 0.0;
+  std::vector<double> cutneighsq, cutneighghostsq;
+  int ghost_rows = 0;
+  int myloc[3], procneigh[3][2];
+  int nranks = 1, me = 0;
+  int maxneed[3];
+  std::vector<Swap> swaps;
+  // atoms (positions/types/tags/forces live in the ctx buffers)
+  int nlocal = 0, nghost = 0;
+  long long natoms = 0;
+  DevBuf<double> v;
+  DevBuf<double4> xhold, xt;
+  DevBuf<double> dmass;          // per type
+  DevBuf<int> itmp, itmp2;
+  DevBuf<double4> x4tmp;
+  DevBuf<double> dtmp;
+  DevBuf<int64_t> scan64;
+  DevBuf<double> sendbuf, recvbuf;
+  // run state
+  long long step = 0, nbuild = 0, ndanger = 0, nextsort = 0;
+  int ago = 0;
+  std::vector<std::vector<double>> rows;    // thermo rows
+  // nccl
+  ncclComm_t nccl = nullptr;
+};
+
+// ================================================================== kernels
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+
+struct Geom {
+  double boxlo[3], h[6], h_inv[6];
+};
+
+// Domain::x2lamda / lamda2x with the reference operation order (no FMA contraction)
+__global__ void __launch_bounds__(BLOCK) k_x2lamda(const __grid_constant__ Geom g, double4 *__restrict__ x, int n)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  double4 p = x[i];
+  const double d0 = p.x - g.boxlo[0], d1 = p.y - g.boxlo[1], d2 = p.z - g.boxlo[2];
+  p.x = add(add(mul(g.h_inv[0], d0), mul(g.h_inv[5], d1)), mul(g.h_inv[4], d2));
+  p.y = add(mul(g.h_inv[1], d1), mul(g.h_inv[3], d2));
+  p.z = mul(g.h_inv[2], d2);
+  x[i] = p;
+}
+__global__ void __launch_bounds__(BLOCK) k_lamda2x(const __grid_constant__ Geom g, double4 *__restrict__ x, int n)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  double4 p = x[i];
+  const double l0 = p.x, l1 = p.y, l2 = p.z;
+  p.x = add(add(add(mul(g.h[0], l0), mul(g.h[5], l1)), mul(g.h[4], l2)), g.boxlo[0]);
+  p.y = add(add(mul(g.h[1], l1), mul(g.h[3], l2)), g.boxlo[1]);
+  p.z = add(mul(g.h[2], l2), g.boxlo[2]);
+  x[i] = p;
+}
+
+// Domain::pbc on owned atoms
+__global__ void __launch_bounds__(BLOCK) k_pbc(double4 *__restrict__ x, int n, double lo0, double lo1, double lo2,
+                                               double hi0, double hi1, double hi2, double p0, double p1, double p2)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  double4 p = x[i];
+  if (p.x < lo0) p.x += p0;
+  if (p.x >= hi0) { p.x -= p0; p.x = fmax(p.x, lo0); }
+  if (p.y < lo1) p.y += p1;
+  if (p.y >= hi1) { p.y -= p1; p.y = fmax(p.y, lo1); }
+  if (p.z < lo2) p.z += p2;
+  if (p.z >= hi2) { p.z -= p2; p.z = fmax(p.z, lo2); }
+  x[i] = p;
+}
+
+__device__ __forceinline__ double comp(const double4 &p, int dim) { return dim == 0 ? p.x : dim == 1 ? p.y : p.z; }
+
+// borders(): flag atoms of [nfirst,nlast) inside the slab, using >= lo && <= hi
+__global__ void __launch_bounds__(BLOCK) k_slab_flags(const double4 *__restrict__ x, int nfirst, int nlast, int dim,
+                                                      double lo, double hi, int *__restrict__ flag)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= nlast - nfirst) return;
+  const double v = comp(x[nfirst + k], dim);
+  flag[k] = (v >= lo && v <= hi) ? 1 : 0;
+}
+__global__ void __launch_bounds__(BLOCK) k_scatter_list(const int *__restrict__ flag, const int64_t *__restrict__ pos,
+                                                        int nfirst, int n, int *__restrict__ list)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  if (flag[k]) list[pos[k]] = nfirst + k;
+}
+// AtomVec::pack_border + unpack_border for a self swap: ghost = copy of list atom shifted by (dx,dy,dz)
+__global__ void __launch_bounds__(BLOCK) k_border_copy(double4 *__restrict__ x, int *__restrict__ type,
+                                                       int *__restrict__ tag, const int *__restrict__ list, int n,
+                                                       int first, double dx, double dy, double dz, int pbc_flag)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = list[k];
+  double4 p = x[j];
+  if (pbc_flag) {
+    p.x = add(p.x, dx);
+    p.y = add(p.y, dy);
+    p.z = add(p.z, dz);
+  }
+  x[first + k] = p;
+  type[first + k] = type[j];
+  tag[first + k] = tag[j];
+}
+// multi-GPU variants: pack to / unpack from a contiguous buffer of 6 doubles per atom (x,y,z,w,type,tag)
+__global__ void __launch_bounds__(BLOCK) k_border_pack(const double4 *__restrict__ x, const int *__restrict__ type,
+                                                       const int *__restrict__ tag, const int *__restrict__ list,
+                                                       int n, double dx, double dy, double dz, int pbc_flag,
+                                                       double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = list[k];
+  double4 p = x[j];
+  if (pbc_flag) {
+    p.x = add(p.x, dx);
+    p.y = add(p.y, dy);
+    p.z = add(p.z, dz);
+  }
+  buf[6 * (size_t) k] = p.x;
+  buf[6 * (size_t) k + 1] = p.y;
+  buf[6 * (size_t) k + 2] = p.z;
+  buf[6 * (size_t) k + 3] = p.w;
+  buf[6 * (size_t) k + 4] = (double) type[j];
+  buf[6 * (size_t) k + 5] = (double) tag[j];
+}
+__global__ void __launch_bounds__(BLOCK) k_border_unpack(double4 *__restrict__ x, int *__restrict__ type,
+                                                         int *__restrict__ tag, int first, int n,
+                                                         const double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  x[first + k] = make_double4(buf[6 * (size_t) k], buf[6 * (size_t) k + 1], buf[6 * (size_t) k + 2], buf[6 * (size_t) k + 3]);
+  type[first + k] = (int) buf[6 * (size_t) k + 4];
+  tag[first + k] = (int) buf[6 * (size_t) k + 5];
+}
+
+// forward_comm: positions of ghosts from their source atoms (self swap)
+__global__ void __launch_bounds__(BLOCK) k_forward_x(double4 *__restrict__ x, const int *__restrict__ list, int n,
+                                                     int first, double dx, double dy, double dz, int pbc_flag)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const double4 p = x[list[k]];
+  double4 q = x[first + k];
+  if (pbc_flag) {
+    q.x = p.x + dx;
+    q.y = p.y + dy;
+    q.z = p.z + dz;
+  } else {
+    q.x = p.x;
+    q.y = p.y;
+    q.z = p.z;
+  }
+  x[first + k] = q;
+}
+__global__ void __launch_bounds__(BLOCK) k_forward_x_pack(const double4 *__restrict__ x, const int *__restrict__ list,
+                                                          int n, double dx, double dy, double dz, int pbc_flag,
+                                                          double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const double4 p = x[list[k]];
+  buf[3 * (size_t) k] = pbc_flag ? p.x + dx : p.x;
+  buf[3 * (size_t) k + 1] = pbc_flag ? p.y + dy : p.y;
+  buf[3 * (size_t) k + 2] = pbc_flag ? p.z + dz : p.z;
+}
+__global__ void __launch_bounds__(BLOCK) k_forward_x_unpack(double4 *__restrict__ x, int first, int n,
+                                                            const double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  double4 q = x[first + k];
+  q.x = buf[3 * (size_t) k];
+  q.y = buf[3 * (size_t) k + 1];
+  q.z = buf[3 * (size_t) k + 2];
+  x[first + k] = q;
+}
+// per-atom scalar pair (rho, fp) forward: PairAEAM::pack/unpack_forward_comm (pair_aeam.cpp:946-965)
+__global__ void __launch_bounds__(BLOCK) k_forward_s2(double *__restrict__ a, double *__restrict__ b,
+                                                      const int *__restrict__ list, int n, int first)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = list[k];
+  a[first + k] = a[j];
+  b[first + k] = b[j];
+}
+__global__ void __launch_bounds__(BLOCK) k_forward_s2_pack(const double *__restrict__ a, const double *__restrict__ b,
+                                                           const int *__restrict__ list, int n, double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = list[k];
+  buf[2 * (size_t) k] = a[j];
+  buf[2 * (size_t) k + 1] = b[j];
+}
+__global__ void __launch_bounds__(BLOCK) k_forward_s2_unpack(double *__restrict__ a, double *__restrict__ b, int first,
+                                                             int n, const double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  a[first + k] = buf[2 * (size_t) k];
+  b[first + k] = buf[2 * (size_t) k + 1];
+}
+// reverse_comm: ghost forces summed into their source atoms; within one swap every source is unique
+__global__ void __launch_bounds__(BLOCK) k_reverse_f(double *__restrict__ f, const int *__restrict__ list, int n,
+                                                     int first)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const size_t j = list[k], g = (size_t) first + k;
+  f[3 * j] += f[3 * g];
+  f[3 * j + 1] += f[3 * g + 1];
+  f[3 * j + 2] += f[3 * g + 2];
+}
+__global__ void __launch_bounds__(BLOCK) k_reverse_f_unpack(double *__restrict__ f, const int *__restrict__ list, int n,
+                                                            const double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const size_t j = list[k];
+  f[3 * j] += buf[3 * (size_t) k];
+  f[3 * j + 1] += buf[3 * (size_t) k + 1];
+  f[3 * j + 2] += buf[3 * (size_t) k + 2];
+}
+
+// FixNVE::initial_integrate fused with Neighbor::check_distance (flag[9] = some atom moved > skin/2)
+__global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict__ x, double *__restrict__ v,
+                                                             const double *__restrict__ f, const int *__restrict__ type,
+                                                             const double *__restrict__ mass, int nlocal, double dtf,
+                                                             double dtv, const double4 *__restrict__ xhold,
+                                                             double triggersq, int *__restrict__ flags)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nlocal) return;
+  const double dtfm = dtf / mass[type[i]];
+  double4 p = x[i];
+  double vx = v[3 * (size_t) i], vy = v[3 * (size_t) i + 1], vz = v[3 * (size_t) i + 2];
+  vx += dtfm * f[3 * (size_t) i];
+  vy += dtfm * f[3 * (size_t) i + 1];
+  vz += dtfm * f[3 * (size_t) i + 2];
+  p.x += dtv * vx;
+  p.y += dtv * vy;
+  p.z += dtv * vz;
+  v[3 * (size_t) i] = vx;
+  v[3 * (size_t) i + 1] = vy;
+  v[3 * (size_t) i + 2] = vz;
+  x[i] = p;
+  const double4 h = xhold[i];
+  const double dx = p.x - h.x, dy = p.y - h.y, dz = p.z - h.z;
+  if (dx * dx + dy * dy + dz * dz > triggersq) flags[9] = 1;
+}
+__global__ void __launch_bounds__(BLOCK) k_final_integrate(double *__restrict__ v, const double *__restrict__ f,
+                                                           const int *__restrict__ type, const double *__restrict__ mass,
+                                                           int nlocal, double dtf)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nlocal) return;
+  const double dtfm = dtf / mass[type[i]];
+  v[3 * (size_t) i] += dtfm * f[3 * (size_t) i];
+  v[3 * (size_t) i + 1] += dtfm * f[3 * (size_t) i + 1];
+  v[3 * (size_t) i + 2] += dtfm * f[3 * (size_t) i + 2];
+}
+// compute temp: sum m v^2 into scal[8]
+__global__ void __launch_bounds__(BLOCK) k_ke(const double *__restrict__ v, const int *__restrict__ type,
+                                              const double *__restrict__ mass, int nlocal, double *__restrict__ scal)
+{
+  double t[1] = {0.0};
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < nlocal; i += gridDim.x * BLOCK) {
+    const double vx = v[3 * (size_t) i], vy = v[3 * (size_t) i + 1], vz = v[3 * (size_t) i + 2];
+    t[0] += (vx * vx + vy * vy + vz * vz) * mass[type[i]];
+  }
+  block_accumulate<1, BLOCK>(t, scal + 8);
+}
+// w component: potential-specific element code from the LAMMPS type
+__global__ void __launch_bounds__(BLOCK) k_set_w(double4 *__restrict__ x, const int *__restrict__ type,
+                                                 const int *__restrict__ map, int use_map, int n)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const int t = type[i];
+  x[i].w = use_map ? (double) map[t] : (double) (t - 1);
+}
+__global__ void __launch_bounds__(BLOCK) k_make_xt(const double4 *__restrict__ x, const int *__restrict__ type, int n,
+                                                   double4 *__restrict__ xt)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  double4 p = x[i];
+  p.w = (double) type[i];
+  xt[i] = p;
+}
+__global__ void __launch_bounds__(BLOCK) k_upload_x(const double *__restrict__ xa, int n, double4 *__restrict__ x)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  x[i] = make_double4(xa[3 * (size_t) i], xa[3 * (size_t) i + 1], xa[3 * (size_t) i + 2], 0.0);
+}
+__global__ void __launch_bounds__(BLOCK) k_download_x(const double4 *__restrict__ x, int n, double *__restrict__ xa)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = x[i];
+  xa[3 * (size_t) i] = p.x;
+  xa[3 * (size_t) i + 1] = p.y;
+  xa[3 * (size_t) i + 2] = p.z;
+}
+
+// Atom::sort: bin index of owned atoms (box coords), clamped
+struct SortGeom {
+  double lo[3], inv[3];
+  int nb[3];
+};
+__global__ void __launch_bounds__(BLOCK) k_sort_bins(const __grid_constant__ SortGeom g, const double4 *__restrict__ x,
+                                                     int n, int *__restrict__ bin_of, int *__restrict__ count)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = x[i];
+  int ix = (int) ((p.x - g.lo[0]) * g.inv[0]);
+  int iy = (int) ((p.y - g.lo[1]) * g.inv[1]);
+  int iz = (int) ((p.z - g.lo[2]) * g.inv[2]);
+  ix = min(max(ix, 0), g.nb[0] - 1);
+  iy = min(max(iy, 0), g.nb[1] - 1);
+  iz = min(max(iz, 0), g.nb[2] - 1);
+  const int b = iz * g.nb[1] * g.nb[0] + iy * g.nb[0] + ix;
+  bin_of[i] = b;
+  atomicAdd(&count[b], 1);
+}
+__global__ void __launch_bounds__(BLOCK) k_sort_fill(const int *__restrict__ bin_of, int n,
+                                                     const int64_t *__restrict__ start, int *__restrict__ cursor,
+                                                     int *__restrict__ perm)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const int b = bin_of[i];
+  perm[start[b] + atomicAdd(&cursor[b], 1)] = i;
+}
+__global__ void __launch_bounds__(BLOCK) k_sort_within(const int64_t *__restrict__ start, int nbins, int *__restrict__ perm)
+{
+  int b = blockIdx.x * BLOCK + threadIdx.x;
+  if (b >= nbins) return;
+  const int s = (int) start[b], e = (int) start[b + 1];
+  for (int a = s + 1; a < e; a++) {
+    const int v = perm[a];
+    int q = a - 1;
+    while (q >= s && perm[q] > v) {
+      perm[q + 1] = perm[q];
+      q--;
+    }
+    perm[q + 1] = v;
+  }
+}
+__global__ void __launch_bounds__(BLOCK) k_permute(const int *__restrict__ perm, int n, const double4 *__restrict__ x,
+                                                   const double *__restrict__ v, const int *__restrict__ type,
+                                                   const int *__restrict__ tag, double4 *__restrict__ xo,
+                                                   double *__restrict__ vo, int *__restrict__ to, int *__restrict__ go)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const int j = perm[i];
+  xo[i] = x[j];
+  vo[3 * (size_t) i] = v[3 * (size_t) j];
+  vo[3 * (size_t) i + 1] = v[3 * (size_t) j + 1];
+  vo[3 * (size_t) i + 2] = v[3 * (size_t) j + 2];
+  to[i] = type[j];
+  go[i] = tag[j];
+}
+
+// ================================================================== host helpers
+static inline int nblk(long long n) { return (int) ((n + BLOCK - 1) / BLOCK); }
+
+#define NCCL_TRY(ctx, call)                                                                          \
+  do {                                                                                               \
+    ncclResult_t r__ = (call);                                                                       \
+    if (r__ != ncclSuccess) {                                                                        \
+      (ctx)->fail(std::string("NCCL error: ") + ncclGetErrorString(r__) + " (" #call ")");           \
+      return B200MD_ERR_NCCL;                                                                        \
+    }                                                                                                \
+  } while (0)
+
+static Geom make_geom(const SystemState *s)
+{
+  Geom g;
+  for (int d = 0; d < 3; d++) g.boxlo[d] = s->boxlo[d];
+  for (int k = 0; k < 6; k++) {
+    g.h[k] = s->h[k];
+    g.h_inv[k] = s->h_inv[k];
+  }
+  return g;
+}
+
+static int ensure_atoms(b200md_ctx *c, SystemState *s, size_t n)
+{
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, c->xq.reserve(n + 64, true, st));
+  CUDA_TRY(c, c->type.reserve(n + 64, true, st));
+  CUDA_TRY(c, c->tag.reserve(n + 64, true, st));
+  CUDA_TRY(c, c->f.reserve(3 * n + 64, true, st));
+  CUDA_TRY(c, s->v.reserve(3 * n + 64, true, st));
+  return B200MD_OK;
+}
+
+// exchange `nsend` doubles*width with the swap partners: send to `sendto`, receive from `recvfrom`
+static int nccl_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, size_t nsend, int sendto, double *rbuf,
+                         size_t nrecv, int recvfrom)
+{
+  NCCL_TRY(c, ncclGroupStart());
+  if (nsend) NCCL_TRY(c, ncclSend(sbuf, nsend, ncclDouble, sendto, s->nccl, c->stream));
+  if (nrecv) NCCL_TRY(c, ncclRecv(rbuf, nrecv, ncclDouble, recvfrom, s->nccl, c->stream));
+  NCCL_TRY(c, ncclGroupEnd());
+  return B200MD_OK;
+}
+
+// ------------------------------------------------------------------ geometry / comm setup
+static void setup_geometry(SystemState *s)
+{
+  const b200md_box &b = s->d.box;
+  s->triclinic = b.triclinic;
+  for (int d = 0; d < 3; d++) {
+    s->boxlo[d] = b.boxlo[d];
+    s->boxhi[d] = b.boxhi[d];
+    s->prd[d] = b.boxhi[d] - b.boxlo[d];
+  }
+  // Domain::set_global_box
+  s->h[0] = s->prd[0];
+  s->h[1] = s->prd[1];
+  s->h[2] = s->prd[2];
+  s->h[3] = b.yz;
+  s->h[4] = b.xz;
+  s->h[5] = b.xy;
+  s->h_inv[0] = 1.0 / s->h[0];
+  s->h_inv[1] = 1.0 / s->h[1];
+  s->h_inv[2] = 1.0 / s->h[2];
+  s->h_inv[3] = -s->h[3] / (s->h[1] * s->h[2]);
+  s->h_inv[4] = (s->h[3] * s->h[5] - s->h[1] * s->h[4]) / (s->h[0] * s->h[1] * s->h[2]);
+  s->h_inv[5] = -s->h[5] / (s->h[0] * s->h[1]);
+  if (!s->triclinic) s->h[3] = s->h[4] = s->h[5] = s->h_inv[3] = s->h_inv[4] = s->h_inv[5] = 0.0;
+
+  // rank -> brick location, x fastest (same numbering as the host engine)
+  const int *pg = s->d.procgrid;
+  s->nranks = pg[0] * pg[1] * pg[2];
+  s->me = s->d.rank;
+  s->myloc[0] = s->me % pg[0];
+  s->myloc[1] = (s->me / pg[0]) % pg[1];
+  s->myloc[2] = s->me / (pg[0] * pg[1]);
+  auto rankof = [&](int ix, int iy, int iz) {
+    ix = (ix + pg[0]) % pg[0];
+    iy = (iy + pg[1]) % pg[1];
+    iz = (iz + pg[2]) % pg[2];
+    return iz * pg[1] * pg[0] + iy * pg[0] + ix;
+  };
+  for (int d = 0; d < 3; d++)
+    for (int dir = 0; dir < 2; dir++) {
+      int l[3] = {s->myloc[0], s->myloc[1], s->myloc[2]};
+      l[d] += dir ? 1 : -1;
+      s->procneigh[d][dir] = rankof(l[0], l[1], l[2]);
+    }
+  // Domain::set_local_box (uniform layout)
+  for (int d = 0; d < 3; d++) {
+    if (!s->triclinic) {
+      s->sublo[d] = s->boxlo[d] + s->prd[d] * (s->myloc[d] * 1.0 / pg[d]);
+      if (s->myloc[d] < pg[d] - 1) s->subhi[d] = s->boxlo[d] + s->prd[d] * ((s->myloc[d] + 1) * 1.0 / pg[d]);
+      else s->subhi[d] = s->boxhi[d];
+    } else {
+      s->sublo[d] = s->myloc[d] * 1.0 / pg[d];
+      s->subhi[d] = (s->myloc[d] < pg[d] - 1) ? (s->myloc[d] + 1) * 1.0 / pg[d] : 1.0;
+    }
+  }
+}
+
+// CommBrick::setup
+static void setup_swaps(SystemState *s)
+{
+  const double cut = s->cutneighmax;
+  double prd[3];
+  if (!s->triclinic) {
+    for (int d = 0; d < 3; d++) {
+      s->cutghost[d] = cut;
+      prd[d] = s->prd[d];
+    }
+  } else {
+    const double *hi = s->h_inv;
+    s->cutghost[0] = cut * sqrt(hi[0] * hi[0] + hi[5] * hi[5] + hi[4] * hi[4]);
+    s->cutghost[1] = cut * sqrt(hi[1] * hi[1] + hi[3] * hi[3]);
+    s->cutghost[2] = cut * hi[2];
+    prd[0] = prd[1] = prd[2] = 1.0;
+  }
+  const int *pg = s->d.procgrid;
+  for (auto &sw : s->swaps) sw.sendlist.release();
+  s->swaps.clear();
+  for (int dim = 0; dim < 3; dim++) {
+    s->maxneed[dim] = static_cast<int>(s->cutghost[dim] * pg[dim] / prd[dim]) + 1;
+    for (int ineed = 0; ineed < 2 * s->maxneed[dim]; ineed++) {
+      Swap sw;
+      sw.dim = dim;
+      if (ineed % 2 == 0) {
+        sw.sendproc = s->procneigh[dim][0];
+        sw.recvproc = s->procneigh[dim][1];
+        sw.lo = (ineed < 2) ? -BIGSLAB : 0.5 * (s->sublo[dim] + s->subhi[dim]);
+        sw.hi = s->sublo[dim] + s->cutghost[dim];
+        if (s->myloc[dim] == 0) {
+          sw.pbc_flag = 1;
+          sw.pbc[dim] = 1;
+          if (s->triclinic) {
+            if (dim == 1) sw.pbc[5] = 1;
+            else if (dim == 2) sw.pbc[4] = sw.pbc[3] = 1;
+          }
+        }
+      } else {
+        sw.sendproc = s->procneigh[dim][1];
+        sw.recvproc = s->procneigh[dim][0];
+        sw.lo = s->subhi[dim] - s->cutghost[dim];
+        sw.hi = (ineed < 2) ? BIGSLAB : 0.5 * (s->sublo[dim] + s->subhi[dim]);
+        if (s->myloc[dim] == pg[dim] - 1) {
+          sw.pbc_flag = 1;
+          sw.pbc[dim] = -1;
+          if (s->triclinic) {
+            if (dim == 1) sw.pbc[5] = -1;
+            else if (dim == 2) sw.pbc[4] = sw.pbc[3] = -1;
+          }
+        }
+      }
+      // AtomVec::pack_border / pack_comm shifts
+      const double xy = s->h[5], xz = s->h[4], yz = s->h[3];
+      if (!s->triclinic) {
+        for (int d = 0; d < 3; d++) sw.bshift[d] = sw.fshift[d] = sw.pbc[d] * s->prd[d];
+      } else {
+        for (int d = 0; d < 3; d++) sw.bshift[d] = sw.pbc[d];
+        sw.fshift[0] = sw.pbc[0] * s->prd[0] + sw.pbc[5] * xy + sw.pbc[4] * xz;
+        sw.fshift[1] = sw.pbc[1] * s->prd[1] + sw.pbc[3] * yz;
+        sw.fshift[2] = sw.pbc[2] * s->prd[2];
+      }
+      s->swaps.push_back(std::move(sw));
+    }
+  }
+}
+
+// neighbor cutoffs per LAMMPS type pair (Pair::init -> init_one, Neighbor::init)
+static int setup_cutoffs(b200md_ctx *c, SystemState *s)
+{
+  const int nt = s->d.ntypes;
+  const double skin = s->d.skin;
+  s->cutneighsq.assign((size_t) (nt + 1) * (nt + 1), 0.0);
+  s->cutneighghostsq.assign((size_t) (nt + 1) * (nt + 1), 0.0);
+  s->cutneighmax = 0.0;
+  // Pair::init:      cutsq[i][j] = init_one(i,j)^2 for i <= j, mirrored
+  // Neighbor::init:  cutneighsq = (sqrt(cutsq) + skin)^2 ; cutneighghostsq = (cutghost + skin)^2
+  // (same operation order as the host code, so the squared cutoffs are bit-identical)
+  if (s->d.style == 0) {
+    ARG_CHECK(c, c->rebomos_ready && c->ntypes == nt, "system_create: call b200md_rebomos_init with the same ntypes first");
+    const double cut3rebo = 3.0 * c->rp.rcmax[0];    // PairREBOMoS::init_one: same cutoff for every type pair
+    for (int i = 1; i <= nt; i++)
+      for (int j = 1; j <= nt; j++) {
+        ARG_CHECK(c, c->map_h[i] >= 0 && c->map_h[j] >= 0, "system_create: NULL-mapped types are not supported");
+        const double cutsq = cut3rebo * cut3rebo;
+        const double cn = sqrt(cutsq) + skin;
+        s->cutneighsq[(size_t) i * (nt + 1) + j] = cn * cn;
+        const double cg = c->rp.rcmax[c->map_h[i] * 2 + c->map_h[j]] + skin;    // cutghost[i][j] = rcmax
+        s->cutneighghostsq[(size_t) i * (nt + 1) + j] = cg * cg;
+        s->cutneighmax = fmax(s->cutneighmax, cn);
+      }
+    s->ghost_rows = 1;
+  } else {
+    ARG_CHECK(c, c->aeam_ready && c->ap.nel == nt, "system_create: call b200md_aeam_init with nelements == ntypes first");
+    for (int i = 1; i <= nt; i++)
+      for (int j = 1; j <= nt; j++) {
+        // Pair::init loops i <= j and mirrors cutsq, so the (i,j) cutoff with i <= j is used for both
+        const int a = i <= j ? i : j, b = i <= j ? j : i;
+        const double cut = c->ap.cut[(a - 1) * nt + (b - 1)];
+        const double cutsq = cut * cut;
+        const double cn = sqrt(cutsq) + skin;
+        s->cutneighsq[(size_t) i * (nt + 1) + j] = cn * cn;
+        s->cutneighghostsq[(size_t) i * (nt + 1) + j] = cn * cn;
+        s->cutneighmax = fmax(s->cutneighmax, cn);
+      }
+    s->ghost_rows = 0;
+  }
+  return B200MD_OK;
+}
+
+// ------------------------------------------------------------------ Atom::sort
+static int sort_atoms(b200md_ctx *c, SystemState *s)
+{
+  const int n = s->nlocal;
+  s->nextsort = (s->step / s->d.sort_every) * s->d.sort_every + s->d.sort_every;
+  // Atom::setup_sort_bins
+  const double binsize = 0.5 * s->cutneighmax;
+  if (binsize == 0.0 || n == 0) return B200MD_OK;
+  const double bininv = 1.0 / binsize;
+  double lo[3], hi[3];
+  if (!s->triclinic) {
+    for (int d = 0; d < 3; d++) {
+      lo[d] = s->sublo[d];
+      hi[d] = s->subhi[d];
+    }
+  } else {
+    for (int d = 0; d < 3; d++) {
+      lo[d] = 1.0e30;
+      hi[d] = -1.0e30;
+    }
+    for (int cc = 0; cc < 8; cc++) {
+      const double l0 = (cc & 1) ? s->subhi[0] : s->sublo[0], l1 = (cc & 2) ? s->subhi[1] : s->sublo[1],
+                   l2 = (cc & 4) ? s->subhi[2] : s->sublo[2];
+      double x[3];
+      x[0] = s->h[0] * l0 + s->h[5] * l1 + s->h[4] * l2 + s->boxlo[0];
+      x[1] = s->h[1] * l1 + s->h[3] * l2 + s->boxlo[1];
+      x[2] = s->h[2] * l2 + s->boxlo[2];
+      for (int d = 0; d < 3; d++) {
+        lo[d] = fmin(lo[d], x[d]);
+        hi[d] = fmax(hi[d], x[d]);
+      }
+    }
+  }
+  SortGeom g;
+  long long nbins = 1;
+  for (int d = 0; d < 3; d++) {
+    g.nb[d] = static_cast<int>((hi[d] - lo[d]) * bininv);
+    if (g.nb[d] == 0) g.nb[d] = 1;
+    g.inv[d] = g.nb[d] / (hi[d] - lo[d]);
+    g.lo[d] = lo[d];
+    nbins *= g.nb[d];
+  }
+  ARG_CHECK(c, nbins < 2000000000LL, "Too many atom sorting bins");
+  if (nbins == 1) return B200MD_OK;
+  const Geom geo = make_geom(s);
+  // for triclinic, atoms must be in box coords (not lamda) to match bbox; LAMMPS converts back after
+  if (s->triclinic) {
+    LaunchScope ls(c, "lamda2x");
+    k_lamda2x<<<nblk(n), BLOCK, 0, c->stream>>>(geo, c->xq.p, n);
+  }
+  CUDA_TRY(c, s->itmp.reserve((size_t) 2 * n + nbins + 64));
+  CUDA_TRY(c, s->itmp2.reserve((size_t) n + nbins + 64));
+  CUDA_TRY(c, s->scan64.reserve((size_t) nbins + 8));
+  int *bin_of = s->itmp.p, *count = s->itmp.p + n;
+  int *perm = s->itmp2.p;
+  CUDA_TRY(c, cudaMemsetAsync(count, 0, nbins * sizeof(int), c->stream));
+  {
+    LaunchScope ls(c, "sort_bins");
+    k_sort_bins<<<nblk(n), BLOCK, 0, c->stream>>>(g, c->xq.p, n, bin_of, count);
+  }
+  int rc = b200md_exclusive_scan_i64(c, count, s->scan64.p, (int) nbins, 1);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(count, 0, nbins * sizeof(int), c->stream));
+  {
+    LaunchScope ls(c, "sort_fill");
+    k_sort_fill<<<nblk(n), BLOCK, 0, c->stream>>>(bin_of, n, s->scan64.p, count, perm);
+  }
+  {
+    LaunchScope ls(c, "sort_within");
+    k_sort_within<<<nblk(nbins), BLOCK, 0, c->stream>>>(s->scan64.p, (int) nbins, perm);
+  }
+  if (s->triclinic) {
+    LaunchScope ls(c, "x2lamda");
+    k_x2lamda<<<nblk(n), BLOCK, 0, c->stream>>>(geo, c->xq.p, n);
+  }
+  // gather into temporaries, then copy back
+  CUDA_TRY(c, s->x4tmp.reserve((size_t) n + 8));
+  CUDA_TRY(c, s->dtmp.reserve(3 * (size_t) n + 8));
+  int *to = s->itmp.p, *go = s->itmp.p + n;    // bin_of/count are no longer needed
+  {
+    LaunchScope ls(c, "permute");
+    k_permute<<<nblk(n), BLOCK, 0, c->stream>>>(perm, n, c->xq.p, s->v.p, c->type.p, c->tag.p, s->x4tmp.p, s->dtmp.p, to, go);
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->xq.p, s->x4tmp.p, n * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(s->v.p, s->dtmp.p, 3 * (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->type.p, to, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->tag.p, go, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// ------------------------------------------------------------------ CommBrick::borders
+static int halo_borders(b200md_ctx *c, SystemState *s)
+{
+  s->nghost = 0;
+  int nfirst = 0, nlast = 0;
+  size_t is = 0;
+  for (int dim = 0; dim < 3; dim++) {
+    nlast = 0;
+    for (int ineed = 0; ineed < 2 * s->maxneed[dim]; ineed++, is++) {
+      Swap &sw = s->swaps[is];
+      if (ineed % 2 == 0) {
+        nfirst = nlast;
+        nlast = s->nlocal + s->nghost;
+      }
+      const int nscan = nlast - nfirst;
+      int nsend = 0;
+      if (nscan > 0) {
+        CUDA_TRY(c, s->itmp.reserve((size_t) nscan + 64));
+        CUDA_TRY(c, s->scan64.reserve((size_t) nscan + 8));
+        {
+          LaunchScope ls(c, "slab_flags");
+          k_slab_flags<<<nblk(nscan), BLOCK, 0, c->stream>>>(c->xq.p, nfirst, nlast, sw.dim, sw.lo, sw.hi, s->itmp.p);
+        }
+        int rc = b200md_exclusive_scan_i64(c, s->itmp.p, s->scan64.p, nscan, 1);
+        if (rc) return rc;
+        int64_t tot = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&tot, s->scan64.p + nscan, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        nsend = (int) tot;
+        CUDA_TRY(c, sw.sendlist.reserve((size_t) nsend + 8));
+        if (nsend) {
+          LaunchScope ls(c, "scatter_list");
+          k_scatter_list<<<nblk(nscan), BLOCK, 0, c->stream>>>(s->itmp.p, s->scan64.p, nfirst, nscan, sw.sendlist.p);
+        }
+      }
+      sw.nsend = nsend;
+      const int first = s->nlocal + s->nghost;
+      int nrecv = 0;
+      if (sw.sendproc == s->me) {
+        nrecv = nsend;
+        int rc = ensure_atoms(c, s, (size_t) first + nrecv);
+        if (rc) return rc;
+        if (nrecv) {
+          LaunchScope ls(c, "border_copy");
+          k_border_copy<<<nblk(nrecv), BLOCK, 0, c->stream>>>(c->xq.p, c->type.p, c->tag.p, sw.sendlist.p, nrecv, first,
+                                                            sw.bshift[0], sw.bshift[1], sw.bshift[2], sw.pbc_flag);
+        }
+      } else {
+        // counts first (host round trip is fine at rebuild time), then the atoms
+        CUDA_TRY(c, s->sendbuf.reserve(6 * (size_t) nsend + 8));
+        double cnt_h = (double) nsend, cnt_r = 0.0;
+        double *dcnt = c->scal.p + 32;
+        CUDA_TRY(c, cudaMemcpyAsync(dcnt, &cnt_h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        int rc = nccl_sendrecv(c, s, dcnt, 1, sw.sendproc, dcnt + 1, 1, sw.recvproc);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(&cnt_r, dcnt + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        nrecv = (int) cnt_r;
+        if ((rc = ensure_atoms(c, s, (size_t) first + nrecv))) return rc;
+        CUDA_TRY(c, s->recvbuf.reserve(6 * (size_t) nrecv + 8));
+        if (nsend) {
+          LaunchScope ls(c, "border_pack");
+          k_border_pack<<<nblk(nsend), BLOCK, 0, c->stream>>>(c->xq.p, c->type.p, c->tag.p, sw.sendlist.p, nsend,
+                                                            sw.bshift[0], sw.bshift[1], sw.bshift[2], sw.pbc_flag,
+                                                            s->sendbuf.p);
+        }
+        if ((rc = nccl_sendrecv(c, s, s->sendbuf.p, 6 * (size_t) nsend, sw.sendproc, s->recvbuf.p, 6 * (size_t) nrecv,
+                                sw.recvproc)))
+          return rc;
+        if (nrecv) {
+          LaunchScope ls(c, "border_unpack");
+          k_border_unpack<<<nblk(nrecv), BLOCK, 0, c->stream>>>(c->xq.p, c->type.p, c->tag.p, first, nrecv, s->recvbuf.p);
+        }
+      }
+      sw.nrecv = nrecv;
+      sw.firstrecv = first;
+      s->nghost += nrecv;
+    }
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int halo_forward_x(b200md_ctx *c, SystemState *s)
+{
+  for (Swap &sw : s->swaps) {
+    if (sw.sendproc == s->me) {
+      if (sw.nsend) {
+        LaunchScope ls(c, "forward_x");
+        k_forward_x<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.firstrecv, sw.fshift[0],
+                                                           sw.fshift[1], sw.fshift[2], sw.pbc_flag);
+      }
+    } else {
+      CUDA_TRY(c, s->sendbuf.reserve(3 * (size_t) sw.nsend + 8));
+      CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nrecv + 8));
+      if (sw.nsend) {
+        LaunchScope ls(c, "forward_x_pack");
+        k_forward_x_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.fshift[0],
+                                                                sw.fshift[1], sw.fshift[2], sw.pbc_flag, s->sendbuf.p);
+      }
+      int rc = nccl_sendrecv(c, s, s->sendbuf.p, 3 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 3 * (size_t) sw.nrecv,
+                             sw.recvproc);
+      if (rc) return rc;
+      if (sw.nrecv) {
+        LaunchScope ls(c, "forward_x_unpack");
+        k_forward_x_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->xq.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
+      }
+    }
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
+{
+  for (Swap &sw : s->swaps) {
+    if (sw.sendproc == s->me) {
+      if (sw.nsend) {
+        LaunchScope ls(c, "forward_fp");
+        k_forward_s2<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+      }
+    } else {
+      CUDA_TRY(c, s->sendbuf.reserve(2 * (size_t) sw.nsend + 8));
+      CUDA_TRY(c, s->recvbuf.reserve(2 * (size_t) sw.nrecv + 8));
+      if (sw.nsend) {
+        LaunchScope ls(c, "forward_fp_pack");
+        k_forward_s2_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, s->sendbuf.p);
+      }
+      int rc = nccl_sendrecv(c, s, s->sendbuf.p, 2 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 2 * (size_t) sw.nrecv,
+                             sw.recvproc);
+      if (rc) return rc;
+      if (sw.nrecv) {
+        LaunchScope ls(c, "forward_fp_unpack");
+        k_forward_s2_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
+      }
+    }
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int halo_reverse_f(b200md_ctx *c, SystemState *s)
+{
+  for (int is = (int) s->swaps.size() - 1; is >= 0; is--) {
+    Swap &sw = s->swaps[is];
+    if (sw.sendproc == s->me) {
+      if (sw.nsend) {
+        LaunchScope ls(c, "reverse_f");
+        k_reverse_f<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+      }
+    } else {
+      // ghost forces are contiguous at f[3*firstrecv ...]: send them back, add what my send-list atoms receive
+      CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nsend + 8));
+      int rc = nccl_sendrecv(c, s, c->f.p + 3 * (size_t) sw.firstrecv, 3 * (size_t) sw.nrecv, sw.recvproc, s->recvbuf.p,
+                             3 * (size_t) sw.nsend, sw.sendproc);
+      if (rc) return rc;
+      if (sw.nsend) {
+        LaunchScope ls(c, "reverse_f_unpack");
+        k_reverse_f_unpack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, s->recvbuf.p);
+      }
+    }
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// ------------------------------------------------------------------ reneighbor + forces
+static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
+{
+  const Geom geo = make_geom(s);
+  int n = s->nlocal;
+  if (s->triclinic && n) {
+    LaunchScope ls(c, "x2lamda");
+    k_x2lamda<<<nblk(n), BLOCK, 0, c->stream>>>(geo, c->xq.p, n);
+  }
+  if (n) {
+    LaunchScope ls(c, "pbc");
+    if (s->triclinic) k_pbc<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, n, 0, 0, 0, 1, 1, 1, 1, 1, 1);
+    else
+      k_pbc<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, n, s->boxlo[0], s->boxlo[1], s->boxlo[2], s->boxhi[0], s->boxhi[1],
+                                             s->boxhi[2], s->prd[0], s->prd[1], s->prd[2]);
+  }
+  if (s->nranks > 1) {
+    c->fail("multi-GPU atom migration is not implemented yet");
+    return B200MD_ERR_ARG;
+  }
+  int rc;
+  if (s->d.sort_every > 0 && (first || s->step >= s->nextsort))
+    if ((rc = sort_atoms(c, s))) return rc;
+  if ((rc = halo_borders(c, s))) return rc;
+  const int nall = s->nlocal + s->nghost;
+  if (s->triclinic && nall) {
+    LaunchScope ls(c, "lamda2x");
+    k_lamda2x<<<nblk(nall), BLOCK, 0, c->stream>>>(geo, c->xq.p, nall);
+  }
+  c->nlocal = s->nlocal;
+  c->nghost = s->nghost;
+  c->nall = nall;
+  // element code in w for the force kernels (ghosts included)
+  {
+    LaunchScope ls(c, "set_w");
+    k_set_w<<<nblk(nall), BLOCK, 0, c->stream>>>(c->xq.p, c->type.p, c->map_d.p, s->d.style == 0 ? 1 : 0, nall);
+  }
+  // Neighbor::build: hold positions of owned atoms, then bins + rows
+  CUDA_TRY(c, s->xhold.reserve((size_t) s->nlocal + 8));
+  CUDA_TRY(c, cudaMemcpyAsync(s->xhold.p, c->xq.p, s->nlocal * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, s->xt.reserve((size_t) nall + 8));
+  {
+    LaunchScope ls(c, "make_xt");
+    k_make_xt<<<nblk(nall), BLOCK, 0, c->stream>>>(c->xq.p, c->type.p, nall, s->xt.p);
+  }
+  b200md_box box = s->d.box;
+  for (int d = 0; d < 3; d++) {
+    box.sublo[d] = s->sublo[d];
+    box.subhi[d] = s->subhi[d];
+    box.cutghost[d] = s->cutghost[d];
+  }
+  box.cutneighmax = s->cutneighmax;
+  if ((rc = b200md_neigh_build_device(c, box, s->d.ntypes, s->cutneighsq.data(), s->cutneighghostsq.data(), s->nlocal,
+                                      s->nghost, s->xt.p, s->ghost_rows, s->d.skin)))
+    return rc;
+  rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
+  if (rc) return rc;
+  s->ago = 0;
+  if (!first) s->nbuild++;
+  return B200MD_OK;
+}
+
+static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
+{
+  const size_t n3 = 3 * (size_t) c->nall;
+  CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+  int rc;
+  if (s->d.style == 0) {
+    if ((rc = b200md_rebomos_forces(c, eflag, vflag))) return rc;
+  } else {
+    if ((rc = b200md_aeam_density(c))) return rc;
+    if ((rc = halo_forward_rho_fp(c, s))) return rc;
+    if ((rc = b200md_aeam_forces(c, eflag, vflag))) return rc;
+  }
+  return halo_reverse_f(c, s);
+}
+
+// compute temp / pressure / pe (global sums over ranks)
+static int thermo(b200md_ctx *c, SystemState *s)
+{
+  {
+    LaunchScope ls(c, "ke");
+    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, c->scal.p);
+  }
+  if (s->nranks > 1) NCCL_TRY(c, ncclAllReduce(c->scal.p, c->scal.p, 9, ncclDouble, ncclSum, s->nccl, c->stream));
+  double h[16];
+  int fl[16];
+  CUDA_TRY(c, cudaMemcpyAsync(h, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (fl[0]) {
+    c->fail("per-atom row overflow in the force kernels (flag " + std::to_string(fl[0]) + ")");
+    return B200MD_ERR_OVERFLOW;
+  }
+  const double dof = fmax(3.0 * (double) s->natoms - 3.0, 0.0);
+  const double tfactor = dof > 0.0 ? s->d.mvv2e / (dof * s->d.boltz) : 0.0;
+  const double temp = h[8] * tfactor;
+  const double vol = s->prd[0] * s->prd[1] * s->prd[2];
+  const double press = (dof * s->d.boltz * temp + h[1] + h[2] + h[3]) / 3.0 / vol * s->d.nktv2p;
+  std::vector<double> row(12);
+  row[0] = (double) s->step;
+  row[1] = temp;
+  row[2] = press;
+  row[3] = h[0];
+  row[4] = temp * 0.5 * dof * s->d.boltz;
+  row[5] = vol;
+  for (int k = 0; k < 6; k++) row[6 + k] = h[1 + k];
+  s->rows.push_back(row);
+  return B200MD_OK;
+}
+
+// ================================================================== C ABI
+void b200md_system_free(b200md_ctx *c)
+{
+  b200md_neigh_forget(c);
+  b200md_aeam_forget(c);
+  SystemState *s = c->sys;
+  if (!s) return;
+  for (auto &sw : s->swaps) sw.sendlist.release();
+  s->v.release(); s->xhold.release(); s->xt.release(); s->dmass.release(); s->itmp.release(); s->itmp2.release();
+  s->x4tmp.release(); s->dtmp.release(); s->scan64.release(); s->sendbuf.release(); s->recvbuf.release();
+  if (s->nccl) ncclCommDestroy(s->nccl);
+  delete s;
+  c->sys = nullptr;
+}
+
+extern "C" int b200md_nccl_unique_id(void *id128)
+{
+  if (!id128) return B200MD_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return B200MD_ERR_NCCL;
+  memcpy(id128, &id, 128);
+  return B200MD_OK;
+}
+
+extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, int nlocal, const double *x,
+                                    const double *v, const int *type, const int *tag)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, d && nlocal >= 0 && (nlocal == 0 || (x && type && tag)), "system_create: NULL arguments");
+  ARG_CHECK(c, d->ntypes >= 1 && d->ntypes <= B200MD_MAX_TYPES && d->mass, "system_create: bad ntypes/mass");
+  ARG_CHECK(c, d->procgrid[0] >= 1 && d->procgrid[1] >= 1 && d->procgrid[2] >= 1, "system_create: bad procgrid");
+  ARG_CHECK(c, d->rank >= 0 && d->rank < d->procgrid[0] * d->procgrid[1] * d->procgrid[2], "system_create: bad rank");
+  ARG_CHECK(c, d->style == 0 || d->style == 1, "system_create: style must be 0 (rebomos) or 1 (aeam)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  ncclComm_t keep = nullptr;
+  if (c->sys) {
+    keep = c->sys->nccl;
+    c->sys->nccl = nullptr;
+    SystemState *old = c->sys;
+    for (auto &sw : old->swaps) sw.sendlist.release();
+    old->v.release(); old->xhold.release(); old->xt.release(); old->dmass.release(); old->itmp.release();
+    old->itmp2.release(); old->x4tmp.release(); old->dtmp.release(); old->scan64.release(); old->sendbuf.release();
+    old->recvbuf.release();
+    delete old;
+    c->sys = nullptr;
+  }
+  SystemState *s = new SystemState();
+  c->sys = s;
+  s->nccl = keep;
+  s->d = *d;
+  s->mass.assign(d->mass, d->mass + d->ntypes + 1);
+  s->d.mass = s->mass.data();
+  int rc = setup_cutoffs(c, s);
+  if (rc) return rc;
+  setup_geometry(s);
+  setup_swaps(s);
+  ARG_CHECK(c, s->nranks == 1 || s->nccl, "system_create: call b200md_system_comm_init before creating a multi-rank system");
+  s->nlocal = nlocal;
+  if ((rc = ensure_atoms(c, s, (size_t) nlocal + nlocal / 2 + 1024))) return rc;
+  CUDA_TRY(c, s->dmass.reserve(B200MD_MAX_TYPES + 2));
+  CUDA_TRY(c, cudaMemcpyAsync(s->dmass.p, s->mass.data(), (d->ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (nlocal) {
+    CUDA_TRY(c, c->x_aos.reserve(3 * (size_t) nlocal + 8));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p, x, 3 * (size_t) nlocal * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    {
+      LaunchScope ls(c, "upload_x");
+      k_upload_x<<<nblk(nlocal), BLOCK, 0, c->stream>>>(c->x_aos.p, nlocal, c->xq.p);
+    }
+    if (v) CUDA_TRY(c, cudaMemcpyAsync(s->v.p, v, 3 * (size_t) nlocal * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    else CUDA_TRY(c, cudaMemsetAsync(s->v.p, 0, 3 * (size_t) nlocal * sizeof(double), c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->type.p, type, nlocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tag.p, tag, nlocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // global atom count
+  s->natoms = nlocal;
+  if (s->nranks > 1) {
+    double cnt = (double) nlocal;
+    CUDA_TRY(c, cudaMemcpyAsync(c->scal.p + 40, &cnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(c, ncclAllReduce(c->scal.p + 40, c->scal.p + 40, 1, ncclDouble, ncclSum, s->nccl, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&cnt, c->scal.p + 40, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    s->natoms = (long long) cnt;
+  }
+  // Verlet::setup: ghosts, lists, forces with energy + virial, thermo row 0
+  s->step = 0;
+  s->nbuild = s->ndanger = 0;
+  if ((rc = reneighbor(c, s, true))) return rc;
+  if ((rc = compute_forces(c, s, 1, 2))) return rc;
+  if ((rc = thermo(c, s))) return rc;
+  return B200MD_OK;
+}
+
+extern "C" int b200md_system_comm_init(b200md_ctx *c, const void *id128, int nranks, int rank)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, id128 && nranks >= 1 && rank >= 0 && rank < nranks, "system_comm_init: bad arguments");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->sys) c->sys = new SystemState();
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NCCL_TRY(c, ncclCommInitRank(&c->sys->nccl, nranks, id, rank));
+  return B200MD_OK;
+}
+
+extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
+{
+  if (!c) return B200MD_ERR_ARG;
+  SystemState *s = c->sys;
+  ARG_CHECK(c, s && s->swaps.size(), "system_run: call b200md_system_create first");
+  ARG_CHECK(c, nsteps >= 0 && thermo_every >= 0, "system_run: bad arguments");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const double dtv = s->d.dt, dtf = 0.5 * s->d.dt * s->d.ftm2v;
+  const double triggersq = 0.25 * s->d.skin * s->d.skin;
+  const long long last = s->step + nsteps;
+  int rc;
+  for (int it = 0; it < nsteps; it++) {
+    s->step++;
+    const bool thermo_step = (s->step == last) || (thermo_every > 0 && s->step % thermo_every == 0);
+    const int n = s->nlocal;
+    if (n) {
+      LaunchScope ls(c, "initial_integrate");
+      k_initial_integrate<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, s->v.p, c->f.p, c->type.p, s->dmass.p, n, dtf, dtv,
+                                                          s->xhold.p, triggersq, c->flags.p);
+    }
+    // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
+    s->ago++;
+    int flag = 0;
+    if (s->nranks > 1) {
+      NCCL_TRY(c, ncclAllReduce(c->flags.p + 9, c->flags.p + 9, 1, ncclInt, ncclMax, s->nccl, c->stream));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (flag) {
+      CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+      if (s->ago == 1) s->ndanger++;
+      if ((rc = reneighbor(c, s, false))) return rc;
+    } else {
+      if ((rc = halo_forward_x(c, s))) return rc;
+    }
+    if ((rc = compute_forces(c, s, thermo_step ? 1 : 0, thermo_step ? 2 : 0))) return rc;
+    if (n) {
+      LaunchScope ls(c, "final_integrate");
+      k_final_integrate<<<nblk(n), BLOCK, 0, c->stream>>>(s->v.p, c->f.p, c->type.p, s->dmass.p, n, dtf);
+    }
+    if (thermo_step)
+      if ((rc = thermo(c, s))) return rc;
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaGetLastError());
+  b200md_collect_timers(c);
+  return B200MD_OK;
+}
+
+extern "C" int b200md_system_thermo_count(b200md_ctx *c)
+{
+  if (!c || !c->sys) return 0;
+  return (int) c->sys->rows.size();
+}
+extern "C" int b200md_system_thermo_row(b200md_ctx *c, int i, double *out)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->sys && out && i >= 0 && i < (int) c->sys->rows.size(), "system_thermo_row: bad index");
+  memcpy(out, c->sys->rows[i].data(), 12 * sizeof(double));
+  return B200MD_OK;
+}
+extern "C" int b200md_system_thermo(b200md_ctx *c, double *out)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->sys && c->sys->rows.size(), "system_thermo: nothing evaluated yet");
+  return b200md_system_thermo_row(c, (int) c->sys->rows.size() - 1, out);
+}
+extern "C" int b200md_system_sizes(b200md_ctx *c, long long *out)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->sys && out, "system_sizes: no system");
+  out[0] = c->sys->nlocal;
+  out[1] = c->sys->nghost;
+  out[2] = c->sys->nbuild;
+  out[3] = c->sys->ndanger;
+  return B200MD_OK;
+}
+extern "C" int b200md_system_download(b200md_ctx *c, double *x, double *v, double *f, int *type, int *tag)
+{
+  if (!c) return B200MD_ERR_ARG;
+  SystemState *s = c->sys;
+  ARG_CHECK(c, s, "system_download: no system");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int nall = s->nlocal + s->nghost;
+  if (x && nall) {
+    CUDA_TRY(c, c->x_aos.reserve(3 * (size_t) nall + 8));
+    {
+      LaunchScope ls(c, "download_x");
+      k_download_x<<<nblk(nall), BLOCK, 0, c->stream>>>(c->xq.p, nall, c->x_aos.p);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(x, c->x_aos.p, 3 * (size_t) nall * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (v && s->nlocal) CUDA_TRY(c, cudaMemcpyAsync(v, s->v.p, 3 * (size_t) s->nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (f && nall) CUDA_TRY(c, cudaMemcpyAsync(f, c->f.p, 3 * (size_t) nall * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (type && nall) CUDA_TRY(c, cudaMemcpyAsync(type, c->type.p, nall * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (tag && nall) CUDA_TRY(c, cudaMemcpyAsync(tag, c->tag.p, nall * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200MD_OK;
+}

@@ -1259,6 +1259,9 @@ void *minilmp_get_ptr(void *ptr, int rank, const char *name)
   if (n == "pair") return l->force->pair;
   if (n == "lammps") return l;
   if (n == "stencil") return l->neighbor->stencil;
+  if (n == "cutneighsq") return l->neighbor->cutneighsq ? (void *) &l->neighbor->cutneighsq[0][0] : nullptr;
+  if (n == "cutneighghostsq")
+    return l->neighbor->cutneighghostsq ? (void *) &l->neighbor->cutneighghostsq[0][0] : nullptr;
   return nullptr;
 }
 

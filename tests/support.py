@@ -202,6 +202,25 @@ class MiniLmp:
     def thermo_clear(self):
         self.L.minilmp_thermo_clear(self.h)
 
+    def cutneighsq(self, ghost=False):
+        nt = self.get_int("ntypes")
+        return self._arr("cutneighghostsq" if ghost else "cutneighsq", 0, (nt + 1) * (nt + 1), np.float64).copy()
+
+    def b200_box(self, rank=0):
+        """b200md_box of this rank's sub-domain (lamda bounds if triclinic), as Neighbor/Comm see it."""
+        from lammps_plugins_b200 import make_box
+        d = self.box()
+        b = make_box(d["boxlo"], d["boxhi"], d["xy"], d["xz"], d["yz"], triclinic=d["triclinic"])
+        for k in range(3):
+            b.sublo[k] = self.get_double("sublo%d" % k, rank)
+            b.subhi[k] = self.get_double("subhi%d" % k, rank)
+            b.cutghost[k] = self.get_double("cutghost%d" % k, rank)
+        b.cutneighmax = self.get_double("cutneighmax", rank)
+        return b
+
+    def units(self):
+        return {k: self.get_double(k) for k in ("boltz", "mvv2e", "ftm2v", "nktv2p")}
+
     def box(self):
         d = {k: self.get_double(k) for k in ("xy", "xz", "yz")}
         d["boxlo"] = [self.get_double("boxlo%d" % k) for k in range(3)]

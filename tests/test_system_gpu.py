@@ -1,0 +1,113 @@
+"""GPU-resident MD system (b200md_system_*): ghosts, lists, NVE loop and thermo entirely on the device,
+checked against (a) the golden thermo table of log.rebomos-bulk.1 and (b) the oracle engine."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lammps_plugins_b200 as b2
+import support as S
+
+pytestmark = pytest.mark.gpu
+
+
+def start_system(ctx, lmp, style, sort_every=1000):
+    """hand the engine's owned atoms (as created, before any setup) to the device system"""
+    nl = lmp.get_int("nlocal")
+    assert lmp.get_int("nghost") == 0
+    d = lmp.box()
+    box = b2.make_box(d["boxlo"], d["boxhi"], d["xy"], d["xz"], d["yz"], triclinic=d["triclinic"])
+    ctx.system_create(style, lmp.get_int("ntypes"), lmp.mass(), box, lmp.x(0, nl).copy(), lmp.v().copy(),
+                      lmp.type()[:nl].copy(), lmp.tag()[:nl].copy(), lmp.get_double("skin"), lmp.get_double("dt"),
+                      lmp.units(), sort_every=sort_every)
+
+
+def aeam_tables():
+    t = S.load_aeam_fixture()
+    return {k: t[k] for k in ("nelements", "nnonangular", "nrho", "drho", "nr", "dr", "cut", "frho", "rhor", "z2r")}
+
+
+def test_golden_log_rebomos_bulk(ctx, oracle_built):
+    """in.rebomos-bulk run on the device reproduces log.rebomos-bulk.1:54-56 to all 8 printed digits,
+    with 4285 ghosts and 0 neighbor list builds in 20 steps."""
+    gold = json.load(open(os.path.join(S.GOLDEN, "log_rebomos_bulk.json")))["log.rebomos-bulk.1"]
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"))
+    ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    start_system(ctx, lmp, "rebomos")
+    ctx.system_run(20, 10)
+    rows = ctx.system_thermo_rows()
+    assert [r["step"] for r in rows] == [0, 10, 20]
+    for r, g in zip(rows, gold["thermo"]):
+        print(r["step"], S.fmt8(r["temp"]), S.fmt8(r["press"]), S.fmt8(r["pe"]), S.fmt8(r["ke"]))
+        assert S.fmt8(r["temp"]) == S.fmt8(g[1])
+        assert S.fmt8(r["press"]) == S.fmt8(g[2])
+        assert S.fmt8(r["pe"]) == S.fmt8(g[3])
+        assert S.fmt8(r["ke"]) == S.fmt8(g[4])
+        assert S.fmt8(r["vol"]) == S.fmt8(g[6])
+    sz = ctx.system_sizes()
+    assert sz["nlocal"] == 288 and sz["nghost"] == int(gold["nghost_ave_max_min"][0])
+    assert sz["nbuild"] == gold["builds"] == 0
+    lmp.close()
+
+
+@pytest.mark.parametrize("style,rep", [("rebomos", (2, 2, 1)), ("aeam", (5, 4, 6))])
+def test_setup_state_matches_engine_bitwise(ctx, oracle_built, style, rep):
+    """After setup the device holds the same atoms in the same order as the host engine: owned order after
+    Atom::sort, ghost order after CommBrick::borders, coordinates bit-identical (incl. the lamda round trip)."""
+    if style == "rebomos":
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), rep, displace=0.1)
+        ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    else:
+        lmp = S.make_aeam_system(S.oracle_plugin("aeam"), rep, si_fraction=0.05, displace=0.1)
+        ctx.aeam_init(aeam_tables())
+    start_system(ctx, lmp, style)
+    got = ctx.system_download()
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    assert got["nlocal"] == snap["nlocal"] and got["nghost"] == snap["nghost"]
+    assert np.array_equal(got["tag"], snap["tag"])
+    assert np.array_equal(got["type"], snap["type"])
+    assert np.array_equal(got["x"], snap["x"])          # bit-exact
+    # forces after reverse comm, energy, pressure
+    lmp.compute(1, 2, reverse=True)
+    nl = snap["nlocal"]
+    assert S.rel_err(got["f"][:nl], lmp.f()[:nl]) < 1e-10
+    row = ctx.system_thermo_rows()[0]
+    ref = lmp.thermo()[0]
+    assert abs(row["pe"] - ref["pe"]) < 1e-12 * abs(ref["pe"])
+    assert abs(row["press"] - ref["press"]) < 1e-9 * max(1.0, abs(ref["press"]))
+    lmp.close()
+
+
+@pytest.mark.parametrize("style", ["rebomos", "aeam"])
+def test_nve_run_with_reneighboring_tracks_engine(ctx, oracle_built, style):
+    """A hot NVE run that rebuilds its lists several times: same number of rebuilds as the host engine,
+    thermo agreeing to 1e-7 relative (trajectories diverge slowly through rounding), energy conserved."""
+    steps = 60
+    if style == "rebomos":
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 1, 1),
+                                    extra=["velocity all create 2000.0 4928459", "neighbor 0.5 bin"])
+        ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    else:
+        lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.02,
+                                 extra=["velocity all create 2000.0 1082337", "neighbor 0.4 bin"])
+        ctx.aeam_init(aeam_tables())
+    start_system(ctx, lmp, style)
+    ctx.system_run(steps, 20)
+    rows = ctx.system_thermo_rows()
+    lmp.commands(["thermo 20", "fix 1 all nve", "run %d" % steps])
+    ref = lmp.thermo()
+    sz = ctx.system_sizes()
+    print(style, "builds", sz["nbuild"], lmp.get_int("nbuild"), "dangerous", sz["ndanger"])
+    assert sz["nbuild"] == lmp.get_int("nbuild") and sz["nbuild"] > 0
+    for r, g in zip(rows, ref):
+        print(r["step"], r["temp"], g["temp"], r["pe"], g["pe"], r["press"], g["press"])
+        assert r["step"] == g["step"]
+        assert abs(r["pe"] - g["pe"]) < 1e-7 * abs(g["pe"])
+        assert abs(r["ke"] - g["ke"]) < 1e-6 * max(abs(g["ke"]), 1.0)
+    e0 = rows[0]["pe"] + rows[0]["ke"]
+    e1 = rows[-1]["pe"] + rows[-1]["ke"]
+    eref = ref[-1]["pe"] + ref[-1]["ke"]
+    assert abs((e1 - e0) - (eref - (ref[0]["pe"] + ref[0]["ke"]))) < 1e-6 * abs(e0)
+    lmp.close()

@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark driver: atom-timesteps/s of the GPU-resident REBOMoS (default) or AEAM force path.
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one JSON line on rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference pair style compiled
+                                                           # verbatim (oracle/_ref) on the host cores
+
+A "step" is one NVE timestep of the whole job: integrate, ghost exchange, (re)neighboring when an atom
+moved more than skin/2, force computation, reverse exchange.  Workload at N = 1: BASELINE.json configs[2],
+the shipped MoS2 cell replicated 14x13x19 = 995 904 atoms, 300 K, dt 1 fs (per GPU: weak scaling,
+configs[4]); `--workload aeam` runs configs[3] (fcc Al + 0.75 % Si, 80^3 cells = 2 048 000 atoms, 863 K).
+
+JSON keys beyond the base contract: roofline (dominant kernel, live CUDA-event time), cpu_baseline,
+e2e (plugin-mode C-ABI call with pinned HOST buffers, H2D/D2H inside the timed region), clocks,
+gpu_launches, kernels (device ms per step by kernel), neighbor (rebuilds in the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "tests"))
+
+# algorithmic work per atom-step (restated in DESIGN.md)
+ALGO = {
+    "rebomos": dict(bytes=2040.0, flops=19.0e3),
+    "aeam": dict(bytes=756.0, flops=6.9e3),
+}
+FP64_NOMINAL_TFLOPS = 37.0
+
+
+def measured_peaks():
+    p = os.path.join(HERE, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def procgrid_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n) or _factor3(n)
+
+
+def _factor3(n):
+    best = (n, 1, 1)
+    for a in range(1, n + 1):
+        if n % a:
+            continue
+        for b in range(1, n // a + 1):
+            if (n // a) % b:
+                continue
+            c = n // a // b
+            t = tuple(sorted((a, b, c), reverse=True))
+            if max(t) - min(t) < max(best) - min(best):
+                best = t
+    return best
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.window = [None, None]
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append((time.time(), float(f[0]), float(f[1]), f[3], f[4], f[5], f[6]))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= (t1 or 1e30)] or self.samples
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        reasons = set()
+        for s in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": inside[0][2],
+                "reasons": sorted(reasons), "samples": len(inside)}
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+def make_workload(kind, rep, nranks):
+    from lammps_plugins_b200 import workloads as W
+    grid = procgrid_for(nranks)
+    if kind == "rebomos":
+        r = rep or (14, 13, 19)
+        full = (r[0] * grid[0], r[1] * grid[1], r[2] * grid[2])      # weak scaling: one block per GPU
+        w = W.mos2_bulk(*full)
+        w["v"] = W.maxwell_velocities(w["type"], w["mass"], 300.0, 12345)
+        w["name"] = "rebomos MoS2 bulk (in.rebomos-bulk cell) replicated %dx%dx%d" % full
+        w["skin"], w["dt"] = 2.0, 0.001
+    else:
+        r = rep or (80, 80, 80)
+        full = (r[0] * grid[0], r[1] * grid[1], r[2] * grid[2])
+        w = W.fcc_alsi(full, 0.0075, 7683797)
+        w["v"] = W.maxwell_velocities(w["type"], w["mass"], 863.0, 1082337)
+        w["name"] = "aeam fcc Al-0.75%%Si a=4.045 %dx%dx%d cells" % full
+        w["skin"], w["dt"] = 1.0, 0.001
+    w["grid"] = grid
+    return w
+
+
+def init_potential(ctx, kind):
+    import support as S
+    if kind == "rebomos":
+        ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    else:
+        t = S.load_aeam_fixture()
+        ctx.aeam_init({k: t[k] for k in ("nelements", "nnonangular", "nrho", "drho", "nr", "dr", "cut", "frho", "rhor", "z2r")})
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import lammps_plugins_b200 as b2
+    from lammps_plugins_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus)
+    kind = args.workload
+    w = make_workload(kind, args.rep, world)
+    natoms = len(w["x"])
+    grid = w["grid"]
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+        owner = W.brick_owner(w["x"], w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], grid)
+        mine = owner == rank
+    else:
+        mine = slice(None)
+
+    ctx = b2.Context(local_rank)
+    init_potential(ctx, kind)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            assert ctx.L.b200md_nccl_unique_id(raw) == 0
+            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        raw = bytes(idbuf.cpu().numpy().tobytes())
+        ctx._check(ctx.L.b200md_system_comm_init(ctx.h, raw, world, rank))
+
+    box = b2.make_box(w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], triclinic=w["triclinic"])
+    t_setup = time.time()
+    ctx.system_create(kind, w["ntypes"], w["mass"], box, w["x"][mine], w["v"][mine], w["type"][mine], w["tag"][mine],
+                      w["skin"], w["dt"], b2.METAL_UNITS, procgrid=grid, rank=rank, sort_every=1000)
+    t_setup = time.time() - t_setup
+    sz0 = ctx.system_sizes()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ctx.system_run(args.warmup, 0)
+    ctx.set_option("sync_timing", 1)
+    ctx.kernel_stats(reset=True)
+    barrier()
+    l0 = ctx.counter("kernel_launches")
+    b0 = ctx.system_sizes()["nbuild"]
+    sampler.window[0] = time.time()
+    ctx.event_record(0)
+    ctx.system_run(args.steps, 0)
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    sampler.window[1] = time.time()
+    barrier()
+    launches = ctx.counter("kernel_launches") - l0
+    kstats = ctx.kernel_stats()
+    ctx.set_option("sync_timing", 0)
+    builds = ctx.system_sizes()["nbuild"] - b0
+    thermo = ctx.system_thermo_rows()
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+
+    value = natoms * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region)
+    hbm_peak, peak_src = measured_peaks()
+    per_step = {k: v[0] / args.steps for k, v in kstats.items()}
+    force_kernels = {"rebomos": ["lj", "bondorder_f", "bondorder_p", "rebo_neigh"],
+                     "aeam": ["aeam_force", "aeam_density", "aeam_embed", "aeam_force_ang", "aeam_density_ang"]}[kind]
+    dom = max(force_kernels, key=lambda k: per_step.get(k, 0.0))
+    dom_ms_launch = kstats[dom][0] / max(kstats[dom][1], 1)
+    atoms_per_gpu = sz0["nlocal"]
+    algo_bytes = ALGO[kind]["bytes"] * atoms_per_gpu          # whole-step algorithmic bytes, charged to the dominant kernel
+    achieved = algo_bytes / (dom_ms_launch * 1e-3) / 1e9
+    step_gbs = ALGO[kind]["bytes"] * natoms / world / (ms_per_step * 1e-3) / 1e9
+    step_tflops = ALGO[kind]["flops"] * natoms / world / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_launch": dom_ms_launch, "kernel_share_of_step": per_step.get(dom, 0.0) / ms_per_step,
+                "algorithmic_bytes_per_atom_step": ALGO[kind]["bytes"],
+                "whole_step": {"hbm_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak, "fp64_tflops": step_tflops,
+                               "fp64_frac_of_nominal": step_tflops / FP64_NOMINAL_TFLOPS,
+                               "fp64_peak_note": "nominal %.0f TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)" % FP64_NOMINAL_TFLOPS}}
+
+    # ---- e2e: plugin-mode C-ABI call with pinned host buffers (N = 1 only; multi-rank plugin mode needs LAMMPS' comm)
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        e2e = run_e2e(ctx, kind, w, args)
+
+    # ---- CPU baseline (reference sources compiled verbatim) on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            cpu = run_cpu_reference(kind, args.cpu_seconds)
+        except Exception as e:      # the GPU number stands on its own; say why the CPU leg is missing
+            cpu = {"value": None, "unit": "atom-steps/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": "atom-timesteps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "pair_style": kind, "atoms": natoms, "atoms_per_gpu": atoms_per_gpu,
+                   "ghosts_per_gpu": sz0["nghost"], "parallelism": "brick %dx%dx%d" % grid, "ensemble": "NVE dt=1fs",
+                   "skin": w["skin"], "l2": "working set (neighbor rows %.2f GB) >> 126 MB L2; no flush needed"
+                   % (ctx.counter("lj_entries") * 4 / 1e9)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+        "gpu_launches": launches,
+        "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "neighbor": {"rebuilds_in_timed_region": builds, "setup_s": t_setup},
+        "thermo_last": {k: (float(v) if not isinstance(v, np.ndarray) else None) for k, v in thermo[-1].items() if k != "virial"},
+    }
+    print(json.dumps(line))
+
+
+def run_e2e(ctx_sys, kind, w, args):
+    """Plugin mode: per step H2D x/type/tag (pinned) -> forces on the device -> D2H f (pinned).
+    The neighbor list is built on the device from the host positions once, outside the timed region
+    (LAMMPS rebuilds every ~10-50 steps; the golden log shows 0 rebuilds in its 20 steps)."""
+    import lammps_plugins_b200 as b2
+    import support as S
+    from lammps_plugins_b200 import workloads as W
+    st = ctx_sys.system_download()
+    nl, ng = st["nlocal"], st["nghost"]
+    nall = nl + ng
+    ctx = b2.Context(0)
+    init_potential(ctx, kind)
+    if kind == "rebomos":
+        P = S.rebomos_params_struct()
+        cs, cg, cmax = W.rebomos_neighbor_cutoffs(list(P.rcmax), [0, 1], w["skin"])
+    else:
+        cs, cg, cmax = W.aeam_neighbor_cutoffs(S.load_aeam_fixture()["cut"], w["skin"])
+    box = W.single_rank_box(w, cmax)
+    x = ctx.pinned_array((nall, 3))
+    f = ctx.pinned_array((nall, 3))
+    x[:] = st["x"]
+    typ, tag = st["type"], st["tag"]
+    ctx.neigh_build(box, w["ntypes"], cs, cg, nl, ng, x, typ, 1 if kind == "rebomos" else 0, w["skin"])
+    ctx.set_option("f_overwrite", 1)
+
+    def one():
+        if kind == "rebomos":
+            ctx.rebomos_compute(nl, ng, x, typ, tag, 0, 0, f=f)
+        else:
+            ctx.aeam_compute(nl, ng, x, typ, tag, 0, 0, f=f)
+
+    for _ in range(3):
+        one()
+    h0, d0 = ctx.counter("h2d_bytes"), ctx.counter("d2h_bytes")
+    n = max(5, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        one()
+    dt = time.perf_counter() - t0
+    out = {"value": nl * n / dt, "unit": "atom-steps/s", "steps": n, "ms_per_step": dt / n * 1e3,
+           "h2d_bytes_per_step": (ctx.counter("h2d_bytes") - h0) // n, "d2h_bytes_per_step": (ctx.counter("d2h_bytes") - d0) // n,
+           "path": "b200md_%s_compute via ctypes, pinned host x/f, device-built neighbor list reused" % kind,
+           "checksum_f": float(np.abs(f[:nl]).sum())}
+    ctx.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def run_cpu_reference(kind, seconds, steps=None):
+    """The reference pair style compiled verbatim (oracle/_ref; the port if _ref is absent) inside the mini
+    LAMMPS engine, domain-decomposed over thread-ranks on the host cores (stand-in for mpirun: no MPI here)."""
+    import support as S
+    ncores = os.cpu_count() or 1
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    nranks = 1
+    for cand in (64, 48, 32, 27, 24, 16, 12, 8, 6, 4, 2, 1):
+        if cand <= ncores:
+            nranks = cand
+            break
+    grid = _factor3(nranks)
+    plugin = S.oracle_plugin(kind)
+    knd = "reference" if "_ref" in plugin else "port"
+    lmp = S.MiniLmp(grid)
+    lmp.command("plugin load " + plugin)
+    # size the sample from a per-core rate guess, then report what was actually run
+    if kind == "rebomos":
+        rate = 3.0e4 * nranks
+        nsteps = steps or 20
+        cells = max(1.0, rate * seconds / nsteps / 288.0)
+        r = max(1, round(cells ** (1 / 3)))
+        rx, ry, rz = max(r, grid[0]), max(r, grid[1]), max(r, grid[2])
+        pot = os.path.join(S.potential_dir(), "MoS.REBO.set5b")
+        for c in S.input_script("in.rebomos-bulk"):
+            wd = c.split()
+            if wd[0] in ("thermo_style", "thermo", "fix", "run"):
+                continue
+            if wd[0] == "region":
+                c = "region box prism 0 %d 0 %d 0 %d %g 0.0 0.0" % (4 * rx, 8 * ry, rz, -2.0 * ry)
+            if wd[0] == "pair_coeff":
+                c = "pair_coeff * * %s M S" % pot
+            lmp.command(c)
+        lmp.command("velocity all create 300.0 12345")
+        sample = "MoS2 bulk %dx%dx%d cells" % (rx, ry, rz)
+    else:
+        rate = 1.5e5 * nranks
+        nsteps = steps or 20
+        n = max(grid[0] * 4, round((rate * seconds / nsteps / 4.0) ** (1 / 3)))
+        lmp.commands(S.aeam_commands((n, n, n), 0.0075))
+        lmp.command("velocity all create 863.0 1082337")
+        sample = "fcc Al-0.75%%Si %dx%dx%d cells" % (n, n, n)
+    natoms = lmp.get_int("natoms")
+    lmp.commands(["fix 1 all nve", "thermo 0", "run %d" % nsteps])
+    t = lmp.get_double("time_loop")
+    out = {"value": natoms * nsteps / t, "unit": "atom-steps/s", "cores": nranks, "kind": knd,
+           "sample": "%s = %d atoms, %d NVE steps, %dx%dx%d thread-ranks (brick decomposition, -O2), loop %.2f s, pair %.0f%%"
+           % (sample, natoms, nsteps, grid[0], grid[1], grid[2], t, 100.0 * lmp.get_double("time_pair") / t),
+           "host_cores_visible": ncores}
+    lmp.close()
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = args.workload
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = run_cpu_reference(kind, args.cpu_seconds / max(args.steps, 1), steps=10)
+        if it >= args.warmup:
+            times.append(last["value"])
+    v = float(np.mean(times))
+    w = make_workload.__doc__
+    line = {"impl": "reference", "metric": "atom-timesteps/s", "value": v, "unit": "atom-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s (bounded sample of the B200 arm's lattice)" % kind, "pair_style": kind},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="rebomos", choices=["rebomos", "aeam"])
+    ap.add_argument("--rep", type=int, nargs=3, default=None, help="per-GPU replication (rebomos cells / fcc cells)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps, args.warmup = 3, 1          # each CPU "step" is a bounded multi-second sample
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -172,7 +172,8 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
 
 /* ---- tuning / introspection ------------------------------------------------ */
 /* option names: "deterministic" (0/1), "margin" (inner-list skin in 1e-3 A, 0 = use skin),
- * "sync_timing" (0/1) */
+ * "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
+ * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
  * "rebo_bonds", "lj_entries", "short_entries" */
@@ -180,8 +181,20 @@ long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
  * ("rebo_neigh","bondorder_p","bondorder_f","lj","fdotr","aeam_density","aeam_force",...) */
 double b200md_last_kernel_ms(b200md_ctx *ctx, const char *name);
+/* accumulated per-kernel device time since the last reset (while "sync_timing" is 1): iterate index from 0
+ * until the return value is 1 */
+int b200md_kernel_stats(b200md_ctx *ctx, int index, char *name_out, int name_cap, double *total_ms,
+                        long long *count);
+int b200md_kernel_stats_reset(b200md_ctx *ctx);
 /* raw CUDA stream the context launches on (cudaStream_t), for external event timing */
 void *b200md_stream(b200md_ctx *ctx);
+/* CUDA-event timing on that stream: record into slot 0..7, then elapsed ms between two slots
+ * (synchronises on the later event) */
+int b200md_event_record(b200md_ctx *ctx, int slot);
+double b200md_event_elapsed_ms(b200md_ctx *ctx, int slot_a, int slot_b);
+/* page-locked host memory for callers that want DMA-speed x/f transfers */
+void *b200md_host_alloc(size_t bytes);
+void b200md_host_free(void *p);
 
 /* =============================================================================
  * GPU-resident MD system (the benchmark driver's run loop; one per GPU/rank)

@@ -110,7 +110,13 @@ SYMBOLS = [
     ("b200md_set_option", c_int, [c_void_p, c_char_p, c_longlong]),
     ("b200md_get_counter", c_longlong, [c_void_p, c_char_p]),
     ("b200md_last_kernel_ms", c_double, [c_void_p, c_char_p]),
+    ("b200md_kernel_stats", c_int, [c_void_p, c_int, c_char_p, c_int, _PD, POINTER(c_longlong)]),
+    ("b200md_kernel_stats_reset", c_int, [c_void_p]),
     ("b200md_stream", c_void_p, [c_void_p]),
+    ("b200md_event_record", c_int, [c_void_p, c_int]),
+    ("b200md_event_elapsed_ms", c_double, [c_void_p, c_int, c_int]),
+    ("b200md_host_alloc", c_void_p, [ctypes.c_size_t]),
+    ("b200md_host_free", None, [c_void_p]),
     ("b200md_system_create", c_int, [c_void_p, POINTER(SystemDesc), c_int, _PD, _PD, _PI, _PI]),
     ("b200md_nccl_unique_id", c_int, [c_void_p]),
     ("b200md_system_comm_init", c_int, [c_void_p, c_void_p, c_int, c_int]),
@@ -169,6 +175,9 @@ class Context:
         if getattr(self, "h", None):
             self.L.b200md_destroy(self.h)
             self.h = None
+            for p in self._keep:
+                self.L.b200md_host_free(p)
+            self._keep = []
 
     def __del__(self):
         try:
@@ -189,6 +198,36 @@ class Context:
 
     def kernel_ms(self, name):
         return float(self.L.b200md_last_kernel_ms(self.h, name.encode()))
+
+    def kernel_stats(self, reset=False):
+        """{kernel name: (total_ms, launches)} accumulated while option sync_timing is on"""
+        out = {}
+        i = 0
+        name = ctypes.create_string_buffer(64)
+        tot = c_double()
+        cnt = c_longlong()
+        while self.L.b200md_kernel_stats(self.h, i, name, 64, ctypes.byref(tot), ctypes.byref(cnt)) == 0:
+            out[name.value.decode()] = (tot.value, cnt.value)
+            i += 1
+        if reset:
+            self.L.b200md_kernel_stats_reset(self.h)
+        return out
+
+    def event_record(self, slot):
+        self._check(self.L.b200md_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        return float(self.L.b200md_event_elapsed_ms(self.h, a, b))
+
+    def pinned_array(self, shape, dtype=np.float64):
+        """numpy array over page-locked host memory (freed with the context)"""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.L.b200md_host_alloc(n)
+        if not p:
+            raise B200MDError("cudaMallocHost failed")
+        self._keep.append(p)
+        buf = (ctypes.c_char * n).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     # -- potentials
     def rebomos_init(self, params: RebomosParams, type_map):

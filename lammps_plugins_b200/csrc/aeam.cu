@@ -809,23 +809,10 @@ static int aeam_begin(b200md_ctx *c, int nlocal, int nghost, const double *x, co
 
 static int aeam_finish(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial)
 {
-  const size_t n3 = 3 * (size_t) c->nall;
-  CUDA_TRY(c, c->pin_f.reserve(n3 + 64));
-  int *pin_flags = (int *) (c->pin_scal.p + 32);
-  if (n3) CUDA_TRY(c, cudaMemcpyAsync(c->pin_f.p, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  c->d2h_bytes += (long long) (n3 * sizeof(double) + 16 * sizeof(double) + 16 * sizeof(int));
-  b200md_collect_timers(c);
-  int rc = aeam_check_flags(c, pin_flags);
+  int fl[16];
+  int rc = b200md_finish_compute(c, eflag, vflag, f, eng_vdwl, virial, fl);
   if (rc) return rc;
-  const double *src = c->pin_f.p;
-  for (size_t k = 0; k < n3; k++) f[k] += src[k];
-  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
-  if (virial)
-    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
-  return B200MD_OK;
+  return aeam_check_flags(c, fl);
 }
 
 // one-shot: ghosts are periodic images of owned atoms (single rank); ghost fp via atom IDs

@@ -116,9 +116,13 @@ struct AeamDev {
 };
 
 // ---------------------------------------------------------------- context
-struct KernelTimer {
-  cudaEvent_t a = nullptr, b = nullptr;
-  bool used = false;
+struct TimedLaunch {
+  int name_id;
+  cudaEvent_t a, b;
+};
+struct KernelStat {
+  double total_ms = 0.0, last_ms = 0.0;
+  long long count = 0;
 };
 
 struct SystemState;    // resident MD system (system.cu)
@@ -133,12 +137,18 @@ struct b200md_ctx {
   int deterministic = 0;
   double margin_opt = 0.0;    // 0 -> use skin
   int sync_timing = 0;
+  int f_overwrite = 0;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // counters
   long long n_launch = 0, n_list_upload = 0, n_inner_rebuild = 0, h2d_bytes = 0, d2h_bytes = 0;
   long long n_rebo_bonds = 0, n_lj_entries = 0, n_short_entries = 0;
-  std::map<std::string, KernelTimer> timers;
-  std::map<std::string, float> last_ms;
+  // per-launch CUDA events while "sync_timing" is on; folded into kstat by b200md_collect_timers()
+  std::vector<std::string> kname;
+  std::map<std::string, int> kname_id;
+  std::vector<TimedLaunch> pending;
+  std::vector<cudaEvent_t> event_pool;
+  std::map<std::string, KernelStat> kstat;
 
   // ---- atoms (device)
   int nlocal = 0, nghost = 0, nall = 0;
@@ -210,31 +220,52 @@ struct b200md_ctx {
   }
 };
 
-// launch bookkeeping + optional per-kernel timing
+// launch bookkeeping + optional per-kernel timing (events on the launching stream)
 struct LaunchScope {
   b200md_ctx *c;
-  KernelTimer *t = nullptr;
+  cudaEvent_t eb = nullptr;
+  static cudaEvent_t get_event(b200md_ctx *c)
+  {
+    if (!c->event_pool.empty()) {
+      cudaEvent_t e = c->event_pool.back();
+      c->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
   LaunchScope(b200md_ctx *ctx, const char *name) : c(ctx)
   {
     c->n_launch++;
     if (c->sync_timing) {
-      KernelTimer &kt = c->timers[name];
-      if (!kt.a) {
-        cudaEventCreate(&kt.a);
-        cudaEventCreate(&kt.b);
-      }
-      t = &kt;
-      t->used = true;
-      cudaEventRecord(t->a, c->stream);
+      auto it = c->kname_id.find(name);
+      int id;
+      if (it == c->kname_id.end()) {
+        id = (int) c->kname.size();
+        c->kname.push_back(name);
+        c->kname_id[name] = id;
+      } else
+        id = it->second;
+      TimedLaunch t;
+      t.name_id = id;
+      t.a = get_event(c);
+      t.b = get_event(c);
+      cudaEventRecord(t.a, c->stream);
+      eb = t.b;
+      c->pending.push_back(t);
     }
   }
   ~LaunchScope()
   {
-    if (t) cudaEventRecord(t->b, c->stream);
+    if (eb) cudaEventRecord(eb, c->stream);
   }
 };
 
 int b200md_collect_timers(b200md_ctx *c);    // after a stream sync: fills last_ms
+// D2H of forces/energy/virial/flags + host-side accumulate (shared by the compute entry points)
+int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
+                          int *flags_out);
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -93,10 +93,13 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->ang_list.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
   c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();
-  for (auto &kv : c->timers) {
-    if (kv.second.a) cudaEventDestroy(kv.second.a);
-    if (kv.second.b) cudaEventDestroy(kv.second.b);
+  for (int k = 0; k < 8; k++)
+    if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  for (TimedLaunch &t : c->pending) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
   }
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -110,6 +113,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->margin_opt = 1.0e-3 * (double) value;
     c->inner_valid = false;
   } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
+  else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
   else {
     c->fail("unknown option " + n);
     return B200MD_ERR_ARG;
@@ -136,22 +140,109 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
 extern "C" double b200md_last_kernel_ms(b200md_ctx *c, const char *name)
 {
   if (!c || !name) return -1.0;
-  auto it = c->last_ms.find(name);
-  if (it == c->last_ms.end()) return -1.0;
-  return it->second;
+  auto it = c->kstat.find(name);
+  if (it == c->kstat.end()) return -1.0;
+  return it->second.last_ms;
+}
+
+extern "C" int b200md_kernel_stats(b200md_ctx *c, int index, char *name_out, int name_cap, double *total_ms,
+                                   long long *count)
+{
+  if (!c) return B200MD_ERR_ARG;
+  if (index < 0 || index >= (int) c->kstat.size()) return 1;
+  auto it = c->kstat.begin();
+  std::advance(it, index);
+  if (name_out && name_cap > 0) {
+    strncpy(name_out, it->first.c_str(), name_cap - 1);
+    name_out[name_cap - 1] = '\0';
+  }
+  if (total_ms) *total_ms = it->second.total_ms;
+  if (count) *count = it->second.count;
+  return B200MD_OK;
+}
+
+extern "C" int b200md_kernel_stats_reset(b200md_ctx *c)
+{
+  if (!c) return B200MD_ERR_ARG;
+  c->kstat.clear();
+  return B200MD_OK;
 }
 
 extern "C" void *b200md_stream(b200md_ctx *c) { return c ? (void *) c->stream : nullptr; }
 
+extern "C" int b200md_event_record(b200md_ctx *c, int slot)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, slot >= 0 && slot < 8, "event_record: slot must be 0..7");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->ev[slot]) CUDA_TRY(c, cudaEventCreate(&c->ev[slot]));
+  CUDA_TRY(c, cudaEventRecord(c->ev[slot], c->stream));
+  return B200MD_OK;
+}
+
+extern "C" double b200md_event_elapsed_ms(b200md_ctx *c, int a, int b)
+{
+  if (!c || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->ev[a] || !c->ev[b]) return -1.0;
+  if (cudaEventSynchronize(c->ev[b]) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) return -1.0;
+  return (double) ms;
+}
+
+extern "C" void *b200md_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void b200md_host_free(void *p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+// forces + scalars + flags back to the host; f accumulated (default) or overwritten
+int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
+                          int *flags_out)
+{
+  const size_t n3 = 3 * (size_t) c->nall;
+  int *pin_flags = (int *) (c->pin_scal.p + 32);
+  if (c->f_overwrite) {
+    if (n3) CUDA_TRY(c, cudaMemcpyAsync(f, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CUDA_TRY(c, c->pin_f.reserve(n3 + 64));
+    if (n3) CUDA_TRY(c, cudaMemcpyAsync(c->pin_f.p, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (long long) (n3 * sizeof(double) + 16 * sizeof(double) + 16 * sizeof(int));
+  b200md_collect_timers(c);
+  memcpy(flags_out, pin_flags, 16 * sizeof(int));
+  if (!c->f_overwrite) {
+    const double *src = c->pin_f.p;
+    for (size_t k = 0; k < n3; k++) f[k] += src[k];
+  }
+  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
+  if (virial)
+    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
+  return B200MD_OK;
+}
+
 int b200md_collect_timers(b200md_ctx *c)
 {
-  if (!c->sync_timing) return 0;
-  for (auto &kv : c->timers) {
-    if (!kv.second.used) continue;
+  // caller has synchronised the stream
+  for (TimedLaunch &t : c->pending) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, kv.second.a, kv.second.b) == cudaSuccess) c->last_ms[kv.first] = ms;
-    kv.second.used = false;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      KernelStat &k = c->kstat[c->kname[t.name_id]];
+      k.total_ms += ms;
+      k.last_ms = ms;
+      k.count++;
+    }
+    c->event_pool.push_back(t.a);
+    c->event_pool.push_back(t.b);
   }
+  c->pending.clear();
   return 0;
 }
 

@@ -783,23 +783,10 @@ extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, con
   if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
   if ((rc = b200md_rebomos_forces(c, eflag, vflag))) return rc;
 
-  CUDA_TRY(c, c->pin_f.reserve(n3 + 64));
-  int *pin_flags = (int *) (c->pin_scal.p + 32);
-  if (n3) CUDA_TRY(c, cudaMemcpyAsync(c->pin_f.p, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  c->d2h_bytes += (long long) (n3 * sizeof(double) + 16 * sizeof(double) + 16 * sizeof(int));
-  b200md_collect_timers(c);
-  if ((rc = check_flags(c, pin_flags))) return rc;
-
-  const double *src = c->pin_f.p;
-  for (size_t k = 0; k < n3; k++) f[k] += src[k];
-  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
-  if (virial) {
-    // scal[1..6] = fdotr (xx,yy,zz,xy,xz,yz) of the many-body part + LJ pair virial in the same order
-    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
-  }
+  int fl[16];
+  if ((rc = b200md_finish_compute(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+  // virial[0..5] = fdotr (xx,yy,zz,xy,xz,yz) of the many-body part + LJ pair virial in the same order
+  if ((rc = check_flags(c, fl))) return rc;
   return B200MD_OK;
 }
 

@@ -1,0 +1,79 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   Shared glue between the LAMMPS-facing pair classes and the b200md C ABI:
+   one device context per Pair instance, neighbor-list hand-over (device build
+   from LAMMPS' box/cutoffs, or upload of LAMMPS' own list), error mapping
+   (status != 0  ->  error->one with the library's message; there is no CPU
+   fallback to fall back to).
+------------------------------------------------------------------------- */
+#ifndef B200MD_HOST_H
+#define B200MD_HOST_H
+
+#include "b200md.h"
+
+#include "atom.h"
+#include "comm.h"
+#include "domain.h"
+#include "error.h"
+#include "neigh_list.h"
+#include "neighbor.h"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace B200MDHost {
+
+// which GPU this rank drives: B200MD_DEVICE if set, else rank modulo the visible device count
+inline int pick_device(int me)
+{
+  const char *env = getenv("B200MD_DEVICE");
+  if (env) return atoi(env);
+  const char *vis = getenv("B200MD_DEVICES_PER_NODE");
+  int per = vis ? atoi(vis) : 0;
+  return per > 0 ? me % per : 0;
+}
+
+// true -> rebuild the list on the device from LAMMPS' positions (default);
+// false -> upload LAMMPS' own NeighList (B200MD_NEIGH=host)
+inline bool device_neighbor_build()
+{
+  const char *env = getenv("B200MD_NEIGH");
+  return !(env && strcmp(env, "host") == 0);
+}
+
+template <class ErrorT> inline void check(ErrorT *error, b200md_ctx *ctx, int rc, const char *what)
+{
+  if (rc != B200MD_OK)
+    error->one(__FILE__, __LINE__, "B200 {} failed ({}): {}", what, rc, b200md_last_error(ctx));
+}
+
+// hand the current neighbor list to the device (called when LAMMPS has just rebuilt it: neighbor->ago == 0)
+inline int sync_neighbor_list(b200md_ctx *ctx, LAMMPS_NS::Atom *atom, LAMMPS_NS::Neighbor *neighbor,
+                              LAMMPS_NS::Comm *comm, LAMMPS_NS::Domain *domain, LAMMPS_NS::NeighList *list,
+                              int ghost_rows)
+{
+  using namespace LAMMPS_NS;
+  if (device_neighbor_build()) {
+    b200md_box box;
+    memset(&box, 0, sizeof(box));
+    box.triclinic = domain->triclinic;
+    for (int d = 0; d < 3; d++) {
+      box.boxlo[d] = domain->boxlo[d];
+      box.boxhi[d] = domain->boxhi[d];
+      box.sublo[d] = domain->triclinic ? domain->sublo_lamda[d] : domain->sublo[d];
+      box.subhi[d] = domain->triclinic ? domain->subhi_lamda[d] : domain->subhi[d];
+      box.cutghost[d] = comm->cutghost[d];
+    }
+    box.xy = domain->xy;
+    box.xz = domain->xz;
+    box.yz = domain->yz;
+    box.cutneighmax = neighbor->cutneighmax;
+    return b200md_neigh_build(ctx, &box, atom->ntypes, &neighbor->cutneighsq[0][0],
+                              &neighbor->cutneighghostsq[0][0], atom->nlocal, atom->nghost, &atom->x[0][0],
+                              atom->type, ghost_rows, neighbor->skin);
+  }
+  return b200md_set_neighbor_list(ctx, list->inum, ghost_rows ? list->gnum : 0, list->numneigh, list->firstneigh,
+                                  neighbor->skin);
+}
+
+}    // namespace B200MDHost
+#endif

@@ -457,6 +457,56 @@ class Pointers {
   FILE *&logfile;
 };
 
+// ---------------------------------------------------------------- lattice.h / region (engine side)
+class Lattice {
+ public:
+  double xlattice, ylattice, zlattice;
+  double a1[3], a2[3], a3[3], origin[3], scale;
+  std::vector<std::vector<double>> basis;
+  Lattice();
+  void setup();
+  void lattice2box(double &x, double &y, double &z) const;
+  void box2lattice(double &x, double &y, double &z) const;
+  void bbox(int flag, double x, double y, double z, double &xmin, double &ymin, double &zmin,
+            double &xmax, double &ymax, double &zmax) const;
+
+ private:
+  double primitive[3][3], priminv[3][3];
+};
+
+struct Region {
+  std::string id, style;
+  double xlo, xhi, ylo, yhi, zlo, zhi, xy, xz, yz;
+};
+
+// ---------------------------------------------------------------- domain.h
+class Domain : protected Pointers {
+ public:
+  int box_exist, box_change, dimension, triclinic;
+  int periodicity[3], xperiodic, yperiodic, zperiodic;
+  double boxlo[3], boxhi[3], xy, xz, yz;
+  double prd[3], prd_half[3], xprd, yprd, zprd;
+  double h[6], h_inv[6];
+  double boxlo_lamda[3], boxhi_lamda[3], prd_lamda[3];
+  double boxlo_bound[3], boxhi_bound[3];
+  double sublo[3], subhi[3], sublo_lamda[3], subhi_lamda[3];
+  Lattice *lattice;
+  std::vector<Region> regions;
+
+  explicit Domain(LAMMPS *lmp);
+  ~Domain() override;
+  void set_global_box();
+  void set_local_box();
+  void x2lamda(int n);
+  void lamda2x(int n);
+  void x2lamda(const double *x, double *lamda) const;
+  void lamda2x(const double *lamda, double *x) const;
+  void bbox(const double *lo, const double *hi, double *bboxlo, double *bboxhi) const;
+  void pbc();
+  void remap(double *x) const;
+  double volume() const { return xprd * yprd * zprd; }
+};
+
 // ---------------------------------------------------------------- atom.h (fields the styles touch)
 class Atom : protected Pointers {
  public:

@@ -1,0 +1,70 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   pair_style aeam -- B200-native implementation.
+
+   Same style name, pair_coeff grammar and potential-file format as the
+   reference USER-AEAM package (lammps/lammps-plugins USER-AEAM/pair_aeam.h:27-83,
+   pair_aeam.cpp:513-746); density, embedding and force passes run on the GPU
+   through the b200md C ABI.  The fp forward exchange declared by the reference
+   (comm_forward = 1) is what carries F'(rho) to ghost atoms between the two
+   device phases.
+------------------------------------------------------------------------- */
+
+#ifdef PAIR_CLASS
+// clang-format off
+PairStyle(aeam,PairAEAM);
+// clang-format on
+#else
+
+#ifndef LMP_PAIR_AEAM_B200_H
+#define LMP_PAIR_AEAM_B200_H
+
+#include "b200md.h"
+#include "pair.h"
+
+#include <string>
+#include <vector>
+
+namespace LAMMPS_NS {
+
+class PairAEAM : public Pair {
+ public:
+  PairAEAM(class LAMMPS *);
+  ~PairAEAM() override;
+  void compute(int, int) override;
+  void settings(int, char **) override;
+  void coeff(int, char **) override;
+  void init_style() override;
+  double init_one(int, int) override;
+
+  int pack_forward_comm(int, int *, double *, int, int *) override;
+  void unpack_forward_comm(int, int, double *) override;
+  int pack_reverse_comm(int, int, double *) override;
+  void unpack_reverse_comm(int, int *, double *) override;
+  double memory_usage() override;
+
+ protected:
+  int nmax;             // allocated size of per-atom arrays
+  double *rho, *fp;     // host mirrors: rho[i] of owned atoms, fp[] of owned + ghost atoms
+
+  // the potential file, as read
+  struct Setfl {
+    int nelements = 0, nnonangular = 0, nangular = 0;
+    std::vector<std::string> elements;
+    std::vector<int> nrho;
+    std::vector<double> drho, mass;
+    std::vector<int> nr;              // [nelements*nelements]
+    std::vector<double> dr, cut;      // [nelements*nelements]
+    std::vector<std::vector<double>> frho, rhor, z2r;
+  };
+  Setfl *setfl;
+
+  b200md_ctx *ctx;
+  int uploaded_nlocal, uploaded_nghost;
+
+  void allocate();
+  virtual void read_file(char *);
+};
+}    // namespace LAMMPS_NS
+
+#endif
+#endif

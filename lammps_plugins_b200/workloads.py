@@ -146,3 +146,59 @@ def brick_owner(x, boxlo, boxhi, xy, xz, yz, procgrid):
     lam -= np.floor(lam)
     idx = np.minimum((lam * np.asarray(procgrid)).astype(np.int64), np.asarray(procgrid) - 1)
     return idx[:, 2] * procgrid[1] * procgrid[0] + idx[:, 1] * procgrid[0] + idx[:, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# what LAMMPS-core would hand to a pair style on ONE rank: neighbor cutoffs and the ghost cutoff of the box
+def rebomos_neighbor_cutoffs(rcmax_2x2, type_map, skin):
+    """(cutneighsq, cutneighghostsq, cutneighmax) as Neighbor::init builds them for pair_style rebomos:
+    init_one returns cut3rebo = 3*rcmax[Mo][Mo] for every pair, cutghost[i][j] = rcmax[map i][map j]."""
+    nt = len(type_map)
+    cs = np.zeros((nt + 1, nt + 1))
+    cg = np.zeros((nt + 1, nt + 1))
+    cut3rebo = 3.0 * rcmax_2x2[0]
+    cmax = 0.0
+    for i in range(1, nt + 1):
+        for j in range(1, nt + 1):
+            cn = float(np.sqrt(cut3rebo * cut3rebo)) + skin
+            cs[i, j] = cn * cn
+            g = rcmax_2x2[type_map[i - 1] * 2 + type_map[j - 1]] + skin
+            cg[i, j] = g * g
+            cmax = max(cmax, cn)
+    return cs, cg, cmax
+
+
+def aeam_neighbor_cutoffs(cut, skin):
+    """Neighbor::init for pair_style aeam: init_one(i,j) = cut[i-1][j-1] for i <= j, mirrored."""
+    cut = np.asarray(cut)
+    nt = cut.shape[0]
+    cs = np.zeros((nt + 1, nt + 1))
+    cmax = 0.0
+    for i in range(1, nt + 1):
+        for j in range(1, nt + 1):
+            a, b = (i, j) if i <= j else (j, i)
+            c = float(cut[a - 1, b - 1])
+            cn = float(np.sqrt(c * c)) + skin
+            cs[i, j] = cn * cn
+            cmax = max(cmax, cn)
+    return cs, cs.copy(), cmax
+
+
+def single_rank_box(w, cutneighmax):
+    """b200md_box of a 1x1x1 decomposition: sub-domain = whole box, Comm::cutghost per CommBrick::setup."""
+    from . import make_box
+    b = make_box(w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], triclinic=w["triclinic"])
+    prd = np.asarray(w["boxhi"]) - np.asarray(w["boxlo"])
+    if w["triclinic"]:
+        h_inv = [1.0 / prd[0], 1.0 / prd[1], 1.0 / prd[2], -w["yz"] / (prd[1] * prd[2]),
+                 (w["yz"] * w["xy"] - prd[1] * w["xz"]) / (prd[0] * prd[1] * prd[2]), -w["xy"] / (prd[0] * prd[1])]
+        cg = [cutneighmax * np.sqrt(h_inv[0] ** 2 + h_inv[5] ** 2 + h_inv[4] ** 2),
+              cutneighmax * np.sqrt(h_inv[1] ** 2 + h_inv[3] ** 2), cutneighmax * h_inv[2]]
+        lo, hi = [0.0] * 3, [1.0] * 3
+    else:
+        cg = [cutneighmax] * 3
+        lo, hi = list(w["boxlo"]), list(w["boxhi"])
+    for d in range(3):
+        b.sublo[d], b.subhi[d], b.cutghost[d] = lo[d], hi[d], cg[d]
+    b.cutneighmax = cutneighmax
+    return b

@@ -96,6 +96,10 @@ struct RebomosDev {
   double b[2][7], bg[2][7];    // [elem][order]
   double a[2][4];
   double rcLJmin[4], rcLJmax[4], sig95[4];    // sig95 = 0.95*sigma
+  // exact rsq equivalents of the reference's tests on rij = sqrt(rsq) (sqrt is monotonic and correctly
+  // rounded on both sides): rij > rcLJmax <=> rsq >= lj_out_hi ; rij < rcLJmin <=> rsq < lj_in_lo ;
+  // rij >= 0.95 sigma <=> rsq >= lj_s95
+  double lj_out_hi[4], lj_in_lo[4], lj_s95[4];
   double lj1[4], lj2[4], lj3[4], lj4[4];
   double c2[4], c3[4];    // cubic taper coefficients (pair_rebomos.cpp:533-538)
   double shortsq[4];      // (rcmax + margin)^2

@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+#include <cmath>
+
 #define TOL 1.0e-9
 #define BLOCK 256
 
@@ -235,20 +237,32 @@ __global__ void __launch_bounds__(BLOCK) rebo_neigh_kernel(
     }
     nb = min(nb, B200MD_MAX_REBO);
   }
-  // slot allocation: warp exclusive scan + one atomic per warp
-  int inc = nb;
+  // slot allocation: warp exclusive scans + one atomic per warp and element.  Bonds of Mo centers fill the
+  // table from the front, bonds of S centers from the back: a warp of the bond kernels then sees one trip
+  // count (Mo: ~11 partners, S: ~2) instead of a mix (v1 ran at 13-15 of 32 active lanes).
+  const int nbA = (ti == 0) ? nb : 0, nbB = (ti == 1) ? nb : 0;
+  int incA = nbA, incB = nbB;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+    const int tA = __shfl_up_sync(0xffffffffu, incA, o);
+    const int tB = __shfl_up_sync(0xffffffffu, incB, o);
+    if (lane >= o) {
+      incA += tA;
+      incB += tB;
+    }
   }
-  const int total = __shfl_sync(0xffffffffu, inc, 31);
-  int wbase = 0;
-  if (lane == 31 && total > 0) wbase = atomicAdd(&flags[2], total);
-  wbase = __shfl_sync(0xffffffffu, wbase, 31);
-  int off = wbase + inc - nb;
+  const int totA = __shfl_sync(0xffffffffu, incA, 31), totB = __shfl_sync(0xffffffffu, incB, 31);
+  int baseA = 0, baseB = 0;
+  if (lane == 31) {
+    if (totA > 0) baseA = atomicAdd(&flags[2], totA);
+    if (totB > 0) baseB = atomicAdd(&flags[10], totB);
+  }
+  baseA = __shfl_sync(0xffffffffu, baseA, 31);
+  baseB = __shfl_sync(0xffffffffu, baseB, 31);
   if (i >= ncenters) return;
-  if (off + nb > bond_cap) {
+  // front: [baseA + exclusive prefix ...) ; back: block of nb slots ending at cap - (baseB + exclusive prefix)
+  int off = (ti == 0) ? baseA + incA - nbA : bond_cap - (baseB + incB);
+  if (baseA + totA + baseB + totB > bond_cap) {    // the two regions would meet
     flags[0] = 2;
     nb = 0;
     off = 0;
@@ -325,14 +339,15 @@ __global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
 // ================================================================== K4a: p_ij, prefactors, pair energy
 __global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ nslots_ptr, const int *__restrict__ bond_center,
+    const int *__restrict__ flags, int bond_cap, const int *__restrict__ bond_center,
     const int *__restrict__ bond_off, const int *__restrict__ bond_num, const double *__restrict__ cenP,
     const double *__restrict__ cendP, const double4 *__restrict__ bond_geo, double *__restrict__ bond_pref,
     double *__restrict__ bond_frad, double *__restrict__ scal)
 {
-  const int nslots = *nslots_ptr;
+  const int nA = flags[2], nB = flags[10];
   double acc[1] = {0.0};
-  for (int s = blockIdx.x * BLOCK + threadIdx.x; s < nslots; s += gridDim.x * BLOCK) {
+  for (int w = blockIdx.x * BLOCK + threadIdx.x; w < nA + nB; w += gridDim.x * BLOCK) {
+    const int s = (w < nA) ? w : bond_cap - nB + (w - nA);
     const int i = bond_center[s];
     const int off = bond_off[i], nb = bond_num[i];
     const int ti = elem_of(xq[i]);
@@ -375,13 +390,14 @@ __global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
 // ================================================================== K4b: forces of the bond-order term
 __global__ void __launch_bounds__(BLOCK) bondorder_f_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ nslots_ptr, const int *__restrict__ bond_center,
+    const int *__restrict__ flags, int bond_cap, const int *__restrict__ bond_center,
     const int *__restrict__ bond_j, const int *__restrict__ bond_off, const int *__restrict__ bond_num,
     const double *__restrict__ cendP, const double4 *__restrict__ bond_geo,
     const double *__restrict__ bond_pref, const double *__restrict__ bond_frad, double *__restrict__ f)
 {
-  const int nslots = *nslots_ptr;
-  for (int s = blockIdx.x * BLOCK + threadIdx.x; s < nslots; s += gridDim.x * BLOCK) {
+  const int nA = flags[2], nB = flags[10];
+  for (int w = blockIdx.x * BLOCK + threadIdx.x; w < nA + nB; w += gridDim.x * BLOCK) {
+    const int s = (w < nA) ? w : bond_cap - nB + (w - nA);
     const int i = bond_center[s];
     const int off = bond_off[i], nb = bond_num[i];
     const int ti = elem_of(xq[i]);
@@ -449,9 +465,12 @@ __global__ void __launch_bounds__(BLOCK) fdotr_kernel(const double4 *__restrict_
 }
 
 // ================================================================== K5: tapered LJ, directed rows
-// 8 lanes per owned atom: each group streams its 32-byte-aligned row as full sectors, gathers one
-// double4 sector per neighbor, reduces with 3 shuffles.  Every directed pair is evaluated from both
-// ends, so nothing is scattered: f_i is complete, energy and virial carry a factor 1/2.
+// 8 lanes per owned atom: each group streams its 32-byte-aligned row as full sectors (4 row loads and 4
+// position gathers in flight per lane), gathers one double4 sector per neighbor, reduces with 3 shuffles.
+// Every directed pair is evaluated from both ends, so nothing is scattered: f_i is complete, energy and
+// virial carry a factor 1/2.  Only ~40 % of the candidates are inside the LJ window, so both sides of that
+// branch are kept minimal: the window and regime tests of pair_rebomos.cpp:518-543 (on rij = sqrt(rsq)) are
+// replaced by their exact rsq equivalents precomputed on the host (no sqrt, no division outside the window).
 template <bool EV>
 __global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ RebomosDev par,
                                                    const double4 *__restrict__ xq,
@@ -470,6 +489,7 @@ __global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ Rebom
     const int ti = elem_of(xi);
     const int n = (ti >= 0) ? lj_num[i] : 0;
     const int *row = lj_val + lj_off[i];
+    const int base = ti * 2;
     for (int e0 = 0; e0 < n; e0 += 32) {
       int jj[4];
       double4 xj[4];
@@ -486,19 +506,17 @@ __global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ Rebom
         if (jj[u] < 0) continue;
         const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
         const double rsq = dx * dx + dy * dy + dz * dz;
-        const int pt = ti * 2 + elem_of(xj[u]);
-        const double rmax = par.rcLJmax[pt];
-        if (rsq > rmax * rmax * (1.0 + 1.0e-14)) continue;    // certainly outside; exact test below
-        const double rij = sqrt(rsq);
-        // regimes exactly as pair_rebomos.cpp:518-543
-        if (rij > rmax || rij < par.rcLJmin[pt]) continue;
+        const int pt = base + (xj[u].w > 0.5 ? 1 : 0);
+        if (rsq >= par.lj_out_hi[pt]) continue;    // rij > rcLJmax
+        if (rsq < par.lj_in_lo[pt]) continue;      // rij < rcLJmin
         double VLJ, fpair;
-        if (rij >= par.sig95[pt]) {
+        if (rsq >= par.lj_s95[pt]) {               // rij >= 0.95 sigma: 12-6 LJ
           const double r2inv = 1.0 / rsq;
           const double r6inv = r2inv * r2inv * r2inv;
-          VLJ = r6inv * (par.lj3[pt] * r6inv - par.lj4[pt]);
           fpair = r6inv * (par.lj1[pt] * r6inv - par.lj2[pt]) * r2inv;
-        } else {
+          if (EV) VLJ = r6inv * (par.lj3[pt] * r6inv - par.lj4[pt]);
+        } else {                                   // cubic taper down to rcLJmin
+          const double rij = sqrt(rsq);
           const double drp = rij - par.rcLJmin[pt];
           VLJ = drp * drp * (drp * par.c3[pt] + par.c2[pt]);
           const double dVLJ = drp * (3.0 * drp * par.c3[pt] + 2.0 * par.c2[pt]);
@@ -534,6 +552,17 @@ __global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ Rebom
 // ================================================================== host side
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
 
+// smallest double x with sqrt(x) > T (strict) or sqrt(x) >= T; sqrt is correctly rounded and monotonic on
+// host and device, so `rsq >= this` is EXACTLY the reference's comparison on rij = sqrt(rsq)
+static double rsq_smallest_with_sqrt(double T, bool strict)
+{
+  auto ok = [&](double x) { return strict ? sqrt(x) > T : sqrt(x) >= T; };
+  double x = T * T;
+  while (ok(x)) x = nextafter(x, 0.0);
+  while (!ok(x)) x = nextafter(x, 1.0e300);
+  return x;
+}
+
 static void derive_params(b200md_ctx *c, const b200md_rebomos_params *p)
 {
   RebomosDev &d = c->rp;
@@ -551,6 +580,9 @@ static void derive_params(b200md_ctx *c, const b200md_rebomos_params *p)
     d.rcLJmax[k] = p->rcLJmax[k];
     const double eps = p->epsilon[k], sig = p->sigma[k];
     d.sig95[k] = 0.95 * sig;
+    d.lj_out_hi[k] = rsq_smallest_with_sqrt(d.rcLJmax[k], true);     // sqrt(rsq) >  rcLJmax
+    d.lj_in_lo[k] = rsq_smallest_with_sqrt(d.rcLJmin[k], false);     // sqrt(rsq) >= rcLJmin
+    d.lj_s95[k] = rsq_smallest_with_sqrt(d.sig95[k], false);         // sqrt(rsq) >= 0.95 sigma
     // init_one (pair_rebomos.cpp:262-265): powint(sigma,12), powint(sigma,6)
     double s2 = sig * sig, s4 = s2 * s2, s8 = s4 * s4;
     double s6 = s2 * s4, s12 = s4 * s8;
@@ -704,6 +736,7 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
   CUDA_TRY(c, c->nM.reserve((size_t) c->nall + 32));
   CUDA_TRY(c, c->nS.reserve((size_t) c->nall + 32));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
   if (ncen == 0) return B200MD_OK;
   const int grid_bonds = c->num_sms * 8;
   {
@@ -716,13 +749,13 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
   {
     LaunchScope ls(c, "bondorder_p");
     bondorder_p_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->flags.p + 2, c->bond_center.p, c->bond_off.p, c->bond_num.p, c->cen_P.p,
+        c->rp, c->xq.p, c->flags.p, (int) c->bond_cap, c->bond_center.p, c->bond_off.p, c->bond_num.p, c->cen_P.p,
         c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->scal.p);
   }
   {
     LaunchScope ls(c, "bondorder_f");
     bondorder_f_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->flags.p + 2, c->bond_center.p, c->bond_j.p, c->bond_off.p, c->bond_num.p,
+        c->rp, c->xq.p, c->flags.p, (int) c->bond_cap, c->bond_center.p, c->bond_j.p, c->bond_off.p, c->bond_num.p,
         c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->f.p);
   }
   if (vflag) {
@@ -745,7 +778,7 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 
 static int check_flags(b200md_ctx *c, const int *fl)
 {
-  c->n_rebo_bonds = fl[2];
+  c->n_rebo_bonds = fl[2] + fl[10];
   if (fl[4] || fl[5]) {
     c->n_short_entries = fl[4];
     c->n_lj_entries = fl[5];

@@ -48,22 +48,13 @@ def measured_peaks():
 
 
 def procgrid_for(n):
-    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n) or _factor3(n)
+    from lammps_plugins_b200.launch import procgrid_for as pf
+    return pf(n)
 
 
 def _factor3(n):
-    best = (n, 1, 1)
-    for a in range(1, n + 1):
-        if n % a:
-            continue
-        for b in range(1, n // a + 1):
-            if (n // a) % b:
-                continue
-            c = n // a // b
-            t = tuple(sorted((a, b, c), reverse=True))
-            if max(t) - min(t) < max(best) - min(best):
-                best = t
-    return best
+    from lammps_plugins_b200.launch import procgrid_for as pf
+    return pf(n) if n not in (1, 2, 4, 8) else {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -141,9 +132,9 @@ def run_b200(args):
     import lammps_plugins_b200 as b2
     from lammps_plugins_b200 import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from lammps_plugins_b200 import launch
+    grp = launch.Group()
+    rank, world, local_rank = grp.rank, grp.world, grp.local_rank
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus)
@@ -151,31 +142,11 @@ def run_b200(args):
     w = make_workload(kind, args.rep, world)
     natoms = len(w["x"])
     grid = w["grid"]
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
-        owner = W.brick_owner(w["x"], w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], grid)
-        mine = owner == rank
-    else:
-        mine = slice(None)
+    mine = launch.my_atoms(w, grid, rank) if world > 1 else slice(None)
 
     ctx = b2.Context(local_rank)
     init_potential(ctx, kind)
-    if world > 1:
-        import torch
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            import ctypes
-            raw = ctypes.create_string_buffer(128)
-            assert ctx.L.b200md_nccl_unique_id(raw) == 0
-            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-        dist.broadcast(idbuf, 0)
-        raw = bytes(idbuf.cpu().numpy().tobytes())
-        ctx._check(ctx.L.b200md_system_comm_init(ctx.h, raw, world, rank))
+    launch.join_system(ctx, grp)
 
     box = b2.make_box(w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], triclinic=w["triclinic"])
     t_setup = time.time()
@@ -188,11 +159,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
 
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+    barrier = grp.barrier
 
     ctx.system_run(args.warmup, 0)
     ctx.set_option("sync_timing", 1)
@@ -212,17 +179,17 @@ def run_b200(args):
     ctx.set_option("sync_timing", 0)
     builds = ctx.system_sizes()["nbuild"] - b0
     thermo = ctx.system_thermo_rows()
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = grp.reduce_scalar(ms, "max")
+    atoms_per_gpu_max = int(grp.reduce_scalar(sz0["nlocal"], "max"))
+    ghosts_per_gpu_max = int(grp.reduce_scalar(sz0["nghost"], "max"))
+    migrated = int(grp.reduce_scalar(ctx.system_sizes()["nmigrated"], "sum"))
     sampler.stop_flag = True
 
     value = natoms * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
 
     if rank != 0:
+        grp.close()
         return
 
     # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region)
@@ -262,17 +229,18 @@ def run_b200(args):
         "metric": "atom-timesteps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "pair_style": kind, "atoms": natoms, "atoms_per_gpu": atoms_per_gpu,
-                   "ghosts_per_gpu": sz0["nghost"], "parallelism": "brick %dx%dx%d" % grid, "ensemble": "NVE dt=1fs",
+        "config": {"workload": w["name"], "pair_style": kind, "atoms": natoms, "atoms_per_gpu": atoms_per_gpu_max,
+                   "ghosts_per_gpu": ghosts_per_gpu_max, "parallelism": "brick %dx%dx%d" % grid, "ensemble": "NVE dt=1fs",
                    "skin": w["skin"], "l2": "working set (neighbor rows %.2f GB) >> 126 MB L2; no flush needed"
                    % (ctx.counter("lj_entries") * 4 / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
         "gpu_launches": launches,
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
-        "neighbor": {"rebuilds_in_timed_region": builds, "setup_s": t_setup},
+        "neighbor": {"rebuilds_in_timed_region": builds, "setup_s": t_setup, "atoms_migrated_total": migrated},
         "thermo_last": {k: (float(v) if not isinstance(v, np.ndarray) else None) for k, v in thermo[-1].items() if k != "virial"},
     }
     print(json.dumps(line))
+    grp.close()
 
 
 def run_e2e(ctx_sys, kind, w, args):

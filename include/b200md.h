@@ -28,6 +28,8 @@
  *   b200md_system_*            the LAMMPS run loop around compute(): Verlet::run,
  *                              fix nve, Neighbor::decide, CommBrick forward/reverse/
  *                              borders/exchange, thermo (GPU-resident driver)
+ *   b200md_local_group_create  the MPI communicator LAMMPS runs in ("2 by 2 by 1 MPI processor
+ *   b200md_system_comm_init*   grid", log.rebomos-bulk.4:22): NCCL ranks or in-process ranks
  *
  * Conventions: positions/forces are AoS double[n][3] exactly like atom->x /
  * atom->f; `type` is the 1-based LAMMPS atom type; `tag` the int32 atom ID;
@@ -218,6 +220,11 @@ int b200md_system_create(b200md_ctx *ctx, const b200md_system_desc *d, int nloca
 /* multi-GPU: 128-byte NCCL unique id from rank 0, then every rank joins */
 int b200md_nccl_unique_id(void *id128);
 int b200md_system_comm_init(b200md_ctx *ctx, const void *id128, int nranks, int rank);
+/* single-process variant (tests on a one-GPU box, or several GPUs driven by host threads of one process):
+ * ranks are contexts of THIS process, one host thread each; messages are device-to-device copies.
+ * b200md_local_group_create returns a group id > 0 (negative B200MD_ERR_* on failure).             */
+int b200md_local_group_create(int nranks);
+int b200md_system_comm_init_local(b200md_ctx *ctx, int group, int nranks, int rank);
 /* advance n NVE steps entirely on the device; thermo quantities are evaluated on the last step
  * (and every thermo_every steps, retrievable with b200md_system_thermo) */
 int b200md_system_run(b200md_ctx *ctx, int nsteps, int thermo_every);
@@ -226,7 +233,8 @@ int b200md_system_run(b200md_ctx *ctx, int nsteps, int thermo_every);
 int b200md_system_thermo(b200md_ctx *ctx, double *out);
 int b200md_system_thermo_count(b200md_ctx *ctx);
 int b200md_system_thermo_row(b200md_ctx *ctx, int i, double *out);
-/* sizes: out[0]=nlocal, out[1]=nghost, out[2]=neighbor builds, out[3]=dangerous builds */
+/* sizes: out[0]=nlocal, out[1]=nghost, out[2]=neighbor builds, out[3]=dangerous builds,
+ * out[4]=atoms this rank sent away in CommBrick::exchange so far, out[5]=global atom count; out[6] */
 int b200md_system_sizes(b200md_ctx *ctx, long long *out);
 /* download owned+ghost state (any pointer may be NULL) */
 int b200md_system_download(b200md_ctx *ctx, double *x, double *v, double *f, int *type, int *tag);

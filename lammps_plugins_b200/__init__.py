@@ -120,6 +120,8 @@ SYMBOLS = [
     ("b200md_system_create", c_int, [c_void_p, POINTER(SystemDesc), c_int, _PD, _PD, _PI, _PI]),
     ("b200md_nccl_unique_id", c_int, [c_void_p]),
     ("b200md_system_comm_init", c_int, [c_void_p, c_void_p, c_int, c_int]),
+    ("b200md_local_group_create", c_int, [c_int]),
+    ("b200md_system_comm_init_local", c_int, [c_void_p, c_int, c_int, c_int]),
     ("b200md_system_run", c_int, [c_void_p, c_int, c_int]),
     ("b200md_system_thermo", c_int, [c_void_p, _PD]),
     ("b200md_system_thermo_count", c_int, [c_void_p]),
@@ -387,9 +389,15 @@ class Context:
         return rows
 
     def system_sizes(self):
-        out = (c_longlong * 4)()
+        out = (c_longlong * 6)()
         self._check(self.L.b200md_system_sizes(self.h, out))
-        return dict(nlocal=out[0], nghost=out[1], nbuild=out[2], ndanger=out[3])
+        return dict(nlocal=out[0], nghost=out[1], nbuild=out[2], ndanger=out[3], nmigrated=out[4], natoms=out[5])
+
+    def comm_init_nccl(self, id128: bytes, nranks, rank):
+        self._check(self.L.b200md_system_comm_init(self.h, id128, nranks, rank))
+
+    def comm_init_local(self, group, nranks, rank):
+        self._check(self.L.b200md_system_comm_init_local(self.h, group, nranks, rank))
 
     def system_download(self):
         sz = self.system_sizes()

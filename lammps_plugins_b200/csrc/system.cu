@@ -19,10 +19,16 @@
 
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <unordered_set>
 
 #define BLOCK 256
 #define BIGSLAB 1.0e20
+#define LOCAL_TIMEOUT_S 120
 
 int b200md_rebomos_build_inner(b200md_ctx *c);
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag);
@@ -34,6 +40,30 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
                               int ghost_rows, double skin);
 void b200md_neigh_forget(b200md_ctx *c);
 void b200md_aeam_forget(b200md_ctx *c);
+
+// In-process rank group ("loopback" transport): every rank is a b200md_ctx driven by its own host thread
+// in ONE process, on the same or on different GPUs; a message is a device-to-device copy from the sender's
+// buffer.  It exists so that the multi-rank code (exchange/borders/forward/reverse with real partners) can
+// be checked on a box with a single GPU, where NCCL refuses two ranks on one device.
+struct LocalSlot {
+  const double *ptr = nullptr;
+  size_t n = 0;
+  long long posted = 0, consumed = 0;
+};
+struct LocalGroup {
+  int nranks = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<LocalSlot> slot;    // [src * nranks + dst]
+  // host-side reductions
+  std::vector<double> red;
+  int red_arrived = 0;
+  long long red_gen = 0;
+  std::vector<double> red_out;
+};
+static std::mutex g_groups_mu;
+static std::map<int, std::shared_ptr<LocalGroup>> g_groups;
+static int g_next_group = 1;
 
 struct Swap {
   int dim = 0, sendproc = 0, recvproc = 0;
@@ -75,8 +105,11 @@ struct SystemState {
   long long step = 0, nbuild = 0, ndanger = 0, nextsort = 0;
   int ago = 0;
   std::vector<std::vector<double>> rows;    // thermo rows
-  // nccl
+  long long nmigrated = 0;
+  // transport between ranks: NCCL (one process per GPU) or the in-process loopback group
   ncclComm_t nccl = nullptr;
+  std::shared_ptr<LocalGroup> local;
+  DevBuf<double> xbuf;    // exchange() staging
 };
 
 // ================================================================== kernels
@@ -194,6 +227,83 @@ __global__ void __launch_bounds__(BLOCK) k_border_unpack(double4 *__restrict__ x
   x[first + k] = make_double4(buf[6 * (size_t) k], buf[6 * (size_t) k + 1], buf[6 * (size_t) k + 2], buf[6 * (size_t) k + 3]);
   type[first + k] = (int) buf[6 * (size_t) k + 4];
   tag[first + k] = (int) buf[6 * (size_t) k + 5];
+}
+
+// CommBrick::exchange ------------------------------------------------------------------------------
+// leavers of one dimension: flag owned atoms with x[dim] < lo || x[dim] >= hi
+__global__ void __launch_bounds__(BLOCK) k_leave_flags(const double4 *__restrict__ x, int n, int dim, double lo,
+                                                       double hi, int *__restrict__ flag)
+{
+  int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const double v = comp(x[i], dim);
+  flag[i] = (v < lo || v >= hi) ? 1 : 0;
+}
+// AtomVecAtomic::pack_exchange in the emission order computed on the host: 8 doubles per atom
+// (x, y, z, vx, vy, vz, tag, type)
+__global__ void __launch_bounds__(BLOCK) k_exchange_pack(const double4 *__restrict__ x, const double *__restrict__ v,
+                                                         const int *__restrict__ type, const int *__restrict__ tag,
+                                                         const int *__restrict__ order, int n, double *__restrict__ buf)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int i = order[k];
+  const double4 p = x[i];
+  double *b = buf + 8 * (size_t) k;
+  b[0] = p.x;
+  b[1] = p.y;
+  b[2] = p.z;
+  b[3] = v[3 * (size_t) i];
+  b[4] = v[3 * (size_t) i + 1];
+  b[5] = v[3 * (size_t) i + 2];
+  b[6] = (double) tag[i];
+  b[7] = (double) type[i];
+}
+// AtomVec::copy(src -> dst) for the (hole, tail stayer) pairs; sources and destinations are disjoint
+__global__ void __launch_bounds__(BLOCK) k_exchange_fill(double4 *__restrict__ x, double *__restrict__ v,
+                                                         int *__restrict__ type, int *__restrict__ tag,
+                                                         const int *__restrict__ moves, int n)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int dst = moves[2 * k], src = moves[2 * k + 1];
+  x[dst] = x[src];
+  v[3 * (size_t) dst] = v[3 * (size_t) src];
+  v[3 * (size_t) dst + 1] = v[3 * (size_t) src + 1];
+  v[3 * (size_t) dst + 2] = v[3 * (size_t) src + 2];
+  type[dst] = type[src];
+  tag[dst] = tag[src];
+}
+// incoming atoms: keep those with lo <= x[dim] < hi, appended in buffer order (one warp, ballot compaction)
+__global__ void __launch_bounds__(32) k_exchange_unpack(const double *__restrict__ buf, int nrecv, int dim, double lo,
+                                                        double hi, double4 *__restrict__ x, double *__restrict__ v,
+                                                        int *__restrict__ type, int *__restrict__ tag, int nlocal,
+                                                        int *__restrict__ nlocal_out)
+{
+  const int lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1u;
+  int n = nlocal;
+  for (int k0 = 0; k0 < nrecv; k0 += 32) {
+    const int k = k0 + lane;
+    bool keep = false;
+    const double *b = buf + 8 * (size_t) k;
+    if (k < nrecv) {
+      const double val = b[dim];
+      keep = val >= lo && val < hi;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int j = n + __popc(mk & lt);
+      x[j] = make_double4(b[0], b[1], b[2], 0.0);
+      v[3 * (size_t) j] = b[3];
+      v[3 * (size_t) j + 1] = b[4];
+      v[3 * (size_t) j + 2] = b[5];
+      tag[j] = (int) b[6];
+      type[j] = (int) b[7];
+    }
+    n += __popc(mk);
+  }
+  if (lane == 0) *nlocal_out = n;
 }
 
 // forward_comm: positions of ghosts from their source atoms (self swap)
@@ -463,14 +573,131 @@ static int ensure_atoms(b200md_ctx *c, SystemState *s, size_t n)
   return B200MD_OK;
 }
 
-// exchange `nsend` doubles*width with the swap partners: send to `sendto`, receive from `recvfrom`
-static int nccl_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, size_t nsend, int sendto, double *rbuf,
+// ------------------------------------------------------------------ transport
+// loopback: sender publishes its device buffer, receiver copies device-to-device, sender waits for the copy
+static int local_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, size_t nsend, int sendto, double *rbuf,
+                          size_t nrecv, int recvfrom)
+{
+  LocalGroup &G = *s->local;
+  const int me = s->me, R = G.nranks;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // my send buffer is complete
+  if (nsend) {
+    std::unique_lock<std::mutex> lk(G.mu);
+    LocalSlot &sl = G.slot[(size_t) me * R + sendto];
+    sl.ptr = sbuf;
+    sl.n = nsend;
+    sl.posted++;
+    G.cv.notify_all();
+  }
+  if (nrecv) {
+    const double *src = nullptr;
+    size_t n = 0;
+    {
+      std::unique_lock<std::mutex> lk(G.mu);
+      LocalSlot &sl = G.slot[(size_t) recvfrom * R + me];
+      if (!G.cv.wait_for(lk, std::chrono::seconds(LOCAL_TIMEOUT_S), [&] { return sl.posted > sl.consumed; })) {
+        c->fail("loopback transport: timed out waiting for a message from rank " + std::to_string(recvfrom));
+        return B200MD_ERR_NCCL;
+      }
+      src = sl.ptr;
+      n = sl.n;
+    }
+    ARG_CHECK(c, n == nrecv, "loopback transport: message size mismatch between ranks");
+    CUDA_TRY(c, cudaMemcpy(rbuf, src, n * sizeof(double), cudaMemcpyDefault));
+    {
+      std::unique_lock<std::mutex> lk(G.mu);
+      G.slot[(size_t) recvfrom * R + me].consumed++;
+      G.cv.notify_all();
+    }
+  }
+  if (nsend) {
+    std::unique_lock<std::mutex> lk(G.mu);
+    LocalSlot &sl = G.slot[(size_t) me * R + sendto];
+    if (!G.cv.wait_for(lk, std::chrono::seconds(LOCAL_TIMEOUT_S), [&] { return sl.consumed == sl.posted; })) {
+      c->fail("loopback transport: rank " + std::to_string(sendto) + " never took my message");
+      return B200MD_ERR_NCCL;
+    }
+  }
+  return B200MD_OK;
+}
+
+// op: 0 = sum, 1 = max; values are doubles on the host.  Returns false on timeout (a peer died).
+static bool local_allreduce_host(SystemState *s, double *v, int n, int op)
+{
+  LocalGroup &G = *s->local;
+  std::unique_lock<std::mutex> lk(G.mu);
+  const long long gen = G.red_gen;
+  if (G.red_arrived == 0) G.red.assign(v, v + n);
+  else
+    for (int k = 0; k < n; k++) G.red[k] = op ? fmax(G.red[k], v[k]) : G.red[k] + v[k];
+  if (++G.red_arrived == G.nranks) {
+    G.red_out = G.red;
+    G.red_arrived = 0;
+    G.red_gen++;
+    G.cv.notify_all();
+  } else if (!G.cv.wait_for(lk, std::chrono::seconds(LOCAL_TIMEOUT_S), [&] { return G.red_gen != gen; }))
+    return false;
+  for (int k = 0; k < n; k++) v[k] = G.red_out[k];
+  // nobody may start the next reduction before everyone has read this one: second phase
+  const long long gen2 = G.red_gen;
+  if (++G.red_arrived == G.nranks) {
+    G.red_arrived = 0;
+    G.red_gen++;
+    G.cv.notify_all();
+  } else if (!G.cv.wait_for(lk, std::chrono::seconds(LOCAL_TIMEOUT_S), [&] { return G.red_gen != gen2; }))
+    return false;
+  return true;
+}
+
+// exchange doubles with the swap partners: send to `sendto`, receive from `recvfrom` (stream-ordered with NCCL)
+static int xfer_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, size_t nsend, int sendto, double *rbuf,
                          size_t nrecv, int recvfrom)
 {
+  if (s->local) return local_sendrecv(c, s, sbuf, nsend, sendto, rbuf, nrecv, recvfrom);
   NCCL_TRY(c, ncclGroupStart());
   if (nsend) NCCL_TRY(c, ncclSend(sbuf, nsend, ncclDouble, sendto, s->nccl, c->stream));
   if (nrecv) NCCL_TRY(c, ncclRecv(rbuf, nrecv, ncclDouble, recvfrom, s->nccl, c->stream));
   NCCL_TRY(c, ncclGroupEnd());
+  return B200MD_OK;
+}
+
+// in-place reductions over ranks of small device arrays
+static int xfer_allreduce_sum(b200md_ctx *c, SystemState *s, double *dbuf, int n)
+{
+  if (s->nranks == 1) return B200MD_OK;
+  if (s->local) {
+    std::vector<double> h(n);
+    CUDA_TRY(c, cudaMemcpyAsync(h.data(), dbuf, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!local_allreduce_host(s, h.data(), n, 0)) {
+      c->fail("loopback transport: allreduce timed out (a peer rank stopped)");
+      return B200MD_ERR_NCCL;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(dbuf, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200MD_OK;
+  }
+  NCCL_TRY(c, ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, s->nccl, c->stream));
+  return B200MD_OK;
+}
+static int xfer_allreduce_max_int(b200md_ctx *c, SystemState *s, int *dbuf)
+{
+  if (s->nranks == 1) return B200MD_OK;
+  if (s->local) {
+    int h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, dbuf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    double v = h;
+    if (!local_allreduce_host(s, &v, 1, 1)) {
+      c->fail("loopback transport: allreduce timed out (a peer rank stopped)");
+      return B200MD_ERR_NCCL;
+    }
+    h = (int) v;
+    CUDA_TRY(c, cudaMemcpyAsync(dbuf, &h, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200MD_OK;
+  }
+  NCCL_TRY(c, ncclAllReduce(dbuf, dbuf, 1, ncclInt, ncclMax, s->nccl, c->stream));
   return B200MD_OK;
 }
 
@@ -785,7 +1012,7 @@ static int halo_borders(b200md_ctx *c, SystemState *s)
         double cnt_h = (double) nsend, cnt_r = 0.0;
         double *dcnt = c->scal.p + 32;
         CUDA_TRY(c, cudaMemcpyAsync(dcnt, &cnt_h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        int rc = nccl_sendrecv(c, s, dcnt, 1, sw.sendproc, dcnt + 1, 1, sw.recvproc);
+        int rc = xfer_sendrecv(c, s, dcnt, 1, sw.sendproc, dcnt + 1, 1, sw.recvproc);
         if (rc) return rc;
         CUDA_TRY(c, cudaMemcpyAsync(&cnt_r, dcnt + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -798,7 +1025,7 @@ static int halo_borders(b200md_ctx *c, SystemState *s)
                                                             sw.bshift[0], sw.bshift[1], sw.bshift[2], sw.pbc_flag,
                                                             s->sendbuf.p);
         }
-        if ((rc = nccl_sendrecv(c, s, s->sendbuf.p, 6 * (size_t) nsend, sw.sendproc, s->recvbuf.p, 6 * (size_t) nrecv,
+        if ((rc = xfer_sendrecv(c, s, s->sendbuf.p, 6 * (size_t) nsend, sw.sendproc, s->recvbuf.p, 6 * (size_t) nrecv,
                                 sw.recvproc)))
           return rc;
         if (nrecv) {
@@ -832,7 +1059,7 @@ static int halo_forward_x(b200md_ctx *c, SystemState *s)
         k_forward_x_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.fshift[0],
                                                                 sw.fshift[1], sw.fshift[2], sw.pbc_flag, s->sendbuf.p);
       }
-      int rc = nccl_sendrecv(c, s, s->sendbuf.p, 3 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 3 * (size_t) sw.nrecv,
+      int rc = xfer_sendrecv(c, s, s->sendbuf.p, 3 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 3 * (size_t) sw.nrecv,
                              sw.recvproc);
       if (rc) return rc;
       if (sw.nrecv) {
@@ -860,7 +1087,7 @@ static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
         LaunchScope ls(c, "forward_fp_pack");
         k_forward_s2_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, s->sendbuf.p);
       }
-      int rc = nccl_sendrecv(c, s, s->sendbuf.p, 2 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 2 * (size_t) sw.nrecv,
+      int rc = xfer_sendrecv(c, s, s->sendbuf.p, 2 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 2 * (size_t) sw.nrecv,
                              sw.recvproc);
       if (rc) return rc;
       if (sw.nrecv) {
@@ -885,13 +1112,128 @@ static int halo_reverse_f(b200md_ctx *c, SystemState *s)
     } else {
       // ghost forces are contiguous at f[3*firstrecv ...]: send them back, add what my send-list atoms receive
       CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nsend + 8));
-      int rc = nccl_sendrecv(c, s, c->f.p + 3 * (size_t) sw.firstrecv, 3 * (size_t) sw.nrecv, sw.recvproc, s->recvbuf.p,
+      int rc = xfer_sendrecv(c, s, c->f.p + 3 * (size_t) sw.firstrecv, 3 * (size_t) sw.nrecv, sw.recvproc, s->recvbuf.p,
                              3 * (size_t) sw.nsend, sw.sendproc);
       if (rc) return rc;
       if (sw.nsend) {
         LaunchScope ls(c, "reverse_f_unpack");
         k_reverse_f_unpack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, s->recvbuf.p);
       }
+    }
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// ------------------------------------------------------------------ CommBrick::exchange
+// Owned atoms that left the sub-box move to the neighbor rank, dimension by dimension.  The reference loop
+// (comm_brick.cpp exchange(): "when atom is deleted, fill it in with last atom") fixes BOTH the order of the
+// atoms that stay and the order in which leavers are packed; the order decides where migrated atoms land in
+// the receiver's arrays and therefore neighbor-row order.  Only the (few) leaver indices go to the host,
+// where that loop is replayed on indices alone; packing, hole filling and unpacking run on the device.
+static int migrate(b200md_ctx *c, SystemState *s)
+{
+  const int *pg = s->d.procgrid;
+  for (int dim = 0; dim < 3; dim++) {
+    if (pg[dim] == 1) continue;    // Domain::pbc already wrapped this dimension: nobody leaves
+    const int n = s->nlocal;
+    const double lo = s->sublo[dim], hi = s->subhi[dim];
+    std::vector<int> leavers;
+    if (n) {
+      CUDA_TRY(c, s->itmp.reserve((size_t) n + 64));
+      CUDA_TRY(c, s->itmp2.reserve((size_t) n + 64));
+      CUDA_TRY(c, s->scan64.reserve((size_t) n + 8));
+      {
+        LaunchScope ls(c, "leave_flags");
+        k_leave_flags<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, n, dim, lo, hi, s->itmp.p);
+      }
+      int rc = b200md_exclusive_scan_i64(c, s->itmp.p, s->scan64.p, n, 1);
+      if (rc) return rc;
+      int64_t tot = 0;
+      CUDA_TRY(c, cudaMemcpyAsync(&tot, s->scan64.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if (tot) {
+        LaunchScope ls(c, "scatter_list");
+        k_scatter_list<<<nblk(n), BLOCK, 0, c->stream>>>(s->itmp.p, s->scan64.p, 0, n, s->itmp2.p);
+        leavers.resize((size_t) tot);
+        CUDA_TRY(c, cudaMemcpyAsync(leavers.data(), s->itmp2.p, tot * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      }
+    }
+    // replay of the reference loop on indices: emission order + (hole <- tail stayer) moves
+    std::vector<int> order, moves;
+    int nl = n;
+    {
+      std::unordered_set<int> L(leavers.begin(), leavers.end());
+      size_t li = 0;
+      while (li < leavers.size() && leavers[li] < nl) {
+        const int i = leavers[li++];
+        order.push_back(i);
+        for (;;) {
+          nl--;
+          if (nl == i) break;
+          if (L.count(nl)) order.push_back(nl);
+          else {
+            moves.push_back(i);
+            moves.push_back(nl);
+            break;
+          }
+        }
+      }
+    }
+    const int nsend = (int) order.size();
+    CUDA_TRY(c, s->xbuf.reserve(8 * (size_t) nsend + 8));
+    if (nsend) {
+      CUDA_TRY(c, s->itmp.reserve((size_t) nsend + 2 * moves.size() + 64));
+      CUDA_TRY(c, cudaMemcpyAsync(s->itmp.p, order.data(), nsend * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      {
+        LaunchScope ls(c, "exchange_pack");
+        k_exchange_pack<<<nblk(nsend), BLOCK, 0, c->stream>>>(c->xq.p, s->v.p, c->type.p, c->tag.p, s->itmp.p, nsend, s->xbuf.p);
+      }
+      if (!moves.empty()) {
+        const int nm = (int) moves.size() / 2;
+        CUDA_TRY(c, cudaMemcpyAsync(s->itmp.p + nsend, moves.data(), moves.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        LaunchScope ls(c, "exchange_fill");
+        k_exchange_fill<<<nblk(nm), BLOCK, 0, c->stream>>>(c->xq.p, s->v.p, c->type.p, c->tag.p, s->itmp.p + nsend, nm);
+      }
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // order/moves are host vectors
+    }
+    s->nlocal = nl;
+    s->nmigrated += nsend;
+    // counts, then atoms: first what the +dim neighbor sent, then (if more than 2 ranks) the -dim neighbor
+    const int npass = pg[dim] > 2 ? 2 : 1;
+    int nrecv[2] = {0, 0};
+    double *dcnt = c->scal.p + 32;
+    for (int pass = 0; pass < npass; pass++) {
+      const int to = s->procneigh[dim][pass == 0 ? 0 : 1], from = s->procneigh[dim][pass == 0 ? 1 : 0];
+      double cnt_h = (double) nsend, cnt_r = 0.0;
+      CUDA_TRY(c, cudaMemcpyAsync(dcnt, &cnt_h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      int rc = xfer_sendrecv(c, s, dcnt, 1, to, dcnt + 1, 1, from);
+      if (rc) return rc;
+      CUDA_TRY(c, cudaMemcpyAsync(&cnt_r, dcnt + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      nrecv[pass] = (int) cnt_r;
+    }
+    const int nrtot = nrecv[0] + nrecv[1];
+    CUDA_TRY(c, s->recvbuf.reserve(8 * (size_t) nrtot + 8));
+    for (int pass = 0; pass < npass; pass++) {
+      const int to = s->procneigh[dim][pass == 0 ? 0 : 1], from = s->procneigh[dim][pass == 0 ? 1 : 0];
+      int rc = xfer_sendrecv(c, s, s->xbuf.p, 8 * (size_t) nsend, to, s->recvbuf.p + 8 * (size_t) (pass ? nrecv[0] : 0),
+                             8 * (size_t) nrecv[pass], from);
+      if (rc) return rc;
+    }
+    if (nrtot) {
+      int rc = ensure_atoms(c, s, (size_t) s->nlocal + nrtot + 64);
+      if (rc) return rc;
+      {
+        LaunchScope ls(c, "exchange_unpack");
+        k_exchange_unpack<<<1, 32, 0, c->stream>>>(s->recvbuf.p, nrtot, dim, lo, hi, c->xq.p, s->v.p, c->type.p, c->tag.p,
+                                                   s->nlocal, c->flags.p + 11);
+      }
+      int nnew = 0;
+      CUDA_TRY(c, cudaMemcpyAsync(&nnew, c->flags.p + 11, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      s->nlocal = nnew;
     }
   }
   CUDA_TRY(c, cudaGetLastError());
@@ -914,11 +1256,11 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
       k_pbc<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, n, s->boxlo[0], s->boxlo[1], s->boxlo[2], s->boxhi[0], s->boxhi[1],
                                              s->boxhi[2], s->prd[0], s->prd[1], s->prd[2]);
   }
-  if (s->nranks > 1) {
-    c->fail("multi-GPU atom migration is not implemented yet");
-    return B200MD_ERR_ARG;
-  }
   int rc;
+  if (s->nranks > 1) {
+    if ((rc = migrate(c, s))) return rc;
+    n = s->nlocal;
+  }
   if (s->d.sort_every > 0 && (first || s->step >= s->nextsort))
     if ((rc = sort_atoms(c, s))) return rc;
   if ((rc = halo_borders(c, s))) return rc;
@@ -983,7 +1325,10 @@ static int thermo(b200md_ctx *c, SystemState *s)
     LaunchScope ls(c, "ke");
     k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, c->scal.p);
   }
-  if (s->nranks > 1) NCCL_TRY(c, ncclAllReduce(c->scal.p, c->scal.p, 9, ncclDouble, ncclSum, s->nccl, c->stream));
+  {
+    int rc = xfer_allreduce_sum(c, s, c->scal.p, 9);
+    if (rc) return rc;
+  }
   double h[16];
   int fl[16];
   CUDA_TRY(c, cudaMemcpyAsync(h, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1020,6 +1365,7 @@ void b200md_system_free(b200md_ctx *c)
   for (auto &sw : s->swaps) sw.sendlist.release();
   s->v.release(); s->xhold.release(); s->xt.release(); s->dmass.release(); s->itmp.release(); s->itmp2.release();
   s->x4tmp.release(); s->dtmp.release(); s->scan64.release(); s->sendbuf.release(); s->recvbuf.release();
+  s->xbuf.release();
   if (s->nccl) ncclCommDestroy(s->nccl);
   delete s;
   c->sys = nullptr;
@@ -1046,20 +1392,24 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
   ARG_CHECK(c, d->style == 0 || d->style == 1, "system_create: style must be 0 (rebomos) or 1 (aeam)");
   CUDA_TRY(c, cudaSetDevice(c->device));
   ncclComm_t keep = nullptr;
+  std::shared_ptr<LocalGroup> keep_local;
   if (c->sys) {
     keep = c->sys->nccl;
+    keep_local = c->sys->local;
     c->sys->nccl = nullptr;
     SystemState *old = c->sys;
     for (auto &sw : old->swaps) sw.sendlist.release();
     old->v.release(); old->xhold.release(); old->xt.release(); old->dmass.release(); old->itmp.release();
     old->itmp2.release(); old->x4tmp.release(); old->dtmp.release(); old->scan64.release(); old->sendbuf.release();
     old->recvbuf.release();
+    old->xbuf.release();
     delete old;
     c->sys = nullptr;
   }
   SystemState *s = new SystemState();
   c->sys = s;
   s->nccl = keep;
+  s->local = keep_local;
   s->d = *d;
   s->mass.assign(d->mass, d->mass + d->ntypes + 1);
   s->d.mass = s->mass.data();
@@ -1067,7 +1417,9 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
   if (rc) return rc;
   setup_geometry(s);
   setup_swaps(s);
-  ARG_CHECK(c, s->nranks == 1 || s->nccl, "system_create: call b200md_system_comm_init before creating a multi-rank system");
+  ARG_CHECK(c, s->nranks == 1 || s->nccl || s->local,
+            "system_create: call b200md_system_comm_init (or _comm_init_local) before creating a multi-rank system");
+  ARG_CHECK(c, !s->local || s->local->nranks == s->nranks, "system_create: procgrid does not match the loopback group size");
   s->nlocal = nlocal;
   if ((rc = ensure_atoms(c, s, (size_t) nlocal + nlocal / 2 + 1024))) return rc;
   CUDA_TRY(c, s->dmass.reserve(B200MD_MAX_TYPES + 2));
@@ -1090,7 +1442,7 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
   if (s->nranks > 1) {
     double cnt = (double) nlocal;
     CUDA_TRY(c, cudaMemcpyAsync(c->scal.p + 40, &cnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NCCL_TRY(c, ncclAllReduce(c->scal.p + 40, c->scal.p + 40, 1, ncclDouble, ncclSum, s->nccl, c->stream));
+    if ((rc = xfer_allreduce_sum(c, s, c->scal.p + 40, 1))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(&cnt, c->scal.p + 40, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     s->natoms = (long long) cnt;
@@ -1113,6 +1465,33 @@ extern "C" int b200md_system_comm_init(b200md_ctx *c, const void *id128, int nra
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NCCL_TRY(c, ncclCommInitRank(&c->sys->nccl, nranks, id, rank));
+  return B200MD_OK;
+}
+
+extern "C" int b200md_local_group_create(int nranks)
+{
+  if (nranks < 1) return B200MD_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto g = std::make_shared<LocalGroup>();
+  g->nranks = nranks;
+  g->slot.resize((size_t) nranks * nranks);
+  const int id = g_next_group++;
+  g_groups[id] = g;
+  return id;
+}
+
+extern "C" int b200md_system_comm_init_local(b200md_ctx *c, int group, int nranks, int rank)
+{
+  if (!c) return B200MD_ERR_ARG;
+  std::shared_ptr<LocalGroup> g;
+  {
+    std::lock_guard<std::mutex> lk(g_groups_mu);
+    auto it = g_groups.find(group);
+    if (it != g_groups.end()) g = it->second;
+  }
+  ARG_CHECK(c, g && g->nranks == nranks && rank >= 0 && rank < nranks, "system_comm_init_local: unknown group or bad rank");
+  if (!c->sys) c->sys = new SystemState();
+  c->sys->local = g;
   return B200MD_OK;
 }
 
@@ -1139,9 +1518,7 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
     s->ago++;
     int flag = 0;
-    if (s->nranks > 1) {
-      NCCL_TRY(c, ncclAllReduce(c->flags.p + 9, c->flags.p + 9, 1, ncclInt, ncclMax, s->nccl, c->stream));
-    }
+    if ((rc = xfer_allreduce_max_int(c, s, c->flags.p + 9))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (flag) {
@@ -1191,6 +1568,8 @@ extern "C" int b200md_system_sizes(b200md_ctx *c, long long *out)
   out[1] = c->sys->nghost;
   out[2] = c->sys->nbuild;
   out[3] = c->sys->ndanger;
+  out[4] = c->sys->nmigrated;
+  out[5] = c->sys->natoms;
   return B200MD_OK;
 }
 extern "C" int b200md_system_download(b200md_ctx *c, double *x, double *v, double *f, int *type, int *tag)

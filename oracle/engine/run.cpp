@@ -720,22 +720,24 @@ void Input::create_atoms(std::vector<std::string> &a)
 void Input::replicate(std::vector<std::string> &a)
 {
   if (a.size() != 3) error->all(FLERR, "Illegal replicate command");
-  if (comm->nprocs != 1) error->all(FLERR, "minilmp replicate runs on 1 rank (use it before decomposing)");
   int nx = utils::inumeric(FLERR, a[0], false, lmp);
   int ny = utils::inumeric(FLERR, a[1], false, lmp);
   int nz = utils::inumeric(FLERR, a[2], false, lmp);
   if (nx <= 0 || ny <= 0 || nz <= 0) error->all(FLERR, "Illegal replicate command");
 
+  // old system: my atoms as 8 doubles each (x, v, type, tag); every rank sees every rank's buffer in turn
   int nold = atom->nlocal;
-  std::vector<double> xo(3 * (size_t) nold), vo(3 * (size_t) nold);
-  std::vector<int> to(nold), go(nold);
-  tagint maxtag = 0;
+  std::vector<double> mine(8 * (size_t) nold + 1);
+  double maxtag_d = 0.0;
   for (int i = 0; i < nold; i++) {
-    for (int d = 0; d < 3; d++) { xo[3 * i + d] = atom->x[i][d]; vo[3 * i + d] = atom->v[i][d]; }
-    to[i] = atom->type[i];
-    go[i] = atom->tag[i];
-    maxtag = MAX(maxtag, atom->tag[i]);
+    double *b = &mine[8 * (size_t) i];
+    for (int d = 0; d < 3; d++) { b[d] = atom->x[i][d]; b[3 + d] = atom->v[i][d]; }
+    b[6] = atom->type[i];
+    b[7] = atom->tag[i];
+    maxtag_d = MAX(maxtag_d, (double) atom->tag[i]);
   }
+  universe->allreduce_max(comm->me, &maxtag_d, 1);
+  const tagint maxtag = (tagint) maxtag_d;
   double old_xprd = domain->xprd, old_yprd = domain->yprd, old_zprd = domain->zprd;
   double old_xy = domain->xy, old_xz = domain->xz, old_yz = domain->yz;
 
@@ -749,30 +751,48 @@ void Input::replicate(std::vector<std::string> &a)
   }
   domain->set_global_box();
   domain->set_local_box();
+  double sublo[3], subhi[3];
+  for (int d = 0; d < 3; d++) {
+    sublo[d] = domain->triclinic ? domain->sublo_lamda[d] : domain->sublo[d];
+    subhi[d] = domain->triclinic ? domain->subhi_lamda[d] : domain->subhi[d];
+  }
 
   atom->nlocal = 0;
   atom->natoms = 0;
-  for (int ix = 0; ix < nx; ix++)
-    for (int iy = 0; iy < ny; iy++)
-      for (int iz = 0; iz < nz; iz++)
-        for (int m = 0; m < nold; m++) {
-          double x[3];
-          if (domain->triclinic == 0) {
-            x[0] = xo[3 * m + 0] + ix * old_xprd;
-            x[1] = xo[3 * m + 1] + iy * old_yprd;
-            x[2] = xo[3 * m + 2] + iz * old_zprd;
-          } else {
-            x[0] = xo[3 * m + 0] + ix * old_xprd + iy * old_xy + iz * old_xz;
-            x[1] = xo[3 * m + 1] + iy * old_yprd + iz * old_yz;
-            x[2] = xo[3 * m + 2] + iz * old_zprd;
+  std::vector<double> buf;
+  for (int iproc = 0; iproc < comm->nprocs; iproc++) {
+    int n8 = universe->sendrecv(comm->me, iproc, mine.data(), 8 * nold, buf);
+    int nb = n8 / 8;
+    for (int ix = 0; ix < nx; ix++)
+      for (int iy = 0; iy < ny; iy++)
+        for (int iz = 0; iz < nz; iz++)
+          for (int m = 0; m < nb; m++) {
+            const double *b = &buf[8 * (size_t) m];
+            double x[3], lamda[3], *coord;
+            if (domain->triclinic == 0) {
+              x[0] = b[0] + ix * old_xprd;
+              x[1] = b[1] + iy * old_yprd;
+              x[2] = b[2] + iz * old_zprd;
+            } else {
+              x[0] = b[0] + ix * old_xprd + iy * old_xy + iz * old_xz;
+              x[1] = b[1] + iy * old_yprd + iz * old_yz;
+              x[2] = b[2] + iz * old_zprd;
+            }
+            domain->remap(x);
+            if (domain->triclinic) { domain->x2lamda(x, lamda); coord = lamda; }
+            else coord = x;
+            if (coord[0] < sublo[0] || coord[0] >= subhi[0] || coord[1] < sublo[1] || coord[1] >= subhi[1] ||
+                coord[2] < sublo[2] || coord[2] >= subhi[2])
+              continue;
+            tagint offset = iz * ny * nx * maxtag + iy * nx * maxtag + ix * maxtag;
+            atom->create_atom((int) b[6], x, (tagint) b[7] + offset);
+            int i = atom->nlocal - 1;
+            for (int d = 0; d < 3; d++) atom->v[i][d] = b[3 + d];
           }
-          domain->remap(x);
-          tagint offset = iz * ny * nx * maxtag + iy * nx * maxtag + ix * maxtag;
-          atom->create_atom(to[m], x, go[m] + offset);
-          int i = atom->nlocal - 1;
-          for (int d = 0; d < 3; d++) atom->v[i][d] = vo[3 * m + d];
-        }
-  atom->natoms = atom->nlocal;
+  }
+  double tot = atom->nlocal;
+  universe->allreduce_sum(comm->me, &tot, 1);
+  atom->natoms = (bigint) tot;
 }
 
 void Input::mass(std::vector<std::string> &a)

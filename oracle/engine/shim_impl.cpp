@@ -286,12 +286,12 @@ void Universe::abort_all()
 }
 int Universe::sendrecv(int me, int src, const double *sbuf, int nsend, std::vector<double> &rbuf)
 {
-  if (nprocs == 1 || src == me) {
+  if (nprocs == 1) {
     if ((int) rbuf.size() < nsend) rbuf.resize(nsend);
     if (nsend) memcpy(rbuf.data(), sbuf, sizeof(double) * nsend);
-    if (nprocs > 1) { barrier(); barrier(); }
     return nsend;
   }
+  // always publish: another rank may be reading from me even when I read my own buffer
   slot_ptr[me] = sbuf;
   slot_n[me] = nsend;
   barrier();

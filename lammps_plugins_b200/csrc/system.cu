@@ -603,7 +603,10 @@ static int local_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, siz
       n = sl.n;
     }
     ARG_CHECK(c, n == nrecv, "loopback transport: message size mismatch between ranks");
-    CUDA_TRY(c, cudaMemcpy(rbuf, src, n * sizeof(double), cudaMemcpyDefault));
+    // device-to-device cudaMemcpy does not block the host: copy on MY stream and wait, so that the copy is
+    // ordered before my next kernels and finished before the sender may reuse its buffer
+    CUDA_TRY(c, cudaMemcpyAsync(rbuf, src, n * sizeof(double), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     {
       std::unique_lock<std::mutex> lk(G.mu);
       G.slot[(size_t) recvfrom * R + me].consumed++;
@@ -1529,9 +1532,9 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
       if ((rc = halo_forward_x(c, s))) return rc;
     }
     if ((rc = compute_forces(c, s, thermo_step ? 1 : 0, thermo_step ? 2 : 0))) return rc;
-    if (n) {
+    if (s->nlocal) {    // not `n`: migration at a reneighboring step changes the owned count
       LaunchScope ls(c, "final_integrate");
-      k_final_integrate<<<nblk(n), BLOCK, 0, c->stream>>>(s->v.p, c->f.p, c->type.p, s->dmass.p, n, dtf);
+      k_final_integrate<<<nblk(s->nlocal), BLOCK, 0, c->stream>>>(s->v.p, c->f.p, c->type.p, s->dmass.p, s->nlocal, dtf);
     }
     if (thermo_step)
       if ((rc = thermo(c, s))) return rc;

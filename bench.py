@@ -167,6 +167,7 @@ def run_b200(args):
     barrier()
     l0 = ctx.counter("kernel_launches")
     b0 = ctx.system_sizes()["nbuild"]
+    i0 = ctx.system_sizes()["ninner"]
     sampler.window[0] = time.time()
     ctx.event_record(0)
     ctx.system_run(args.steps, 0)
@@ -178,6 +179,7 @@ def run_b200(args):
     kstats = ctx.kernel_stats()
     ctx.set_option("sync_timing", 0)
     builds = ctx.system_sizes()["nbuild"] - b0
+    inner = ctx.system_sizes()["ninner"] - i0
     thermo = ctx.system_thermo_rows()
     ms = grp.reduce_scalar(ms, "max")
     atoms_per_gpu_max = int(grp.reduce_scalar(sz0["nlocal"], "max"))
@@ -236,7 +238,7 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
         "gpu_launches": launches,
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
-        "neighbor": {"rebuilds_in_timed_region": builds, "setup_s": t_setup, "atoms_migrated_total": migrated},
+        "neighbor": {"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner, "setup_s": t_setup, "atoms_migrated_total": migrated},
         "thermo_last": {k: (float(v) if not isinstance(v, np.ndarray) else None) for k, v in thermo[-1].items() if k != "virial"},
     }
     print(json.dumps(line))

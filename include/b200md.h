@@ -173,7 +173,7 @@ int b200md_aeam_force_phase(b200md_ctx *ctx, const double *rho_all, const double
 int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
 
 /* ---- tuning / introspection ------------------------------------------------ */
-/* option names: "deterministic" (0/1), "margin" (inner-list skin in 1e-3 A, 0 = use skin),
+/* option names: "deterministic" (0/1), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
  * "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
  * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
@@ -234,7 +234,8 @@ int b200md_system_thermo(b200md_ctx *ctx, double *out);
 int b200md_system_thermo_count(b200md_ctx *ctx);
 int b200md_system_thermo_row(b200md_ctx *ctx, int i, double *out);
 /* sizes: out[0]=nlocal, out[1]=nghost, out[2]=neighbor builds, out[3]=dangerous builds,
- * out[4]=atoms this rank sent away in CommBrick::exchange so far, out[5]=global atom count; out[6] */
+ * out[4]=atoms this rank sent away in CommBrick::exchange so far, out[5]=global atom count,
+ * out[6]=inner-list refreshes between master rebuilds; out[7] */
 int b200md_system_sizes(b200md_ctx *ctx, long long *out);
 /* download owned+ghost state (any pointer may be NULL) */
 int b200md_system_download(b200md_ctx *ctx, double *x, double *v, double *f, int *type, int *tag);

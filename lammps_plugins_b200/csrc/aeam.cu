@@ -627,7 +627,7 @@ int b200md_aeam_pack(b200md_ctx *c)
 int b200md_aeam_build_inner(b200md_ctx *c)
 {
   const int inum = c->list_inum;
-  double m = (c->margin_opt > 0.0) ? c->margin_opt : c->skin;
+  double m = (c->margin_opt > 0.0) ? c->margin_opt : 0.5 * c->skin;    // default: two-level list, inner skin = skin/2
   if (m > c->skin) m = c->skin;
   c->margin = m;
   const int nel = c->ap.nel;

@@ -611,7 +611,7 @@ static void derive_params(b200md_ctx *c, const b200md_rebomos_params *p)
 
 static void set_margin(b200md_ctx *c)
 {
-  double m = (c->margin_opt > 0.0) ? c->margin_opt : c->skin;
+  double m = (c->margin_opt > 0.0) ? c->margin_opt : 0.5 * c->skin;    // default: two-level list, inner skin = skin/2
   if (m > c->skin) m = c->skin;    // the master rows only cover cut + skin
   c->margin = m;
   for (int k = 0; k < 4; k++) {

@@ -105,7 +105,7 @@ struct SystemState {
   long long step = 0, nbuild = 0, ndanger = 0, nextsort = 0;
   int ago = 0;
   std::vector<std::vector<double>> rows;    // thermo rows
-  long long nmigrated = 0;
+  long long nmigrated = 0, ninner = 0;
   // transport between ranks: NCCL (one process per GPU) or the in-process loopback group
   ncclComm_t nccl = nullptr;
   std::shared_ptr<LocalGroup> local;
@@ -396,12 +396,15 @@ __global__ void __launch_bounds__(BLOCK) k_reverse_f_unpack(double *__restrict__
   f[3 * j + 2] += buf[3 * (size_t) k + 2];
 }
 
-// FixNVE::initial_integrate fused with Neighbor::check_distance (flag[9] = some atom moved > skin/2)
+// FixNVE::initial_integrate fused with Neighbor::check_distance.  flags[9] = 2: some atom moved more than
+// skin/2 since the master list was built (LAMMPS' rebuild rule); 1: some atom moved more than margin/2 since
+// the inner lists were derived from it (two-level Verlet list: only the cheap inner filter is redone)
 __global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict__ x, double *__restrict__ v,
                                                              const double *__restrict__ f, const int *__restrict__ type,
                                                              const double *__restrict__ mass, int nlocal, double dtf,
                                                              double dtv, const double4 *__restrict__ xhold,
-                                                             double triggersq, int *__restrict__ flags)
+                                                             double triggersq, const double4 *__restrict__ xhold_inner,
+                                                             double innersq, int *__restrict__ flags)
 {
   int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= nlocal) return;
@@ -420,7 +423,12 @@ __global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict
   x[i] = p;
   const double4 h = xhold[i];
   const double dx = p.x - h.x, dy = p.y - h.y, dz = p.z - h.z;
-  if (dx * dx + dy * dy + dz * dz > triggersq) flags[9] = 1;
+  if (dx * dx + dy * dy + dz * dz > triggersq) atomicMax(&flags[9], 2);
+  else if (xhold_inner) {
+    const double4 g = xhold_inner[i];
+    const double ex = p.x - g.x, ey = p.y - g.y, ez = p.z - g.z;
+    if (ex * ex + ey * ey + ez * ez > innersq) atomicMax(&flags[9], 1);
+  }
 }
 __global__ void __launch_bounds__(BLOCK) k_final_integrate(double *__restrict__ v, const double *__restrict__ f,
                                                            const int *__restrict__ type, const double *__restrict__ mass,
@@ -1515,8 +1523,12 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     const int n = s->nlocal;
     if (n) {
       LaunchScope ls(c, "initial_integrate");
+      const bool two_level = c->inner_valid && c->margin < s->d.skin;
+      const double innersq = 0.25 * c->margin * c->margin;
       k_initial_integrate<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, s->v.p, c->f.p, c->type.p, s->dmass.p, n, dtf, dtv,
-                                                          s->xhold.p, triggersq, c->flags.p);
+                                                          s->xhold.p, triggersq,
+                                                          two_level ? (const double4 *) c->xhold.p : nullptr, innersq,
+                                                          c->flags.p);
     }
     // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
     s->ago++;
@@ -1524,12 +1536,17 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     if ((rc = xfer_allreduce_max_int(c, s, c->flags.p + 9))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (flag) {
-      CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+    if (flag) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+    if (flag >= 2) {
       if (s->ago == 1) s->ndanger++;
       if ((rc = reneighbor(c, s, false))) return rc;
     } else {
       if ((rc = halo_forward_x(c, s))) return rc;
+      if (flag == 1) {    // master list still valid: re-derive the inner lists from it at the current positions
+        rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
+        if (rc) return rc;
+        s->ninner++;
+      }
     }
     if ((rc = compute_forces(c, s, thermo_step ? 1 : 0, thermo_step ? 2 : 0))) return rc;
     if (s->nlocal) {    // not `n`: migration at a reneighboring step changes the owned count
@@ -1573,6 +1590,7 @@ extern "C" int b200md_system_sizes(b200md_ctx *c, long long *out)
   out[3] = c->sys->ndanger;
   out[4] = c->sys->nmigrated;
   out[5] = c->sys->natoms;
+  out[6] = c->sys->ninner;
   return B200MD_OK;
 }
 extern "C" int b200md_system_download(b200md_ctx *c, double *x, double *v, double *f, int *type, int *tag)

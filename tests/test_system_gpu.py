@@ -111,3 +111,32 @@ def test_nve_run_with_reneighboring_tracks_engine(ctx, oracle_built, style):
     eref = ref[-1]["pe"] + ref[-1]["ke"]
     assert abs((e1 - e0) - (eref - (ref[0]["pe"] + ref[0]["ke"]))) < 1e-6 * abs(e0)
     lmp.close()
+
+
+@pytest.mark.parametrize("style", ["rebomos", "aeam"])
+def test_two_level_list_refresh_matches_single_level(ctx, oracle_built, style):
+    """default inner margin = skin/2: inner lists are re-derived from the master list whenever an atom moved more
+    than margin/2, master rebuilds stay on LAMMPS' schedule; the trajectory equals the run whose inner lists
+    carry the full skin (no refresh) to rounding"""
+    if style == "rebomos":
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 1, 1), extra=["velocity all create 1500.0 4928459"])
+        ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    else:
+        lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.02,
+                                 extra=["velocity all create 1500.0 1082337"])
+        ctx.aeam_init(aeam_tables())
+    out = {}
+    for label, margin in (("full", int(1000 * lmp.get_double("skin"))), ("half", 0)):
+        ctx.set_option("margin", margin)
+        start_system(ctx, lmp, style)
+        ctx.system_run(80, 20)
+        out[label] = (ctx.system_thermo_rows(), ctx.system_sizes(), ctx.system_download())
+    ctx.set_option("margin", 0)
+    (ra, sa, da), (rb, sb, db) = out["full"], out["half"]
+    print(style, "builds", sa["nbuild"], sb["nbuild"], "inner refreshes", sa["ninner"], sb["ninner"])
+    assert sa["ninner"] == 0 and sb["ninner"] > 0 and sa["nbuild"] == sb["nbuild"]
+    for q, g in zip(rb, ra):
+        assert abs(q["pe"] - g["pe"]) < 1e-11 * abs(g["pe"]) and abs(q["ke"] - g["ke"]) < 1e-9 * max(g["ke"], 1.0)
+        assert abs(q["press"] - g["press"]) < 1e-8 * max(abs(g["press"]), 1.0)
+    assert S.rel_err(db["f"][:db["nlocal"]], da["f"][:da["nlocal"]]) < 1e-9
+    lmp.close()

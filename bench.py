@@ -147,6 +147,9 @@ def run_b200(args):
     ctx = b2.Context(local_rank)
     init_potential(ctx, kind)
     launch.join_system(ctx, grp)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     box = b2.make_box(w["boxlo"], w["boxhi"], w["xy"], w["xz"], w["yz"], triclinic=w["triclinic"])
     t_setup = time.time()
@@ -382,6 +385,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

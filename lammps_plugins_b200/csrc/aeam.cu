@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+#include <cmath>
+
 #define BLOCK 256
 #define ANG_CAP 96    // staged neighbors per angular center
 
@@ -129,6 +131,30 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
       d.z2r_off[i * nel + j] = tri_off[hi * nel + lo];
     }
 
+  // fused per-pair rows for the density and force kernels: {rhor(i,j) c3..c6 | z2r(i,j) c3..c6} = 64 bytes,
+  // one gather per neighbor.  Both halves are indexed with the SAME row m computed from nr/dr of (i,j), exactly
+  // as the reference does (pair_aeam.cpp:352-372).
+  std::vector<double> p_pair;
+  for (int i = 0; i < nel; i++)
+    for (int j = 0; j < nel; j++) {
+      const int ij = i * nel + j;
+      const int n = d.nr[ij];
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      const int ntri = t->nr[hi * nel + lo];
+      d.pair_off[ij] = (int) (p_pair.size() / 8);
+      for (int m = 0; m <= n; m++) {
+        for (int k = 0; k < 4; k++) p_pair.push_back(p_rhor[4 * ((size_t) d.rhor_off[ij] + m) + k]);
+        const int mz = m < ntri ? m : ntri;
+        for (int k = 0; k < 4; k++) p_pair.push_back(p_z2r[4 * ((size_t) d.z2r_off[ij] + mz) + k]);
+      }
+      // exact rsq form of the reference's `r > cut` (sqrt is monotone and correctly rounded)
+      double x = t->cut[ij] * t->cut[ij];
+      while (sqrt(x) > t->cut[ij]) x = nextafter(x, 0.0);
+      while (!(sqrt(x) > t->cut[ij])) x = nextafter(x, 1.0e300);
+      d.cut_gt_sq[ij] = x;
+    }
+  CUDA_TRY(c, c->spl_pair.reserve(p_pair.size() + 8));
+  CUDA_TRY(c, cudaMemcpyAsync(c->spl_pair.p, p_pair.data(), p_pair.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, c->spl_frho.reserve(p_frho.size() + 8));
   CUDA_TRY(c, c->spl_rhor.reserve(p_rhor.size() + 8));
   CUDA_TRY(c, c->spl_z2r.reserve(p_z2r.size() + 8));
@@ -159,7 +185,16 @@ extern "C" int b200md_aeam_get_spline(b200md_ctx *c, int kind, int index, double
 void b200md_aeam_forget(b200md_ctx *c) { g_aeam_host.erase(c); }
 
 // ================================================================== device helpers
-__device__ __forceinline__ int etype(const double4 &q) { return __double2int_rn(q.w); }
+// xq.w of the AEAM path carries TWO things: the 0-based element in the two lowest mantissa bits and, in the
+// remaining bits, the gated embedding derivative (1-del)*Fptmp*F'(rho) of the atom (aeam_gate_kernel), so the
+// force kernel gets position, element and fp_j of a neighbor from ONE 32-byte sector.  Overwriting two mantissa
+// bits perturbs fp by <= 3 ulp (7e-16 relative).
+__device__ __forceinline__ int etype(const double4 &q) { return (int) (__double_as_longlong(q.w) & 3LL); }
+__device__ __forceinline__ double w_encode(double g, int t)
+{
+  return __longlong_as_double((__double_as_longlong(g) & ~3LL) | (long long) t);
+}
+__device__ __forceinline__ double w_gate(const double4 &q) { return __longlong_as_double(__double_as_longlong(q.w) & ~3LL); }
 
 __device__ __forceinline__ void spl_index(double x, double rdx, int n, int &m, double &p)
 {
@@ -190,7 +225,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_pack_kernel(const double *__restri
     flags[3] = 1;
     t = 1;
   }
-  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (double) (t - 1));
+  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], w_encode(0.0, t - 1));
 }
 
 // inner rows: master row filtered to r <= max(cut_ij, cut_ji) + margin, 8-aligned, order preserved
@@ -230,12 +265,32 @@ __global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
   }
 }
 
+// per-type-pair constants staged in shared memory: indexing the kernel-parameter bank with a per-lane pair
+// type serialises in the address-divergence unit (ncu r01, lj v1: pipe_adu 66 %); LDS with mostly equal
+// addresses is a broadcast
+struct PairPar {
+  double cutgt, rdr;
+  int nr, off;
+};
+__device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, bool rhor_table = false)
+{
+  if (threadIdx.x < 16) {
+    sp[threadIdx.x].cutgt = par.cut_gt_sq[threadIdx.x];
+    sp[threadIdx.x].rdr = par.rdr[threadIdx.x];
+    sp[threadIdx.x].nr = par.nr[threadIdx.x];
+    sp[threadIdx.x].off = rhor_table ? par.rhor_off[threadIdx.x] : par.pair_off[threadIdx.x];
+  }
+  __syncthreads();
+}
+
 // ================================================================== A1: density of non-angular atoms
 __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
     int inum, double *__restrict__ rho)
 {
+  __shared__ PairPar sp[16];
+  load_pair_par(par, sp, true);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
   const int i = tid >> 3, sub = tid & 7;
   double acc = 0.0;
@@ -247,6 +302,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     if (mine) {
       const int n = ea_num[i];
       const int *row = ea_val + ea_off[i];
+      const int tbase = ti * par.nel;
       for (int e0 = 0; e0 < n; e0 += 32) {
         int jj[4];
         double4 xj[4];
@@ -257,18 +313,19 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          if (jj[u] >= 0) xj[u] = xq[jj[u]];
+          if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           if (jj[u] < 0) continue;
           const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
-          const double r1 = sqrt(dx * dx + dy * dy + dz * dz);
-          const int pt = ti * par.nel + etype(xj[u]);
-          if (r1 > par.cut[pt]) continue;    // i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          const PairPar pp = sp[tbase + etype(xj[u])];
+          if (rsq >= pp.cutgt) continue;    // r > cut; i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
+          const double r1 = sqrt(rsq);
           int m;
           double p;
-          spl_index(r1, par.rdr[pt], par.nr[pt], m, p);
-          acc += spl_val(rhor[par.rhor_off[pt] + m], p);
+          spl_index(r1, pp.rdr, pp.nr, m, p);
+          acc += spl_val(ld_sector(rhor + pp.off + m), p);
         }
       }
     }
@@ -422,15 +479,26 @@ __global__ void __launch_bounds__(BLOCK) aeam_ghost_fill_kernel(const int *__res
   rho[g] = rho[o];
 }
 
+// (1-del) * Fptmp * fp of every owned and ghost atom in one array: zero for angular atoms and for
+// rho <= minrho (pair_aeam.cpp:128,329-332), so the force kernel gathers ONE double per neighbor
+__global__ void __launch_bounds__(BLOCK) aeam_gate_kernel(double4 *__restrict__ xq, const double *__restrict__ rho,
+                                                          const double *__restrict__ fp, int nna, int nall)
+{
+  const int a = blockIdx.x * BLOCK + threadIdx.x;
+  if (a >= nall) return;
+  const int t = (int) (__double_as_longlong(xq[a].w) & 3LL);
+  xq[a].w = w_encode((t < nna && rho[a] > 0.0000000000001) ? fp[a] : 0.0, t);
+}
+
 // ================================================================== B1: pair + embedding forces (gather)
 template <bool EV>
 __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
-    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
-    const double4 *__restrict__ z2r, const double *__restrict__ rho, const double *__restrict__ fp, int inum,
-    double *__restrict__ f, double *__restrict__ scal)
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ ptab,
+    int inum, double *__restrict__ f, double *__restrict__ scal)
 {
-  const double minrho = 0.0000000000001;
+  __shared__ PairPar sp[16];
+  load_pair_par(par, sp);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
   const int i = tid >> 3, sub = tid & 7;
   double fx = 0.0, fy = 0.0, fz = 0.0;
@@ -438,8 +506,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
   if (i < inum) {
     const double4 xi = xq[i];
     const int ti = etype(xi);
-    // (1-deli) * Fptmp * fp[i]: zero for angular i (deli = 1), fp[i] for non-angular i with rho > minrho
-    const double gi = (ti < par.nnonangular && rho[i] > minrho) ? fp[i] : 0.0;
+    const int nel = par.nel;
+    const double gi = w_gate(xi);
     const int n = ea_num[i];
     const int *row = ea_val + ea_off[i];
     for (int e0 = 0; e0 < n; e0 += 32) {
@@ -452,28 +520,35 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (jj[u] >= 0) xj[u] = xq[jj[u]];
+        if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if (jj[u] < 0) continue;
-        const int j = jj[u];
         const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
         const double rsq = dx * dx + dy * dy + dz * dz;
-        const double r1 = sqrt(rsq);
         const int tj = etype(xj[u]);
-        const int pij = ti * par.nel + tj, pji = tj * par.nel + ti;
+        const PairPar pij = sp[ti * nel + tj];
+        const bool same = (tj == ti);
+        const bool in_ij = rsq < pij.cutgt;    // !(r > cut[ti][tj])
+        if (same && !in_ij) continue;
+        const double r1 = sqrt(rsq);
         const double recip = 1.0 / r1;
+        const double gj = w_gate(xj[u]);
         double coef = 0.0;    // fpair of visit (i,j) + fpair of visit (j,i)
-        if (!(r1 > par.cut[pij])) {
+        if (in_ij) {
           // visit (i,j): pair_aeam.cpp:350-393
           int m;
           double p;
-          spl_index(r1, par.rdr[pij], par.nr[pij], m, p);
-          const double dfij = spl_der(rhor[par.rhor_off[pij] + m], p, par.rdr[pij]);
-          const double4 cz = z2r[par.z2r_off[pij] + m];
-          const double phip = spl_der(cz, p, par.rdr[pij]);
+          spl_index(r1, pij.rdr, pij.nr, m, p);
+          const double4 cr = ld_sector(ptab + 2 * (size_t) (pij.off + m));
+          const double4 cz = ld_sector(ptab + 2 * (size_t) (pij.off + m) + 1);
+          const double dfij = spl_der(cr, p, pij.rdr);
+          const double phip = spl_der(cz, p, pij.rdr);
           const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
-          coef += fpair;
+          coef = fpair;
+          // same element: visit (j,i) reads the same rows with the same (m, p) -- evaluated without a
+          // second gather (98.5 % of the pairs of the AlSi workload)
+          if (same) coef += -gj * dfij * recip + 0.5 * (-phip * recip);
           if (EV) {
             ev[0] += 0.5 * spl_val(cz, p);
             ev[1] += dx * dx * fpair;
@@ -484,15 +559,17 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
             ev[6] += dy * dz * fpair;
           }
         }
-        if (!(r1 > par.cut[pji])) {
-          // visit (j,i), evaluated here instead of scattering from j's row
-          int m;
-          double p;
-          spl_index(r1, par.rdr[pji], par.nr[pji], m, p);
-          const double gj = (tj < par.nnonangular && rho[j] > minrho) ? fp[j] : 0.0;
-          const double dfji = spl_der(rhor[par.rhor_off[pji] + m], p, par.rdr[pji]);
-          const double phip = spl_der(z2r[par.z2r_off[pji] + m], p, par.rdr[pji]);
-          coef += -gj * dfji * recip + 0.5 * (-phip * recip);
+        if (!same) {
+          const PairPar pji = sp[tj * nel + ti];
+          if (rsq < pji.cutgt) {
+            // visit (j,i), evaluated here instead of scattering from j's row
+            int m;
+            double p;
+            spl_index(r1, pji.rdr, pji.nr, m, p);
+            const double dfji = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m)), p, pji.rdr);
+            const double phip = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m) + 1), p, pji.rdr);
+            coef += -gj * dfji * recip + 0.5 * (-phip * recip);
+          }
         }
         fx -= dx * coef;
         fy -= dy * coef;
@@ -742,17 +819,22 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
   const int inum = c->list_inum;
   if (inum == 0) return B200MD_OK;
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
-  const double4 *z2r = (const double4 *) c->spl_z2r.p;
+  const double4 *ptab = (const double4 *) c->spl_pair.p;
   const bool ev = eflag || vflag;
+  {
+    LaunchScope ls(c, "aeam_gate");
+    aeam_gate_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, c->rho.p, c->fp.p, c->ap.nnonangular,
+                                                                     c->nall);
+  }
   {
     LaunchScope ls(c, "aeam_force");
     const int nb = nblocks((long long) inum * 8, BLOCK);
     if (ev)
       aeam_force_kernel<true><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
-                                                          rhor, z2r, c->rho.p, c->fp.p, inum, c->f.p, c->scal.p);
+                                                          ptab, inum, c->f.p, c->scal.p);
     else
       aeam_force_kernel<false><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
-                                                           rhor, z2r, c->rho.p, c->fp.p, inum, c->f.p, c->scal.p);
+                                                           ptab, inum, c->f.p, c->scal.p);
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_force_ang");

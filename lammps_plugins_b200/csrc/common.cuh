@@ -117,6 +117,8 @@ struct AeamDev {
   int nrho[4];
   int frho_off[4];
   double cutsq_list[16];    // (cut+margin)^2 for the inner list
+  int pair_off[16];         // row offset (in 64-byte rows) of the fused {rhor | z2r} table of pair (i,j)
+  double cut_gt_sq[16];     // smallest rsq with sqrt(rsq) > cut[i][j]: `rsq >= this` is the reference's `r > cut`
 };
 
 // ---------------------------------------------------------------- context
@@ -202,7 +204,8 @@ struct b200md_ctx {
   // ---- AEAM
   bool aeam_ready = false;
   AeamDev ap;
-  DevBuf<double> spl_frho, spl_rhor, spl_z2r;    // 7 coefficients per row (reference layout)
+  DevBuf<double> spl_frho, spl_rhor, spl_z2r;    // {c3,c4,c5,c6} per row
+  DevBuf<double> spl_pair;                       // fused rows {rhor c3..c6 | z2r c3..c6} per ordered type pair
   std::vector<int> frho_rows, rhor_rows, z2r_rows;
   DevBuf<double> rho, fp;
   DevBuf<int64_t> ea_off;
@@ -302,6 +305,15 @@ template <int N, int BLOCK> __device__ __forceinline__ void block_accumulate(dou
     for (int w = 0; w < BLOCK / 32; w++) s += sh[threadIdx.x][w];
     atomicAdd(&out[threadIdx.x], s);
   }
+}
+// One 32-byte sector with ONE instruction (LDG.E.ENL2.256, sm_100+): a double4 gather written as `p[j]`
+// compiles to two LDG.E.128 because double4 is only 16-byte aligned as a type; every element of the arrays
+// gathered here sits on a 32-byte boundary.  Halves the LSU wavefronts of the neighbor gathers.
+__device__ __forceinline__ double4 ld_sector(const double4 *p)
+{
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
 }
 __device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
 {

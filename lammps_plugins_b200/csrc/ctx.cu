@@ -88,7 +88,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->bond_off.release(); c->bond_num.release(); c->cen_P.release(); c->cen_dP.release();
   c->nM.release(); c->nS.release(); c->bond_center.release(); c->bond_j.release();
   c->bond_geo.release(); c->bond_pref.release(); c->bond_frad.release();
-  c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release();
+  c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
   c->ang_list.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();

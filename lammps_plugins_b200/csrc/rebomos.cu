@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(BLOCK) rebo_neigh_kernel(
     const int n = (ti >= 0) ? short_num[i] : 0;
     for (int e = 0; e < n; e++) {
       const int j = short_idx[(size_t) e * short_pad + i];
-      const double4 xj = xq[j];
+      const double4 xj = ld_sector(xq + j);
       const int tj = elem_of(xj);
       const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
       // same operation order as the reference, no FMA contraction: membership must be bit-exact
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(BLOCK) rebo_neigh_kernel(
   }
   for (int b = 0; b < nb; b++) {
     const int j = jb[b];
-    const double4 xj = xq[j];
+    const double4 xj = ld_sector(xq + j);
     const int tj = elem_of(xj);
     const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     const double rsq = dx * dx + dy * dy + dz * dz;
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
     const int i = bond_center[s];
     const int off = bond_off[i], nb = bond_num[i];
     const int ti = elem_of(xq[i]);
-    const double4 gm = bond_geo[2 * (size_t) s];
-    const double4 hm = bond_geo[2 * (size_t) s + 1];
+    const double4 gm = ld_sector(bond_geo + 2 * (size_t) s);
+    const double4 hm = ld_sector(bond_geo + 2 * (size_t) s + 1);
     const double wm = hm.x, dwm = hm.y, r = hm.z;
     const int tj = __double2int_rn(hm.w);
     double pref = 0.0, frad = 0.0;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
       double S = 0.0;
       for (int q = off; q < off + nb; q++) {
         if (q == s) continue;
-        const double4 gn = bond_geo[2 * (size_t) q];
+        const double4 gn = ld_sector(bond_geo + 2 * (size_t) q);
         const double wn = bond_geo[2 * (size_t) q + 1].x;
         double c = (gm.x * gn.x + gm.y * gn.y + gm.z * gn.z) * (gm.w * gn.w);
         c = fmin(c, 1.0);
@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(BLOCK) bondorder_f_kernel(
     const int i = bond_center[s];
     const int off = bond_off[i], nb = bond_num[i];
     const int ti = elem_of(xq[i]);
-    const double4 gm = bond_geo[2 * (size_t) s];
-    const double4 hm = bond_geo[2 * (size_t) s + 1];
+    const double4 gm = ld_sector(bond_geo + 2 * (size_t) s);
+    const double4 hm = ld_sector(bond_geo + 2 * (size_t) s + 1);
     const double wm = hm.x, dwm = hm.y;
     const double prefm = bond_pref[s];
     const double dP = cendP[i];
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(BLOCK) bondorder_f_kernel(
     for (int q = off; q < off + nb; q++) {
       if (q == s) continue;
       const double prefn = bond_pref[q];
-      const double4 gn = bond_geo[2 * (size_t) q];
+      const double4 gn = ld_sector(bond_geo + 2 * (size_t) q);
       const double wn = bond_geo[2 * (size_t) q + 1].x;
       const double ca = -(prefm * wn + prefn * wm);
       const double cb = prefn * dwm;
@@ -471,8 +471,28 @@ __global__ void __launch_bounds__(BLOCK) fdotr_kernel(const double4 *__restrict_
 // virial carry a factor 1/2.  Only ~40 % of the candidates are inside the LJ window, so both sides of that
 // branch are kept minimal: the window and regime tests of pair_rebomos.cpp:518-543 (on rij = sqrt(rsq)) are
 // replaced by their exact rsq equivalents precomputed on the host (no sqrt, no division outside the window).
-template <bool EV>
-__global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ RebomosDev par,
+// 1/a for a normal, positive a in a harmless range (here 1 <= rsq <= 200 A^2): MUFU.RCP64H seed + two Newton
+// steps, no slow path.  Relative error <= 2 ulp, far inside the 1e-10 force tolerance.
+__device__ __forceinline__ double rcp_nr(double a)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
+
+// keep a value loaded from the constant bank in a register: without this the compiler re-materialises
+// `cond ? par.a[k] : par.a[k+1]` as an indexed constant load at every use
+__device__ __forceinline__ double pin(double v)
+{
+  asm volatile("" : "+d"(v));
+  return v;
+}
+
+template <bool EV, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__ RebomosDev par,
                                                    const double4 *__restrict__ xq,
                                                    const int64_t *__restrict__ lj_off,
                                                    const int *__restrict__ lj_num,
@@ -489,33 +509,44 @@ __global__ void __launch_bounds__(BLOCK) lj_kernel(const __grid_constant__ Rebom
     const int ti = elem_of(xi);
     const int n = (ti >= 0) ? lj_num[i] : 0;
     const int *row = lj_val + lj_off[i];
-    const int base = ti * 2;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      int jj[4];
-      double4 xj[4];
+    const int base = max(ti, 0) * 2;
+    // Constants of both partner elements live in registers and are SELECTED per candidate.  Indexing the
+    // kernel-parameter bank with a per-lane pair type (v1) serialises in the address-divergence unit:
+    // ncu r01 showed pipe_adu at 66 % -- the busiest pipe of the kernel, ahead of FP64 at 31 %.
+    const double hiA = pin(par.lj_out_hi[base]), hiB = pin(par.lj_out_hi[base + 1]);
+    const double loA = pin(par.lj_in_lo[base]), loB = pin(par.lj_in_lo[base + 1]);
+    const double s95A = pin(par.lj_s95[base]), s95B = pin(par.lj_s95[base + 1]);
+    const double lj1A = pin(par.lj1[base]), lj1B = pin(par.lj1[base + 1]);
+    const double lj2A = pin(par.lj2[base]), lj2B = pin(par.lj2[base + 1]);
+    const double lj3A = EV ? pin(par.lj3[base]) : 0.0, lj3B = EV ? pin(par.lj3[base + 1]) : 0.0;
+    const double lj4A = EV ? pin(par.lj4[base]) : 0.0, lj4B = EV ? pin(par.lj4[base + 1]) : 0.0;
+    for (int e0 = 0; e0 < n; e0 += 8 * U) {
+      int jj[U];
+      double4 xj[U];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < U; u++) {
         const int e = e0 + u * 8 + sub;
         jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (jj[u] >= 0) xj[u] = xq[jj[u]];
+      for (int u = 0; u < U; u++)
+        if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < U; u++) {
         if (jj[u] < 0) continue;
         const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
         const double rsq = dx * dx + dy * dy + dz * dz;
-        const int pt = base + (xj[u].w > 0.5 ? 1 : 0);
-        if (rsq >= par.lj_out_hi[pt]) continue;    // rij > rcLJmax
-        if (rsq < par.lj_in_lo[pt]) continue;      // rij < rcLJmin
+        const bool tB = xj[u].w > 0.5;
+        // rij > rcLJmax  <=>  rsq >= hi ;  rij < rcLJmin  <=>  rsq < lo   (exact, see rsq_smallest_with_sqrt)
+        if (rsq >= (tB ? hiB : hiA) || rsq < (tB ? loB : loA)) continue;
         double VLJ, fpair;
-        if (rsq >= par.lj_s95[pt]) {               // rij >= 0.95 sigma: 12-6 LJ
-          const double r2inv = 1.0 / rsq;
+        if (rsq >= (tB ? s95B : s95A)) {           // rij >= 0.95 sigma: 12-6 LJ
+          const double r2inv = rcp_nr(rsq);
           const double r6inv = r2inv * r2inv * r2inv;
-          fpair = r6inv * (par.lj1[pt] * r6inv - par.lj2[pt]) * r2inv;
-          if (EV) VLJ = r6inv * (par.lj3[pt] * r6inv - par.lj4[pt]);
-        } else {                                   // cubic taper down to rcLJmin
+          fpair = r6inv * ((tB ? lj1B : lj1A) * r6inv - (tB ? lj2B : lj2A)) * r2inv;
+          if (EV) VLJ = r6inv * ((tB ? lj3B : lj3A) * r6inv - (tB ? lj4B : lj4A));
+        } else {                                   // cubic taper down to rcLJmin (rare)
+          const int pt = base + (tB ? 1 : 0);
           const double rij = sqrt(rsq);
           const double drp = rij - par.rcLJmin[pt];
           VLJ = drp * drp * (drp * par.c3[pt] + par.c2[pt]);
@@ -765,12 +796,10 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
   {
     LaunchScope ls(c, "lj");
     const int nb = nblocks((long long) ncen * 8, BLOCK);
-    if (eflag || vflag)
-      lj_kernel<true><<<nb, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p,
-                                                  ncen, c->f.p, c->scal.p);
-    else
-      lj_kernel<false><<<nb, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p,
-                                                   ncen, c->f.p, c->scal.p);
+#define LJ_ARGS c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, ncen, c->f.p, c->scal.p
+    // 3 candidates in flight per lane at 80 registers (3 CTAs/SM) beat 4 at 104 (2 CTAs/SM): 1.20 vs 1.42 ms (r01)
+    if (eflag || vflag) lj_kernel<true, 4, 1><<<nb, BLOCK, 0, c->stream>>>(LJ_ARGS);
+    else lj_kernel<false, 3, 3><<<nb, BLOCK, 0, c->stream>>>(LJ_ARGS);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;

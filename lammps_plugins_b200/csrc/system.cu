@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(BLOCK) k_set_w(double4 *__restrict__ x, const 
   int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n) return;
   const int t = type[i];
-  x[i].w = use_map ? (double) map[t] : (double) (t - 1);
+  // rebomos: element code as a double; aeam: element in the two low mantissa bits (aeam.cu, w_encode)
+  x[i].w = use_map ? (double) map[t] : __longlong_as_double((long long) (t - 1));
 }
 __global__ void __launch_bounds__(BLOCK) k_make_xt(const double4 *__restrict__ x, const int *__restrict__ type, int n,
                                                    double4 *__restrict__ xt)

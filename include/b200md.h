@@ -173,15 +173,16 @@ int b200md_aeam_force_phase(b200md_ctx *ctx, const double *rho_all, const double
 int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
 
 /* ---- tuning / introspection ------------------------------------------------ */
-/* option names: "deterministic" (0/1), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
+/* option names: "deterministic" (0/1: rebomos bond forces are written to a (center, slot) table and summed by
+ * destination in a fixed order instead of FP64 atomics -- forces are then bitwise reproducible run to run), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
  * "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
  * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
- * "rebo_bonds", "lj_entries", "short_entries" */
+ * "lj_entries", "short_entries", "num_sms" */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
- * ("rebo_neigh","bondorder_p","bondorder_f","lj","fdotr","aeam_density","aeam_force",...) */
+ * ("rebo_center_wide","rebo_center_narrow","lj","fdotr","aeam_density","aeam_force",...) */
 double b200md_last_kernel_ms(b200md_ctx *ctx, const char *name);
 /* accumulated per-kernel device time since the last reset (while "sync_timing" is 1): iterate index from 0
  * until the return value is 1 */

@@ -148,7 +148,7 @@ struct b200md_ctx {
 
   // counters
   long long n_launch = 0, n_list_upload = 0, n_inner_rebuild = 0, h2d_bytes = 0, d2h_bytes = 0;
-  long long n_rebo_bonds = 0, n_lj_entries = 0, n_short_entries = 0;
+  long long n_lj_entries = 0, n_short_entries = 0;
   // per-launch CUDA events while "sync_timing" is on; folded into kstat by b200md_collect_timers()
   std::vector<std::string> kname;
   std::map<std::string, int> kname_id;
@@ -185,21 +185,16 @@ struct b200md_ctx {
   int map_h[B200MD_MAX_TYPES + 1];
   DevBuf<int> map_d;
   // inner lists
-  int short_pad = 0;         // padded row count (stride of the transposed short rows)
-  DevBuf<int> short_idx;     // [B200MD_SHORT_WIDTH * short_pad] transposed
+  DevBuf<int> short_idx;     // [rows][B200MD_SHORT_WIDTH] candidates within rcmax + margin, master-row order
   DevBuf<int> short_num;     // [rows]
   DevBuf<int64_t> lj_off;    // [inum+1] 8-aligned row offsets
   DevBuf<int> lj_num;        // [inum]
   DevBuf<int> lj_val;        // directed LJ-window rows
   int64_t lj_capacity = 0;
-  // per-step bond table
-  DevBuf<int> bond_off, bond_num;    // per center
-  DevBuf<double> cen_P, cen_dP;      // per center P(N), P'(N)
-  DevBuf<double> nM, nS;
-  DevBuf<int> bond_center, bond_j;   // per directed bond slot
-  DevBuf<double> bond_geo;           // [slots*8]: dx,dy,dz,rinv,w,dw,r,pad
-  DevBuf<double> bond_pref, bond_frad;
-  size_t bond_cap = 0;
+  DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow]
+  DevBuf<double> nM, nS;             // parity API (b200md_rebomos_neigh)
+  DevBuf<double> det_fb;             // deterministic mode: per-bond and per-center forces
+  DevBuf<int> det_j;
 
   // ---- AEAM
   bool aeam_ready = false;

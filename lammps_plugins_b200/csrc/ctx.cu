@@ -85,9 +85,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release();
-  c->bond_off.release(); c->bond_num.release(); c->cen_P.release(); c->cen_dP.release();
-  c->nM.release(); c->nS.release(); c->bond_center.release(); c->bond_j.release();
-  c->bond_geo.release(); c->bond_pref.release(); c->bond_frad.release();
+  c->cen_list.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
   c->ang_list.release();
@@ -130,7 +128,6 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
   if (n == "inner_rebuilds") return c->n_inner_rebuild;
   if (n == "h2d_bytes") return c->h2d_bytes;
   if (n == "d2h_bytes") return c->d2h_bytes;
-  if (n == "rebo_bonds") return c->n_rebo_bonds;
   if (n == "lj_entries") return c->n_lj_entries;
   if (n == "short_entries") return c->n_short_entries;
   if (n == "num_sms") return c->num_sms;

@@ -8,9 +8,8 @@
 // scatters 3 forces per (bond,k) triplet.  Here the energy is regrouped by CENTER atom,
 //   E = sum_i E_i,  E_i = sum_{j in R(i)} 1/2 [ VR_ij + p_ij VA_ij ],
 // p_ij depends only on i and its REBO neighbors, so all forces of E_i land on i and R(i):
-//   K3  rebo_neigh     thread / owned atom : ordered filter of the short row, N_i, bond table
-//   K4a bondorder_p    thread / directed bond (i->m): S = sum_k w_k G(cos), p, prefactors, energy
-//   K4b bondorder_f    thread / directed bond: F_m (all terms in which m takes part), F_i = -sum F_m
+//   K3+K4 rebo_center  lane group / owned atom: ordered filter of the short row (REBO sub-list), N_i,
+//                      p_im and prefactors, forces F_m of all terms in which m takes part, F_i = -sum F_m
 //   K5  lj             8 lanes / owned atom over the directed LJ-window row, no atomics
 //   K8  fdotr          sum_{nall} x (x) f for the many-body part
 // FP64 throughout; neighbor-position gathers are one 32-byte sector (double4 {x,y,z,elem}).
@@ -24,6 +23,14 @@
 
 // ================================================================== device math
 __device__ __forceinline__ int elem_of(const double4 &q) { return __double2int_rn(q.w); }
+
+// keep a value loaded from the constant bank in a register: without this the compiler re-materialises
+// `cond ? par.a[k] : par.a[k+1]` as an indexed constant load at every use
+__device__ __forceinline__ double pin(double v)
+{
+  asm volatile("" : "+d"(v));
+  return v;
+}
 
 // Sp cutoff (pair_rebomos.h:195-211): value and derivative
 __device__ __forceinline__ double sp_switch(double r, double rmin, double rw, double &dS)
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(BLOCK) check_disp_kernel(const double4 *__rest
 __global__ void __launch_bounds__(BLOCK) build_inner_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
     const int64_t *__restrict__ list_off, const int *__restrict__ list_num,
-    const int *__restrict__ list_val, int rows, int inum, int short_pad, int *__restrict__ short_idx,
+    const int *__restrict__ list_val, int rows, int inum, int *__restrict__ short_idx,
     int *__restrict__ short_num, const int64_t *__restrict__ lj_off, int *__restrict__ lj_num,
     int *__restrict__ lj_val, int *__restrict__ flags)
 {
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(BLOCK) build_inner_kernel(
     const unsigned ml = __ballot_sync(0xffffffffu, pl);
     if (ps) {
       const int pos = ns + __popc(ms & lt);
-      if (pos < B200MD_SHORT_WIDTH) short_idx[(size_t) pos * short_pad + i] = j;
+      if (pos < B200MD_SHORT_WIDTH) short_idx[(size_t) i * B200MD_SHORT_WIDTH + pos] = j;
       else flags[0] = 1;
     }
     if (pl) {
@@ -194,116 +201,11 @@ __global__ void __launch_bounds__(BLOCK) build_inner_kernel(
   }
 }
 
-// ================================================================== K3: REBO sub-list, N_i, bond table
-// One thread per center.  Scanning the short row sequentially keeps the reference's neighbor order
-// (lists bit-exact) and its nM/nS summation order (pair_rebomos.cpp:328-343; sums equal to rounding
-// of cos: sincospi(t) here vs cos(t*pi) there).
-__global__ void __launch_bounds__(BLOCK) rebo_neigh_kernel(
-    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ short_idx, const int *__restrict__ short_num, int short_pad, int ncenters,
-    int *__restrict__ bond_off, int *__restrict__ bond_num, double *__restrict__ cenP,
-    double *__restrict__ cendP, double *__restrict__ nM_out, double *__restrict__ nS_out,
-    int *__restrict__ bond_center, int *__restrict__ bond_j, double4 *__restrict__ bond_geo, int bond_cap,
-    int *__restrict__ flags)
-{
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int jb[B200MD_MAX_REBO];
-  int nb = 0;
-  double nM = 0.0, nS = 0.0;
-  double4 xi = make_double4(0, 0, 0, -1);
-  int ti = -1;
-  if (i < ncenters) {
-    xi = xq[i];
-    ti = elem_of(xi);
-    const int n = (ti >= 0) ? short_num[i] : 0;
-    for (int e = 0; e < n; e++) {
-      const int j = short_idx[(size_t) e * short_pad + i];
-      const double4 xj = ld_sector(xq + j);
-      const int tj = elem_of(xj);
-      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-      // same operation order as the reference, no FMA contraction: membership must be bit-exact
-      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      const int pt = ti * 2 + tj;
-      if (rsq < par.rcmaxsq[pt]) {
-        if (nb < B200MD_MAX_REBO) jb[nb] = j;
-        else flags[0] = 1;
-        nb++;
-        double dS;
-        const double w = sp_switch(sqrt(rsq), par.rcmin[pt], par.rcw[pt], dS);
-        if (tj == 0) nM += w;
-        else nS += w;
-      }
-    }
-    nb = min(nb, B200MD_MAX_REBO);
-  }
-  // slot allocation: warp exclusive scans + one atomic per warp and element.  Bonds of Mo centers fill the
-  // table from the front, bonds of S centers from the back: a warp of the bond kernels then sees one trip
-  // count (Mo: ~11 partners, S: ~2) instead of a mix (v1 ran at 13-15 of 32 active lanes).
-  const int nbA = (ti == 0) ? nb : 0, nbB = (ti == 1) ? nb : 0;
-  int incA = nbA, incB = nbB;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int tA = __shfl_up_sync(0xffffffffu, incA, o);
-    const int tB = __shfl_up_sync(0xffffffffu, incB, o);
-    if (lane >= o) {
-      incA += tA;
-      incB += tB;
-    }
-  }
-  const int totA = __shfl_sync(0xffffffffu, incA, 31), totB = __shfl_sync(0xffffffffu, incB, 31);
-  int baseA = 0, baseB = 0;
-  if (lane == 31) {
-    if (totA > 0) baseA = atomicAdd(&flags[2], totA);
-    if (totB > 0) baseB = atomicAdd(&flags[10], totB);
-  }
-  baseA = __shfl_sync(0xffffffffu, baseA, 31);
-  baseB = __shfl_sync(0xffffffffu, baseB, 31);
-  if (i >= ncenters) return;
-  // front: [baseA + exclusive prefix ...) ; back: block of nb slots ending at cap - (baseB + exclusive prefix)
-  int off = (ti == 0) ? baseA + incA - nbA : bond_cap - (baseB + incB);
-  if (baseA + totA + baseB + totB > bond_cap) {    // the two regions would meet
-    flags[0] = 2;
-    nb = 0;
-    off = 0;
-  }
-  bond_off[i] = off;
-  bond_num[i] = nb;
-  nM_out[i] = nM;
-  nS_out[i] = nS;
-  if (ti >= 0) {
-    // PijSpline (pair_rebomos.h:173-179)
-    const double N = nM + nS;
-    const double *a = par.a[ti];
-    const double ex = exp(-a[2] * N);
-    cendP[i] = -a[0] + a[1] * a[2] * ex;
-    cenP[i] = -a[0] * (N - 1.0) - a[1] * ex + a[3];
-  } else {
-    cendP[i] = 0.0;
-    cenP[i] = 0.0;
-  }
-  for (int b = 0; b < nb; b++) {
-    const int j = jb[b];
-    const double4 xj = ld_sector(xq + j);
-    const int tj = elem_of(xj);
-    const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    const double rsq = dx * dx + dy * dy + dz * dz;
-    const double r = sqrt(rsq);
-    const int pt = ti * 2 + tj;
-    double dw;
-    const double w = sp_switch(r, par.rcmin[pt], par.rcw[pt], dw);
-    const int s = off + b;
-    bond_center[s] = i;
-    bond_j[s] = j;
-    bond_geo[2 * (size_t) s] = make_double4(dx, dy, dz, 1.0 / r);
-    bond_geo[2 * (size_t) s + 1] = make_double4(w, dw, r, (double) tj);
-  }
-}
-
+// ================================================================== REBO rows (parity API)
 // parity/debug variant: REBO rows for owned AND ghost atoms written to caller-visible arrays
 __global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ short_idx, const int *__restrict__ short_num, int short_pad, int nrows,
+    const int *__restrict__ short_idx, const int *__restrict__ short_num, int nrows,
     int stride, int *__restrict__ out_num, int *__restrict__ out_rows, double *__restrict__ nM_out,
     double *__restrict__ nS_out, int *__restrict__ flags)
 {
@@ -315,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
   int nb = 0;
   double nM = 0.0, nS = 0.0;
   for (int e = 0; e < n; e++) {
-    const int j = short_idx[(size_t) e * short_pad + i];
+    const int j = short_idx[(size_t) i * B200MD_SHORT_WIDTH + e];
     const double4 xj = xq[j];
     const int tj = elem_of(xj);
     const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
@@ -336,113 +238,281 @@ __global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
   nS_out[i] = nS;
 }
 
-// ================================================================== K4a: p_ij, prefactors, pair energy
-__global__ void __launch_bounds__(BLOCK) bondorder_p_kernel(
-    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ flags, int bond_cap, const int *__restrict__ bond_center,
-    const int *__restrict__ bond_off, const int *__restrict__ bond_num, const double *__restrict__ cenP,
-    const double *__restrict__ cendP, const double4 *__restrict__ bond_geo, double *__restrict__ bond_pref,
-    double *__restrict__ bond_frad, double *__restrict__ scal)
+// ================================================================== K3+K4 fused: one lane GROUP per center
+// REBO_neigh + FREBO + bondorder for one owned center i entirely inside a group of G lanes:
+//   A  the group scans i's short row (G candidates per trip), keeps rsq < rcmax^2 with the reference's
+//      operation order, and stages the bonds in row order in shared memory {d, 1/r, w, w', j, elem};
+//      N_i = nM + nS by a group reduction, P(N), P'(N)
+//   B  lane m: S_m = sum_{n != m} w_n G(cos_mn), p_m, VR/VA, radial coefficient, prefactor dE/dS_m, energy
+//   C  lane m: force on neighbor j_m from every term of E_i it appears in; one FP64 atomic triple per bond,
+//      -sum_m F_m to the center by a group reduction
+// Nothing but the forces goes through global memory (v1 wrote and re-read a 500 B/atom bond table between
+// three kernels).  Centers are launched by element (Mo: G = 16, S: G = 4) so that every group of a warp
+// has the same trip counts; a center with more bonds than its class' staging capacity is deferred to an
+// overflow list handled by a G = 16, CAP = 16 launch.
+// DET: per-bond forces go to a (center, slot) table instead of atomics; rebo_gather_kernel sums them by
+// destination in a fixed order (deterministic mode).
+struct DetTables {
+  double *fb;    // [ncen * MAX_REBO * 3] force of bond slot m on its neighbor
+  double *fi;    // [ncen * 3]            force on the center
+  int *j;        // [ncen * MAX_REBO]     neighbor of bond slot m
+  int *nb;       // [ncen]
+};
+
+template <int G, int CAP, bool EV, bool DET>
+__global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int *__restrict__ short_idx,
+    const int *__restrict__ short_num, const int *__restrict__ cen_list, const int *__restrict__ cen_count_ptr,
+    int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
+    double *__restrict__ scal, int *__restrict__ flags)
 {
-  const int nA = flags[2], nB = flags[10];
-  double acc[1] = {0.0};
-  for (int w = blockIdx.x * BLOCK + threadIdx.x; w < nA + nB; w += gridDim.x * BLOCK) {
-    const int s = (w < nA) ? w : bond_cap - nB + (w - nA);
-    const int i = bond_center[s];
-    const int off = bond_off[i], nb = bond_num[i];
-    const int ti = elem_of(xq[i]);
-    const double4 gm = ld_sector(bond_geo + 2 * (size_t) s);
-    const double4 hm = ld_sector(bond_geo + 2 * (size_t) s + 1);
-    const double wm = hm.x, dwm = hm.y, r = hm.z;
-    const int tj = __double2int_rn(hm.w);
-    double pref = 0.0, frad = 0.0;
-    if (wm > TOL) {
-      double S = 0.0;
-      for (int q = off; q < off + nb; q++) {
-        if (q == s) continue;
-        const double4 gn = ld_sector(bond_geo + 2 * (size_t) q);
-        const double wn = bond_geo[2 * (size_t) q + 1].x;
-        double c = (gm.x * gn.x + gm.y * gn.y + gm.z * gn.z) * (gm.w * gn.w);
+  constexpr int NG = BLOCK / G;    // groups per block
+  constexpr unsigned GBITS = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  __shared__ double s_dx[NG * CAP], s_dy[NG * CAP], s_dz[NG * CAP], s_ri[NG * CAP], s_w[NG * CAP], s_dw[NG * CAP],
+      s_pref[NG * CAP], s_frad[NG * CAP];
+  __shared__ int s_j[NG * CAP], s_tj[NG * CAP];
+  const int lane = threadIdx.x & 31;
+  const int sub = threadIdx.x & (G - 1);
+  const int gl = threadIdx.x / G;    // group within the block
+  const int gshift = lane & ~(G - 1);
+  const unsigned gmask = GBITS << gshift;
+  const int sb = gl * CAP;    // this group's staging base
+  const int count = *cen_count_ptr;
+  double eacc[1] = {0.0};
+  for (int g = blockIdx.x * NG + gl; g < count; g += gridDim.x * NG) {
+    const int i = cen_list[g];
+    const double4 xi = xq[i];
+    const int ti = elem_of(xi);
+    const int n = (ti >= 0) ? short_num[i] : 0;
+    const int tb = max(ti, 0) * 2;
+    // pair constants of (ti, Mo) and (ti, S) in registers (see lj_kernel)
+    const double rsqA = pin(par.rcmaxsq[tb]), rsqB = pin(par.rcmaxsq[tb + 1]);
+    const double rminA = pin(par.rcmin[tb]), rminB = pin(par.rcmin[tb + 1]);
+    const double rcwA = pin(par.rcw[tb]), rcwB = pin(par.rcw[tb + 1]);
+    // ---- A: ordered REBO sub-list (pair_rebomos.cpp:328-343)
+    int nb = 0;
+    double nM = 0.0, nS = 0.0;
+    const int *row = short_idx + (size_t) i * B200MD_SHORT_WIDTH;
+    for (int e0 = 0; e0 < n; e0 += G) {
+      const int e = e0 + sub;
+      bool in = false;
+      int j = 0, tj = 0;
+      double dx = 0, dy = 0, dz = 0, rsq = 1.0;
+      if (e < n) {
+        j = row[e];
+        const double4 xj = ld_sector(xq + j);
+        tj = elem_of(xj);
+        dx = xi.x - xj.x;
+        dy = xi.y - xj.y;
+        dz = xi.z - xj.z;
+        // same operation order as the reference, no FMA contraction: membership must be bit-exact
+        rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        in = rsq < (tj ? rsqB : rsqA);
+      }
+      const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
+      if (in) {
+        const int pos = nb + __popc(bits & ((1u << sub) - 1u));
+        const double r = sqrt(rsq);
+        double dw;
+        const double w = sp_switch(r, tj ? rminB : rminA, tj ? rcwB : rcwA, dw);
+        if (tj == 0) nM += w;
+        else nS += w;
+        if (pos < CAP) {
+          s_dx[sb + pos] = dx;
+          s_dy[sb + pos] = dy;
+          s_dz[sb + pos] = dz;
+          s_ri[sb + pos] = 1.0 / r;
+          s_w[sb + pos] = w;
+          s_dw[sb + pos] = dw;
+          s_j[sb + pos] = j;
+          s_tj[sb + pos] = tj;
+        }
+      }
+      nb += __popc(bits);
+    }
+    __syncwarp(gmask);
+    if (nb > CAP) {
+      // more bonds than this launch class stages: hand the center to the wide launch, or fail at the cap
+      if (sub == 0) {
+        if (CAP < B200MD_MAX_REBO) ovf_list[atomicAdd(ovf_count, 1)] = i;
+        else flags[0] = 1;
+      }
+      nb = 0;
+      if (CAP < B200MD_MAX_REBO) continue;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      nM += __shfl_xor_sync(gmask, nM, o);
+      nS += __shfl_xor_sync(gmask, nS, o);
+    }
+    // PijSpline (pair_rebomos.h:173-179); N_i includes j (pair_rebomos.cpp:596-599)
+    double P = 0.0, dP = 0.0;
+    if (ti >= 0) {
+      const double N = nM + nS;
+      const double *a = par.a[ti];
+      const double ex = exp(-a[2] * N);
+      dP = -a[0] + a[1] * a[2] * ex;
+      P = -a[0] * (N - 1.0) - a[1] * ex + a[3];
+    }
+    // ---- B: bond order and pair terms of bond m
+    for (int m = sub; m < nb; m += G) {
+      const double mx = s_dx[sb + m], my = s_dy[sb + m], mz = s_dz[sb + m], rinv = s_ri[sb + m];
+      const double wm = s_w[sb + m], dwm = s_dw[sb + m];
+      double pref = 0.0, frad = 0.0;
+      if (wm > TOL) {
+        double S = 0.0;
+        for (int q = 0; q < nb; q++) {
+          if (q == m) continue;
+          double c = (mx * s_dx[sb + q] + my * s_dy[sb + q] + mz * s_dz[sb + q]) * (rinv * s_ri[sb + q]);
+          c = fmin(c, 1.0);
+          c = fmax(c, -1.0);
+          S += s_w[sb + q] * gspline_val(par, c, ti);
+        }
+        const double p = 1.0 / sqrt(1.0 + S + P);
+        const int pt = tb + s_tj[sb + m];
+        const double r = 1.0 / rinv;
+        const double Q = par.Q[pt], al = par.alpha[pt];
+        const double pre = wm * par.A[pt] * exp(-al * r);
+        const double VR = pre * (1.0 + Q * rinv);
+        const double dVR = pre * (-al - Q * rinv * rinv - Q * al * rinv) + VR / wm * dwm;
+        const double be = par.Beta[pt];
+        const double VA = -wm * par.BIJc[pt] * exp(-be * r);
+        const double dVA = -be * VA + VA / wm * dwm;
+        pref = VA * 0.5 * (-0.5 * p * p * p);
+        frad = 0.5 * (dVR + p * dVA) * rinv + pref * dP * dwm * rinv;
+        if (EV) eacc[0] += 0.5 * (VR + p * VA);
+      }
+      s_pref[sb + m] = pref;
+      s_frad[sb + m] = frad;
+    }
+    __syncwarp(gmask);
+    // ---- C: forces
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    for (int m = sub; m < nb; m += G) {
+      const double mx = s_dx[sb + m], my = s_dy[sb + m], mz = s_dz[sb + m], rinvm = s_ri[sb + m];
+      const double wm = s_w[sb + m], dwm = s_dw[sb + m], prefm = s_pref[sb + m];
+      const double rinvm2 = rinvm * rinvm;
+      double fx = 0.0, fy = 0.0, fz = 0.0;
+      for (int q = 0; q < nb; q++) {
+        if (q == m) continue;
+        const double prefn = s_pref[sb + q];
+        const double wn = s_w[sb + q];
+        const double ca = -(prefm * wn + prefn * wm);
+        const double cb = prefn * dwm;
+        if (ca == 0.0 && cb == 0.0) continue;
+        const double nx = s_dx[sb + q], ny = s_dy[sb + q], nz = s_dz[sb + q];
+        const double rr = rinvm * s_ri[sb + q];
+        double c = (mx * nx + my * ny + mz * nz) * rr;
         c = fmin(c, 1.0);
         c = fmax(c, -1.0);
-        S += wn * gspline_val(par, c, ti);
+        double dg;
+        const double gg = gspline(par, c, ti, dg);
+        const double A = ca * dg;
+        const double B = cb * (gg + dP) * rinvm;
+        const double cm = A * c * rinvm2 + B;    // multiplies d_m
+        const double cn = -A * rr;               // multiplies d_n
+        fx += cm * mx + cn * nx;
+        fy += cm * my + cn * ny;
+        fz += cm * mz + cn * nz;
       }
-      const double p = 1.0 / sqrt(1.0 + S + cenP[i]);
-      const int pt = ti * 2 + tj;
-      const double rinv = gm.w;
-      const double Q = par.Q[pt], al = par.alpha[pt];
-      const double pre = wm * par.A[pt] * exp(-al * r);
-      const double VR = pre * (1.0 + Q * rinv);
-      const double dVR = pre * (-al - Q * rinv * rinv - Q * al * rinv) + VR / wm * dwm;
-      const double be = par.Beta[pt];
-      const double VA = -wm * par.BIJc[pt] * exp(-be * r);
-      const double dVA = -be * VA + VA / wm * dwm;
-      pref = VA * 0.5 * (-0.5 * p * p * p);
-      frad = 0.5 * (dVR + p * dVA) * rinv + pref * cendP[i] * dwm * rinv;
-      acc[0] += 0.5 * (VR + p * VA);
+      const double fr = s_frad[sb + m];
+      fx += fr * mx;
+      fy += fr * my;
+      fz += fr * mz;
+      fix -= fx;
+      fiy -= fy;
+      fiz -= fz;
+      if (DET) {
+        const size_t k = (size_t) i * B200MD_MAX_REBO + m;
+        det.fb[3 * k] = fx;
+        det.fb[3 * k + 1] = fy;
+        det.fb[3 * k + 2] = fz;
+        det.j[k] = s_j[sb + m];
+      } else {
+        const size_t j = s_j[sb + m];
+        atomicAdd(&f[3 * j], fx);
+        atomicAdd(&f[3 * j + 1], fy);
+        atomicAdd(&f[3 * j + 2], fz);
+      }
     }
-    bond_pref[s] = pref;
-    bond_frad[s] = frad;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      fix += __shfl_xor_sync(gmask, fix, o);
+      fiy += __shfl_xor_sync(gmask, fiy, o);
+      fiz += __shfl_xor_sync(gmask, fiz, o);
+    }
+    if (sub == 0) {
+      if (DET) {
+        det.nb[i] = nb;
+        det.fi[3 * (size_t) i] = fix;
+        det.fi[3 * (size_t) i + 1] = fiy;
+        det.fi[3 * (size_t) i + 2] = fiz;
+      } else if (nb > 0) {
+        atomicAdd(&f[3 * (size_t) i], fix);
+        atomicAdd(&f[3 * (size_t) i + 1], fiy);
+        atomicAdd(&f[3 * (size_t) i + 2], fiz);
+      }
+    }
+    __syncwarp(gmask);
   }
-  block_accumulate<1, BLOCK>(acc, scal);
+  if (EV) block_accumulate<1, BLOCK>(eacc, scal);
 }
 
-// ================================================================== K4b: forces of the bond-order term
-__global__ void __launch_bounds__(BLOCK) bondorder_f_kernel(
-    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq,
-    const int *__restrict__ flags, int bond_cap, const int *__restrict__ bond_center,
-    const int *__restrict__ bond_j, const int *__restrict__ bond_off, const int *__restrict__ bond_num,
-    const double *__restrict__ cendP, const double4 *__restrict__ bond_geo,
-    const double *__restrict__ bond_pref, const double *__restrict__ bond_frad, double *__restrict__ f)
+// deterministic mode: f[a] = F_center(a) + sum over the REBO neighbors k of a (in short-row order) of the
+// force that center k's bond to a exerts on a.  Plain stores, fixed order -> bitwise reproducible.
+__global__ void __launch_bounds__(BLOCK) rebo_gather_kernel(const int *__restrict__ short_idx,
+                                                            const int *__restrict__ short_num, int rows, int ncen,
+                                                            const DetTables det, double *__restrict__ f)
 {
-  const int nA = flags[2], nB = flags[10];
-  for (int w = blockIdx.x * BLOCK + threadIdx.x; w < nA + nB; w += gridDim.x * BLOCK) {
-    const int s = (w < nA) ? w : bond_cap - nB + (w - nA);
-    const int i = bond_center[s];
-    const int off = bond_off[i], nb = bond_num[i];
-    const int ti = elem_of(xq[i]);
-    const double4 gm = ld_sector(bond_geo + 2 * (size_t) s);
-    const double4 hm = ld_sector(bond_geo + 2 * (size_t) s + 1);
-    const double wm = hm.x, dwm = hm.y;
-    const double prefm = bond_pref[s];
-    const double dP = cendP[i];
-    const double rinvm = gm.w;
-    const double rinvm2 = rinvm * rinvm;
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int q = off; q < off + nb; q++) {
-      if (q == s) continue;
-      const double prefn = bond_pref[q];
-      const double4 gn = ld_sector(bond_geo + 2 * (size_t) q);
-      const double wn = bond_geo[2 * (size_t) q + 1].x;
-      const double ca = -(prefm * wn + prefn * wm);
-      const double cb = prefn * dwm;
-      if (ca == 0.0 && cb == 0.0) continue;
-      const double rr = rinvm * gn.w;
-      double c = (gm.x * gn.x + gm.y * gn.y + gm.z * gn.z) * rr;
-      c = fmin(c, 1.0);
-      c = fmax(c, -1.0);
-      double dg;
-      const double g = gspline(par, c, ti, dg);
-      const double A = ca * dg;
-      const double B = cb * (g + dP) * rinvm;
-      const double cm = A * c * rinvm2 + B;    // multiplies d_m
-      const double cn = -A * rr;               // multiplies d_n
-      fx += cm * gm.x + cn * gn.x;
-      fy += cm * gm.y + cn * gn.y;
-      fz += cm * gm.z + cn * gn.z;
-    }
-    const double fr = bond_frad[s];
-    fx += fr * gm.x;
-    fy += fr * gm.y;
-    fz += fr * gm.z;
-    const int j = bond_j[s];
-    atomicAdd(&f[3 * (size_t) j], fx);
-    atomicAdd(&f[3 * (size_t) j + 1], fy);
-    atomicAdd(&f[3 * (size_t) j + 2], fz);
-    atomicAdd(&f[3 * (size_t) i], -fx);
-    atomicAdd(&f[3 * (size_t) i + 1], -fy);
-    atomicAdd(&f[3 * (size_t) i + 2], -fz);
+  const int a = blockIdx.x * BLOCK + threadIdx.x;
+  if (a >= rows) return;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  if (a < ncen) {
+    fx = det.fi[3 * (size_t) a];
+    fy = det.fi[3 * (size_t) a + 1];
+    fz = det.fi[3 * (size_t) a + 2];
   }
+  const int n = short_num[a];
+  const int *row = short_idx + (size_t) a * B200MD_SHORT_WIDTH;
+  for (int e = 0; e < n; e++) {
+    const int k = row[e];
+    if (k >= ncen) continue;    // bonds centered on ghosts are evaluated by the ghost's owner
+    const int nbk = det.nb[k];
+    const int *jl = det.j + (size_t) k * B200MD_MAX_REBO;
+    for (int m = 0; m < nbk; m++)
+      if (jl[m] == a) {
+        const size_t q = (size_t) k * B200MD_MAX_REBO + m;
+        fx += det.fb[3 * q];
+        fy += det.fb[3 * q + 1];
+        fz += det.fb[3 * q + 2];
+        break;
+      }
+  }
+  f[3 * (size_t) a] += fx;
+  f[3 * (size_t) a + 1] += fy;
+  f[3 * (size_t) a + 2] += fz;
+}
+
+// centers by element (static between list builds): warp-aggregated append, so list order follows atom order
+// at warp granularity
+__global__ void __launch_bounds__(BLOCK) center_lists_kernel(const double4 *__restrict__ xq, int ncen,
+                                                             int *__restrict__ listA, int *__restrict__ listB,
+                                                             int *__restrict__ counts)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int t = (i < ncen) ? elem_of(xq[i]) : -1;
+  const unsigned mA = __ballot_sync(0xffffffffu, t == 0), mB = __ballot_sync(0xffffffffu, t == 1);
+  int bA = 0, bB = 0;
+  if (lane == 0) {
+    if (mA) bA = atomicAdd(&counts[0], __popc(mA));
+    if (mB) bB = atomicAdd(&counts[1], __popc(mB));
+  }
+  bA = __shfl_sync(0xffffffffu, bA, 0);
+  bB = __shfl_sync(0xffffffffu, bB, 0);
+  const unsigned lt = (1u << lane) - 1u;
+  if (t == 0) listA[bA + __popc(mA & lt)] = i;
+  if (t == 1) listB[bB + __popc(mB & lt)] = i;
 }
 
 // ================================================================== K8: fdotr virial over owned + ghost
@@ -481,14 +551,6 @@ __device__ __forceinline__ double rcp_nr(double a)
   r = fma(r, e, r);
   e = fma(-a, r, 1.0);
   return fma(r, e, r);
-}
-
-// keep a value loaded from the constant bank in a register: without this the compiler re-materialises
-// `cond ? par.a[k] : par.a[k+1]` as an indexed constant load at every use
-__device__ __forceinline__ double pin(double v)
-{
-  asm volatile("" : "+d"(v));
-  return v;
 }
 
 template <bool EV, int U, int MINB>
@@ -696,8 +758,7 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   const int rows = c->list_inum + c->list_gnum;
   const int inum = c->list_inum;
   set_margin(c);
-  c->short_pad = (rows + 31) / 32 * 32;
-  CUDA_TRY(c, c->short_idx.reserve((size_t) B200MD_SHORT_WIDTH * c->short_pad + 32));
+  CUDA_TRY(c, c->short_idx.reserve((size_t) B200MD_SHORT_WIDTH * rows + 64));
   CUDA_TRY(c, c->short_num.reserve((size_t) rows + 32));
   CUDA_TRY(c, c->lj_off.reserve((size_t) inum + 2));
   CUDA_TRY(c, c->lj_num.reserve((size_t) inum + 32));
@@ -712,12 +773,21 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   if (rows > 0) {
     LaunchScope ls(c, "build_inner");
     build_inner_kernel<<<nblocks((long long) rows * 32, BLOCK), BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, rows, inum, c->short_pad,
+        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, rows, inum,
         c->short_idx.p, c->short_num.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, c->flags.p);
     CUDA_TRY(c, cudaGetLastError());
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->xhold.p, c->xq.p, (size_t) c->nall * sizeof(double4),
                               cudaMemcpyDeviceToDevice, c->stream));
+  // owned centers by element for the fused bond-order launches (flags[12], [13] = counts)
+  CUDA_TRY(c, c->cen_list.reserve(3 * (size_t) inum + 96));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 12, 0, 2 * sizeof(int), c->stream));
+  if (inum > 0) {
+    LaunchScope ls(c, "center_lists");
+    center_lists_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, inum, c->cen_list.p,
+                                                                      c->cen_list.p + inum + 32, c->flags.p + 12);
+    CUDA_TRY(c, cudaGetLastError());
+  }
   c->inner_valid = true;
   c->n_inner_rebuild++;
   return B200MD_OK;
@@ -748,46 +818,66 @@ int b200md_rebomos_refresh_inner(b200md_ctx *c)
 }
 
 // force kernels on whatever is resident: xq, inner lists.  f and scal must be zeroed by the caller.
+template <bool EV, bool DET>
+static void launch_centers(b200md_ctx *c, const DetTables &det)
+{
+  const int inum = c->list_inum;
+  int *listA = c->cen_list.p, *listB = c->cen_list.p + inum + 32, *ovf = c->cen_list.p + 2 * ((size_t) inum + 32);
+  int *cntA = c->flags.p + 12, *cntB = c->flags.p + 13, *cntO = c->flags.p + 14;
+  // Mo-like centers: 16 lanes; S-like centers: 4 lanes, 8 staged bonds; overflow: 16/16 over whatever was deferred.
+  // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
+  const int gridA = min(nblocks((long long) inum * 16, BLOCK), c->num_sms * 32);
+  const int gridB = min(nblocks((long long) inum * 4, BLOCK), c->num_sms * 32);
+  {
+    LaunchScope ls(c, "rebo_center_wide");
+    rebo_center_kernel<16, 16, EV, DET><<<gridA, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p, c->short_num.p,
+                                                                        listA, cntA, ovf, cntO, c->f.p, det, c->scal.p,
+                                                                        c->flags.p);
+  }
+  {
+    LaunchScope ls(c, "rebo_center_narrow");
+    rebo_center_kernel<4, 8, EV, DET><<<gridB, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p, c->short_num.p,
+                                                                      listB, cntB, ovf, cntO, c->f.p, det, c->scal.p,
+                                                                      c->flags.p);
+  }
+  {
+    LaunchScope ls(c, "rebo_center_overflow");
+    rebo_center_kernel<16, 16, EV, DET><<<c->num_sms, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p,
+                                                                             c->short_num.p, ovf, cntO, ovf, cntO, c->f.p,
+                                                                             det, c->scal.p, c->flags.p);
+  }
+}
+
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 {
   const int ncen = c->list_inum;
-  const size_t cap = (size_t) 10 * ncen + 4096;
-  if (cap > c->bond_cap) {
-    CUDA_TRY(c, c->bond_center.reserve(cap));
-    CUDA_TRY(c, c->bond_j.reserve(cap));
-    CUDA_TRY(c, c->bond_geo.reserve(8 * cap));
-    CUDA_TRY(c, c->bond_pref.reserve(cap));
-    CUDA_TRY(c, c->bond_frad.reserve(cap));
-    c->bond_cap = cap;
-  }
-  CUDA_TRY(c, c->bond_off.reserve((size_t) ncen + 32));
-  CUDA_TRY(c, c->bond_num.reserve((size_t) ncen + 32));
-  CUDA_TRY(c, c->cen_P.reserve((size_t) ncen + 32));
-  CUDA_TRY(c, c->cen_dP.reserve((size_t) ncen + 32));
-  CUDA_TRY(c, c->nM.reserve((size_t) c->nall + 32));
-  CUDA_TRY(c, c->nS.reserve((size_t) c->nall + 32));
-  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
+  const int rows = c->list_inum + c->list_gnum;
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 14, 0, sizeof(int), c->stream));
   if (ncen == 0) return B200MD_OK;
-  const int grid_bonds = c->num_sms * 8;
-  {
-    LaunchScope ls(c, "rebo_neigh");
-    rebo_neigh_kernel<<<nblocks(ncen, BLOCK), BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->short_idx.p, c->short_num.p, c->short_pad, ncen, c->bond_off.p, c->bond_num.p,
-        c->cen_P.p, c->cen_dP.p, c->nM.p, c->nS.p, c->bond_center.p, c->bond_j.p,
-        (double4 *) c->bond_geo.p, (int) c->bond_cap, c->flags.p);
+  DetTables det = {nullptr, nullptr, nullptr, nullptr};
+  const bool detmode = c->deterministic != 0;
+  if (detmode) {
+    ARG_CHECK(c, c->list_gnum > 0 || c->nghost == 0,
+              "deterministic mode needs the ghost rows of the neighbor list (REQ_GHOST / ghost_rows = 1)");
+    CUDA_TRY(c, c->det_fb.reserve(3 * (size_t) ncen * (B200MD_MAX_REBO + 1) + 32));
+    CUDA_TRY(c, c->det_j.reserve((size_t) ncen * (B200MD_MAX_REBO + 1) + 32));
+    det.fb = c->det_fb.p;
+    det.fi = c->det_fb.p + 3 * (size_t) ncen * B200MD_MAX_REBO;
+    det.j = c->det_j.p;
+    det.nb = c->det_j.p + (size_t) ncen * B200MD_MAX_REBO;
+    CUDA_TRY(c, cudaMemsetAsync(det.nb, 0, ncen * sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(det.fi, 0, 3 * (size_t) ncen * sizeof(double), c->stream));
   }
-  {
-    LaunchScope ls(c, "bondorder_p");
-    bondorder_p_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->flags.p, (int) c->bond_cap, c->bond_center.p, c->bond_off.p, c->bond_num.p, c->cen_P.p,
-        c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->scal.p);
-  }
-  {
-    LaunchScope ls(c, "bondorder_f");
-    bondorder_f_kernel<<<grid_bonds, BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->flags.p, (int) c->bond_cap, c->bond_center.p, c->bond_j.p, c->bond_off.p, c->bond_num.p,
-        c->cen_dP.p, (const double4 *) c->bond_geo.p, c->bond_pref.p, c->bond_frad.p, c->f.p);
+  const bool ev = eflag != 0;
+  if (detmode) {
+    if (ev) launch_centers<true, true>(c, det);
+    else launch_centers<false, true>(c, det);
+    LaunchScope ls(c, "rebo_gather");
+    rebo_gather_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, rows, ncen, det,
+                                                                     c->f.p);
+  } else {
+    if (ev) launch_centers<true, false>(c, det);
+    else launch_centers<false, false>(c, det);
   }
   if (vflag) {
     LaunchScope ls(c, "fdotr");
@@ -807,7 +897,6 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 
 static int check_flags(b200md_ctx *c, const int *fl)
 {
-  c->n_rebo_bonds = fl[2] + fl[10];
   if (fl[4] || fl[5]) {
     c->n_short_entries = fl[4];
     c->n_lj_entries = fl[5];
@@ -873,7 +962,7 @@ extern "C" int b200md_rebomos_neigh(b200md_ctx *c, int nlocal, int nghost, const
   if (rows) {
     LaunchScope ls(c, "rebo_rows");
     rebo_rows_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->short_idx.p, c->short_num.p, c->short_pad, rows, stride, d_num.p, d_rows.p,
+        c->rp, c->xq.p, c->short_idx.p, c->short_num.p, rows, stride, d_num.p, d_rows.p,
         c->nM.p, c->nS.p, c->flags.p);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(rebo_numneigh, d_num.p, rows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -52,9 +52,9 @@ def test_forces_energy_virial(ctx, oracle_built, case):
     ferr = S.rel_err(f, f_ref)
     eerr = abs(e - e_ref) / abs(e_ref)
     verr = S.rel_err(v, v_ref)
-    print("\n%s: nlocal %d nghost %d  max|f| %.4g  ferr %.3e  E %.10f eerr %.3e  verr %.3e  bonds %d lj %d"
+    print("\n%s: nlocal %d nghost %d  max|f| %.4g  ferr %.3e  E %.10f eerr %.3e  verr %.3e  short %d lj %d"
           % (case["id"], snap["nlocal"], snap["nghost"], np.abs(f_ref).max(), ferr, e, eerr, verr,
-             ctx.counter("rebo_bonds"), ctx.counter("lj_entries")))
+             ctx.counter("short_entries"), ctx.counter("lj_entries")))
     assert ferr < FTOL
     assert eerr < ETOL
     assert verr < FTOL
@@ -162,4 +162,51 @@ def test_rebo_sublist_bit_exact(ctx, oracle_built):
         w = np.where(t <= 0, 1.0, np.where(t >= 1, 0.0, 0.5 * (1 + np.cos(t * np.pi))))
         worst = max(worst, abs(nM[i] - w[el[ref] == 0].sum()), abs(nS[i] - w[el[ref] == 1].sum()))
     assert worst < 1e-13
+    lmp.close()
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[4]], ids=["bulk288-d0.05", "rep2x1x2-d0.6"])
+def test_deterministic_mode(ctx, oracle_built, case):
+    """option "deterministic": bond forces go through the (center, slot) table + fixed-order gather instead of
+    FP64 atomics.  Same parity bar against the oracle; ghost AND owned forces bitwise identical between
+    repeated calls; agrees with the atomic path to rounding."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), case["replicate"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    args = (snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], 1, 2)
+    fa, ea, va = ctx.rebomos_compute(*args)
+    try:
+        ctx.set_option("deterministic", 1)
+        runs = [ctx.rebomos_compute(*args) for _ in range(4)]
+    finally:
+        ctx.set_option("deterministic", 0)
+    for f, e, v in runs[1:]:
+        assert np.array_equal(f, runs[0][0]), "deterministic forces differ between calls"
+    f, e, v = runs[0]
+    assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], snap["nlocal"]), f_ref) < FTOL
+    assert abs(e - e_ref) / abs(e_ref) < ETOL and S.rel_err(v, v_ref) < FTOL
+    assert S.rel_err(f, fa) < 1e-13
+    lmp.close()
+
+
+def test_many_rebo_neighbors_overflow_path(ctx, oracle_built):
+    """a compressed cell gives S atoms more than 8 REBO neighbors: those centers leave the narrow launch through
+    the overflow list and are evaluated by the wide one -- same parity bar"""
+    lmp = S.MiniLmp()
+    lmp.command("plugin load " + S.oracle_plugin("rebomos"))
+    lmp.commands([c.replace("lattice custom 1.0", "lattice custom 0.8") for c in S.rebomos_bulk_commands((2, 1, 2))])
+    lmp.command("displace_atoms all random 0.05 0.05 0.05 12345")
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    init_ctx(ctx)
+    f, e, v = gpu_forces(ctx, snap)
+    num, rows, nM, nS = ctx.rebomos_neigh(snap["nlocal"], snap["nghost"], snap["x"], snap["type"])
+    styp = np.asarray(snap["type"])[:snap["nlocal"]] == 2
+    print("max REBO neighbors: S %d, Mo %d" % (num[:snap["nlocal"]][styp].max(), num[:snap["nlocal"]][~styp].max()))
+    assert num[:snap["nlocal"]][styp].max() > 8
+    assert S.rel_err(f, f_ref) < FTOL and abs(e - e_ref) / abs(e_ref) < ETOL
     lmp.close()

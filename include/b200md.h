@@ -182,7 +182,7 @@ int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
  * "lj_entries", "short_entries", "num_sms" */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
- * ("rebo_center_wide","rebo_center_narrow","lj","fdotr","aeam_density","aeam_force",...) */
+ * ("rebo_center_mo","rebo_center_s","lj","fdotr","aeam_density","aeam_force",...) */
 double b200md_last_kernel_ms(b200md_ctx *ctx, const char *name);
 /* accumulated per-kernel device time since the last reset (while "sync_timing" is 1): iterate index from 0
  * until the return value is 1 */

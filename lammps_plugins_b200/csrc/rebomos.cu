@@ -243,13 +243,18 @@ __global__ void __launch_bounds__(BLOCK) rebo_rows_kernel(
 //   A  the group scans i's short row (G candidates per trip), keeps rsq < rcmax^2 with the reference's
 //      operation order, and stages the bonds in row order in shared memory {d, 1/r, w, w', j, elem};
 //      N_i = nM + nS by a group reduction, P(N), P'(N)
-//   B  lane m: S_m = sum_{n != m} w_n G(cos_mn), p_m, VR/VA, radial coefficient, prefactor dE/dS_m, energy
+//   P  the nb(nb-1)/2 UNORDERED bond pairs are dealt to the lanes: cos_mq, G(cos), G'(cos) once per pair into
+//      a triangular shared table.  The reference evaluates gSpline four times per pair (twice per ordered
+//      pair, pair_rebomos.cpp:611-622 and :639-667); cos and G are symmetric in (m, q).
+//   B  lane m: S_m = sum_{q != m} w_q G_mq, p_m, VR/VA, radial coefficient, prefactor dE/dS_m, energy
 //   C  lane m: force on neighbor j_m from every term of E_i it appears in; one FP64 atomic triple per bond,
 //      -sum_m F_m to the center by a group reduction
 // Nothing but the forces goes through global memory (v1 wrote and re-read a 500 B/atom bond table between
-// three kernels).  Centers are launched by element (Mo: G = 16, S: G = 4) so that every group of a warp
-// has the same trip counts; a center with more bonds than its class' staging capacity is deferred to an
-// overflow list handled by a G = 16, CAP = 16 launch.
+// three kernels).  Centers are launched by element (Mo: G = 16, S: G = 4), which makes every group of a warp
+// run the same trip counts AND turns every spline / P(N) coefficient into an immediate constant-bank
+// operand (ELEM is a template argument; indexing the parameter bank with a runtime element costs one LDC
+// per Horner step: ncu r01 pipe_adu 39 %).  A center with more bonds than its class' staging capacity is
+// deferred to an overflow list handled by a G = 16, CAP = 16 launch of the same element.
 // DET: per-bond forces go to a (center, slot) table instead of atomics; rebo_gather_kernel sums them by
 // destination in a fixed order (deterministic mode).
 struct DetTables {
@@ -259,36 +264,86 @@ struct DetTables {
   int *nb;       // [ncen]
 };
 
-template <int G, int CAP, bool EV, bool DET>
-__global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
+// G(cos) and dG/dcos for a compile-time element; `blend` = some lane of the calling group has cos >= 1/2
+template <int ELEM>
+__device__ __forceinline__ double gspline_e(const RebomosDev &par, double c, bool blend, double &dgdc)
+{
+  const double *b = par.b[ELEM];
+  double g = b[6];
+  double dg = 6.0 * b[6];
+  g = fma(g, c, b[5]);
+  dg = fma(dg, c, 5.0 * b[5]);
+  g = fma(g, c, b[4]);
+  dg = fma(dg, c, 4.0 * b[4]);
+  g = fma(g, c, b[3]);
+  dg = fma(dg, c, 3.0 * b[3]);
+  g = fma(g, c, b[2]);
+  dg = fma(dg, c, 2.0 * b[2]);
+  g = fma(g, c, b[1]);
+  dg = fma(dg, c, b[1]);
+  g = fma(g, c, b[0]);
+  if (blend) {
+    const double *bg = par.bg[ELEM];
+    double gam = bg[6];
+    double dgam = 6.0 * bg[6];
+    gam = fma(gam, c, bg[5]);
+    dgam = fma(dgam, c, 5.0 * bg[5]);
+    gam = fma(gam, c, bg[4]);
+    dgam = fma(dgam, c, 4.0 * bg[4]);
+    gam = fma(gam, c, bg[3]);
+    dgam = fma(dgam, c, 3.0 * bg[3]);
+    gam = fma(gam, c, bg[2]);
+    dgam = fma(dgam, c, 2.0 * bg[2]);
+    gam = fma(gam, c, bg[1]);
+    dgam = fma(dgam, c, bg[1]);
+    gam = fma(gam, c, bg[0]);
+    double sn, cs;
+    sincospi(2.0 * (c - 0.5), &sn, &cs);
+    const double psi = 0.5 * (1.0 - cs);
+    const double dpsi = 3.14159265358979323846 * sn;
+    if (c >= 0.5) {
+      dg = dg + dpsi * (gam - g) + psi * (dgam - dg);
+      g = g + psi * (gam - g);
+    }
+  }
+  dgdc = dg;
+  return g;
+}
+
+__device__ __forceinline__ int tri_index(int m, int q)
+{
+  const int hi = max(m, q), lo = min(m, q);
+  return (hi * (hi - 1)) / 2 + lo;
+}
+
+template <int NT, int G, int CAP, int ELEM, bool EV, bool DET>
+__global__ void __launch_bounds__(NT) rebo_center_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int *__restrict__ short_idx,
     const int *__restrict__ short_num, const int *__restrict__ cen_list, const int *__restrict__ cen_count_ptr,
     int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
     double *__restrict__ scal, int *__restrict__ flags)
 {
-  constexpr int NG = BLOCK / G;    // groups per block
+  constexpr int NG = NT / G;    // groups per block
+  constexpr int NTRI = CAP * (CAP - 1) / 2;
   constexpr unsigned GBITS = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  constexpr int tb = ELEM * 2;
   __shared__ double s_dx[NG * CAP], s_dy[NG * CAP], s_dz[NG * CAP], s_ri[NG * CAP], s_w[NG * CAP], s_dw[NG * CAP],
       s_pref[NG * CAP], s_frad[NG * CAP];
+  __shared__ double s_c[NG * NTRI], s_g[NG * NTRI], s_dg[NG * NTRI];
   __shared__ int s_j[NG * CAP], s_tj[NG * CAP];
   const int lane = threadIdx.x & 31;
   const int sub = threadIdx.x & (G - 1);
   const int gl = threadIdx.x / G;    // group within the block
   const int gshift = lane & ~(G - 1);
   const unsigned gmask = GBITS << gshift;
-  const int sb = gl * CAP;    // this group's staging base
+  const int sb = gl * CAP;     // this group's staging base
+  const int st = gl * NTRI;    // ... and pair-table base
   const int count = *cen_count_ptr;
   double eacc[1] = {0.0};
   for (int g = blockIdx.x * NG + gl; g < count; g += gridDim.x * NG) {
     const int i = cen_list[g];
     const double4 xi = xq[i];
-    const int ti = elem_of(xi);
-    const int n = (ti >= 0) ? short_num[i] : 0;
-    const int tb = max(ti, 0) * 2;
-    // pair constants of (ti, Mo) and (ti, S) in registers (see lj_kernel)
-    const double rsqA = pin(par.rcmaxsq[tb]), rsqB = pin(par.rcmaxsq[tb + 1]);
-    const double rminA = pin(par.rcmin[tb]), rminB = pin(par.rcmin[tb + 1]);
-    const double rcwA = pin(par.rcw[tb]), rcwB = pin(par.rcw[tb + 1]);
+    const int n = short_num[i];
     // ---- A: ordered REBO sub-list (pair_rebomos.cpp:328-343)
     int nb = 0;
     double nM = 0.0, nS = 0.0;
@@ -307,14 +362,14 @@ __global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
         dz = xi.z - xj.z;
         // same operation order as the reference, no FMA contraction: membership must be bit-exact
         rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        in = rsq < (tj ? rsqB : rsqA);
+        in = rsq < (tj ? par.rcmaxsq[tb + 1] : par.rcmaxsq[tb]);
       }
       const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
       if (in) {
         const int pos = nb + __popc(bits & ((1u << sub) - 1u));
         const double r = sqrt(rsq);
         double dw;
-        const double w = sp_switch(r, tj ? rminB : rminA, tj ? rcwB : rcwA, dw);
+        const double w = sp_switch(r, tj ? par.rcmin[tb + 1] : par.rcmin[tb], tj ? par.rcw[tb + 1] : par.rcw[tb], dw);
         if (tj == 0) nM += w;
         else nS += w;
         if (pos < CAP) {
@@ -346,28 +401,45 @@ __global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
       nS += __shfl_xor_sync(gmask, nS, o);
     }
     // PijSpline (pair_rebomos.h:173-179); N_i includes j (pair_rebomos.cpp:596-599)
-    double P = 0.0, dP = 0.0;
-    if (ti >= 0) {
-      const double N = nM + nS;
-      const double *a = par.a[ti];
-      const double ex = exp(-a[2] * N);
-      dP = -a[0] + a[1] * a[2] * ex;
-      P = -a[0] * (N - 1.0) - a[1] * ex + a[3];
+    const double N = nM + nS;
+    const double ex = exp(-par.a[ELEM][2] * N);
+    const double dP = -par.a[ELEM][0] + par.a[ELEM][1] * par.a[ELEM][2] * ex;
+    const double P = -par.a[ELEM][0] * (N - 1.0) - par.a[ELEM][1] * ex + par.a[ELEM][3];
+    // ---- P: cos, G, G' of every unordered bond pair
+    const int npairs = nb * (nb - 1) / 2;
+    for (int p0 = 0; p0 < npairs; p0 += G) {
+      const int p = p0 + sub;
+      const bool act = p < npairs;
+      int hi = (int) ((1.0f + sqrtf(1.0f + 8.0f * (float) p)) * 0.5f);
+      if ((hi * (hi - 1)) / 2 > p) hi--;
+      if (((hi + 1) * hi) / 2 <= p) hi++;
+      const int lo = p - (hi * (hi - 1)) / 2;
+      double c = 0.0;
+      if (act) {
+        c = (s_dx[sb + hi] * s_dx[sb + lo] + s_dy[sb + hi] * s_dy[sb + lo] + s_dz[sb + hi] * s_dz[sb + lo]) *
+            (s_ri[sb + hi] * s_ri[sb + lo]);
+        c = fmin(c, 1.0);
+        c = fmax(c, -1.0);
+      }
+      const bool blend = __any_sync(gmask, act && c >= 0.5);
+      double dg;
+      const double gg = gspline_e<ELEM>(par, c, blend, dg);
+      if (act) {
+        s_c[st + p] = c;
+        s_g[st + p] = gg;
+        s_dg[st + p] = dg;
+      }
     }
+    __syncwarp(gmask);
     // ---- B: bond order and pair terms of bond m
     for (int m = sub; m < nb; m += G) {
-      const double mx = s_dx[sb + m], my = s_dy[sb + m], mz = s_dz[sb + m], rinv = s_ri[sb + m];
+      const double rinv = s_ri[sb + m];
       const double wm = s_w[sb + m], dwm = s_dw[sb + m];
       double pref = 0.0, frad = 0.0;
       if (wm > TOL) {
         double S = 0.0;
-        for (int q = 0; q < nb; q++) {
-          if (q == m) continue;
-          double c = (mx * s_dx[sb + q] + my * s_dy[sb + q] + mz * s_dz[sb + q]) * (rinv * s_ri[sb + q]);
-          c = fmin(c, 1.0);
-          c = fmax(c, -1.0);
-          S += s_w[sb + q] * gspline_val(par, c, ti);
-        }
+        for (int q = 0; q < nb; q++)
+          if (q != m) S += s_w[sb + q] * s_g[st + tri_index(m, q)];
         const double p = 1.0 / sqrt(1.0 + S + P);
         const int pt = tb + s_tj[sb + m];
         const double r = 1.0 / rinv;
@@ -396,24 +468,17 @@ __global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
       for (int q = 0; q < nb; q++) {
         if (q == m) continue;
         const double prefn = s_pref[sb + q];
-        const double wn = s_w[sb + q];
-        const double ca = -(prefm * wn + prefn * wm);
+        const double ca = -(prefm * s_w[sb + q] + prefn * wm);
         const double cb = prefn * dwm;
-        if (ca == 0.0 && cb == 0.0) continue;
-        const double nx = s_dx[sb + q], ny = s_dy[sb + q], nz = s_dz[sb + q];
-        const double rr = rinvm * s_ri[sb + q];
-        double c = (mx * nx + my * ny + mz * nz) * rr;
-        c = fmin(c, 1.0);
-        c = fmax(c, -1.0);
-        double dg;
-        const double gg = gspline(par, c, ti, dg);
-        const double A = ca * dg;
-        const double B = cb * (gg + dP) * rinvm;
-        const double cm = A * c * rinvm2 + B;    // multiplies d_m
-        const double cn = -A * rr;               // multiplies d_n
-        fx += cm * mx + cn * nx;
-        fy += cm * my + cn * ny;
-        fz += cm * mz + cn * nz;
+        const int t = st + tri_index(m, q);
+        const double c = s_c[t];
+        const double A = ca * s_dg[t];
+        const double B = cb * (s_g[t] + dP) * rinvm;
+        const double cm = A * c * rinvm2 + B;          // multiplies d_m
+        const double cn = -A * (rinvm * s_ri[sb + q]);    // multiplies d_q
+        fx += cm * mx + cn * s_dx[sb + q];
+        fy += cm * my + cn * s_dy[sb + q];
+        fz += cm * mz + cn * s_dz[sb + q];
       }
       const double fr = s_frad[sb + m];
       fx += fr * mx;
@@ -455,7 +520,7 @@ __global__ void __launch_bounds__(BLOCK) rebo_center_kernel(
     }
     __syncwarp(gmask);
   }
-  if (EV) block_accumulate<1, BLOCK>(eacc, scal);
+  if (EV) block_accumulate<1, NT>(eacc, scal);
 }
 
 // deterministic mode: f[a] = F_center(a) + sum over the REBO neighbors k of a (in short-row order) of the
@@ -822,29 +887,24 @@ template <bool EV, bool DET>
 static void launch_centers(b200md_ctx *c, const DetTables &det)
 {
   const int inum = c->list_inum;
-  int *listA = c->cen_list.p, *listB = c->cen_list.p + inum + 32, *ovf = c->cen_list.p + 2 * ((size_t) inum + 32);
-  int *cntA = c->flags.p + 12, *cntB = c->flags.p + 13, *cntO = c->flags.p + 14;
-  // Mo-like centers: 16 lanes; S-like centers: 4 lanes, 8 staged bonds; overflow: 16/16 over whatever was deferred.
+  int *list0 = c->cen_list.p, *list1 = c->cen_list.p + inum + 32, *ovf = c->cen_list.p + 2 * ((size_t) inum + 32);
+  int *cnt0 = c->flags.p + 12, *cnt1 = c->flags.p + 13, *cntO = c->flags.p + 14;
+  // Mo centers: 16 lanes, 16 staged bonds; S centers: 4 lanes, 8 staged bonds, overflow to 16/16.
   // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
-  const int gridA = min(nblocks((long long) inum * 16, BLOCK), c->num_sms * 32);
-  const int gridB = min(nblocks((long long) inum * 4, BLOCK), c->num_sms * 32);
+  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
+  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
+#define RC_ARGS(list, cnt) c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ovf, cntO, c->f.p, det, c->scal.p, c->flags.p
   {
-    LaunchScope ls(c, "rebo_center_wide");
-    rebo_center_kernel<16, 16, EV, DET><<<gridA, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p, c->short_num.p,
-                                                                        listA, cntA, ovf, cntO, c->f.p, det, c->scal.p,
-                                                                        c->flags.p);
+    LaunchScope ls(c, "rebo_center_mo");
+    rebo_center_kernel<128, 16, 16, 0, EV, DET><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0));
   }
   {
-    LaunchScope ls(c, "rebo_center_narrow");
-    rebo_center_kernel<4, 8, EV, DET><<<gridB, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p, c->short_num.p,
-                                                                      listB, cntB, ovf, cntO, c->f.p, det, c->scal.p,
-                                                                      c->flags.p);
+    LaunchScope ls(c, "rebo_center_s");
+    rebo_center_kernel<128, 4, 8, 1, EV, DET><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1));
   }
   {
     LaunchScope ls(c, "rebo_center_overflow");
-    rebo_center_kernel<16, 16, EV, DET><<<c->num_sms, BLOCK, 0, c->stream>>>(c->rp, c->xq.p, c->short_idx.p,
-                                                                             c->short_num.p, ovf, cntO, ovf, cntO, c->f.p,
-                                                                             det, c->scal.p, c->flags.p);
+    rebo_center_kernel<128, 16, 16, 1, EV, DET><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO));
   }
 }
 

@@ -200,7 +200,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region)
     hbm_peak, peak_src = measured_peaks()
     per_step = {k: v[0] / args.steps for k, v in kstats.items()}
-    force_kernels = {"rebomos": ["lj", "rebo_center_mo", "rebo_center_s", "rebo_center_overflow", "rebo_gather"],
+    force_kernels = {"rebomos": ["lj_mo", "lj_s", "rebo_center_mo", "rebo_center_s", "rebo_center_overflow", "rebo_gather"],
                      "aeam": ["aeam_force", "aeam_density", "aeam_embed", "aeam_force_ang", "aeam_density_ang"]}[kind]
     dom = max(force_kernels, key=lambda k: per_step.get(k, 0.0))
     dom_ms_launch = kstats[dom][0] / max(kstats[dom][1], 1)

@@ -161,16 +161,17 @@ __global__ void __launch_bounds__(BLOCK) build_inner_kernel(
   const int n = list_num[i];
   const int64_t base = list_off[i];
   const int64_t ljbase = (i < inum) ? lj_off[i] : 0;
+  const int ljcap = (i < inum) ? (int) (lj_off[i + 1] - lj_off[i]) : 0;
   const unsigned lt = (1u << lane) - 1u;
-  int ns = 0, nl = 0;
+  int ns = 0, nlA = 0, nlB = 0;
   for (int e0 = 0; e0 < n; e0 += 32) {
     const int e = e0 + lane;
     bool ps = false, pl = false;
-    int j = 0;
+    int j = 0, tj = 0;
     if (e < n) {
       j = ld_stream_int(list_val + base + e) & B200MD_NEIGHMASK;
       const double4 xj = xq[j];
-      const int tj = elem_of(xj);
+      tj = elem_of(xj);
       if (ti >= 0 && tj >= 0) {
         const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         const double rsq = dx * dx + dy * dy + dz * dz;
@@ -180,24 +181,31 @@ __global__ void __launch_bounds__(BLOCK) build_inner_kernel(
       }
     }
     const unsigned ms = __ballot_sync(0xffffffffu, ps);
-    const unsigned ml = __ballot_sync(0xffffffffu, pl);
+    // LJ rows are segmented by the partner's element so that lj_kernel runs each segment with compile-time
+    // pair constants: Mo partners fill the row's slots from the front, S partners from the back
+    const unsigned mA = __ballot_sync(0xffffffffu, pl && tj == 0);
+    const unsigned mB = __ballot_sync(0xffffffffu, pl && tj == 1);
     if (ps) {
       const int pos = ns + __popc(ms & lt);
       if (pos < B200MD_SHORT_WIDTH) short_idx[(size_t) i * B200MD_SHORT_WIDTH + pos] = j;
       else flags[0] = 1;
     }
     if (pl) {
-      const int pos = nl + __popc(ml & lt);
-      lj_val[ljbase + pos] = j;
+      if (tj == 0) lj_val[ljbase + nlA + __popc(mA & lt)] = j;
+      else lj_val[ljbase + ljcap - 1 - (nlB + __popc(mB & lt))] = j;
     }
     ns += __popc(ms);
-    nl += __popc(ml);
+    nlA += __popc(mA);
+    nlB += __popc(mB);
   }
   if (lane == 0) {
     short_num[i] = min(ns, B200MD_SHORT_WIDTH);
-    if (i < inum) lj_num[i] = nl;
+    if (i < inum) {
+      lj_num[2 * i] = nlA;
+      lj_num[2 * i + 1] = nlB;
+    }
     atomicAdd(&flags[4], ns);    // statistics (low contention: one per row, only at rebuilds)
-    atomicAdd(&flags[5], nl);
+    atomicAdd(&flags[5], nlA + nlB);
   }
 }
 
@@ -600,8 +608,9 @@ __global__ void __launch_bounds__(BLOCK) fdotr_kernel(const double4 *__restrict_
 }
 
 // ================================================================== K5: tapered LJ, directed rows
-// 8 lanes per owned atom: each group streams its 32-byte-aligned row as full sectors (4 row loads and 4
-// position gathers in flight per lane), gathers one double4 sector per neighbor, reduces with 3 shuffles.
+// 8 lanes per owned atom, centers launched by element, rows segmented by partner element (all pair constants are
+// immediate operands): each group streams its row segments as full sectors (U row loads and U position
+// gathers in flight per lane), gathers one double4 sector per neighbor, reduces with 3 shuffles.
 // Every directed pair is evaluated from both ends, so nothing is scattered: f_i is complete, energy and
 // virial carry a factor 1/2.  Only ~40 % of the candidates are inside the LJ window, so both sides of that
 // branch are kept minimal: the window and regime tests of pair_rebomos.cpp:518-543 (on rij = sqrt(rsq)) are
@@ -618,91 +627,102 @@ __device__ __forceinline__ double rcp_nr(double a)
   return fma(r, e, r);
 }
 
-template <bool EV, int U, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__ RebomosDev par,
-                                                   const double4 *__restrict__ xq,
-                                                   const int64_t *__restrict__ lj_off,
-                                                   const int *__restrict__ lj_num,
-                                                   const int *__restrict__ lj_val, int inum,
-                                                   double *__restrict__ f, double *__restrict__ scal)
+// one row segment [lo, hi) whose partners all have element TJ: every pair constant is an immediate operand
+template <bool EV, int PT, int U>
+__device__ __forceinline__ void lj_segment(const RebomosDev &par, const double4 *__restrict__ xq,
+                                           const int *__restrict__ row, int lo, int hi, int sub, const double4 &xi,
+                                           double &fx, double &fy, double &fz, double (&ev)[7])
 {
-  const int tid = blockIdx.x * BLOCK + threadIdx.x;
-  const int i = tid >> 3;
-  const int sub = tid & 7;
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
-  if (i < inum) {
-    const double4 xi = xq[i];
-    const int ti = elem_of(xi);
-    const int n = (ti >= 0) ? lj_num[i] : 0;
-    const int *row = lj_val + lj_off[i];
-    const int base = max(ti, 0) * 2;
-    // Constants of both partner elements live in registers and are SELECTED per candidate.  Indexing the
-    // kernel-parameter bank with a per-lane pair type (v1) serialises in the address-divergence unit:
-    // ncu r01 showed pipe_adu at 66 % -- the busiest pipe of the kernel, ahead of FP64 at 31 %.
-    const double hiA = pin(par.lj_out_hi[base]), hiB = pin(par.lj_out_hi[base + 1]);
-    const double loA = pin(par.lj_in_lo[base]), loB = pin(par.lj_in_lo[base + 1]);
-    const double s95A = pin(par.lj_s95[base]), s95B = pin(par.lj_s95[base + 1]);
-    const double lj1A = pin(par.lj1[base]), lj1B = pin(par.lj1[base + 1]);
-    const double lj2A = pin(par.lj2[base]), lj2B = pin(par.lj2[base + 1]);
-    const double lj3A = EV ? pin(par.lj3[base]) : 0.0, lj3B = EV ? pin(par.lj3[base + 1]) : 0.0;
-    const double lj4A = EV ? pin(par.lj4[base]) : 0.0, lj4B = EV ? pin(par.lj4[base + 1]) : 0.0;
-    for (int e0 = 0; e0 < n; e0 += 8 * U) {
-      int jj[U];
-      double4 xj[U];
+  int e = (lo & ~7) + sub;    // sector-aligned start; entries before lo belong to nobody
+  int jn[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int e = e0 + u * 8 + sub;
-        jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+  for (int u = 0; u < U; u++) {
+    const int k = e + 8 * u;
+    jn[u] = (k >= lo && k < hi) ? ld_stream_int(row + k) : -1;
+  }
+  for (; e - sub < hi; e += 8 * U) {
+    int jj[U];
+    double4 xj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      jj[u] = jn[u];
+      if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
+    }
+    // indices of the NEXT trip are requested before this trip's arithmetic: the row stream comes from HBM
+    // (ncu r01: long-scoreboard stalls 8 per issue, all on the index load -> gather chain)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = e + 8 * (U + u);
+      jn[u] = (k < hi) ? ld_stream_int(row + k) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (jj[u] < 0) continue;
+      const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      // rij > rcLJmax  <=>  rsq >= lj_out_hi ;  rij < rcLJmin  <=>  rsq < lj_in_lo   (exact, rsq_smallest_with_sqrt)
+      if (rsq >= par.lj_out_hi[PT] || rsq < par.lj_in_lo[PT]) continue;
+      double VLJ, fpair;
+      if (rsq >= par.lj_s95[PT]) {               // rij >= 0.95 sigma: 12-6 LJ
+        const double r2inv = rcp_nr(rsq);
+        const double r6inv = r2inv * r2inv * r2inv;
+        fpair = r6inv * (par.lj1[PT] * r6inv - par.lj2[PT]) * r2inv;
+        if (EV) VLJ = r6inv * (par.lj3[PT] * r6inv - par.lj4[PT]);
+      } else {                                   // cubic taper down to rcLJmin (rare)
+        const double rij = sqrt(rsq);
+        const double drp = rij - par.rcLJmin[PT];
+        VLJ = drp * drp * (drp * par.c3[PT] + par.c2[PT]);
+        const double dVLJ = drp * (3.0 * drp * par.c3[PT] + 2.0 * par.c2[PT]);
+        fpair = -dVLJ / rij;
       }
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (jj[u] < 0) continue;
-        const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
-        const double rsq = dx * dx + dy * dy + dz * dz;
-        const bool tB = xj[u].w > 0.5;
-        // rij > rcLJmax  <=>  rsq >= hi ;  rij < rcLJmin  <=>  rsq < lo   (exact, see rsq_smallest_with_sqrt)
-        if (rsq >= (tB ? hiB : hiA) || rsq < (tB ? loB : loA)) continue;
-        double VLJ, fpair;
-        if (rsq >= (tB ? s95B : s95A)) {           // rij >= 0.95 sigma: 12-6 LJ
-          const double r2inv = rcp_nr(rsq);
-          const double r6inv = r2inv * r2inv * r2inv;
-          fpair = r6inv * ((tB ? lj1B : lj1A) * r6inv - (tB ? lj2B : lj2A)) * r2inv;
-          if (EV) VLJ = r6inv * ((tB ? lj3B : lj3A) * r6inv - (tB ? lj4B : lj4A));
-        } else {                                   // cubic taper down to rcLJmin (rare)
-          const int pt = base + (tB ? 1 : 0);
-          const double rij = sqrt(rsq);
-          const double drp = rij - par.rcLJmin[pt];
-          VLJ = drp * drp * (drp * par.c3[pt] + par.c2[pt]);
-          const double dVLJ = drp * (3.0 * drp * par.c3[pt] + 2.0 * par.c2[pt]);
-          fpair = -dVLJ / rij;
-        }
-        fx += dx * fpair;
-        fy += dy * fpair;
-        fz += dz * fpair;
-        if (EV) {
-          ev[0] += 0.5 * VLJ;
-          const double hf = 0.5 * fpair;
-          ev[1] += dx * dx * hf;
-          ev[2] += dy * dy * hf;
-          ev[3] += dz * dz * hf;
-          ev[4] += dx * dy * hf;
-          ev[5] += dx * dz * hf;
-          ev[6] += dy * dz * hf;
-        }
+      fx += dx * fpair;
+      fy += dy * fpair;
+      fz += dz * fpair;
+      if (EV) {
+        ev[0] += 0.5 * VLJ;
+        const double hf = 0.5 * fpair;
+        ev[1] += dx * dx * hf;
+        ev[2] += dy * dy * hf;
+        ev[3] += dz * dz * hf;
+        ev[4] += dx * dy * hf;
+        ev[5] += dx * dz * hf;
+        ev[6] += dy * dz * hf;
       }
     }
   }
-  fx = group_sum<8>(fx);
-  fy = group_sum<8>(fy);
-  fz = group_sum<8>(fz);
-  if (i < inum && sub == 0) {
-    f[3 * (size_t) i] += fx;
-    f[3 * (size_t) i + 1] += fy;
-    f[3 * (size_t) i + 2] += fz;
+}
+
+template <bool EV, int ELEM, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__ RebomosDev par,
+                                                         const double4 *__restrict__ xq,
+                                                         const int64_t *__restrict__ lj_off,
+                                                         const int *__restrict__ lj_num,
+                                                         const int *__restrict__ lj_val,
+                                                         const int *__restrict__ cen_list,
+                                                         const int *__restrict__ cen_count_ptr,
+                                                         double *__restrict__ f, double *__restrict__ scal)
+{
+  const int count = *cen_count_ptr;
+  const int sub = threadIdx.x & 7;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int g = (blockIdx.x * BLOCK + threadIdx.x) >> 3; g < count; g += (gridDim.x * BLOCK) >> 3) {
+    const int i = cen_list[g];
+    const double4 xi = xq[i];
+    const int64_t off = lj_off[i];
+    const int cap = (int) (lj_off[i + 1] - off);
+    const int nA = lj_num[2 * i], nB = lj_num[2 * i + 1];
+    const int *row = lj_val + off;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    lj_segment<EV, ELEM * 2, U>(par, xq, row, 0, nA, sub, xi, fx, fy, fz, ev);
+    lj_segment<EV, ELEM * 2 + 1, U>(par, xq, row, cap - nB, cap, sub, xi, fx, fy, fz, ev);
+    fx = group_sum<8>(fx);
+    fy = group_sum<8>(fy);
+    fz = group_sum<8>(fz);
+    if (sub == 0) {
+      f[3 * (size_t) i] += fx;
+      f[3 * (size_t) i + 1] += fy;
+      f[3 * (size_t) i + 2] += fz;
+    }
   }
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
 }
@@ -826,7 +846,7 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   CUDA_TRY(c, c->short_idx.reserve((size_t) B200MD_SHORT_WIDTH * rows + 64));
   CUDA_TRY(c, c->short_num.reserve((size_t) rows + 32));
   CUDA_TRY(c, c->lj_off.reserve((size_t) inum + 2));
-  CUDA_TRY(c, c->lj_num.reserve((size_t) inum + 32));
+  CUDA_TRY(c, c->lj_num.reserve(2 * (size_t) inum + 32));
   int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->lj_off.p, inum, 8);
   if (rc) return rc;
   // capacity bound without a host round trip: every row padded to a multiple of 8
@@ -944,12 +964,22 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
     fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, c->scal.p);
   }
   {
-    LaunchScope ls(c, "lj");
-    const int nb = nblocks((long long) ncen * 8, BLOCK);
-#define LJ_ARGS c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, ncen, c->f.p, c->scal.p
-    // 3 candidates in flight per lane at 80 registers (3 CTAs/SM) beat 4 at 104 (2 CTAs/SM): 1.20 vs 1.42 ms (r01)
-    if (eflag || vflag) lj_kernel<true, 4, 1><<<nb, BLOCK, 0, c->stream>>>(LJ_ARGS);
-    else lj_kernel<false, 3, 3><<<nb, BLOCK, 0, c->stream>>>(LJ_ARGS);
+    // grid: 8 lanes per center, capped (grid-stride loop); counts are read on the device.  Occupancy decides:
+    // 2 candidates in flight per lane at 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10;
+    // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
+    const int grid = min(nblocks((long long) ncen * 8, BLOCK), c->num_sms * 64);
+    int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
+#define LJ_ARGS(list, cnt) c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, c->flags.p + cnt, c->f.p, c->scal.p
+    {
+      LaunchScope ls(c, "lj_mo");
+      if (eflag || vflag) lj_kernel<true, 0, 3, 1><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+      else lj_kernel<false, 0, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+    }
+    {
+      LaunchScope ls(c, "lj_s");
+      if (eflag || vflag) lj_kernel<true, 1, 3, 1><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+      else lj_kernel<false, 1, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+    }
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;

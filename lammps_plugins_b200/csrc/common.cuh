@@ -277,10 +277,15 @@ __device__ __forceinline__ double warp_sum(double v)
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// sum over an aligned group of W lanes.  The mask names ONLY the group: groups of one warp may sit in
+// different iterations of a grid-stride loop (or have left it), and a full-warp mask would then wait for
+// lanes that never arrive
 template <int W> __device__ __forceinline__ double group_sum(double v)
 {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(unsigned) (W - 1)));
 #pragma unroll
-  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 // block-level sum of `n` doubles per thread into global accumulators (one atomic per block per value)

@@ -200,22 +200,47 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region)
     hbm_peak, peak_src = measured_peaks()
     per_step = {k: v[0] / args.steps for k, v in kstats.items()}
-    force_kernels = {"rebomos": ["lj_mo", "lj_s", "rebo_center_mo", "rebo_center_s", "rebo_center_overflow", "rebo_gather"],
-                     "aeam": ["aeam_force", "aeam_density", "aeam_embed", "aeam_force_ang", "aeam_density_ang"]}[kind]
-    dom = max(force_kernels, key=lambda k: per_step.get(k, 0.0))
-    dom_ms_launch = kstats[dom][0] / max(kstats[dom][1], 1)
+    # a "kernel" = one __global__ template; lj and rebo_center are launched once per center element
+    groups = {"rebomos": {"lj": ["lj_mo", "lj_s"],
+                          "rebo_center": ["rebo_center_mo", "rebo_center_s", "rebo_center_overflow", "rebo_gather"]},
+              "aeam": {"aeam_force": ["aeam_force"], "aeam_density": ["aeam_density"],
+                       "aeam_angular": ["aeam_force_ang", "aeam_density_ang"]}}[kind]
+    gtime = {g: sum(per_step.get(k, 0.0) for k in ks) for g, ks in groups.items()}
+    dom = max(gtime, key=gtime.get)
+    dom_ms = gtime[dom]
     atoms_per_gpu = sz0["nlocal"]
-    algo_bytes = ALGO[kind]["bytes"] * atoms_per_gpu          # whole-step algorithmic bytes, charged to the dominant kernel
-    achieved = algo_bytes / (dom_ms_launch * 1e-3) / 1e9
+    # algorithmic bytes per atom-step of the reference formulation of this pass (one pass over the
+    # full neighbor row + x, f, type, tag); DESIGN.md section 7 lists the figure per kernel
+    algo_bytes = ALGO[kind]["bytes"] * atoms_per_gpu
+    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
     step_gbs = ALGO[kind]["bytes"] * natoms / world / (ms_per_step * 1e-3) / 1e9
     step_tflops = ALGO[kind]["flops"] * natoms / world / (ms_per_step * 1e-3) / 1e12
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms_per_launch": dom_ms_launch, "kernel_share_of_step": per_step.get(dom, 0.0) / ms_per_step,
+    try:
+        fp64_peak, hbm_here = ctx.measure_peaks()
+    except Exception:
+        fp64_peak, hbm_here = None, None
+    traffic = None
+    tpath = os.path.join(HERE, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and world == 1 and not args.rep:
+        traffic = json.load(open(tpath)).get(kind, {}).get(dom)
+    # bytes this implementation's kernel has to stream (its own derived rows), for comparison with `traffic`
+    rows_entries = ctx.counter("lj_entries")
+    own_bytes = None
+    if dom in ("lj", "aeam_force", "aeam_density"):
+        own_bytes = 4.0 * rows_entries + 80.0 * atoms_per_gpu
+    roofline = {"bound": "hbm", "kernel": dom, "launches_per_step": len([k for k in groups[dom] if k in per_step]),
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
                 "algorithmic_bytes_per_atom_step": ALGO[kind]["bytes"],
+                "own_row_bytes_per_launch_set": own_bytes,
+                "hbm_copy_measured_here_gbs": hbm_here,
                 "whole_step": {"hbm_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak, "fp64_tflops": step_tflops,
+                               "fp64_peak_measured_tflops": fp64_peak,
+                               "fp64_frac": (step_tflops / fp64_peak) if fp64_peak else None,
                                "fp64_frac_of_nominal": step_tflops / FP64_NOMINAL_TFLOPS,
-                               "fp64_peak_note": "nominal %.0f TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)" % FP64_NOMINAL_TFLOPS}}
+                               "fp64_note": "flops counted as the reference writes them (SURVEY 8d); peak = DFMA-saturating "
+                                            "kernel on this GPU; nominal %.0f TFLOP/s" % FP64_NOMINAL_TFLOPS}}
 
     # ---- e2e: plugin-mode C-ABI call with pinned host buffers (N = 1 only; multi-rank plugin mode needs LAMMPS' comm)
     e2e = None
@@ -241,10 +266,11 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
         "gpu_launches": launches,
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "kernel_groups_ms_per_step": {g: round(v, 5) for g, v in gtime.items()},
         "neighbor": {"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner, "setup_s": t_setup, "atoms_migrated_total": migrated},
         "thermo_last": {k: (float(v) if not isinstance(v, np.ndarray) else None) for k, v in thermo[-1].items() if k != "virial"},
     }
-    print(json.dumps(line))
+    emit(line)
     grp.close()
 
 
@@ -370,10 +396,29 @@ def run_reference(args):
             "config": {"workload": "%s (bounded sample of the B200 arm's lattice)" % kind, "pair_style": kind},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything but the one JSON line goes to stderr -- including C-level prints of libraries (NCCL writes its
+    version banner to fd 1 when NCCL_DEBUG is set on the box)."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

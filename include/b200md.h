@@ -195,6 +195,9 @@ void *b200md_stream(b200md_ctx *ctx);
  * (synchronises on the later event) */
 int b200md_event_record(b200md_ctx *ctx, int slot);
 double b200md_event_elapsed_ms(b200md_ctx *ctx, int slot_a, int slot_b);
+/* roofline denominators measured in place on this context's device: a DFMA-saturating kernel (TFLOP/s FP64) and
+ * a 2 GiB device-to-device copy (GB/s, read + write bytes).  Either pointer may be NULL. */
+int b200md_measure_peaks(b200md_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
 /* page-locked host memory for callers that want DMA-speed x/f transfers */
 void *b200md_host_alloc(size_t bytes);
 void b200md_host_free(void *p);

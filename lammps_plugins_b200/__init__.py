@@ -115,6 +115,7 @@ SYMBOLS = [
     ("b200md_stream", c_void_p, [c_void_p]),
     ("b200md_event_record", c_int, [c_void_p, c_int]),
     ("b200md_event_elapsed_ms", c_double, [c_void_p, c_int, c_int]),
+    ("b200md_measure_peaks", c_int, [c_void_p, _PD, _PD]),
     ("b200md_host_alloc", c_void_p, [ctypes.c_size_t]),
     ("b200md_host_free", None, [c_void_p]),
     ("b200md_system_create", c_int, [c_void_p, POINTER(SystemDesc), c_int, _PD, _PD, _PI, _PI]),
@@ -220,6 +221,12 @@ class Context:
 
     def event_elapsed_ms(self, a, b):
         return float(self.L.b200md_event_elapsed_ms(self.h, a, b))
+
+    def measure_peaks(self):
+        """(FP64 TFLOP/s of a DFMA-saturating kernel, GB/s of a 2 GiB device copy) on this device"""
+        tf, gb = c_double(), c_double()
+        self._check(self.L.b200md_measure_peaks(self.h, ctypes.byref(tf), ctypes.byref(gb)))
+        return tf.value, gb.value
 
     def pinned_array(self, shape, dtype=np.float64):
         """numpy array over page-locked host memory (freed with the context)"""

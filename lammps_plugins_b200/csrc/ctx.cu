@@ -197,6 +197,72 @@ extern "C" void b200md_host_free(void *p)
   if (p) cudaFreeHost(p);
 }
 
+// ---------------------------------------------------------------- roofline denominators measured in place
+// DFMA-saturating kernel: 8 independent chains per thread (MEASURED_PEAKS.json carries HBM and bf16 numbers
+// only; the FP64 roofline fraction needs its own denominator on the same box, same clocks)
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int k = 0; k < iters; k++) {
+    v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+    v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+  }
+  const double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+  if (s == 123.456) out[0] = s;    // never true; keeps the chains alive
+}
+__global__ void __launch_bounds__(256) copy_peak_kernel(const double4 *__restrict__ in, double4 *__restrict__ out, size_t n)
+{
+  for (size_t i = blockIdx.x * (size_t) 256 + threadIdx.x; i < n; i += (size_t) gridDim.x * 256) out[i] = in[i];
+}
+
+extern "C" int b200md_measure_peaks(b200md_ctx *c, double *fp64_tflops, double *hbm_gbs)
+{
+  if (!c) return B200MD_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(c, cudaEventCreate(&e0));
+  CUDA_TRY(c, cudaEventCreate(&e1));
+  float ms = 0.f;
+  if (fp64_tflops) {
+    const int iters = 1 << 14, blocks = c->num_sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, c->stream);
+      dfma_peak_kernel<<<blocks, 256, 0, c->stream>>>(c->scal.p + 48, iters, 1.0000001, 1.0e-9);
+      cudaEventRecord(e1, c->stream);
+      CUDA_TRY(c, cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    *fp64_tflops = best;
+  }
+  if (hbm_gbs) {
+    const size_t n = (size_t) 1 << 25;    // 2 x 1 GiB of double4: far beyond the 126 MB L2
+    DevBuf<double4> a, b;
+    CUDA_TRY(c, a.reserve(n));
+    CUDA_TRY(c, b.reserve(n));
+    CUDA_TRY(c, cudaMemsetAsync(a.p, 0, n * sizeof(double4), c->stream));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, c->stream);
+      copy_peak_kernel<<<c->num_sms * 16, 256, 0, c->stream>>>(a.p, b.p, n);
+      cudaEventRecord(e1, c->stream);
+      CUDA_TRY(c, cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double gbs = 2.0 * n * sizeof(double4) / (ms * 1e-3) / 1e9;
+      if (rep > 0 && gbs > best) best = gbs;
+    }
+    a.release();
+    b.release();
+    *hbm_gbs = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
 // forces + scalars + flags back to the host; f accumulated (default) or overwritten
 int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
                           int *flags_out)

@@ -913,18 +913,18 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
   const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
   const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
-#define RC_ARGS(list, cnt) c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ovf, cntO, c->f.p, det, c->scal.p, c->flags.p
+#define RC_ARGS(list, cnt, ol, oc) c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p
   {
     LaunchScope ls(c, "rebo_center_mo");
-    rebo_center_kernel<128, 16, 16, 0, EV, DET><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0));
+    rebo_center_kernel<128, 16, 16, 0, EV, DET><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
   }
   {
     LaunchScope ls(c, "rebo_center_s");
-    rebo_center_kernel<128, 4, 8, 1, EV, DET><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1));
+    rebo_center_kernel<128, 4, 8, 1, EV, DET><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
   }
   {
     LaunchScope ls(c, "rebo_center_overflow");
-    rebo_center_kernel<128, 16, 16, 1, EV, DET><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO));
+    rebo_center_kernel<128, 16, 16, 1, EV, DET><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
   }
 }
 
@@ -972,12 +972,12 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 #define LJ_ARGS(list, cnt) c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, c->flags.p + cnt, c->f.p, c->scal.p
     {
       LaunchScope ls(c, "lj_mo");
-      if (eflag || vflag) lj_kernel<true, 0, 3, 1><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+      if (eflag || vflag) lj_kernel<true, 0, 2, 2><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
       else lj_kernel<false, 0, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
     }
     {
       LaunchScope ls(c, "lj_s");
-      if (eflag || vflag) lj_kernel<true, 1, 3, 1><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+      if (eflag || vflag) lj_kernel<true, 1, 2, 2><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
       else lj_kernel<false, 1, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
     }
   }

@@ -673,6 +673,50 @@ static int xfer_sendrecv(b200md_ctx *c, SystemState *s, const double *sbuf, size
   return B200MD_OK;
 }
 
+// several exchanges that do not depend on each other (the -d and +d swaps of one dimension when one layer of
+// neighbors suffices): ONE NCCL group = one fused send/recv kernel instead of one per swap
+struct Xfer {
+  const double *sbuf;
+  size_t nsend;
+  int to;
+  double *rbuf;
+  size_t nrecv;
+  int from;
+};
+static int xfer_multi(b200md_ctx *c, SystemState *s, const Xfer *x, int n)
+{
+  if (s->local) {
+    for (int k = 0; k < n; k++) {
+      int rc = local_sendrecv(c, s, x[k].sbuf, x[k].nsend, x[k].to, x[k].rbuf, x[k].nrecv, x[k].from);
+      if (rc) return rc;
+    }
+    return B200MD_OK;
+  }
+  NCCL_TRY(c, ncclGroupStart());
+  for (int k = 0; k < n; k++) {
+    if (x[k].nsend) NCCL_TRY(c, ncclSend(x[k].sbuf, x[k].nsend, ncclDouble, x[k].to, s->nccl, c->stream));
+    if (x[k].nrecv) NCCL_TRY(c, ncclRecv(x[k].rbuf, x[k].nrecv, ncclDouble, x[k].from, s->nccl, c->stream));
+  }
+  NCCL_TRY(c, ncclGroupEnd());
+  return B200MD_OK;
+}
+
+// swaps [first, first + count) of dimension `dim`; `paired` = exactly the -d/+d pair, both with a remote partner
+struct DimSwaps {
+  int first, count;
+  bool paired;
+};
+static DimSwaps dim_swaps(const SystemState *s, int dim)
+{
+  DimSwaps d = {0, 0, false};
+  int is = 0;
+  for (int k = 0; k < dim; k++) is += 2 * s->maxneed[k];
+  d.first = is;
+  d.count = 2 * s->maxneed[dim];
+  d.paired = d.count == 2 && s->swaps[is].sendproc != s->me && s->swaps[is + 1].sendproc != s->me;
+  return d;
+}
+
 // in-place reductions over ranks of small device arrays
 static int xfer_allreduce_sum(b200md_ctx *c, SystemState *s, double *dbuf, int n)
 {
@@ -1054,83 +1098,190 @@ static int halo_borders(b200md_ctx *c, SystemState *s)
   return B200MD_OK;
 }
 
+// one swap of the forward position halo, self or remote, on its own
+static int forward_x_one(b200md_ctx *c, SystemState *s, Swap &sw)
+{
+  if (sw.sendproc == s->me) {
+    if (sw.nsend) {
+      LaunchScope ls(c, "forward_x");
+      k_forward_x<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.firstrecv, sw.fshift[0],
+                                                         sw.fshift[1], sw.fshift[2], sw.pbc_flag);
+    }
+    return B200MD_OK;
+  }
+  CUDA_TRY(c, s->sendbuf.reserve(3 * (size_t) sw.nsend + 8));
+  CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nrecv + 8));
+  if (sw.nsend) {
+    LaunchScope ls(c, "forward_x_pack");
+    k_forward_x_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.fshift[0], sw.fshift[1],
+                                                            sw.fshift[2], sw.pbc_flag, s->sendbuf.p);
+  }
+  int rc = xfer_sendrecv(c, s, s->sendbuf.p, 3 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 3 * (size_t) sw.nrecv,
+                         sw.recvproc);
+  if (rc) return rc;
+  if (sw.nrecv) {
+    LaunchScope ls(c, "forward_x_unpack");
+    k_forward_x_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->xq.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
+  }
+  return B200MD_OK;
+}
+
 static int halo_forward_x(b200md_ctx *c, SystemState *s)
 {
-  for (Swap &sw : s->swaps) {
-    if (sw.sendproc == s->me) {
-      if (sw.nsend) {
-        LaunchScope ls(c, "forward_x");
-        k_forward_x<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.firstrecv, sw.fshift[0],
-                                                           sw.fshift[1], sw.fshift[2], sw.pbc_flag);
+  for (int dim = 0; dim < 3; dim++) {
+    const DimSwaps d = dim_swaps(s, dim);
+    if (!d.paired) {
+      for (int k = 0; k < d.count; k++) {
+        int rc = forward_x_one(c, s, s->swaps[d.first + k]);
+        if (rc) return rc;
       }
-    } else {
-      CUDA_TRY(c, s->sendbuf.reserve(3 * (size_t) sw.nsend + 8));
-      CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nrecv + 8));
-      if (sw.nsend) {
-        LaunchScope ls(c, "forward_x_pack");
-        k_forward_x_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->xq.p, sw.sendlist.p, sw.nsend, sw.fshift[0],
-                                                                sw.fshift[1], sw.fshift[2], sw.pbc_flag, s->sendbuf.p);
-      }
-      int rc = xfer_sendrecv(c, s, s->sendbuf.p, 3 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 3 * (size_t) sw.nrecv,
-                             sw.recvproc);
-      if (rc) return rc;
-      if (sw.nrecv) {
-        LaunchScope ls(c, "forward_x_unpack");
-        k_forward_x_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->xq.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
-      }
+      continue;
+    }
+    // -d and +d swaps scan the same atoms (CommBrick::borders updates its window every second swap): independent
+    Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    const size_t sa = 3 * (size_t) a.nsend, sb = 3 * (size_t) b.nsend, ra = 3 * (size_t) a.nrecv, rb = 3 * (size_t) b.nrecv;
+    CUDA_TRY(c, s->sendbuf.reserve(sa + sb + 16));
+    CUDA_TRY(c, s->recvbuf.reserve(ra + rb + 16));
+    if (a.nsend) {
+      LaunchScope ls(c, "forward_x_pack");
+      k_forward_x_pack<<<nblk(a.nsend), BLOCK, 0, c->stream>>>(c->xq.p, a.sendlist.p, a.nsend, a.fshift[0], a.fshift[1],
+                                                             a.fshift[2], a.pbc_flag, s->sendbuf.p);
+    }
+    if (b.nsend) {
+      LaunchScope ls(c, "forward_x_pack");
+      k_forward_x_pack<<<nblk(b.nsend), BLOCK, 0, c->stream>>>(c->xq.p, b.sendlist.p, b.nsend, b.fshift[0], b.fshift[1],
+                                                             b.fshift[2], b.pbc_flag, s->sendbuf.p + sa);
+    }
+    const Xfer x[2] = {{s->sendbuf.p, sa, a.sendproc, s->recvbuf.p, ra, a.recvproc},
+                       {s->sendbuf.p + sa, sb, b.sendproc, s->recvbuf.p + ra, rb, b.recvproc}};
+    int rc = xfer_multi(c, s, x, 2);
+    if (rc) return rc;
+    if (a.nrecv) {
+      LaunchScope ls(c, "forward_x_unpack");
+      k_forward_x_unpack<<<nblk(a.nrecv), BLOCK, 0, c->stream>>>(c->xq.p, a.firstrecv, a.nrecv, s->recvbuf.p);
+    }
+    if (b.nrecv) {
+      LaunchScope ls(c, "forward_x_unpack");
+      k_forward_x_unpack<<<nblk(b.nrecv), BLOCK, 0, c->stream>>>(c->xq.p, b.firstrecv, b.nrecv, s->recvbuf.p + ra);
     }
   }
   CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+static int forward_rho_fp_one(b200md_ctx *c, SystemState *s, Swap &sw)
+{
+  if (sw.sendproc == s->me) {
+    if (sw.nsend) {
+      LaunchScope ls(c, "forward_fp");
+      k_forward_s2<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+    }
+    return B200MD_OK;
+  }
+  CUDA_TRY(c, s->sendbuf.reserve(2 * (size_t) sw.nsend + 8));
+  CUDA_TRY(c, s->recvbuf.reserve(2 * (size_t) sw.nrecv + 8));
+  if (sw.nsend) {
+    LaunchScope ls(c, "forward_fp_pack");
+    k_forward_s2_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, s->sendbuf.p);
+  }
+  int rc = xfer_sendrecv(c, s, s->sendbuf.p, 2 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 2 * (size_t) sw.nrecv,
+                         sw.recvproc);
+  if (rc) return rc;
+  if (sw.nrecv) {
+    LaunchScope ls(c, "forward_fp_unpack");
+    k_forward_s2_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
+  }
   return B200MD_OK;
 }
 
 static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
 {
-  for (Swap &sw : s->swaps) {
-    if (sw.sendproc == s->me) {
-      if (sw.nsend) {
-        LaunchScope ls(c, "forward_fp");
-        k_forward_s2<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+  for (int dim = 0; dim < 3; dim++) {
+    const DimSwaps d = dim_swaps(s, dim);
+    if (!d.paired) {
+      for (int k = 0; k < d.count; k++) {
+        int rc = forward_rho_fp_one(c, s, s->swaps[d.first + k]);
+        if (rc) return rc;
       }
-    } else {
-      CUDA_TRY(c, s->sendbuf.reserve(2 * (size_t) sw.nsend + 8));
-      CUDA_TRY(c, s->recvbuf.reserve(2 * (size_t) sw.nrecv + 8));
-      if (sw.nsend) {
-        LaunchScope ls(c, "forward_fp_pack");
-        k_forward_s2_pack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.sendlist.p, sw.nsend, s->sendbuf.p);
-      }
-      int rc = xfer_sendrecv(c, s, s->sendbuf.p, 2 * (size_t) sw.nsend, sw.sendproc, s->recvbuf.p, 2 * (size_t) sw.nrecv,
-                             sw.recvproc);
-      if (rc) return rc;
-      if (sw.nrecv) {
-        LaunchScope ls(c, "forward_fp_unpack");
-        k_forward_s2_unpack<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, sw.firstrecv, sw.nrecv, s->recvbuf.p);
-      }
+      continue;
+    }
+    Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    const size_t sa = 2 * (size_t) a.nsend, sb = 2 * (size_t) b.nsend, ra = 2 * (size_t) a.nrecv, rb = 2 * (size_t) b.nrecv;
+    CUDA_TRY(c, s->sendbuf.reserve(sa + sb + 16));
+    CUDA_TRY(c, s->recvbuf.reserve(ra + rb + 16));
+    if (a.nsend) {
+      LaunchScope ls(c, "forward_fp_pack");
+      k_forward_s2_pack<<<nblk(a.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, a.sendlist.p, a.nsend, s->sendbuf.p);
+    }
+    if (b.nsend) {
+      LaunchScope ls(c, "forward_fp_pack");
+      k_forward_s2_pack<<<nblk(b.nsend), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, b.sendlist.p, b.nsend, s->sendbuf.p + sa);
+    }
+    const Xfer x[2] = {{s->sendbuf.p, sa, a.sendproc, s->recvbuf.p, ra, a.recvproc},
+                       {s->sendbuf.p + sa, sb, b.sendproc, s->recvbuf.p + ra, rb, b.recvproc}};
+    int rc = xfer_multi(c, s, x, 2);
+    if (rc) return rc;
+    if (a.nrecv) {
+      LaunchScope ls(c, "forward_fp_unpack");
+      k_forward_s2_unpack<<<nblk(a.nrecv), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, a.firstrecv, a.nrecv, s->recvbuf.p);
+    }
+    if (b.nrecv) {
+      LaunchScope ls(c, "forward_fp_unpack");
+      k_forward_s2_unpack<<<nblk(b.nrecv), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, b.firstrecv, b.nrecv, s->recvbuf.p + ra);
     }
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
 }
 
+static int reverse_f_one(b200md_ctx *c, SystemState *s, Swap &sw)
+{
+  if (sw.sendproc == s->me) {
+    if (sw.nsend) {
+      LaunchScope ls(c, "reverse_f");
+      k_reverse_f<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+    }
+    return B200MD_OK;
+  }
+  // ghost forces are contiguous at f[3*firstrecv ...]: send them back, add what my send-list atoms receive
+  CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nsend + 8));
+  int rc = xfer_sendrecv(c, s, c->f.p + 3 * (size_t) sw.firstrecv, 3 * (size_t) sw.nrecv, sw.recvproc, s->recvbuf.p,
+                         3 * (size_t) sw.nsend, sw.sendproc);
+  if (rc) return rc;
+  if (sw.nsend) {
+    LaunchScope ls(c, "reverse_f_unpack");
+    k_reverse_f_unpack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, s->recvbuf.p);
+  }
+  return B200MD_OK;
+}
+
 static int halo_reverse_f(b200md_ctx *c, SystemState *s)
 {
-  for (int is = (int) s->swaps.size() - 1; is >= 0; is--) {
-    Swap &sw = s->swaps[is];
-    if (sw.sendproc == s->me) {
-      if (sw.nsend) {
-        LaunchScope ls(c, "reverse_f");
-        k_reverse_f<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, sw.firstrecv);
+  for (int dim = 2; dim >= 0; dim--) {
+    const DimSwaps d = dim_swaps(s, dim);
+    if (!d.paired) {
+      for (int k = d.count - 1; k >= 0; k--) {
+        int rc = reverse_f_one(c, s, s->swaps[d.first + k]);
+        if (rc) return rc;
       }
-    } else {
-      // ghost forces are contiguous at f[3*firstrecv ...]: send them back, add what my send-list atoms receive
-      CUDA_TRY(c, s->recvbuf.reserve(3 * (size_t) sw.nsend + 8));
-      int rc = xfer_sendrecv(c, s, c->f.p + 3 * (size_t) sw.firstrecv, 3 * (size_t) sw.nrecv, sw.recvproc, s->recvbuf.p,
-                             3 * (size_t) sw.nsend, sw.sendproc);
-      if (rc) return rc;
-      if (sw.nsend) {
-        LaunchScope ls(c, "reverse_f_unpack");
-        k_reverse_f_unpack<<<nblk(sw.nsend), BLOCK, 0, c->stream>>>(c->f.p, sw.sendlist.p, sw.nsend, s->recvbuf.p);
-      }
+      continue;
+    }
+    // the +d swap is folded first, then the -d swap, as in the sequential order; their ghost ranges are disjoint and
+    // neither send list contains the other's ghosts, so both transfers travel in one group
+    Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    const size_t sa = 3 * (size_t) a.nsend, sb = 3 * (size_t) b.nsend;
+    CUDA_TRY(c, s->recvbuf.reserve(sa + sb + 16));
+    const Xfer x[2] = {{c->f.p + 3 * (size_t) b.firstrecv, 3 * (size_t) b.nrecv, b.recvproc, s->recvbuf.p + sa, sb, b.sendproc},
+                       {c->f.p + 3 * (size_t) a.firstrecv, 3 * (size_t) a.nrecv, a.recvproc, s->recvbuf.p, sa, a.sendproc}};
+    int rc = xfer_multi(c, s, x, 2);
+    if (rc) return rc;
+    if (b.nsend) {
+      LaunchScope ls(c, "reverse_f_unpack");
+      k_reverse_f_unpack<<<nblk(b.nsend), BLOCK, 0, c->stream>>>(c->f.p, b.sendlist.p, b.nsend, s->recvbuf.p + sa);
+    }
+    if (a.nsend) {
+      LaunchScope ls(c, "reverse_f_unpack");
+      k_reverse_f_unpack<<<nblk(a.nsend), BLOCK, 0, c->stream>>>(c->f.p, a.sendlist.p, a.nsend, s->recvbuf.p);
     }
   }
   CUDA_TRY(c, cudaGetLastError());

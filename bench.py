@@ -264,7 +264,9 @@ def run_b200(args):
                    "skin": w["skin"], "l2": "working set (neighbor rows %.2f GB) >> 126 MB L2; no flush needed"
                    % (ctx.counter("lj_entries") * 4 / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
-        "gpu_launches": launches,
+        "gpu_launches": launches, "halo": {"peer_memory_exchanges": ctx.counter("p2p_exchanges"),
+                                           "transport": "cuda-ipc peer windows over NVLink" if ctx.counter("p2p_exchanges") > 0
+                                           else ("nccl send/recv" if world > 1 else "self (periodic images)")},
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "kernel_groups_ms_per_step": {g: round(v, 5) for g, v in gtime.items()},
         "neighbor": {"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner, "setup_s": t_setup, "atoms_migrated_total": migrated},

@@ -175,11 +175,13 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
 /* ---- tuning / introspection ------------------------------------------------ */
 /* option names: "deterministic" (0/1: rebomos bond forces are written to a (center, slot) table and summed by
  * destination in a fixed order instead of FP64 atomics -- forces are then bitwise reproducible run to run), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
+ * "p2p_halo" (0/1, default 1: multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the sender packs
+ * straight into the receiver's HBM over NVLink -- falling back to NCCL send/recv when IPC is unavailable),
  * "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
  * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
- * "lj_entries", "short_entries", "num_sms" */
+ * "lj_entries", "short_entries", "num_sms", "p2p_exchanges" */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
  * ("rebo_center_mo","rebo_center_s","lj","fdotr","aeam_density","aeam_force",...) */

@@ -144,6 +144,8 @@ struct b200md_ctx {
   double margin_opt = 0.0;    // 0 -> use skin
   int sync_timing = 0;
   int f_overwrite = 0;
+  int p2p_halo = 1;    // multi-GPU halo through peer memory (CUDA IPC) when available; 0 = NCCL send/recv only
+  long long n_p2p = 0;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // counters

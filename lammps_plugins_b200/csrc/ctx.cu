@@ -112,6 +112,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->inner_valid = false;
   } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
+  else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
   else {
     c->fail("unknown option " + n);
     return B200MD_ERR_ARG;
@@ -131,6 +132,7 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
   if (n == "lj_entries") return c->n_lj_entries;
   if (n == "short_entries") return c->n_short_entries;
   if (n == "num_sms") return c->num_sms;
+  if (n == "p2p_exchanges") return c->n_p2p;
   return -1;
 }
 

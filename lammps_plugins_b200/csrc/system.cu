@@ -29,6 +29,7 @@
 #define BLOCK 256
 #define BIGSLAB 1.0e20
 #define LOCAL_TIMEOUT_S 120
+#define P2P_SLOTS 18    // 3 message kinds x 3 dimensions x 2 directions
 
 int b200md_rebomos_build_inner(b200md_ctx *c);
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag);
@@ -110,6 +111,18 @@ struct SystemState {
   ncclComm_t nccl = nullptr;
   std::shared_ptr<LocalGroup> local;
   DevBuf<double> xbuf;    // exchange() staging
+  // peer-memory halo (one process per GPU, CUDA IPC over NVLink): windows the neighbors write into directly
+  struct PeerHalo {
+    bool ok = false;
+    int want = 1;                  // option "p2p_halo"
+    double *win = nullptr;         // [P2P_SLOTS * 2 parities * slot_cap]
+    int *flag = nullptr;           // [P2P_SLOTS * 2] epoch of the last completed write
+    int *done = nullptr;           // block-completion counter of the push kernels
+    size_t slot_cap = 0;           // doubles per slot
+    std::vector<double *> pwin;    // peers' windows mapped here (index = rank)
+    std::vector<int *> pflag;
+    int epoch[3] = {0, 0, 0};      // forward x, forward rho/fp, reverse f
+  } p2p;
 };
 
 // ================================================================== kernels
@@ -394,6 +407,132 @@ __global__ void __launch_bounds__(BLOCK) k_reverse_f_unpack(double *__restrict__
   f[3 * j] += buf[3 * (size_t) k];
   f[3 * j + 1] += buf[3 * (size_t) k + 1];
   f[3 * j + 2] += buf[3 * (size_t) k + 2];
+}
+
+// ------------------------------------------------------------------ peer-memory halo kernels
+// The sender packs straight into the RECEIVER's window over NVLink (no staging copy, no NCCL launch), then the last
+// block to finish publishes the epoch in the receiver's flag; the receiver's unpack kernel waits for the epoch.
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+struct PushDesc {
+  const int *list[2];    // send lists of the -d and +d swap (forward) -- unused for reverse
+  int n[2];              // items
+  int first[2];          // reverse: first ghost of the swap
+  double *dst[2];        // slot in the peer's window
+  int *flag[2];          // the peer's flag for that slot
+  double shift[2][3];
+  int pbc[2];
+};
+__device__ __forceinline__ void push_finish(const PushDesc &d, int epoch, int *done)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(done, 1) == (int) gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      st_release_sys(d.flag[0], epoch);
+      st_release_sys(d.flag[1], epoch);
+    }
+  }
+}
+__global__ void __launch_bounds__(BLOCK) k_p2p_push_x(const double4 *__restrict__ x, const __grid_constant__ PushDesc d,
+                                                      int epoch, int *done)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const int w = k < d.n[0] ? 0 : 1;
+  const int q = w ? k - d.n[0] : k;
+  if (q < d.n[w]) {
+    const double4 p = x[d.list[w][q]];
+    double *o = d.dst[w] + 3 * (size_t) q;
+    o[0] = d.pbc[w] ? p.x + d.shift[w][0] : p.x;
+    o[1] = d.pbc[w] ? p.y + d.shift[w][1] : p.y;
+    o[2] = d.pbc[w] ? p.z + d.shift[w][2] : p.z;
+  }
+  push_finish(d, epoch, done);
+}
+__global__ void __launch_bounds__(BLOCK) k_p2p_push_s2(const double *__restrict__ a, const double *__restrict__ b,
+                                                       const __grid_constant__ PushDesc d, int epoch, int *done)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const int w = k < d.n[0] ? 0 : 1;
+  const int q = w ? k - d.n[0] : k;
+  if (q < d.n[w]) {
+    const int j = d.list[w][q];
+    double *o = d.dst[w] + 2 * (size_t) q;
+    o[0] = a[j];
+    o[1] = b[j];
+  }
+  push_finish(d, epoch, done);
+}
+// reverse: the ghost forces of a swap are contiguous at f[3*first ...]
+__global__ void __launch_bounds__(BLOCK) k_p2p_push_f(const double *__restrict__ f, const __grid_constant__ PushDesc d,
+                                                      int epoch, int *done)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;    // one double per thread
+  const int n0 = 3 * d.n[0];
+  const int w = k < n0 ? 0 : 1;
+  const int q = w ? k - n0 : k;
+  if (q < 3 * d.n[w]) d.dst[w][q] = f[3 * (size_t) d.first[w] + q];
+  push_finish(d, epoch, done);
+}
+__device__ __forceinline__ void wait_epoch(const int *flag0, const int *flag1, int epoch)
+{
+  if (threadIdx.x == 0) {
+    while (ld_acquire_sys(flag0) != epoch) {}
+    if (flag1) while (ld_acquire_sys(flag1) != epoch) {}
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(BLOCK) k_p2p_unpack_x(double4 *__restrict__ x, const double *src0, int first0, int n0,
+                                                        const int *flag0, const double *src1, int first1, int n1,
+                                                        const int *flag1, int epoch)
+{
+  wait_epoch(flag0, flag1, epoch);
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const int w = k < n0 ? 0 : 1;
+  const int q = w ? k - n0 : k;
+  if (q >= (w ? n1 : n0)) return;
+  const double *b = (w ? src1 : src0) + 3 * (size_t) q;
+  const size_t g = (size_t) (w ? first1 : first0) + q;
+  double4 v = x[g];
+  v.x = __ldcg(b);
+  v.y = __ldcg(b + 1);
+  v.z = __ldcg(b + 2);
+  x[g] = v;
+}
+__global__ void __launch_bounds__(BLOCK) k_p2p_unpack_s2(double *__restrict__ a, double *__restrict__ bb, const double *src0,
+                                                         int first0, int n0, const int *flag0, const double *src1,
+                                                         int first1, int n1, const int *flag1, int epoch)
+{
+  wait_epoch(flag0, flag1, epoch);
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const int w = k < n0 ? 0 : 1;
+  const int q = w ? k - n0 : k;
+  if (q >= (w ? n1 : n0)) return;
+  const double *b = (w ? src1 : src0) + 2 * (size_t) q;
+  const size_t g = (size_t) (w ? first1 : first0) + q;
+  a[g] = __ldcg(b);
+  bb[g] = __ldcg(b + 1);
+}
+__global__ void __launch_bounds__(BLOCK) k_p2p_unpack_f(double *__restrict__ f, const int *__restrict__ list, int n,
+                                                        const double *src, const int *flag, int epoch)
+{
+  wait_epoch(flag, nullptr, epoch);
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const size_t j = list[k];
+  f[3 * j] += __ldcg(src + 3 * (size_t) k);
+  f[3 * j + 1] += __ldcg(src + 3 * (size_t) k + 1);
+  f[3 * j + 2] += __ldcg(src + 3 * (size_t) k + 2);
 }
 
 // FixNVE::initial_integrate fused with Neighbor::check_distance.  flags[9] = 2: some atom moved more than
@@ -1015,6 +1154,8 @@ static int sort_atoms(b200md_ctx *c, SystemState *s)
   return B200MD_OK;
 }
 
+static int p2p_setup(b200md_ctx *c, SystemState *s);
+
 // ------------------------------------------------------------------ CommBrick::borders
 static int halo_borders(b200md_ctx *c, SystemState *s)
 {
@@ -1095,8 +1236,107 @@ static int halo_borders(b200md_ctx *c, SystemState *s)
     }
   }
   CUDA_TRY(c, cudaGetLastError());
+  return p2p_setup(c, s);
+}
+
+// ------------------------------------------------------------------ peer-memory halo: windows + IPC mapping
+static void p2p_release(SystemState *s)
+{
+  SystemState::PeerHalo &P = s->p2p;
+  for (size_t r = 0; r < P.pwin.size(); r++) {
+    if (P.pwin[r]) cudaIpcCloseMemHandle(P.pwin[r]);
+    if (P.pflag[r]) cudaIpcCloseMemHandle(P.pflag[r]);
+  }
+  P.pwin.clear();
+  P.pflag.clear();
+  if (P.win) cudaFree(P.win);
+  if (P.flag) cudaFree(P.flag);
+  if (P.done) cudaFree(P.done);
+  P.win = nullptr;
+  P.flag = P.done = nullptr;
+  P.slot_cap = 0;
+  P.ok = false;
+}
+
+// Collective (called by every rank at every list rebuild, after borders): make sure each rank owns a window whose
+// slots hold the largest halo message of any rank, and that every rank has every other rank's window mapped.
+// Any failure (IPC not permitted, no peer access) switches the peer path off on ALL ranks; NCCL send/recv stays.
+static int p2p_setup(b200md_ctx *c, SystemState *s)
+{
+  SystemState::PeerHalo &P = s->p2p;
+  P.want = c->p2p_halo;
+  if (!s->nccl || s->local || s->nranks == 1 || !P.want) {
+    P.ok = false;
+    return B200MD_OK;
+  }
+  double need = 0.0;
+  for (const Swap &sw : s->swaps) need = fmax(need, (double) (sw.nsend > sw.nrecv ? sw.nsend : sw.nrecv));
+  double *dn = c->scal.p + 44;
+  CUDA_TRY(c, cudaMemcpyAsync(dn, &need, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, ncclAllReduce(dn, dn, 1, ncclDouble, ncclMax, s->nccl, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(&need, dn, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const size_t want_cap = 3 * (size_t) need + 64;
+  if (P.ok && want_cap <= P.slot_cap) return B200MD_OK;
+  if (P.slot_cap == (size_t) -1) return B200MD_OK;    // tried before and failed: stay on NCCL
+  p2p_release(s);
+  const size_t cap = want_cap + want_cap / 4;
+  double okv = 1.0;
+  if (cudaMalloc((void **) &P.win, (size_t) P2P_SLOTS * 2 * cap * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void **) &P.flag, P2P_SLOTS * 2 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **) &P.done, 4 * sizeof(int)) != cudaSuccess)
+    okv = 0.0;
+  struct Handles {
+    cudaIpcMemHandle_t win, flag;
+  } mine;
+  memset(&mine, 0, sizeof(mine));
+  if (okv > 0.0) {
+    cudaMemsetAsync(P.flag, 0, P2P_SLOTS * 2 * sizeof(int), c->stream);
+    cudaMemsetAsync(P.done, 0, 4 * sizeof(int), c->stream);
+    if (cudaIpcGetMemHandle(&mine.win, P.win) != cudaSuccess || cudaIpcGetMemHandle(&mine.flag, P.flag) != cudaSuccess)
+      okv = 0.0;
+  }
+  cudaGetLastError();
+  // everybody's handles to everybody (tiny all-gather on the library's own communicator)
+  DevBuf<char> hb;
+  CUDA_TRY(c, hb.reserve(sizeof(Handles) * ((size_t) s->nranks + 1)));
+  CUDA_TRY(c, cudaMemcpyAsync(hb.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, ncclAllGather(hb.p, hb.p + sizeof(Handles), sizeof(Handles), ncclChar, s->nccl, c->stream));
+  std::vector<Handles> all(s->nranks);
+  CUDA_TRY(c, cudaMemcpyAsync(all.data(), hb.p + sizeof(Handles), sizeof(Handles) * s->nranks, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  hb.release();
+  P.pwin.assign(s->nranks, nullptr);
+  P.pflag.assign(s->nranks, nullptr);
+  if (okv > 0.0) {
+    for (int r = 0; r < s->nranks && okv > 0.0; r++) {
+      if (r == s->me) continue;
+      void *pw = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pw, all[r].win, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, all[r].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        okv = 0.0;
+      P.pwin[r] = (double *) pw;
+      P.pflag[r] = (int *) pf;
+    }
+  }
+  cudaGetLastError();
+  CUDA_TRY(c, cudaMemcpyAsync(dn, &okv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, ncclAllReduce(dn, dn, 1, ncclDouble, ncclMin, s->nccl, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(&okv, dn, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (okv > 0.0) {
+    P.ok = true;
+    P.slot_cap = cap;
+    P.epoch[0] = P.epoch[1] = P.epoch[2] = 0;
+  } else {
+    p2p_release(s);
+    P.slot_cap = (size_t) -1;
+  }
   return B200MD_OK;
 }
+
+// slot of message kind (0 forward x, 1 forward rho/fp, 2 reverse f) for swap (dim, dir) and epoch parity
+static inline size_t p2p_slot(int kind, int dim, int dir, int epoch) { return (size_t) ((kind * 6 + dim * 2 + dir) * 2 + (epoch & 1)); }
 
 // one swap of the forward position halo, self or remote, on its own
 static int forward_x_one(b200md_ctx *c, SystemState *s, Swap &sw)
@@ -1128,6 +1368,7 @@ static int forward_x_one(b200md_ctx *c, SystemState *s, Swap &sw)
 
 static int halo_forward_x(b200md_ctx *c, SystemState *s)
 {
+  s->p2p.epoch[0]++;    // one epoch per halo call, whichever dimensions take the peer path
   for (int dim = 0; dim < 3; dim++) {
     const DimSwaps d = dim_swaps(s, dim);
     if (!d.paired) {
@@ -1139,6 +1380,35 @@ static int halo_forward_x(b200md_ctx *c, SystemState *s)
     }
     // -d and +d swaps scan the same atoms (CommBrick::borders updates its window every second swap): independent
     Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    if (s->p2p.ok) {
+      SystemState::PeerHalo &P = s->p2p;
+      const int ep = P.epoch[0];
+      PushDesc pd;
+      const Swap *sw2[2] = {&a, &b};
+      for (int w = 0; w < 2; w++) {
+        const size_t slot = p2p_slot(0, dim, w, ep);
+        pd.list[w] = sw2[w]->sendlist.p;
+        pd.n[w] = sw2[w]->nsend;
+        pd.first[w] = 0;
+        pd.dst[w] = P.pwin[sw2[w]->sendproc] + slot * P.slot_cap;
+        pd.flag[w] = P.pflag[sw2[w]->sendproc] + slot;
+        for (int k = 0; k < 3; k++) pd.shift[w][k] = sw2[w]->fshift[k];
+        pd.pbc[w] = sw2[w]->pbc_flag;
+      }
+      {
+        LaunchScope ls(c, "p2p_push_x");
+        k_p2p_push_x<<<max(1, nblk(a.nsend + b.nsend)), BLOCK, 0, c->stream>>>(c->xq.p, pd, ep, P.done);
+      }
+      {
+        LaunchScope ls(c, "p2p_unpack_x");
+        const size_t s0 = p2p_slot(0, dim, 0, ep), s1 = p2p_slot(0, dim, 1, ep);
+        k_p2p_unpack_x<<<max(1, nblk(a.nrecv + b.nrecv)), BLOCK, 0, c->stream>>>(
+            c->xq.p, P.win + s0 * P.slot_cap, a.firstrecv, a.nrecv, P.flag + s0, P.win + s1 * P.slot_cap, b.firstrecv,
+            b.nrecv, P.flag + s1, ep);
+      }
+      c->n_p2p++;
+      continue;
+    }
     const size_t sa = 3 * (size_t) a.nsend, sb = 3 * (size_t) b.nsend, ra = 3 * (size_t) a.nrecv, rb = 3 * (size_t) b.nrecv;
     CUDA_TRY(c, s->sendbuf.reserve(sa + sb + 16));
     CUDA_TRY(c, s->recvbuf.reserve(ra + rb + 16));
@@ -1196,6 +1466,7 @@ static int forward_rho_fp_one(b200md_ctx *c, SystemState *s, Swap &sw)
 
 static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
 {
+  s->p2p.epoch[1]++;
   for (int dim = 0; dim < 3; dim++) {
     const DimSwaps d = dim_swaps(s, dim);
     if (!d.paired) {
@@ -1206,6 +1477,34 @@ static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
       continue;
     }
     Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    if (s->p2p.ok) {
+      SystemState::PeerHalo &P = s->p2p;
+      const int ep = P.epoch[1];
+      PushDesc pd;
+      const Swap *sw2[2] = {&a, &b};
+      for (int w = 0; w < 2; w++) {
+        const size_t slot = p2p_slot(1, dim, w, ep);
+        pd.list[w] = sw2[w]->sendlist.p;
+        pd.n[w] = sw2[w]->nsend;
+        pd.first[w] = 0;
+        pd.dst[w] = P.pwin[sw2[w]->sendproc] + slot * P.slot_cap;
+        pd.flag[w] = P.pflag[sw2[w]->sendproc] + slot;
+        for (int k = 0; k < 3; k++) pd.shift[w][k] = 0.0;
+        pd.pbc[w] = 0;
+      }
+      {
+        LaunchScope ls(c, "p2p_push_fp");
+        k_p2p_push_s2<<<max(1, nblk(a.nsend + b.nsend)), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, pd, ep, P.done + 1);
+      }
+      {
+        LaunchScope ls(c, "p2p_unpack_fp");
+        const size_t s0 = p2p_slot(1, dim, 0, ep), s1 = p2p_slot(1, dim, 1, ep);
+        k_p2p_unpack_s2<<<max(1, nblk(a.nrecv + b.nrecv)), BLOCK, 0, c->stream>>>(
+            c->rho.p, c->fp.p, P.win + s0 * P.slot_cap, a.firstrecv, a.nrecv, P.flag + s0, P.win + s1 * P.slot_cap,
+            b.firstrecv, b.nrecv, P.flag + s1, ep);
+      }
+      continue;
+    }
     const size_t sa = 2 * (size_t) a.nsend, sb = 2 * (size_t) b.nsend, ra = 2 * (size_t) a.nrecv, rb = 2 * (size_t) b.nrecv;
     CUDA_TRY(c, s->sendbuf.reserve(sa + sb + 16));
     CUDA_TRY(c, s->recvbuf.reserve(ra + rb + 16));
@@ -1257,6 +1556,7 @@ static int reverse_f_one(b200md_ctx *c, SystemState *s, Swap &sw)
 
 static int halo_reverse_f(b200md_ctx *c, SystemState *s)
 {
+  s->p2p.epoch[2]++;
   for (int dim = 2; dim >= 0; dim--) {
     const DimSwaps d = dim_swaps(s, dim);
     if (!d.paired) {
@@ -1269,6 +1569,35 @@ static int halo_reverse_f(b200md_ctx *c, SystemState *s)
     // the +d swap is folded first, then the -d swap, as in the sequential order; their ghost ranges are disjoint and
     // neither send list contains the other's ghosts, so both transfers travel in one group
     Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+    if (s->p2p.ok) {
+      SystemState::PeerHalo &P = s->p2p;
+      const int ep = P.epoch[2];
+      PushDesc pd;
+      const Swap *sw2[2] = {&a, &b};
+      for (int w = 0; w < 2; w++) {
+        // my ghosts of swap (dim, w) came from recvproc; their forces go back into ITS slot (dim, w)
+        const size_t slot = p2p_slot(2, dim, w, ep);
+        pd.list[w] = nullptr;
+        pd.n[w] = sw2[w]->nrecv;
+        pd.first[w] = sw2[w]->firstrecv;
+        pd.dst[w] = P.pwin[sw2[w]->recvproc] + slot * P.slot_cap;
+        pd.flag[w] = P.pflag[sw2[w]->recvproc] + slot;
+        for (int k = 0; k < 3; k++) pd.shift[w][k] = 0.0;
+        pd.pbc[w] = 0;
+      }
+      {
+        LaunchScope ls(c, "p2p_push_f");
+        k_p2p_push_f<<<max(1, nblk(3 * (long long) (a.nrecv + b.nrecv))), BLOCK, 0, c->stream>>>(c->f.p, pd, ep, P.done + 2);
+      }
+      // fold +d first, then -d, in two launches: an atom may sit in both send lists
+      for (int w = 1; w >= 0; w--) {
+        LaunchScope ls(c, "p2p_unpack_f");
+        const size_t slot = p2p_slot(2, dim, w, ep);
+        k_p2p_unpack_f<<<max(1, nblk(sw2[w]->nsend)), BLOCK, 0, c->stream>>>(c->f.p, sw2[w]->sendlist.p, sw2[w]->nsend,
+                                                                           P.win + slot * P.slot_cap, P.flag + slot, ep);
+      }
+      continue;
+    }
     const size_t sa = 3 * (size_t) a.nsend, sb = 3 * (size_t) b.nsend;
     CUDA_TRY(c, s->recvbuf.reserve(sa + sb + 16));
     const Xfer x[2] = {{c->f.p + 3 * (size_t) b.firstrecv, 3 * (size_t) b.nrecv, b.recvproc, s->recvbuf.p + sa, sb, b.sendproc},
@@ -1529,6 +1858,7 @@ void b200md_system_free(b200md_ctx *c)
   s->v.release(); s->xhold.release(); s->xt.release(); s->dmass.release(); s->itmp.release(); s->itmp2.release();
   s->x4tmp.release(); s->dtmp.release(); s->scan64.release(); s->sendbuf.release(); s->recvbuf.release();
   s->xbuf.release();
+  p2p_release(s);
   if (s->nccl) ncclCommDestroy(s->nccl);
   delete s;
   c->sys = nullptr;
@@ -1566,6 +1896,7 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
     old->itmp2.release(); old->x4tmp.release(); old->dtmp.release(); old->scan64.release(); old->sendbuf.release();
     old->recvbuf.release();
     old->xbuf.release();
+    p2p_release(old);
     delete old;
     c->sys = nullptr;
   }

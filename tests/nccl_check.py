@@ -56,6 +56,7 @@ def main():
         launch.join_system(ctx, grp)
         system(ctx, launch.my_atoms(w, grid, grp.rank) if grp.world > 1 else slice(None), grid, grp.rank)
         ctx.system_run(steps, 10)
+        p2p = ctx.counter("p2p_exchanges")
         sz = ctx.system_sizes()
         nl_sum = int(grp.reduce_scalar(sz["nlocal"], "sum"))
         moved = int(grp.reduce_scalar(sz["nmigrated"], "sum"))
@@ -72,9 +73,10 @@ def main():
             e0, e1 = rows[0]["pe"] + rows[0]["ke"], rows[-1]["pe"] + rows[-1]["ke"]
             good = (nl_sum == len(w["x"]) and sz["natoms"] == len(w["x"]) and moved > 0 and worst < 1e-9
                     and sz["nbuild"] == one.system_sizes()["nbuild"] and abs(e1 - e0) < 1e-3 * abs(rows[0]["ke"] + 1.0))
-            print("NCCL_CHECK %s ranks %d grid %s atoms %d migrated %d builds %d/%d worst_rel %.2e drift %.3e %s"
+            print("NCCL_CHECK %s ranks %d grid %s atoms %d migrated %d builds %d/%d worst_rel %.2e drift %.3e "
+                  "peer-memory exchanges %d %s"
                   % (style, grp.world, grid, len(w["x"]), moved, sz["nbuild"], one.system_sizes()["nbuild"], worst,
-                     e1 - e0, "OK" if good else "FAIL"), flush=True)
+                     e1 - e0, p2p, "OK" if good else "FAIL"), flush=True)
             ok = ok and good
             one.close()
         grp.barrier()

@@ -142,6 +142,8 @@ int b200md_neigh_download(b200md_ctx *ctx, int *numneigh, int64_t *offsets, int 
 /* ---- REBOMoS compute (host buffers in, host buffers out) ------------------
  * f is ACCUMULATED into (like atom->f after force_clear()); eng_vdwl and
  * virial[6] are overwritten with this call's contribution (caller adds).
+ * type[] and tag[] are read on the first call after a neighbor-list hand-over (b200md_set_neighbor_* or
+ * b200md_neigh_build) and kept on the device until the next one; x[] is read every call.
  * Forces are complete after LAMMPS' reverse_comm; the split of a pair's force
  * between an owner and its ghost image differs from the reference. */
 int b200md_rebomos_compute(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
@@ -231,6 +233,10 @@ int b200md_system_comm_init(b200md_ctx *ctx, const void *id128, int nranks, int 
  * b200md_local_group_create returns a group id > 0 (negative B200MD_ERR_* on failure).             */
 int b200md_local_group_create(int nranks);
 int b200md_system_comm_init_local(b200md_ctx *ctx, int group, int nranks, int rank);
+/* host-only helper (no device needed): the order in which CommBrick::exchange packs leaving atoms and fills the
+ * holes, replayed on indices -- what makes per-rank atom order equal to LAMMPS' after migration.  leavers[]
+ * ascending; order[nleave]; moves[2*nleave] receives (dst, src) pairs; returns 0 or B200MD_ERR_ARG. */
+int b200md_exchange_plan(int n, const int *leavers, int nleave, int *order, int *moves, int *nmoves, int *nlocal_out);
 /* advance n NVE steps entirely on the device; thermo quantities are evaluated on the last step
  * (and every thermo_every steps, retrievable with b200md_system_thermo) */
 int b200md_system_run(b200md_ctx *ctx, int nsteps, int thermo_every);

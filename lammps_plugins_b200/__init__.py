@@ -123,6 +123,7 @@ SYMBOLS = [
     ("b200md_system_comm_init", c_int, [c_void_p, c_void_p, c_int, c_int]),
     ("b200md_local_group_create", c_int, [c_int]),
     ("b200md_system_comm_init_local", c_int, [c_void_p, c_int, c_int, c_int]),
+    ("b200md_exchange_plan", c_int, [c_int, _PI, c_int, _PI, _PI, _PI, _PI]),
     ("b200md_system_run", c_int, [c_void_p, c_int, c_int]),
     ("b200md_system_thermo", c_int, [c_void_p, _PD]),
     ("b200md_system_thermo_count", c_int, [c_void_p]),

@@ -164,6 +164,7 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->ntypes = nel;
   c->aeam_ready = true;
+  c->type_on_device = c->tag_on_device = false;
   c->rebomos_ready = false;
   c->inner_valid = false;
   return B200MD_OK;

@@ -160,6 +160,8 @@ struct b200md_ctx {
 
   // ---- atoms (device)
   int nlocal = 0, nghost = 0, nall = 0;
+  bool type_on_device = false, tag_on_device = false;    // host type/tag arrays already uploaded for this list
+  int ids_nall = -1;
   DevBuf<double> x_aos;      // [nall*3] staging of host x
   DevBuf<double4> xq;        // packed {x,y,z,elem-as-double}
   DevBuf<double> f;          // [nall*3]

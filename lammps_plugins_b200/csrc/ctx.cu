@@ -326,13 +326,23 @@ int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, 
   CUDA_TRY(c, c->f.reserve(3 * n + 8));
   CUDA_TRY(c, c->type.reserve(n + 8));
   CUDA_TRY(c, c->tag.reserve(n + 8));
+  // types and IDs only change when the host re-sorts or migrates atoms, i.e. together with its neighbor list:
+  // they travel once per list hand-over (b200md_set_neighbor_* / b200md_neigh_build reset the marks), positions
+  // every call
+  if (nall != c->ids_nall) c->type_on_device = c->tag_on_device = false;
+  c->ids_nall = nall;
   if (n) {
     CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->type.p, type, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += (long long) (3 * n * sizeof(double) + n * sizeof(int));
-    if (tag) {
+    c->h2d_bytes += (long long) (3 * n * sizeof(double));
+    if (!c->type_on_device) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->type.p, type, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      c->h2d_bytes += (long long) (n * sizeof(int));
+      c->type_on_device = true;
+    }
+    if (tag && !c->tag_on_device) {
       CUDA_TRY(c, cudaMemcpyAsync(c->tag.p, tag, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
       c->h2d_bytes += (long long) (n * sizeof(int));
+      c->tag_on_device = true;
     }
   }
   return B200MD_OK;
@@ -454,6 +464,7 @@ static int finish_list(b200md_ctx *c, int inum, int gnum, int64_t total, double 
   c->skin = skin;
   c->list_valid = true;
   c->inner_valid = false;
+  c->type_on_device = c->tag_on_device = false;
   c->n_list_upload++;
   return B200MD_OK;
 }

@@ -399,6 +399,7 @@ extern "C" int b200md_neigh_build(b200md_ctx *c, const b200md_box *box, int ntyp
             "neigh_build: bad arguments");
   ARG_CHECK(c, box->cutneighmax > 0.0, "neigh_build: cutneighmax must be > 0");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  c->type_on_device = c->tag_on_device = false;    // a new list means the host may have re-sorted its atoms
   int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, nullptr);
   if (rc) return rc;
   NeighScratch &S = g_scratch[c];

@@ -821,6 +821,7 @@ extern "C" int b200md_rebomos_init(b200md_ctx *c, const b200md_rebomos_params *p
                               c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->rebomos_ready = true;
+  c->type_on_device = c->tag_on_device = false;
   c->aeam_ready = false;
   c->inner_valid = false;
   return B200MD_OK;

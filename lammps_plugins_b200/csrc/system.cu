@@ -1617,6 +1617,37 @@ static int halo_reverse_f(b200md_ctx *c, SystemState *s)
   return B200MD_OK;
 }
 
+// Replay of CommBrick::exchange's compaction loop on indices alone (host, no CUDA):
+//   while (i < nlocal) { if (leaves(i)) { pack(i); copy(nlocal-1 -> i); nlocal--; } else i++; }
+// `leavers` ascending.  order[k] = k-th atom packed; moves = (dst, src) pairs of the copies that survive;
+// every leaver is packed exactly once, so order has nleave entries.
+extern "C" int b200md_exchange_plan(int n, const int *leavers, int nleave, int *order, int *moves, int *nmoves,
+                                    int *nlocal_out)
+{
+  if (n < 0 || nleave < 0 || nleave > n || (nleave && (!leavers || !order || !moves)) || !nmoves || !nlocal_out)
+    return B200MD_ERR_ARG;
+  std::unordered_set<int> L(leavers, leavers + nleave);
+  int nl = n, no = 0, nm = 0, li = 0;
+  while (li < nleave && leavers[li] < nl) {
+    const int i = leavers[li++];
+    order[no++] = i;
+    for (;;) {
+      nl--;
+      if (nl == i) break;
+      if (L.count(nl)) order[no++] = nl;
+      else {
+        moves[2 * nm] = i;
+        moves[2 * nm + 1] = nl;
+        nm++;
+        break;
+      }
+    }
+  }
+  *nmoves = nm;
+  *nlocal_out = nl;
+  return no == nleave ? B200MD_OK : B200MD_ERR_ARG;
+}
+
 // ------------------------------------------------------------------ CommBrick::exchange
 // Owned atoms that left the sub-box move to the neighbor rank, dimension by dimension.  The reference loop
 // (comm_brick.cpp exchange(): "when atom is deleted, fill it in with last atom") fixes BOTH the order of the
@@ -1653,26 +1684,10 @@ static int migrate(b200md_ctx *c, SystemState *s)
       }
     }
     // replay of the reference loop on indices: emission order + (hole <- tail stayer) moves
-    std::vector<int> order, moves;
-    int nl = n;
-    {
-      std::unordered_set<int> L(leavers.begin(), leavers.end());
-      size_t li = 0;
-      while (li < leavers.size() && leavers[li] < nl) {
-        const int i = leavers[li++];
-        order.push_back(i);
-        for (;;) {
-          nl--;
-          if (nl == i) break;
-          if (L.count(nl)) order.push_back(nl);
-          else {
-            moves.push_back(i);
-            moves.push_back(nl);
-            break;
-          }
-        }
-      }
-    }
+    std::vector<int> order(leavers.size()), moves(2 * leavers.size() + 2);
+    int nl = n, nmoves = 0;
+    b200md_exchange_plan(n, leavers.data(), (int) leavers.size(), order.data(), moves.data(), &nmoves, &nl);
+    moves.resize(2 * (size_t) nmoves);
     const int nsend = (int) order.size();
     CUDA_TRY(c, s->xbuf.reserve(8 * (size_t) nsend + 8));
     if (nsend) {

@@ -140,3 +140,32 @@ def test_two_level_list_refresh_matches_single_level(ctx, oracle_built, style):
         assert abs(q["press"] - g["press"]) < 1e-8 * max(abs(g["press"]), 1.0)
     assert S.rel_err(db["f"][:db["nlocal"]], da["f"][:da["nlocal"]]) < 1e-9
     lmp.close()
+
+
+def test_energy_drift_1000_nve_steps_matches_reference(ctx, oracle_built):
+    """north star: "energy drift over 1000 NVE steps matching the reference's".  The shipped 288-atom cell at 300 K,
+    dt = 1 fs, 1000 steps on the device and in the engine with the reference plugin.  Early on the two runs are the same
+    trajectory (thermo equal to 1e-9); over the whole run the total-energy excursion and the end-to-end drift of the
+    device run equal the reference's (same integrator error, no extra energy source or sink)."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), extra=["velocity all create 300.0 4928459"])
+    ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    start_system(ctx, lmp, "rebomos")
+    ctx.system_run(1000, 50)
+    rows = ctx.system_thermo_rows()
+    lmp.commands(["thermo 50", "fix 1 all nve", "run 1000"])
+    ref = lmp.thermo()
+    assert [r["step"] for r in rows] == [g["step"] for g in ref] and len(rows) == 21
+    et = np.array([r["pe"] + r["ke"] for r in rows])
+    er = np.array([g["pe"] + g["ke"] for g in ref])
+    ke_scale = max(g["ke"] for g in ref)
+    for r, g in zip(rows[:5], ref[:5]):          # first 200 steps: same trajectory
+        assert abs(r["pe"] - g["pe"]) < 1e-9 * abs(g["pe"]) and abs(r["ke"] - g["ke"]) < 1e-7 * ke_scale
+    exc_t, exc_r = np.abs(et - et[0]).max(), np.abs(er - er[0]).max()
+    drift_t, drift_r = et[-1] - et[0], er[-1] - er[0]
+    print("max excursion  device %.3e  reference %.3e eV;  end-to-end drift  device %.3e  reference %.3e eV;  KE %.3f eV"
+          % (exc_t, exc_r, drift_t, drift_r, ke_scale))
+    assert exc_r < 1e-2 * ke_scale                      # the reference itself: 0.5 % of KE at dt = 1 fs (measured 5.3e-2 eV)
+    assert abs(exc_t - exc_r) < 0.05 * exc_r + 1e-9
+    assert abs(drift_t - drift_r) < 0.05 * exc_r + 1e-9
+    assert np.abs(et - er).max() < 0.05 * exc_r + 1e-9  # the whole E_tot(t) curve lies on the reference's
+    lmp.close()

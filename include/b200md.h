@@ -150,6 +150,14 @@ int b200md_rebomos_compute(b200md_ctx *ctx, int nlocal, int nghost, const double
                            const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
                            double *virial);
 
+/* same, plus per-atom energy eatom[nlocal+nghost] and per-atom virial vatom[(nlocal+nghost)*6] (xx,yy,zz,xy,xz,yz),
+ * both ACCUMULATED into like Pair::eatom / Pair::vatom; either may be NULL.  Distribution follows the reference's
+ * tallies: ev_tally halves (pair_rebomos.cpp:444,554), v_tally3 thirds (:710), v_tally2 halves (:725).  Ghost entries
+ * carry the share of ghost atoms (LAMMPS reverse-communicates them in compute pe/atom, stress/atom). */
+int b200md_rebomos_compute_peratom(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                                   const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
+                                   double *virial, double *eatom, double *vatom);
+
 /* REBO short-range sub-list for owned AND ghost atoms from the current list and
  * positions: numneigh[nall], rows packed with stride `stride`, nM[nall], nS[nall] */
 int b200md_rebomos_neigh(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
@@ -171,6 +179,14 @@ int b200md_aeam_density_phase(b200md_ctx *ctx, int nlocal, int nghost, const dou
                               double *rho, double *fp);
 int b200md_aeam_force_phase(b200md_ctx *ctx, const double *rho_all, const double *fp_all, int eflag,
                             int vflag, double *f, double *eng_vdwl, double *virial);
+/* per-atom variants (Pair::eatom / Pair::vatom, accumulated into; either may be NULL): embedding energy F to the atom
+ * (F/3 for angular atoms, pair_aeam.cpp:295-300), phi/2 of visit (i,j) to i (:389), ev_tally halves (:393), ev_tally3
+ * thirds (:472).  In the two-phase form set option "peratom" = 1 BEFORE the density phase. */
+int b200md_aeam_compute_peratom(b200md_ctx *ctx, int nlocal, int nghost, const double *x, const int *type,
+                                const int *tag, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
+                                double *eatom, double *vatom);
+int b200md_aeam_force_phase_peratom(b200md_ctx *ctx, const double *rho_all, const double *fp_all, int eflag, int vflag,
+                                    double *f, double *eng_vdwl, double *virial, double *eatom, double *vatom);
 /* rho[nlocal], fp[nlocal] of the last compute */
 int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
 
@@ -179,7 +195,7 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  * destination in a fixed order instead of FP64 atomics -- forces are then bitwise reproducible run to run), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
  * "p2p_halo" (0/1, default 1: multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the sender packs
  * straight into the receiver's HBM over NVLink -- falling back to NCCL send/recv when IPC is unavailable),
- * "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
+ * "peratom" (0/1, AEAM two-phase API only), "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
  * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",

@@ -102,10 +102,13 @@ SYMBOLS = [
     ("b200md_neigh_size", c_int, [c_void_p, _PI, _PL]),
     ("b200md_neigh_download", c_int, [c_void_p, _PI, _PL, _PI]),
     ("b200md_rebomos_compute", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD]),
+    ("b200md_rebomos_compute_peratom", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD, _PD, _PD]),
     ("b200md_rebomos_neigh", c_int, [c_void_p, c_int, c_int, _PD, _PI, c_int, _PI, _PI, _PD, _PD]),
     ("b200md_aeam_compute", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD]),
     ("b200md_aeam_density_phase", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PD, _PD]),
     ("b200md_aeam_force_phase", c_int, [c_void_p, _PD, _PD, c_int, c_int, _PD, _PD, _PD]),
+    ("b200md_aeam_compute_peratom", c_int, [c_void_p, c_int, c_int, _PD, _PI, _PI, c_int, c_int, _PD, _PD, _PD, _PD, _PD]),
+    ("b200md_aeam_force_phase_peratom", c_int, [c_void_p, _PD, _PD, c_int, c_int, _PD, _PD, _PD, _PD, _PD]),
     ("b200md_aeam_get_rho_fp", c_int, [c_void_p, c_int, _PD, _PD]),
     ("b200md_set_option", c_int, [c_void_p, c_char_p, c_longlong]),
     ("b200md_get_counter", c_longlong, [c_void_p, c_char_p]),
@@ -309,6 +312,19 @@ class Context:
                                                   _dp(f), ctypes.byref(eng), _dp(vir)))
         return f, eng.value, vir
 
+    def rebomos_compute_peratom(self, nlocal, nghost, x, type_, tag, eflag=3, vflag=6):
+        """returns f, eng, virial, eatom[nall], vatom[nall, 6]"""
+        nall = nlocal + nghost
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
+        f, ea, va = np.zeros((nall, 3)), np.zeros(nall), np.zeros((nall, 6))
+        eng = c_double()
+        vir = np.zeros(6)
+        self._check(self.L.b200md_rebomos_compute_peratom(self.h, nlocal, nghost, _dp(x), _ip(type_), _ip(tag), eflag,
+                                                          vflag, _dp(f), ctypes.byref(eng), _dp(vir), _dp(ea), _dp(va)))
+        return f, eng.value, vir, ea, va
+
     def rebomos_neigh(self, nlocal, nghost, x, type_, stride=32):
         nall = nlocal + nghost
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -333,6 +349,19 @@ class Context:
         self._check(self.L.b200md_aeam_compute(self.h, nlocal, nghost, _dp(x), _ip(type_), _ip(tag), eflag, vflag,
                                                _dp(f), ctypes.byref(eng), _dp(vir)))
         return f, eng.value, vir
+
+    def aeam_compute_peratom(self, nlocal, nghost, x, type_, tag, eflag=3, vflag=6):
+        """returns f, eng, virial, eatom[nall], vatom[nall, 6]"""
+        nall = nlocal + nghost
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        tag = np.ascontiguousarray(tag, dtype=np.int32)
+        f, ea, va = np.zeros((nall, 3)), np.zeros(nall), np.zeros((nall, 6))
+        eng = c_double()
+        vir = np.zeros(6)
+        self._check(self.L.b200md_aeam_compute_peratom(self.h, nlocal, nghost, _dp(x), _ip(type_), _ip(tag), eflag, vflag,
+                                                       _dp(f), ctypes.byref(eng), _dp(vir), _dp(ea), _dp(va)))
+        return f, eng.value, vir, ea, va
 
     def aeam_density_phase(self, nlocal, nghost, x, type_):
         x = np.ascontiguousarray(x, dtype=np.float64)

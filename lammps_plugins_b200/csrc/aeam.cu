@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_embed_kernel(const __grid_constant
                                                            const double4 *__restrict__ xq,
                                                            const double4 *__restrict__ frho,
                                                            const double *__restrict__ rho, int inum,
-                                                           double *__restrict__ fp, double *__restrict__ scal)
+                                                           double *__restrict__ fp, double *__restrict__ scal,
+                                                           double *__restrict__ pa_e)
 {
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   double e[1] = {0.0};
@@ -449,6 +450,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_embed_kernel(const __grid_constant
     const double4 cf = frho[par.frho_off[ti] + m];
     fp[i] = spl_der(cf, p, par.rdrho[ti]);
     e[0] = spl_val(cf, p);
+    // pair_aeam.cpp:295-300: an angular atom's own share of its embedding energy is one third
+    if (pa_e) pa_e[i] += (ti < par.nnonangular) ? e[0] : e[0] * (1.0 / 3.0);
   }
   block_accumulate<1, BLOCK>(e, scal);
 }
@@ -492,11 +495,12 @@ __global__ void __launch_bounds__(BLOCK) aeam_gate_kernel(double4 *__restrict__ 
 }
 
 // ================================================================== B1: pair + embedding forces (gather)
-template <bool EV>
+template <bool EV, bool ATOM>
 __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ ptab,
-    int inum, double *__restrict__ f, double *__restrict__ scal)
+    int inum, double *__restrict__ f, double *__restrict__ scal, double *__restrict__ pa_e,
+    double *__restrict__ pa_v)
 {
   __shared__ PairPar sp[16];
   load_pair_par(par, sp);
@@ -504,6 +508,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
   const int i = tid >> 3, sub = tid & 7;
   double fx = 0.0, fy = 0.0, fz = 0.0;
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  double av[6] = {0, 0, 0, 0, 0, 0};    // ATOM: ev_tally halves of visit (i,j) AND of visit (j,i) both land on i
   if (i < inum) {
     const double4 xi = xq[i];
     const int ti = etype(xi);
@@ -575,6 +580,15 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
         fx -= dx * coef;
         fy -= dy * coef;
         fz -= dz * coef;
+        if (ATOM) {
+          const double h = 0.5 * coef;
+          av[0] += dx * dx * h;
+          av[1] += dy * dy * h;
+          av[2] += dz * dz * h;
+          av[3] += dx * dy * h;
+          av[4] += dx * dz * h;
+          av[5] += dy * dz * h;
+        }
       }
     }
   }
@@ -586,16 +600,29 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
     f[3 * (size_t) i + 1] += fy;
     f[3 * (size_t) i + 2] += fz;
   }
+  if (ATOM) {
+    // pair_aeam.cpp:389-393: eatom[i] += phi/2 per visit (i,j); ev_tally(i,j,..,0,0,fpair,del): del (x) del fpair, half
+    // to each end -- as i of its own visits and as j of its neighbors' visits this atom collects (fpair_ij + fpair_ji)/2
+    const double ea = group_sum<8>(ev[0]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) av[k] = group_sum<8>(av[k]);
+    if (i < inum && sub == 0) {
+      pa_e[i] += ea;
+#pragma unroll
+      for (int k = 0; k < 6; k++) pa_v[6 * (size_t) i + k] += av[k];
+    }
+  }
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
 }
 
 // ================================================================== B2: 3-body forces of angular atoms
-template <bool EV>
+template <bool EV, bool ATOM>
 __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
     const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, const double *__restrict__ rho,
-    const double *__restrict__ fp, double *__restrict__ f, double *__restrict__ scal, int *__restrict__ flags)
+    const double *__restrict__ fp, double *__restrict__ f, double *__restrict__ scal, int *__restrict__ flags,
+    double *__restrict__ pa_v)
 {
   __shared__ AngStage stage[4];
   const double minrho = 0.0000000000001;
@@ -647,6 +674,18 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
         atomicAdd(&f[3 * (size_t) k], fk0);
         atomicAdd(&f[3 * (size_t) k + 1], fk1);
         atomicAdd(&f[3 * (size_t) k + 2], fk2);
+        if (ATOM) {    // ev_tally3: thirds to i, j, k
+          const double t[6] = {(d1x * fj0 + d2x * fk0) * (1.0 / 3.0), (d1y * fj1 + d2y * fk1) * (1.0 / 3.0),
+                               (d1z * fj2 + d2z * fk2) * (1.0 / 3.0), (d1x * fj1 + d2x * fk1) * (1.0 / 3.0),
+                               (d1x * fj2 + d2x * fk2) * (1.0 / 3.0), (d1y * fj2 + d2y * fk2) * (1.0 / 3.0)};
+          double *vi = pa_v + 6 * (size_t) i, *vj = pa_v + 6 * (size_t) S.j[p], *vk = pa_v + 6 * (size_t) k;
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            atomicAdd(vi + m, t[m]);
+            atomicAdd(vj + m, t[m]);
+            atomicAdd(vk + m, t[m]);
+          }
+        }
         if (EV) {    // ev_tally3 (delr1, delr2 are x_j - x_i, x_k - x_i)
           v[0] += d1x * fj0 + d2x * fk0;
           v[1] += d1y * fj1 + d2y * fk1;
@@ -789,7 +828,7 @@ int b200md_aeam_density(b200md_ctx *c)
   {
     LaunchScope ls(c, "aeam_embed");
     aeam_embed_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->ap, c->xq.p, (const double4 *) c->spl_frho.p,
-                                                                   c->rho.p, inum, c->fp.p, c->scal.p);
+                                                                   c->rho.p, inum, c->fp.p, c->scal.p, c->pa_e);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
@@ -827,26 +866,23 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
     aeam_gate_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, c->rho.p, c->fp.p, c->ap.nnonangular,
                                                                      c->nall);
   }
+  const bool atom = c->pa_e != nullptr;
   {
     LaunchScope ls(c, "aeam_force");
     const int nb = nblocks((long long) inum * 8, BLOCK);
-    if (ev)
-      aeam_force_kernel<true><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
-                                                          ptab, inum, c->f.p, c->scal.p);
-    else
-      aeam_force_kernel<false><<<nb, BLOCK, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p,
-                                                           ptab, inum, c->f.p, c->scal.p);
+#define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
+    if (atom) aeam_force_kernel<true, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+    else if (ev) aeam_force_kernel<true, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+    else aeam_force_kernel<false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_force_ang");
-    if (ev)
-      aeam_force_ang_kernel<true><<<c->num_sms * 2, 128, 0, c->stream>>>(
-          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p,
-          c->fp.p, c->f.p, c->scal.p, c->flags.p);
-    else
-      aeam_force_ang_kernel<false><<<c->num_sms * 2, 128, 0, c->stream>>>(
-          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p,
-          c->fp.p, c->f.p, c->scal.p, c->flags.p);
+#define AA_ARGS \
+  c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, \
+      c->scal.p, c->flags.p, c->pa_v
+    if (atom) aeam_force_ang_kernel<true, true><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
+    else if (ev) aeam_force_ang_kernel<true, false><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
+    else aeam_force_ang_kernel<false, false><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
@@ -903,18 +939,31 @@ extern "C" int b200md_aeam_compute(b200md_ctx *c, int nlocal, int nghost, const 
                                    const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
                                    double *virial)
 {
+  return b200md_aeam_compute_peratom(c, nlocal, nghost, x, type, tag, eflag, vflag, f, eng_vdwl, virial, nullptr, nullptr);
+}
+
+extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
+                                           const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
+                                           double *virial, double *eatom, double *vatom)
+{
   if (!c) return B200MD_ERR_ARG;
   ARG_CHECK(c, f != nullptr, "aeam_compute: f is NULL");
   ARG_CHECK(c, tag != nullptr || nghost == 0, "aeam_compute: atom IDs are needed to give ghosts their fp");
   int rc = aeam_begin(c, nlocal, nghost, x, type, tag);
   if (rc) return rc;
-  if ((rc = b200md_aeam_density(c))) return rc;
-  if (nghost) {
+  if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
+  rc = b200md_aeam_density(c);
+  if (!rc && nghost) {
     int maxtag = 0;
     for (int i = 0; i < nlocal; i++) maxtag = tag[i] > maxtag ? tag[i] : maxtag;
-    if ((rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag))) return rc;
+    rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag);
   }
-  if ((rc = b200md_aeam_forces(c, eflag, vflag))) return rc;
+  if (!rc) rc = b200md_aeam_forces(c, eflag, vflag);
+  if (rc) {
+    c->pa_e = c->pa_v = nullptr;
+    return rc;
+  }
+  if ((rc = b200md_peratom_finish(c, eatom, vatom))) return rc;
   return aeam_finish(c, eflag, vflag, f, eng_vdwl, virial);
 }
 
@@ -925,6 +974,8 @@ extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, 
   if (!c) return B200MD_ERR_ARG;
   int rc = aeam_begin(c, nlocal, nghost, x, type, nullptr);
   if (rc) return rc;
+  // option "peratom": the embedding energy of this phase is tallied per atom and handed out by the force phase
+  if ((rc = b200md_peratom_begin(c, c->peratom_opt != 0))) return rc;
   if ((rc = b200md_aeam_density(c))) return rc;
   if (nlocal) {
     if (rho_out) CUDA_TRY(c, cudaMemcpyAsync(rho_out, c->rho.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -940,8 +991,17 @@ extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, 
 extern "C" int b200md_aeam_force_phase(b200md_ctx *c, const double *rho_all, const double *fp_all, int eflag,
                                        int vflag, double *f, double *eng_vdwl, double *virial)
 {
+  return b200md_aeam_force_phase_peratom(c, rho_all, fp_all, eflag, vflag, f, eng_vdwl, virial, nullptr, nullptr);
+}
+
+extern "C" int b200md_aeam_force_phase_peratom(b200md_ctx *c, const double *rho_all, const double *fp_all, int eflag,
+                                               int vflag, double *f, double *eng_vdwl, double *virial, double *eatom,
+                                               double *vatom)
+{
   if (!c) return B200MD_ERR_ARG;
   ARG_CHECK(c, c->aeam_ready && c->inner_valid && f && rho_all && fp_all, "aeam_force_phase: call the density phase first");
+  ARG_CHECK(c, !(eatom || vatom) || c->pa_e,
+            "aeam_force_phase: per-atom output needs option \"peratom\" = 1 before the density phase");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int ng = c->nghost;
   if (ng) {
@@ -951,7 +1011,11 @@ extern "C" int b200md_aeam_force_phase(b200md_ctx *c, const double *rho_all, con
     c->h2d_bytes += 2LL * ng * sizeof(double);
   }
   int rc = b200md_aeam_forces(c, eflag, vflag);
-  if (rc) return rc;
+  if (rc) {
+    c->pa_e = c->pa_v = nullptr;
+    return rc;
+  }
+  if ((rc = b200md_peratom_finish(c, eatom, vatom))) return rc;
   return aeam_finish(c, eflag, vflag, f, eng_vdwl, virial);
 }
 

@@ -144,6 +144,7 @@ struct b200md_ctx {
   double margin_opt = 0.0;    // 0 -> use skin
   int sync_timing = 0;
   int f_overwrite = 0;
+  int peratom_opt = 0;    // AEAM two-phase API: tally per-atom energy/virial from the density phase on
   int p2p_halo = 1;    // multi-GPU halo through peer memory (CUDA IPC) when available; 0 = NCCL send/recv only
   long long n_p2p = 0;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -168,6 +169,9 @@ struct b200md_ctx {
   DevBuf<int> type, tag;
   PinBuf<double> pin_f;      // D2H staging
   PinBuf<double> pin_scal;   // small scalar results
+  DevBuf<double> eatom_d, vatom_d;    // per-atom energy [nall] / virial [nall*6] of one call (on request)
+  double *pa_e = nullptr, *pa_v = nullptr;    // non-null while a per-atom call is in flight
+  PinBuf<double> pin_pa;
   DevBuf<double> scal;       // [64] device accumulators: 0 = energy, 1..6 virial, 8.. misc
   DevBuf<int> flags;         // [16] device flags: 0 = overflow, 1 = inner rebuild needed, 2.. counters
 
@@ -336,6 +340,8 @@ __device__ __forceinline__ int ld_stream_int(const int *p)
 #endif
 
 // shared internal entry points
+int b200md_peratom_begin(b200md_ctx *c, bool wanted);                      // zeroed device arrays, sets pa_e / pa_v
+int b200md_peratom_finish(b200md_ctx *c, double *eatom, double *vatom);    // D2H + accumulate into the host arrays
 int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
                         const int *tag);
 int b200md_exclusive_scan_i64(b200md_ctx *c, const int *in, int64_t *out, int n, int align);

@@ -81,7 +81,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   cudaStreamSynchronize(c->stream);
   b200md_system_free(c);
   c->x_aos.release(); c->xq.release(); c->f.release(); c->type.release(); c->tag.release();
-  c->pin_f.release(); c->pin_scal.release(); c->scal.release(); c->flags.release();
+  c->pin_f.release(); c->pin_scal.release(); c->pin_pa.release(); c->eatom_d.release(); c->vatom_d.release(); c->scal.release(); c->flags.release();
   c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release();
@@ -112,6 +112,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->inner_valid = false;
   } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
+  else if (n == "peratom") c->peratom_opt = value ? 1 : 0;
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
   else {
     c->fail("unknown option " + n);
@@ -290,6 +291,41 @@ int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double
   if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
   if (virial)
     for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
+  return B200MD_OK;
+}
+
+// per-atom energy / virial of one compute call (Pair::eatom, Pair::vatom: accumulated into, like f)
+int b200md_peratom_begin(b200md_ctx *c, bool wanted)
+{
+  c->pa_e = c->pa_v = nullptr;
+  if (!wanted) return B200MD_OK;
+  const size_t n = (size_t) c->nall;
+  CUDA_TRY(c, c->eatom_d.reserve(n + 8));
+  CUDA_TRY(c, c->vatom_d.reserve(6 * n + 8));
+  CUDA_TRY(c, cudaMemsetAsync(c->eatom_d.p, 0, (n + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->vatom_d.p, 0, (6 * n + 8) * sizeof(double), c->stream));
+  c->pa_e = c->eatom_d.p;
+  c->pa_v = c->vatom_d.p;
+  return B200MD_OK;
+}
+
+int b200md_peratom_finish(b200md_ctx *c, double *eatom, double *vatom)
+{
+  if (!c->pa_e) return B200MD_OK;
+  const size_t n = (size_t) c->nall;
+  c->pa_e = c->pa_v = nullptr;
+  CUDA_TRY(c, c->pin_pa.reserve(7 * n + 8));
+  if (eatom && n) CUDA_TRY(c, cudaMemcpyAsync(c->pin_pa.p, c->eatom_d.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (vatom && n) CUDA_TRY(c, cudaMemcpyAsync(c->pin_pa.p + n, c->vatom_d.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (eatom) {
+    for (size_t k = 0; k < n; k++) eatom[k] += c->pin_pa.p[k];
+    c->d2h_bytes += (long long) (n * sizeof(double));
+  }
+  if (vatom) {
+    for (size_t k = 0; k < 6 * n; k++) vatom[k] += c->pin_pa.p[n + k];
+    c->d2h_bytes += (long long) (6 * n * sizeof(double));
+  }
   return B200MD_OK;
 }
 

@@ -324,12 +324,12 @@ __device__ __forceinline__ int tri_index(int m, int q)
   return (hi * (hi - 1)) / 2 + lo;
 }
 
-template <int NT, int G, int CAP, int ELEM, bool EV, bool DET>
+template <int NT, int G, int CAP, int ELEM, bool EV, bool DET, bool ATOM>
 __global__ void __launch_bounds__(NT) rebo_center_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int *__restrict__ short_idx,
     const int *__restrict__ short_num, const int *__restrict__ cen_list, const int *__restrict__ cen_count_ptr,
     int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
-    double *__restrict__ scal, int *__restrict__ flags)
+    double *__restrict__ scal, int *__restrict__ flags, double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
   constexpr int NG = NT / G;    // groups per block
   constexpr int NTRI = CAP * (CAP - 1) / 2;
@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
     }
     __syncwarp(gmask);
     // ---- B: bond order and pair terms of bond m
+    double ei_atom = 0.0;
     for (int m = sub; m < nb; m += G) {
       const double rinv = s_ri[sb + m];
       const double wm = s_w[sb + m], dwm = s_dw[sb + m];
@@ -461,6 +462,13 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
         pref = VA * 0.5 * (-0.5 * p * p * p);
         frad = 0.5 * (dVR + p * dVA) * rinv + pref * dP * dwm * rinv;
         if (EV) eacc[0] += 0.5 * (VR + p * VA);
+        if (ATOM) {
+          // ev_tally (pair_rebomos.cpp:443-444): the half-bond energy VR + bbar*VA goes half to i, half to j;
+          // bbar = (p_ij + p_ji)/2, so each DIRECTED piece (VR + p_ij VA)/2 is split the same way
+          const double q4 = 0.25 * (VR + p * VA);
+          ei_atom += q4;
+          atomicAdd(&pa_e[s_j[sb + m]], q4);
+        }
       }
       s_pref[sb + m] = pref;
       s_frad[sb + m] = frad;
@@ -468,11 +476,13 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
     __syncwarp(gmask);
     // ---- C: forces
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    double vi[6] = {0, 0, 0, 0, 0, 0};    // ATOM: this lane's share of the center's per-atom virial
     for (int m = sub; m < nb; m += G) {
       const double mx = s_dx[sb + m], my = s_dy[sb + m], mz = s_dz[sb + m], rinvm = s_ri[sb + m];
       const double wm = s_w[sb + m], dwm = s_dw[sb + m], prefm = s_pref[sb + m];
       const double rinvm2 = rinvm * rinvm;
       double fx = 0.0, fy = 0.0, fz = 0.0;
+      double vm[6] = {0, 0, 0, 0, 0, 0};
       for (int q = 0; q < nb; q++) {
         if (q == m) continue;
         const double prefn = s_pref[sb + q];
@@ -484,14 +494,36 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
         const double B = cb * (s_g[t] + dP) * rinvm;
         const double cm = A * c * rinvm2 + B;          // multiplies d_m
         const double cn = -A * (rinvm * s_ri[sb + q]);    // multiplies d_q
-        fx += cm * mx + cn * s_dx[sb + q];
-        fy += cm * my + cn * s_dy[sb + q];
-        fz += cm * mz + cn * s_dz[sb + q];
+        const double qx = cm * mx + cn * s_dx[sb + q], qy = cm * my + cn * s_dy[sb + q], qz = cm * mz + cn * s_dz[sb + q];
+        fx += qx;
+        fy += qy;
+        fz += qz;
+        if (ATOM) {
+          // v_tally3 (pair_rebomos.cpp:707-711): each (bond, k) triplet's r_ji (x) f_j + r_ki (x) f_k goes in thirds
+          // to i, j, k.  (qx,qy,qz) is what bond m receives from its pairing with q -- once as the triplet's j, once
+          // as the other triplet's k -- so (-d_m) (x) q is this lane's part of both; thirds to i, m, q.
+          const double t0 = -mx * qx * (1.0 / 3.0), t1 = -my * qy * (1.0 / 3.0), t2 = -mz * qz * (1.0 / 3.0);
+          const double t3 = -mx * qy * (1.0 / 3.0), t4 = -mx * qz * (1.0 / 3.0), t5 = -my * qz * (1.0 / 3.0);
+          vi[0] += t0; vi[1] += t1; vi[2] += t2; vi[3] += t3; vi[4] += t4; vi[5] += t5;
+          vm[0] += t0; vm[1] += t1; vm[2] += t2; vm[3] += t3; vm[4] += t4; vm[5] += t5;
+          double *vq = pa_v + 6 * (size_t) s_j[sb + q];
+          atomicAdd(vq, t0); atomicAdd(vq + 1, t1); atomicAdd(vq + 2, t2);
+          atomicAdd(vq + 3, t3); atomicAdd(vq + 4, t4); atomicAdd(vq + 5, t5);
+        }
       }
       const double fr = s_frad[sb + m];
       fx += fr * mx;
       fy += fr * my;
       fz += fr * mz;
+      if (ATOM) {
+        // radial part: ev_tally (:444) and v_tally2 (:725): -d (x) (fr d), half to i, half to j
+        const double h = -0.5 * fr;
+        const double r0 = h * mx * mx, r1 = h * my * my, r2 = h * mz * mz, r3 = h * mx * my, r4 = h * mx * mz, r5 = h * my * mz;
+        vi[0] += r0; vi[1] += r1; vi[2] += r2; vi[3] += r3; vi[4] += r4; vi[5] += r5;
+        double *vj = pa_v + 6 * (size_t) s_j[sb + m];
+        atomicAdd(vj, vm[0] + r0); atomicAdd(vj + 1, vm[1] + r1); atomicAdd(vj + 2, vm[2] + r2);
+        atomicAdd(vj + 3, vm[3] + r3); atomicAdd(vj + 4, vm[4] + r4); atomicAdd(vj + 5, vm[5] + r5);
+      }
       fix -= fx;
       fiy -= fy;
       fiz -= fz;
@@ -525,6 +557,11 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
         atomicAdd(&f[3 * (size_t) i + 1], fiy);
         atomicAdd(&f[3 * (size_t) i + 2], fiz);
       }
+    }
+    if (ATOM) {
+      atomicAdd(&pa_e[i], ei_atom);
+#pragma unroll
+      for (int k = 0; k < 6; k++) atomicAdd(&pa_v[6 * (size_t) i + k], vi[k]);
     }
     __syncwarp(gmask);
   }
@@ -692,7 +729,7 @@ __device__ __forceinline__ void lj_segment(const RebomosDev &par, const double4 
   }
 }
 
-template <bool EV, int ELEM, int U, int MINB>
+template <bool EV, int ELEM, int U, int MINB, bool ATOM>
 __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__ RebomosDev par,
                                                          const double4 *__restrict__ xq,
                                                          const int64_t *__restrict__ lj_off,
@@ -700,7 +737,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
                                                          const int *__restrict__ lj_val,
                                                          const int *__restrict__ cen_list,
                                                          const int *__restrict__ cen_count_ptr,
-                                                         double *__restrict__ f, double *__restrict__ scal)
+                                                         double *__restrict__ f, double *__restrict__ scal,
+                                                         double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
   const int count = *cen_count_ptr;
   const int sub = threadIdx.x & 7;
@@ -713,8 +751,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
     const int nA = lj_num[2 * i], nB = lj_num[2 * i + 1];
     const int *row = lj_val + off;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    lj_segment<EV, ELEM * 2, U>(par, xq, row, 0, nA, sub, xi, fx, fy, fz, ev);
-    lj_segment<EV, ELEM * 2 + 1, U>(par, xq, row, cap - nB, cap, sub, xi, fx, fy, fz, ev);
+    double ca[7] = {0, 0, 0, 0, 0, 0, 0};    // this center's energy/virial share (every pair visited from both ends)
+    lj_segment<EV, ELEM * 2, U>(par, xq, row, 0, nA, sub, xi, fx, fy, fz, ca);
+    lj_segment<EV, ELEM * 2 + 1, U>(par, xq, row, cap - nB, cap, sub, xi, fx, fy, fz, ca);
     fx = group_sum<8>(fx);
     fy = group_sum<8>(fy);
     fz = group_sum<8>(fz);
@@ -722,6 +761,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
       f[3 * (size_t) i] += fx;
       f[3 * (size_t) i + 1] += fy;
       f[3 * (size_t) i + 2] += fz;
+    }
+    if (EV) {
+#pragma unroll
+      for (int k = 0; k < 7; k++) ev[k] += ca[k];
+    }
+    if (ATOM) {
+      // ev_tally (pair_rebomos.cpp:554): half of the pair's energy and virial to each end = exactly what this
+      // center accumulated over its directed row; rebo_center_kernel added its part with atomics before this kernel
+#pragma unroll
+      for (int k = 0; k < 7; k++) ca[k] = group_sum<8>(ca[k]);
+      if (sub == 0) {
+        pa_e[i] += ca[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) i + k] += ca[1 + k];
+      }
     }
   }
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
@@ -904,7 +958,7 @@ int b200md_rebomos_refresh_inner(b200md_ctx *c)
 }
 
 // force kernels on whatever is resident: xq, inner lists.  f and scal must be zeroed by the caller.
-template <bool EV, bool DET>
+template <bool EV, bool DET, bool ATOM>
 static void launch_centers(b200md_ctx *c, const DetTables &det)
 {
   const int inum = c->list_inum;
@@ -914,18 +968,19 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
   const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
   const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
-#define RC_ARGS(list, cnt, ol, oc) c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p
+#define RC_ARGS(list, cnt, ol, oc) \
+  c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
   {
     LaunchScope ls(c, "rebo_center_mo");
-    rebo_center_kernel<128, 16, 16, 0, EV, DET><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
+    rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
   }
   {
     LaunchScope ls(c, "rebo_center_s");
-    rebo_center_kernel<128, 4, 8, 1, EV, DET><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
+    rebo_center_kernel<128, 4, 8, 1, EV, DET, ATOM><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
   }
   {
     LaunchScope ls(c, "rebo_center_overflow");
-    rebo_center_kernel<128, 16, 16, 1, EV, DET><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
+    rebo_center_kernel<128, 16, 16, 1, EV, DET, ATOM><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
   }
 }
 
@@ -950,15 +1005,18 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
     CUDA_TRY(c, cudaMemsetAsync(det.fi, 0, 3 * (size_t) ncen * sizeof(double), c->stream));
   }
   const bool ev = eflag != 0;
-  if (detmode) {
-    if (ev) launch_centers<true, true>(c, det);
-    else launch_centers<false, true>(c, det);
+  const bool atom = c->pa_e != nullptr;
+  ARG_CHECK(c, !(atom && detmode), "per-atom energy/virial is not available in deterministic mode");
+  if (atom) launch_centers<true, false, true>(c, det);
+  else if (detmode) {
+    if (ev) launch_centers<true, true, false>(c, det);
+    else launch_centers<false, true, false>(c, det);
     LaunchScope ls(c, "rebo_gather");
     rebo_gather_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, rows, ncen, det,
                                                                      c->f.p);
   } else {
-    if (ev) launch_centers<true, false>(c, det);
-    else launch_centers<false, false>(c, det);
+    if (ev) launch_centers<true, false, false>(c, det);
+    else launch_centers<false, false, false>(c, det);
   }
   if (vflag) {
     LaunchScope ls(c, "fdotr");
@@ -970,16 +1028,19 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
     // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
     const int grid = min(nblocks((long long) ncen * 8, BLOCK), c->num_sms * 64);
     int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
-#define LJ_ARGS(list, cnt) c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, c->flags.p + cnt, c->f.p, c->scal.p
+#define LJ_ARGS(list, cnt) \
+  c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, c->flags.p + cnt, c->f.p, c->scal.p, c->pa_e, c->pa_v
     {
       LaunchScope ls(c, "lj_mo");
-      if (eflag || vflag) lj_kernel<true, 0, 2, 2><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
-      else lj_kernel<false, 0, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+      if (atom) lj_kernel<true, 0, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+      else if (eflag || vflag) lj_kernel<true, 0, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
+      else lj_kernel<false, 0, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
     }
     {
       LaunchScope ls(c, "lj_s");
-      if (eflag || vflag) lj_kernel<true, 1, 2, 2><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
-      else lj_kernel<false, 1, 2, 4><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+      if (atom) lj_kernel<true, 1, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+      else if (eflag || vflag) lj_kernel<true, 1, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
+      else lj_kernel<false, 1, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
     }
   }
   CUDA_TRY(c, cudaGetLastError());
@@ -1010,6 +1071,14 @@ extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, con
                                       const int *type, const int *tag, int eflag, int vflag, double *f,
                                       double *eng_vdwl, double *virial)
 {
+  return b200md_rebomos_compute_peratom(c, nlocal, nghost, x, type, tag, eflag, vflag, f, eng_vdwl, virial, nullptr,
+                                        nullptr);
+}
+
+extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int nghost, const double *x,
+                                              const int *type, const int *tag, int eflag, int vflag, double *f,
+                                              double *eng_vdwl, double *virial, double *eatom, double *vatom)
+{
   if (!c) return B200MD_ERR_ARG;
   ARG_CHECK(c, c->rebomos_ready, "rebomos_compute: call b200md_rebomos_init first");
   ARG_CHECK(c, c->list_valid, "rebomos_compute: no neighbor list (b200md_set_neighbor_list / b200md_neigh_build)");
@@ -1023,9 +1092,14 @@ extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, con
   CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
   if ((rc = b200md_rebomos_pack(c))) return rc;
   if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
-  if ((rc = b200md_rebomos_forces(c, eflag, vflag))) return rc;
-
+  if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
+  rc = b200md_rebomos_forces(c, (eatom || vatom) ? 1 : eflag, vflag);
+  if (rc) {
+    c->pa_e = c->pa_v = nullptr;
+    return rc;
+  }
   int fl[16];
+  if ((rc = b200md_peratom_finish(c, eatom, vatom))) return rc;
   if ((rc = b200md_finish_compute(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
   // virial[0..5] = fdotr (xx,yy,zz,xy,xz,yz) of the many-body part + LJ pair virial in the same order
   if ((rc = check_flags(c, fl))) return rc;

@@ -62,9 +62,6 @@ void PairAEAM::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
 
-  if (eflag_atom || vflag_atom)
-    error->all(FLERR, "Pair style aeam (B200) does not provide per-atom energy or virial");
-
   if (atom->nmax > nmax) {
     memory->destroy(rho);
     memory->destroy(fp);
@@ -84,6 +81,10 @@ void PairAEAM::compute(int eflag, int vflag)
     uploaded_nghost = nghost;
   }
 
+  // per-atom tallies (compute pe/atom, stress/atom) start in the density phase: the embedding energy is an atom's own
+  const int want_atom = (eflag_atom || vflag_atom) ? 1 : 0;
+  B200MDHost::check(error, ctx, b200md_set_option(ctx, "peratom", want_atom), "option");
+
   // phase 1 on the device: density + embedding of owned atoms
   int rc = b200md_aeam_density_phase(ctx, nlocal, nghost, nall ? &atom->x[0][0] : nullptr, atom->type, rho, fp);
   B200MDHost::check(error, ctx, rc, "aeam density pass");
@@ -97,8 +98,9 @@ void PairAEAM::compute(int eflag, int vflag)
   // phase 2 on the device: pair + embedding forces, angular 3-body forces, energy, virial
   double eng = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const int want_virial = (vflag_fdotr || vflag_global) ? B200MD_VIRIAL_FDOTR : 0;
-  rc = b200md_aeam_force_phase(ctx, rho, fp, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
-                               nall ? &atom->f[0][0] : nullptr, &eng, vir);
+  rc = b200md_aeam_force_phase_peratom(ctx, rho, fp, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
+                                       nall ? &atom->f[0][0] : nullptr, &eng, vir, eflag_atom ? eatom : nullptr,
+                                       (vflag_atom && vatom) ? &vatom[0][0] : nullptr);
   B200MDHost::check(error, ctx, rc, "aeam force pass");
 
   if (eflag_global) eng_vdwl += eng;

@@ -61,9 +61,6 @@ void PairREBOMoS::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
 
-  if (eflag_atom || vflag_atom)
-    error->all(FLERR, "Pair style rebomos (B200) does not provide per-atom energy or virial");
-
   const int nlocal = atom->nlocal;
   const int nghost = atom->nghost;
 
@@ -77,9 +74,13 @@ void PairREBOMoS::compute(int eflag, int vflag)
 
   double eng = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const int want_virial = (vflag_fdotr || vflag_global) ? B200MD_VIRIAL_FDOTR : 0;
-  int rc = b200md_rebomos_compute(ctx, nlocal, nghost, nlocal + nghost ? &atom->x[0][0] : nullptr, atom->type,
-                                  atom->tag, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
-                                  nlocal + nghost ? &atom->f[0][0] : nullptr, &eng, vir);
+  // per-atom tallies (compute pe/atom, stress/atom): Pair::eatom / Pair::vatom are accumulated on the device with the
+  // reference's distribution (ev_tally halves, v_tally3 thirds, v_tally2 halves) and added here
+  double *ea = eflag_atom ? eatom : nullptr;
+  double *va = (vflag_atom && vatom) ? &vatom[0][0] : nullptr;
+  int rc = b200md_rebomos_compute_peratom(ctx, nlocal, nghost, nlocal + nghost ? &atom->x[0][0] : nullptr, atom->type,
+                                          atom->tag, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
+                                          nlocal + nghost ? &atom->f[0][0] : nullptr, &eng, vir, ea, va);
   B200MDHost::check(error, ctx, rc, "rebomos force computation");
 
   if (eflag_global) eng_vdwl += eng;

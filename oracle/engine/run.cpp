@@ -1277,6 +1277,8 @@ void *minilmp_get_ptr(void *ptr, int rank, const char *name)
   if (n == "numneigh") return l->neighbor->list ? l->neighbor->list->numneigh : nullptr;
   if (n == "ilist") return l->neighbor->list ? l->neighbor->list->ilist : nullptr;
   if (n == "pair") return l->force->pair;
+  if (n == "eatom") return l->force->pair ? (void *) l->force->pair->eatom : nullptr;
+  if (n == "vatom") return (l->force->pair && l->force->pair->vatom) ? (void *) &l->force->pair->vatom[0][0] : nullptr;
   if (n == "lammps") return l;
   if (n == "stencil") return l->neighbor->stencil;
   if (n == "cutneighsq") return l->neighbor->cutneighsq ? (void *) &l->neighbor->cutneighsq[0][0] : nullptr;

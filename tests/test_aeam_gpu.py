@@ -150,3 +150,37 @@ def test_flags_and_accumulate(ctx, oracle_built):
     f1, _, _ = ctx.aeam_compute(nl, ng, snap["x"], snap["type"], snap["tag"], 1, 2, f=np.full((nl + ng, 3), 2.0))
     assert np.allclose(f1 - 2.0, f0, rtol=0, atol=1e-12)
     lmp.close()
+
+
+def fold_ghost_rows(a, swaps, nlocal):
+    a = np.array(a, dtype=np.float64, copy=True)
+    for s in reversed(swaps):
+        if s["recvnum"]:
+            np.add.at(a, s["sendlist"], a[s["firstrecv"]:s["firstrecv"] + s["recvnum"]])
+    return a[:nlocal]
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[3]], ids=[CASES[1]["id"], CASES[3]["id"]])
+def test_per_atom_energy_and_virial(ctx, oracle_built, case):
+    """Pair::eatom / Pair::vatom of pair_style aeam: embedding energy to the atom (one third for angular atoms,
+    pair_aeam.cpp:295-300), phi/2 per visit (:389), ev_tally halves (:393), ev_tally3 thirds (:472) -- compared per
+    atom with the reference plugin after folding ghost shares into their owners."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), case["cells"], si_fraction=case["si"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    nl, nall = snap["nlocal"], snap["nlocal"] + snap["nghost"]
+    lmp.compute(1 | 2, 2 | 4, reverse=True)
+    ea_ref = fold_ghost_rows(lmp._arr("eatom", 0, nall, np.float64), snap["swaps"], nl)
+    va_ref = fold_ghost_rows(lmp._arr("vatom", 0, nall, np.float64, 6), snap["swaps"], nl)
+    f_ref = lmp.f()[:nl].copy()
+    ctx.aeam_init(aeam_tables())
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    f, e, v, ea, va = ctx.aeam_compute_peratom(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"])
+    ea, va = fold_ghost_rows(ea, snap["swaps"], nl), fold_ghost_rows(va, snap["swaps"], nl)
+    print("\\n%s: sum eatom %.8f  max|eatom| %.4f err %.2e  max|vatom| %.4f err %.2e"
+          % (case["id"], ea.sum(), np.abs(ea_ref).max(), np.abs(ea - ea_ref).max(), np.abs(va_ref).max(),
+             np.abs(va - va_ref).max()))
+    assert S.rel_err(ea, ea_ref) < 1e-10
+    assert S.rel_err(va, va_ref) < 1e-10
+    assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], nl), f_ref) < 1e-10
+    lmp.close()

@@ -71,3 +71,33 @@ def test_forces_lockstep_along_reference_trajectory(ctx, oracle_built):
         assert abs(e - e_ref) < 1e-12 * abs(e_ref)
     print("worst relative force error along the trajectory: %.3e" % worst)
     a.close()
+
+
+@pytest.mark.parametrize("style", ["rebomos", "aeam"])
+def test_per_atom_tallies_through_the_plugin(oracle_built, style):
+    """compute pe/atom / stress/atom path: the host application asks the pair style for ENERGY_ATOM | VIRIAL_ATOM;
+    the B200 plugin fills Pair::eatom / Pair::vatom like the reference plugin does (owned + ghost entries)."""
+    out = {}
+    for which in ("ref", "b200"):
+        if style == "rebomos":
+            so = S.oracle_plugin("rebomos") if which == "ref" else S.B200_REBOMOS_SO
+            lmp = S.make_rebomos_system(so, (2, 1, 1), displace=0.2)
+        else:
+            so = S.oracle_plugin("aeam") if which == "ref" else S.B200_AEAM_SO
+            lmp = S.make_aeam_system(so, (5, 5, 5), si_fraction=0.1, displace=0.2)
+        lmp.setup(1, 2)
+        lmp.compute(1 | 2, 2 | 4, reverse=False)
+        nl, nall = lmp.get_int("nlocal"), lmp.nall()
+        swaps = lmp.swaps()
+        ea = lmp._arr("eatom", 0, nall, np.float64).copy()
+        va = lmp._arr("vatom", 0, nall, np.float64, 6).copy()
+        for s in reversed(swaps):           # what compute pe/atom does: reverse-communicate the ghost shares
+            if s["recvnum"]:
+                np.add.at(ea, s["sendlist"], ea[s["firstrecv"]:s["firstrecv"] + s["recvnum"]])
+                np.add.at(va, s["sendlist"], va[s["firstrecv"]:s["firstrecv"] + s["recvnum"]])
+        out[which] = (ea[:nl], va[:nl], lmp.get_double("eng_vdwl"))
+        lmp.close()
+    (ea0, va0, e0), (ea1, va1, e1) = out["ref"], out["b200"]
+    assert abs(e1 - e0) < 1e-12 * abs(e0)
+    assert S.rel_err(ea1, ea0) < 1e-10 and S.rel_err(va1, va0) < 1e-10
+    assert abs(ea1.sum() - e0) < 1e-10 * abs(e0)

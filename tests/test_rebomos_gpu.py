@@ -210,3 +210,43 @@ def test_many_rebo_neighbors_overflow_path(ctx, oracle_built):
     assert num[:snap["nlocal"]][styp].max() > 8
     assert S.rel_err(f, f_ref) < FTOL and abs(e - e_ref) / abs(e_ref) < ETOL
     lmp.close()
+
+
+def fold_ghost_rows(a, swaps, nlocal):
+    """reverse communication of a per-atom array with any number of columns (what compute pe/atom and
+    stress/atom do with Pair::eatom / vatom): ghost rows added to the atoms they image, swaps in reverse"""
+    a = np.array(a, dtype=np.float64, copy=True)
+    for s in reversed(swaps):
+        if s["recvnum"]:
+            np.add.at(a, s["sendlist"], a[s["firstrecv"]:s["firstrecv"] + s["recvnum"]])
+    return a[:nlocal]
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[4]], ids=["bulk288-d0.05", "bulk288-d0.3", "rep2x1x2-d0.6"])
+def test_per_atom_energy_and_virial(ctx, oracle_built, case):
+    """Pair::eatom / Pair::vatom (ENERGY_ATOM | VIRIAL_ATOM): the device distributes energy and virial over atoms the
+    way the reference's tallies do -- ev_tally halves, v_tally3 thirds, v_tally2 halves -- so after folding ghost
+    shares into their owners every atom's energy and 6 virial components agree with the reference plugin."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), case["replicate"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    nl, nall = snap["nlocal"], snap["nlocal"] + snap["nghost"]
+    lmp.compute(1 | 2, 2 | 4, reverse=True)             # ENERGY_GLOBAL|ENERGY_ATOM, VIRIAL_FDOTR|VIRIAL_ATOM
+    e_ref = lmp.get_double("eng_vdwl")
+    ea_ref = fold_ghost_rows(lmp._arr("eatom", 0, nall, np.float64), snap["swaps"], nl)
+    va_ref = fold_ghost_rows(lmp._arr("vatom", 0, nall, np.float64, 6), snap["swaps"], nl)
+    f_ref = lmp.f()[:nl].copy()
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    f, e, v, ea, va = ctx.rebomos_compute_peratom(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"])
+    ea, va = fold_ghost_rows(ea, snap["swaps"], nl), fold_ghost_rows(va, snap["swaps"], nl)
+    print("\\n%s: sum eatom %.10f (E %.10f)  max|eatom| %.4f err %.2e  max|vatom| %.4f err %.2e"
+          % (case["id"], ea.sum(), e_ref, np.abs(ea_ref).max(), np.abs(ea - ea_ref).max(), np.abs(va_ref).max(),
+             np.abs(va - va_ref).max()))
+    assert abs(ea.sum() - e_ref) < 1e-11 * abs(e_ref) and abs(e - e_ref) < ETOL * abs(e_ref)
+    assert S.rel_err(ea, ea_ref) < 1e-10
+    assert S.rel_err(va, va_ref) < 1e-10
+    assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], nl), f_ref) < FTOL
+    # per-atom virial sums to the global virial the same call reports
+    assert S.rel_err(va.sum(axis=0), v) < 1e-10
+    lmp.close()

@@ -53,7 +53,6 @@ struct AeamHost {
   std::vector<std::vector<double>> frho7, rhor7, z2r7;    // 7-coefficient tables (reference layout)
   std::vector<int> frho_n, rhor_n, z2r_n;
 };
-static std::map<b200md_ctx *, AeamHost> g_aeam_host;
 
 static int pack4(const std::vector<double> &s7, int n, std::vector<double> &out)
 {
@@ -70,7 +69,8 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
   ARG_CHECK(c, t->nnonangular >= 0 && t->nnonangular <= t->nelements, "aeam_init: bad nnonangular");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int nel = t->nelements;
-  AeamHost &H = g_aeam_host[c];
+  if (!c->aeam_host) c->aeam_host = new AeamHost();
+  AeamHost &H = *c->aeam_host;
   H = AeamHost();
   H.nel = nel;
   AeamDev &d = c->ap;
@@ -174,7 +174,8 @@ extern "C" int b200md_aeam_get_spline(b200md_ctx *c, int kind, int index, double
 {
   if (!c) return B200MD_ERR_ARG;
   ARG_CHECK(c, c->aeam_ready && out, "aeam_get_spline: call b200md_aeam_init first");
-  AeamHost &H = g_aeam_host[c];
+  ARG_CHECK(c, c->aeam_host, "aeam_get_spline: call b200md_aeam_init first");
+  AeamHost &H = *c->aeam_host;
   const std::vector<std::vector<double>> *tab = kind == 0 ? &H.frho7 : kind == 1 ? &H.rhor7 : kind == 2 ? &H.z2r7 : nullptr;
   const std::vector<int> *ns = kind == 0 ? &H.frho_n : kind == 1 ? &H.rhor_n : &H.z2r_n;
   ARG_CHECK(c, tab && index >= 0 && index < (int) tab->size(), "aeam_get_spline: bad table");
@@ -183,7 +184,11 @@ extern "C" int b200md_aeam_get_spline(b200md_ctx *c, int kind, int index, double
   return B200MD_OK;
 }
 
-void b200md_aeam_forget(b200md_ctx *c) { g_aeam_host.erase(c); }
+void b200md_aeam_forget(b200md_ctx *c)
+{
+  delete c->aeam_host;
+  c->aeam_host = nullptr;
+}
 
 // ================================================================== device helpers
 // xq.w of the AEAM path carries TWO things: the 0-based element in the two lowest mantissa bits and, in the

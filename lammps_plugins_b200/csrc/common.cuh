@@ -132,6 +132,8 @@ struct KernelStat {
 };
 
 struct SystemState;    // resident MD system (system.cu)
+struct NeighScratch;   // device-build scratch (neigh.cu)
+struct AeamHost;       // 7-coefficient spline tables kept for b200md_aeam_get_spline (aeam.cu)
 
 struct b200md_ctx {
   int device = 0;
@@ -222,6 +224,8 @@ struct b200md_ctx {
   DevBuf<int64_t> scan_tmp64;
 
   SystemState *sys = nullptr;
+  NeighScratch *neigh_scratch = nullptr;
+  AeamHost *aeam_host = nullptr;
 
   int fail(const std::string &m)
   {

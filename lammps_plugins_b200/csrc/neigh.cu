@@ -288,18 +288,24 @@ struct NeighScratch {
   DevBuf<double> cutsq, cutghostsq;
   DevBuf<int64_t> bin_start;
 };
-static std::map<b200md_ctx *, NeighScratch> g_scratch;
+// per-context scratch (contexts are driven by different host threads in multi-rank runs: no shared state)
+static NeighScratch &scratch_of(b200md_ctx *c)
+{
+  if (!c->neigh_scratch) c->neigh_scratch = new NeighScratch();
+  return *c->neigh_scratch;
+}
 
 void b200md_neigh_forget(b200md_ctx *c)
 {
-  auto it = g_scratch.find(c);
-  if (it == g_scratch.end()) return;
-  it->second.xt.release();
-  it->second.runs.release();
-  it->second.cutsq.release();
-  it->second.cutghostsq.release();
-  it->second.bin_start.release();
-  g_scratch.erase(it);
+  if (!c->neigh_scratch) return;
+  NeighScratch &S = *c->neigh_scratch;
+  S.xt.release();
+  S.runs.release();
+  S.cutsq.release();
+  S.cutghostsq.release();
+  S.bin_start.release();
+  delete c->neigh_scratch;
+  c->neigh_scratch = nullptr;
 }
 
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
@@ -310,7 +316,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
                               const double *cutneighghostsq_h, int nlocal, int nghost, const double4 *xt,
                               int ghost_rows, double skin)
 {
-  NeighScratch &S = g_scratch[c];
+  NeighScratch &S = scratch_of(c);
   BinGeom g;
   std::vector<int4> runs;
   int rc = b200md_neigh_setup_bins(c, box, ntypes, g, runs);
@@ -402,7 +408,7 @@ extern "C" int b200md_neigh_build(b200md_ctx *c, const b200md_box *box, int ntyp
   c->type_on_device = c->tag_on_device = false;    // a new list means the host may have re-sorted its atoms
   int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, nullptr);
   if (rc) return rc;
-  NeighScratch &S = g_scratch[c];
+  NeighScratch &S = scratch_of(c);
   const int nall = nlocal + nghost;
   CUDA_TRY(c, S.xt.reserve((size_t) nall + 8));
   if (nall) {

@@ -328,6 +328,9 @@ def run_e2e(ctx_sys, kind, w, args, device=0, rank=0, world=1):
     typ, tag = st["type"], st["tag"]
     ctx.neigh_build(box, w["ntypes"], cs, cg, nl, ng, x, typ, 1 if kind == "rebomos" else 0, w["skin"])
     ctx.set_option("f_overwrite", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     rho_all, fp_all = np.ones(nall), np.zeros(nall)
 

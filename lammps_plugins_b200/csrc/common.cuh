@@ -135,9 +135,19 @@ struct SystemState;    // resident MD system (system.cu)
 struct NeighScratch;   // device-build scratch (neigh.cu)
 struct AeamHost;       // 7-coefficient spline tables kept for b200md_aeam_get_spline (aeam.cu)
 
+#define B200MD_MAX_D2H_CHUNKS 16
+
 struct b200md_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;    // plugin mode: D2H of finished force ranges runs beside the remaining kernels
+  cudaEvent_t copy_ev[B200MD_MAX_D2H_CHUNKS + 2] = {};      // "range finished on the compute stream"
+  cudaEvent_t copy_done[B200MD_MAX_D2H_CHUNKS + 2] = {};    // "range has arrived on the host"
+  struct D2HRange {
+    int slot;
+    size_t lo, hi;
+  };
+  std::vector<D2HRange> d2h_ranges;
   std::string err;
   int num_sms = 148;
 
@@ -147,6 +157,10 @@ struct b200md_ctx {
   int sync_timing = 0;
   int f_overwrite = 0;
   int peratom_opt = 0;    // AEAM two-phase API: tally per-atom energy/virial from the density phase on
+  int overlap = 0;       // resident loop: LJ launches on a second stream beside the bond-order launches
+  int lj_ctas = 64, rebo_ctas = 48;    // grid caps in CTAs per SM (grid-stride kernels)
+  int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency
+  int d2h_chunks = 6;    // plugin mode: owned-atom index ranges whose forces go home while the next range computes
   int p2p_halo = 1;    // multi-GPU halo through peer memory (CUDA IPC) when available; 0 = NCCL send/recv only
   long long n_p2p = 0;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -201,7 +215,9 @@ struct b200md_ctx {
   DevBuf<int> lj_num;        // [inum]
   DevBuf<int> lj_val;        // directed LJ-window rows
   int64_t lj_capacity = 0;
-  DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow]
+  DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow], ascending index
+  DevBuf<int> cen_key;               // scan input: 1 per Mo-like center, 2^30 per S-like center
+  DevBuf<int64_t> cen_scan;          // [inum+1] exclusive scan of cen_key: list position of every index threshold
   DevBuf<double> nM, nS;             // parity API (b200md_rebomos_neigh)
   DevBuf<double> det_fb;             // deterministic mode: per-bond and per-center forces
   DevBuf<int> det_j;
@@ -280,6 +296,13 @@ int b200md_collect_timers(b200md_ctx *c);    // after a stream sync: fills last_
 // D2H of forces/energy/virial/flags + host-side accumulate (shared by the compute entry points)
 int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
                           int *flags_out);
+
+// ranged D2H of finished forces on the copy stream (f_overwrite mode): begin, one call per finished range (each
+// waits for what the compute stream has queued so far), finish = scalars + flags + join of both streams
+int b200md_d2h_begin(b200md_ctx *c);
+int b200md_d2h_range(b200md_ctx *c, int slot, double *f_host, size_t lo, size_t hi);
+int b200md_d2h_finish(b200md_ctx *c, int eflag, int vflag, double *f_host, double *eng_vdwl, double *virial,
+                      int *flags_out);
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -85,7 +85,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release();
-  c->cen_list.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
+  c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
   c->ang_list.release();
@@ -98,6 +98,11 @@ extern "C" void b200md_destroy(b200md_ctx *c)
     cudaEventDestroy(t.b);
   }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->copy_ev)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->copy_done)
+    if (e) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -114,6 +119,11 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
   else if (n == "peratom") c->peratom_opt = value ? 1 : 0;
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
+  else if (n == "overlap") c->overlap = value ? 1 : 0;
+  else if (n == "lj_ctas") c->lj_ctas = (int) (value < 1 ? 1 : value);
+  else if (n == "rebo_ctas") c->rebo_ctas = (int) (value < 1 ? 1 : value);
+  else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;
+  else if (n == "d2h_chunks") c->d2h_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
   else {
     c->fail("unknown option " + n);
     return B200MD_ERR_ARG;
@@ -288,6 +298,56 @@ int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double
     const double *src = c->pin_f.p;
     for (size_t k = 0; k < n3; k++) f[k] += src[k];
   }
+  if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
+  if (virial)
+    for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;
+  return B200MD_OK;
+}
+
+int b200md_d2h_begin(b200md_ctx *c)
+{
+  if (!c->copy_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->d2h_ranges.clear();
+  if (!c->f_overwrite) CUDA_TRY(c, c->pin_f.reserve(3 * (size_t) c->nall + 64));
+  return B200MD_OK;
+}
+
+int b200md_d2h_range(b200md_ctx *c, int slot, double *f_host, size_t lo, size_t hi)
+{
+  if (hi <= lo) return B200MD_OK;
+  if (slot < 0 || slot >= B200MD_MAX_D2H_CHUNKS + 2) return c->fail("d2h_range: bad slot"), B200MD_ERR_ARG;
+  if (!c->copy_ev[slot]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->copy_ev[slot], cudaEventDisableTiming));
+  if (!c->copy_done[slot]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->copy_done[slot], cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventRecord(c->copy_ev[slot], c->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[slot], 0));
+  double *dst = c->f_overwrite ? f_host : c->pin_f.p;
+  CUDA_TRY(c, cudaMemcpyAsync(dst + lo, c->f.p + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost,
+                              c->copy_stream));
+  CUDA_TRY(c, cudaEventRecord(c->copy_done[slot], c->copy_stream));
+  c->d2h_ranges.push_back({slot, lo, hi});
+  c->d2h_bytes += (long long) ((hi - lo) * sizeof(double));
+  return B200MD_OK;
+}
+
+int b200md_d2h_finish(b200md_ctx *c, int eflag, int vflag, double *f_host, double *eng_vdwl, double *virial,
+                      int *flags_out)
+{
+  int *pin_flags = (int *) (c->pin_scal.p + 32);
+  CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (!c->f_overwrite) {
+    // accumulate mode: the host adds every range as soon as it has arrived, while later ranges still compute
+    const double *src = c->pin_f.p;
+    for (const b200md_ctx::D2HRange &r : c->d2h_ranges) {
+      CUDA_TRY(c, cudaEventSynchronize(c->copy_done[r.slot]));
+      for (size_t k = r.lo; k < r.hi; k++) f_host[k] += src[k];
+    }
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+  c->d2h_bytes += (long long) (16 * sizeof(double) + 16 * sizeof(int));
+  b200md_collect_timers(c);
+  memcpy(flags_out, pin_flags, 16 * sizeof(int));
   if (eng_vdwl) *eng_vdwl = eflag ? c->pin_scal.p[0] : 0.0;
   if (virial)
     for (int k = 0; k < 6; k++) virial[k] = vflag ? c->pin_scal.p[1 + k] : 0.0;

@@ -605,24 +605,36 @@ __global__ void __launch_bounds__(BLOCK) rebo_gather_kernel(const int *__restric
 
 // centers by element (static between list builds): warp-aggregated append, so list order follows atom order
 // at warp granularity
-__global__ void __launch_bounds__(BLOCK) center_lists_kernel(const double4 *__restrict__ xq, int ncen,
+// Center lists in ASCENDING index order (stable compaction through a scan, not atomics): consecutive groups of a
+// launch work on neighboring atoms, and an index range [t_lo, t_hi) of owned atoms maps to a contiguous piece of
+// each list -- cen_scan[t] holds the list positions of threshold t for both elements (Mo count in the low 30
+// bits, S count above), so ranged LJ launches need no host round trip.
+#define CEN_SHIFT 30
+#define CEN_MASK ((1LL << CEN_SHIFT) - 1)
+__global__ void __launch_bounds__(BLOCK) center_key_kernel(const double4 *__restrict__ xq, int ncen,
+                                                           int *__restrict__ key)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= ncen) return;
+  const int t = elem_of(xq[i]);
+  key[i] = (t == 0) ? 1 : ((t == 1) ? (1 << CEN_SHIFT) : 0);
+}
+__global__ void __launch_bounds__(BLOCK) center_lists_kernel(const int *__restrict__ key,
+                                                             const long long *__restrict__ scan, int ncen,
                                                              int *__restrict__ listA, int *__restrict__ listB,
                                                              int *__restrict__ counts)
 {
   const int i = blockIdx.x * BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int t = (i < ncen) ? elem_of(xq[i]) : -1;
-  const unsigned mA = __ballot_sync(0xffffffffu, t == 0), mB = __ballot_sync(0xffffffffu, t == 1);
-  int bA = 0, bB = 0;
-  if (lane == 0) {
-    if (mA) bA = atomicAdd(&counts[0], __popc(mA));
-    if (mB) bB = atomicAdd(&counts[1], __popc(mB));
+  if (i >= ncen) return;
+  const int k = key[i];
+  const long long s = scan[i];
+  if (k == 1) listA[(int) (s & CEN_MASK)] = i;
+  else if (k != 0) listB[(int) (s >> CEN_SHIFT)] = i;
+  if (i == ncen - 1) {
+    const long long tot = s + k;
+    counts[0] = (int) (tot & CEN_MASK);
+    counts[1] = (int) (tot >> CEN_SHIFT);
   }
-  bA = __shfl_sync(0xffffffffu, bA, 0);
-  bB = __shfl_sync(0xffffffffu, bB, 0);
-  const unsigned lt = (1u << lane) - 1u;
-  if (t == 0) listA[bA + __popc(mA & lt)] = i;
-  if (t == 1) listB[bB + __popc(mB & lt)] = i;
 }
 
 // ================================================================== K8: fdotr virial over owned + ghost
@@ -736,14 +748,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
                                                          const int *__restrict__ lj_num,
                                                          const int *__restrict__ lj_val,
                                                          const int *__restrict__ cen_list,
-                                                         const int *__restrict__ cen_count_ptr,
+                                                         const long long *__restrict__ cen_scan, int t_lo, int t_hi,
                                                          double *__restrict__ f, double *__restrict__ scal,
                                                          double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
-  const int count = *cen_count_ptr;
+  // centers of this element whose atom index lies in [t_lo, t_hi): a contiguous piece of the ascending list
+  const long long s0 = cen_scan[t_lo], s1 = cen_scan[t_hi];
+  const int first = (ELEM == 0) ? (int) (s0 & CEN_MASK) : (int) (s0 >> CEN_SHIFT);
+  const int count = (ELEM == 0) ? (int) (s1 & CEN_MASK) : (int) (s1 >> CEN_SHIFT);
   const int sub = threadIdx.x & 7;
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int g = (blockIdx.x * BLOCK + threadIdx.x) >> 3; g < count; g += (gridDim.x * BLOCK) >> 3) {
+  for (int g = first + ((blockIdx.x * BLOCK + threadIdx.x) >> 3); g < count; g += (gridDim.x * BLOCK) >> 3) {
     const int i = cen_list[g];
     const double4 xi = xq[i];
     const int64_t off = lj_off[i];
@@ -758,9 +773,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
     fy = group_sum<8>(fy);
     fz = group_sum<8>(fz);
     if (sub == 0) {
-      f[3 * (size_t) i] += fx;
-      f[3 * (size_t) i + 1] += fy;
-      f[3 * (size_t) i + 2] += fz;
+      // one add per owned atom; atomic because the bond-order launches (which scatter into f) may run beside this
+      // kernel on another stream.  A single adder per address: the result does not depend on the schedule.
+      atomicAdd(f + 3 * (size_t) i, fx);
+      atomicAdd(f + 3 * (size_t) i + 1, fy);
+      atomicAdd(f + 3 * (size_t) i + 2, fz);
     }
     if (EV) {
 #pragma unroll
@@ -922,12 +939,21 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   // owned centers by element for the fused bond-order launches (flags[12], [13] = counts)
   CUDA_TRY(c, c->cen_list.reserve(3 * (size_t) inum + 96));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 12, 0, 2 * sizeof(int), c->stream));
+  CUDA_TRY(c, c->cen_key.reserve((size_t) inum + 32));
+  CUDA_TRY(c, c->cen_scan.reserve((size_t) inum + 2));
   if (inum > 0) {
+    {
+      LaunchScope ls(c, "center_lists");
+      center_key_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, inum, c->cen_key.p);
+    }
+    if ((rc = b200md_exclusive_scan_i64(c, c->cen_key.p, c->cen_scan.p, inum, 1))) return rc;
     LaunchScope ls(c, "center_lists");
-    center_lists_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, inum, c->cen_list.p,
-                                                                      c->cen_list.p + inum + 32, c->flags.p + 12);
+    center_lists_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(
+        c->cen_key.p, (const long long *) c->cen_scan.p, inum, c->cen_list.p, c->cen_list.p + inum + 32,
+        c->flags.p + 12);
     CUDA_TRY(c, cudaGetLastError());
-  }
+  } else
+    CUDA_TRY(c, cudaMemsetAsync(c->cen_scan.p, 0, sizeof(int64_t), c->stream));
   c->inner_valid = true;
   c->n_inner_rebuild++;
   return B200MD_OK;
@@ -966,8 +992,8 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   int *cnt0 = c->flags.p + 12, *cnt1 = c->flags.p + 13, *cntO = c->flags.p + 14;
   // Mo centers: 16 lanes, 16 staged bonds; S centers: 4 lanes, 8 staged bonds, overflow to 16/16.
   // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
-  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
-  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
+  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * c->rebo_ctas);
+  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * c->rebo_ctas);
 #define RC_ARGS(list, cnt, ol, oc) \
   c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
   {
@@ -984,7 +1010,8 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   }
 }
 
-int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
+// many-body part (REBO_neigh + FREBO + bondorder, fdotr virial) on c->stream
+static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag)
 {
   const int ncen = c->list_inum;
   const int rows = c->list_inum + c->list_gnum;
@@ -1022,29 +1049,63 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
     LaunchScope ls(c, "fdotr");
     fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, c->scal.p);
   }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
+// tapered LJ for the owned atoms with index in [t_lo, t_hi) on c->stream: completes f of exactly those atoms
+static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi)
+{
+  const int ncen = c->list_inum;
+  if (t_hi <= t_lo) return B200MD_OK;
+  const bool atom = c->pa_e != nullptr;
+  // grid: 8 lanes per center, capped (grid-stride loop); list pieces are located on the device.  Occupancy decides:
+  // 2 candidates in flight per lane at 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10;
+  // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
+  const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * c->lj_ctas);
+  int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
+#define LJ_ARGS(list) \
+  c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, \
+      c->scal.p, c->pa_e, c->pa_v
   {
-    // grid: 8 lanes per center, capped (grid-stride loop); counts are read on the device.  Occupancy decides:
-    // 2 candidates in flight per lane at 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10;
-    // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
-    const int grid = min(nblocks((long long) ncen * 8, BLOCK), c->num_sms * 64);
-    int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
-#define LJ_ARGS(list, cnt) \
-  c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, c->flags.p + cnt, c->f.p, c->scal.p, c->pa_e, c->pa_v
-    {
-      LaunchScope ls(c, "lj_mo");
-      if (atom) lj_kernel<true, 0, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
-      else if (eflag || vflag) lj_kernel<true, 0, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
-      else lj_kernel<false, 0, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0, 12));
-    }
-    {
-      LaunchScope ls(c, "lj_s");
-      if (atom) lj_kernel<true, 1, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
-      else if (eflag || vflag) lj_kernel<true, 1, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
-      else lj_kernel<false, 1, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1, 13));
-    }
+    LaunchScope ls(c, "lj_mo");
+    if (atom) lj_kernel<true, 0, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0));
+    else if (eflag || vflag) lj_kernel<true, 0, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0));
+    else lj_kernel<false, 0, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0));
+  }
+  {
+    LaunchScope ls(c, "lj_s");
+    if (atom) lj_kernel<true, 1, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1));
+    else if (eflag || vflag) lj_kernel<true, 1, 2, 2, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1));
+    else lj_kernel<false, 1, 2, 4, false><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list1));
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
+}
+
+int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
+{
+  int rc;
+  if (c->overlap && !vflag && !c->deterministic && !c->pa_e && c->list_inum > 0) {    // fdotr must not see LJ forces
+    // LJ (bound by the L1 data pipe) beside the bond-order launches (bound by instruction issue) on a second stream;
+    // both grids are capped so that CTAs of both kinds are resident on every SM.  f is only ever added to atomically.
+    if (!c->copy_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++)
+      if (!c->copy_ev[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->copy_ev[k], cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventRecord(c->copy_ev[0], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->copy_stream;
+    rc = rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
+    c->stream = main_stream;
+    if (rc) return rc;
+    if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->copy_ev[1], c->copy_stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->copy_ev[1], 0));
+    return B200MD_OK;
+  }
+  if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
+  return rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
 }
 
 static int check_flags(b200md_ctx *c, const int *fl)
@@ -1093,12 +1154,28 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
   if ((rc = b200md_rebomos_pack(c))) return rc;
   if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
   if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
+  int fl[16];
+  if (!eatom && !vatom && c->d2h_chunks > 1 && nlocal >= c->d2h_min_atoms) {
+    // Forces go home while the LJ kernels are still running: the many-body launches scatter into owned and ghost
+    // entries, so they run first; ghost forces are then final and travel during the first LJ range, and every LJ
+    // range [t_k, t_k+1) completes f of exactly those owned atoms, which travel during the next range.
+    if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
+    if ((rc = b200md_d2h_begin(c))) return rc;
+    const int K = c->d2h_chunks;
+    if ((rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, 3 * (size_t) c->nall))) return rc;
+    for (int k = 0; k < K; k++) {
+      const int t0 = (int) ((long long) nlocal * k / K), t1 = (int) ((long long) nlocal * (k + 1) / K);
+      if ((rc = rebomos_forces_lj(c, eflag, vflag, t0, t1))) return rc;
+      if ((rc = b200md_d2h_range(c, k + 1, f, 3 * (size_t) t0, 3 * (size_t) t1))) return rc;
+    }
+    if ((rc = b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+    return check_flags(c, fl);
+  }
   rc = b200md_rebomos_forces(c, (eatom || vatom) ? 1 : eflag, vflag);
   if (rc) {
     c->pa_e = c->pa_v = nullptr;
     return rc;
   }
-  int fl[16];
   if ((rc = b200md_peratom_finish(c, eatom, vatom))) return rc;
   if ((rc = b200md_finish_compute(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
   // virial[0..5] = fdotr (xx,yy,zz,xy,xz,yz) of the many-body part + LJ pair virial in the same order

@@ -250,3 +250,37 @@ def test_per_atom_energy_and_virial(ctx, oracle_built, case):
     # per-atom virial sums to the global virial the same call reports
     assert S.rel_err(va.sum(axis=0), v) < 1e-10
     lmp.close()
+
+
+@pytest.mark.parametrize("overwrite", [0, 1], ids=["accumulate", "overwrite"])
+@pytest.mark.parametrize("chunks", [2, 5, 16])
+def test_ranged_force_return_equals_single_copy(ctx, oracle_built, overwrite, chunks):
+    """Plugin-mode pipelining: forces of finished atom-index ranges travel to the host while the remaining LJ ranges
+    still compute (d2h_chunks > 1).  Forced on for a small system here; results must equal the single-copy path
+    bit for bit per owned atom up to the order of the two adds on f (<= 1 ulp), energy/virial to rounding, in both the
+    accumulate (Pair::compute semantics: f +=) and the overwrite mode."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), displace=0.15)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    args = (snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], 1, 2)
+    nall = snap["nlocal"] + snap["nghost"]
+    base = np.full((nall, 3), 0.25)                  # what is in f before the call
+    ctx.set_option("f_overwrite", overwrite)
+    ctx.set_option("d2h_chunks", 1)
+    f1, e1, v1 = ctx.rebomos_compute(*args, f=base.copy())
+    ctx.set_option("d2h_min_atoms", 0)
+    ctx.set_option("d2h_chunks", chunks)
+    f2, e2, v2 = ctx.rebomos_compute(*args, f=base.copy())
+    ctx.set_option("f_overwrite", 0)
+    ctx.set_option("d2h_chunks", 6)
+    ctx.set_option("d2h_min_atoms", 65536)
+    assert S.rel_err(f2, f1) < 1e-14
+    assert abs(e2 - e1) < 1e-13 * abs(e1) and S.rel_err(v2, v1) < 1e-13
+    off = 0.0 if overwrite else 0.25
+    f = S.fold_ghost_forces(f2 - off, snap["swaps"], snap["nlocal"])
+    assert S.rel_err(f, f_ref) < FTOL
+    assert abs(e2 - e_ref) < ETOL * abs(e_ref)
+    lmp.close()

@@ -157,10 +157,9 @@ struct b200md_ctx {
   int sync_timing = 0;
   int f_overwrite = 0;
   int peratom_opt = 0;    // AEAM two-phase API: tally per-atom energy/virial from the density phase on
-  int overlap = 0;       // resident loop: LJ launches on a second stream beside the bond-order launches
-  int lj_ctas = 64, rebo_ctas = 48;    // grid caps in CTAs per SM (grid-stride kernels)
+  int lj_pairs = 1;      // LJ over pairs of neighboring centers sharing one union row (0: one row per center)
   int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency
-  int d2h_chunks = 6;    // plugin mode: owned-atom index ranges whose forces go home while the next range computes
+  int d2h_chunks = 4;    // plugin mode: owned-atom index ranges whose forces go home while the next range computes
   int p2p_halo = 1;    // multi-GPU halo through peer memory (CUDA IPC) when available; 0 = NCCL send/recv only
   long long n_p2p = 0;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -215,6 +214,8 @@ struct b200md_ctx {
   DevBuf<int> lj_num;        // [inum]
   DevBuf<int> lj_val;        // directed LJ-window rows
   int64_t lj_capacity = 0;
+  DevBuf<int> ljp_ab;        // pair mode: {a, b} atom indices of every pair row, [2][P] by element
+  int ljp_P = 0;             // pair slots per element
   DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow], ascending index
   DevBuf<int> cen_key;               // scan input: 1 per Mo-like center, 2^30 per S-like center
   DevBuf<int64_t> cen_scan;          // [inum+1] exclusive scan of cen_key: list position of every index threshold

@@ -84,7 +84,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->pin_f.release(); c->pin_scal.release(); c->pin_pa.release(); c->eatom_d.release(); c->vatom_d.release(); c->scal.release(); c->flags.release();
   c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
-  c->lj_off.release(); c->lj_num.release(); c->lj_val.release();
+  c->lj_off.release(); c->lj_num.release(); c->lj_val.release(); c->ljp_ab.release();
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
@@ -119,10 +119,10 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
   else if (n == "peratom") c->peratom_opt = value ? 1 : 0;
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
-  else if (n == "overlap") c->overlap = value ? 1 : 0;
-  else if (n == "lj_ctas") c->lj_ctas = (int) (value < 1 ? 1 : value);
-  else if (n == "rebo_ctas") c->rebo_ctas = (int) (value < 1 ? 1 : value);
-  else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;
+  else if (n == "lj_pairs") {
+    c->lj_pairs = value ? 1 : 0;
+    c->inner_valid = false;
+  } else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;
   else if (n == "d2h_chunks") c->d2h_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
   else {
     c->fail("unknown option " + n);

@@ -676,6 +676,16 @@ __device__ __forceinline__ double rcp_nr(double a)
   return fma(r, e, r);
 }
 
+// seed + ONE Newton step: relative error <= 2^-46 = 1.4e-14 (the seed is good to 2^-23), four orders inside the
+// 1e-10 force tolerance; used by the pair kernel, whose FP64 pipe is the limiter
+__device__ __forceinline__ double rcp_nr1(double a)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
+
 // one row segment [lo, hi) whose partners all have element TJ: every pair constant is an immediate operand
 template <bool EV, int PT, int U>
 __device__ __forceinline__ void lj_segment(const RebomosDev &par, const double4 *__restrict__ xq,
@@ -798,6 +808,307 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
 }
 
+// ================================================================== K5b: tapered LJ over PAIRS of centers
+// ncu (r01/r02): lj_kernel is bound by the L1 data pipe, which delivers one gathered 32-byte position sector per
+// cycle and SM -- one per (center, candidate).  Two neighboring centers of the same element share most of their
+// candidates (spheres of radius rcLJmax + margin whose centers are ~3-5 A apart: union = 1.2-1.3 x one sphere), so a
+// lane group works on a PAIR (a, b) of consecutive centers of the ascending center list and streams the UNION row:
+// one gathered sector serves two interactions, 30-40 % fewer sectors per atom for one extra distance test per
+// candidate.  Row layout, element segmentation, exact rsq window thresholds and arithmetic are those of lj_kernel.
+// A center without partner (odd count) has b = -1 and a far-away dummy position (every candidate fails the window).
+// One (center, candidate) term, BRANCH-FREE in the 12-6 regime: ncu r02 showed the branchy form bound by
+// fixed-latency dependency stalls ("wait" 4.2 per issue) -- every term was its own divergent region, so the FP64 chains
+// of the 2 x U terms of a trip could not overlap.  Here a term outside the window runs the same arithmetic on a
+// harmless rsq (1.0) and contributes fpair = 0, and the compiler interleaves all chains of a trip.  The cubic-taper
+// regime (rcLJmin <= r < 0.95 sigma; no pair of a bulk crystal is in it) stays a branch, taken only by warps that have one.
+template <bool EV, int PT>
+__device__ __forceinline__ bool lj_term(const RebomosDev &par, const double xi, const double yi, const double zi,
+                                        const double4 &xj, double &fx, double &fy, double &fz, double (&ev)[7])
+{
+  const double dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  // rsq >= 0: comparing the bit patterns as integers is the same (exact) comparison and runs on the integer pipe
+  // instead of the FP64 pipe, which is the busiest one in this kernel
+  const long long rb = __double_as_longlong(rsq);
+  const bool in126 = rb < __double_as_longlong(par.lj_out_hi[PT]) && rb >= __double_as_longlong(par.lj_s95[PT]);
+  const double r2inv = rcp_nr1(in126 ? rsq : 1.0);
+  const double r6inv = r2inv * r2inv * r2inv;
+  double fpair = r6inv * (par.lj1[PT] * r6inv - par.lj2[PT]) * r2inv;
+  fpair = in126 ? fpair : 0.0;
+  fx += dx * fpair;
+  fy += dy * fpair;
+  fz += dz * fpair;
+  if (EV) {
+    double VLJ = r6inv * (par.lj3[PT] * r6inv - par.lj4[PT]);
+    VLJ = in126 ? VLJ : 0.0;
+    ev[0] += 0.5 * VLJ;
+    const double hf = 0.5 * fpair;
+    ev[1] += dx * dx * hf;
+    ev[2] += dy * dy * hf;
+    ev[3] += dz * dz * hf;
+    ev[4] += dx * dy * hf;
+    ev[5] += dx * dz * hf;
+    ev[6] += dy * dz * hf;
+  }
+  // the caller takes ONE rarely-taken branch per trip for all terms that report the taper regime
+  return rb < __double_as_longlong(par.lj_s95[PT]) && rb >= __double_as_longlong(par.lj_in_lo[PT]);
+}
+
+// cubic taper down to rcLJmin (pair_rebomos.cpp:533-543) for a term lj_term() reported: {fpair, VLJ} by value, so
+// that the out-of-line call does not force the caller's accumulators into local memory
+template <int PT>
+__device__ __noinline__ double2 lj_taper(const RebomosDev &par, double rsq)
+{
+  if (!(rsq < par.lj_s95[PT] && rsq >= par.lj_in_lo[PT])) return make_double2(0.0, 0.0);
+  const double rij = sqrt(rsq);
+  const double drp = rij - par.rcLJmin[PT];
+  const double VLJ = drp * drp * (drp * par.c3[PT] + par.c2[PT]);
+  const double dVLJ = drp * (3.0 * drp * par.c3[PT] + 2.0 * par.c2[PT]);
+  return make_double2(-dVLJ / rij, VLJ);
+}
+template <bool EV, int PT>
+__device__ __forceinline__ void lj_term_taper(const RebomosDev &par, const double xi, const double yi, const double zi,
+                                              const double4 &xj, double &fx, double &fy, double &fz, double (&ev)[7])
+{
+  const double dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
+  const double2 t = lj_taper<PT>(par, dx * dx + dy * dy + dz * dz);
+  fx += dx * t.x;
+  fy += dy * t.x;
+  fz += dz * t.x;
+  if (EV) {
+    ev[0] += 0.5 * t.y;
+    const double hf = 0.5 * t.x;
+    ev[1] += dx * dx * hf;
+    ev[2] += dy * dy * hf;
+    ev[3] += dz * dz * hf;
+    ev[4] += dx * dy * hf;
+    ev[5] += dx * dz * hf;
+    ev[6] += dy * dz * hf;
+  }
+}
+
+// One row segment [lo, hi) of a union row for the two centers of a pair, software-pipelined: D position buffers per
+// lane; while the two terms of one buffer are computed the gathers of the other D-1 are in flight, and the row indices
+// run two rounds ahead of the gathers (ncu r02: with load-then-use in the same trip the kernel sat on long-scoreboard
+// stalls, 6.3 per issue at 34 % occupancy).  An empty slot holds a far-away dummy position that fails every window test.
+template <bool EV, int PT, int D>
+__device__ __forceinline__ void ljp_segment(const RebomosDev &par, const double4 *__restrict__ xq,
+                                            const int *__restrict__ row, int lo, int hi, int sub, const double4 &xa,
+                                            const double4 &xb, double (&fa)[3], double (&fb)[3], double (&eva)[7],
+                                            double (&evb)[7])
+{
+  int e = (lo & ~7) + sub;
+  double4 xj[D];
+  int jn[D];
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    const int k = e + 8 * d;
+    const int j = (k >= lo && k < hi) ? ld_stream_int(row + k) : -1;
+    xj[d] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+    if (j >= 0) xj[d] = ld_sector(xq + j);
+  }
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    const int k = e + 8 * (D + d);
+    jn[d] = (k < hi) ? ld_stream_int(row + k) : -1;
+  }
+  for (; e - sub < hi; e += 8 * D) {
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      const double4 x = xj[d];
+      bool taper = lj_term<EV, PT>(par, xa.x, xa.y, xa.z, x, fa[0], fa[1], fa[2], eva);
+      taper |= lj_term<EV, PT>(par, xb.x, xb.y, xb.z, x, fb[0], fb[1], fb[2], evb);
+      if (taper) {
+        lj_term_taper<EV, PT>(par, xa.x, xa.y, xa.z, x, fa[0], fa[1], fa[2], eva);
+        lj_term_taper<EV, PT>(par, xb.x, xb.y, xb.z, x, fb[0], fb[1], fb[2], evb);
+      }
+      const int j = jn[d];
+      xj[d] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+      if (j >= 0) xj[d] = ld_sector(xq + j);
+      const int k = e + 8 * (2 * D + d);
+      jn[d] = (k < hi) ? ld_stream_int(row + k) : -1;
+    }
+  }
+}
+
+template <bool EV, int ELEM, int D, int MINB, bool ATOM>
+__global__ void __launch_bounds__(BLOCK, MINB) lj_pair_kernel(const __grid_constant__ RebomosDev par,
+                                                              const double4 *__restrict__ xq,
+                                                              const int64_t *__restrict__ ljp_off,
+                                                              const int *__restrict__ ljp_num,
+                                                              const int2 *__restrict__ ljp_ab,
+                                                              const int *__restrict__ lj_val, int P,
+                                                              const long long *__restrict__ cen_scan, int t_lo, int t_hi,
+                                                              double *__restrict__ f, double *__restrict__ scal,
+                                                              double *__restrict__ pa_e, double *__restrict__ pa_v)
+{
+  // pairs of this element with a center whose atom index lies in [t_lo, t_hi): list positions [s0, s1) -> pairs
+  // [(s0+1)/2, (s1+1)/2); the pair straddling t_lo was done by the range below, the one straddling t_hi is done here
+  const long long c0 = cen_scan[t_lo], c1 = cen_scan[t_hi];
+  const int s0 = (ELEM == 0) ? (int) (c0 & CEN_MASK) : (int) (c0 >> CEN_SHIFT);
+  const int s1 = (ELEM == 0) ? (int) (c1 & CEN_MASK) : (int) (c1 >> CEN_SHIFT);
+  const int first = (s0 + 1) >> 1, last = (s1 + 1) >> 1;
+  const int sub = threadIdx.x & 7;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int g = first + ((blockIdx.x * BLOCK + threadIdx.x) >> 3); g < last; g += (gridDim.x * BLOCK) >> 3) {
+    const int q = ELEM * P + g;
+    const int2 ab = ljp_ab[q];
+    const double4 xa = xq[ab.x];
+    double4 xb = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);    // no partner: nothing is in its window
+    if (ab.y >= 0) xb = xq[ab.y];
+    const int64_t off = ljp_off[q];
+    const int cap = (int) (ljp_off[q + 1] - off);
+    const int nA = ljp_num[2 * q], nB = ljp_num[2 * q + 1];
+    const int *row = lj_val + off;
+    double fa[3] = {0, 0, 0}, fb[3] = {0, 0, 0};
+    double ca[7] = {0, 0, 0, 0, 0, 0, 0}, cb[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (ATOM) {
+      ljp_segment<EV, ELEM * 2, D>(par, xq, row, 0, nA, sub, xa, xb, fa, fb, ca, cb);
+      ljp_segment<EV, ELEM * 2 + 1, D>(par, xq, row, cap - nB, cap, sub, xa, xb, fa, fb, ca, cb);
+    } else {
+      ljp_segment<EV, ELEM * 2, D>(par, xq, row, 0, nA, sub, xa, xb, fa, fb, ev, ev);
+      ljp_segment<EV, ELEM * 2 + 1, D>(par, xq, row, cap - nB, cap, sub, xa, xb, fa, fb, ev, ev);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      fa[k] = group_sum<8>(fa[k]);
+      fb[k] = group_sum<8>(fb[k]);
+    }
+    // one add per owned atom (a single adder per address: schedule-independent)
+    if (sub < 3) atomicAdd(f + 3 * (size_t) ab.x + sub, sub == 0 ? fa[0] : (sub == 1 ? fa[1] : fa[2]));
+    else if (sub < 6 && ab.y >= 0) atomicAdd(f + 3 * (size_t) ab.y + (sub - 3), sub == 3 ? fb[0] : (sub == 4 ? fb[1] : fb[2]));
+    if (ATOM) {
+      // ev_tally (pair_rebomos.cpp:554): half of each pair's energy and virial to each end = what a center accumulated
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        ca[k] = group_sum<8>(ca[k]);
+        cb[k] = group_sum<8>(cb[k]);
+        ev[k] += (sub == 0) ? ca[k] + cb[k] : 0.0;
+      }
+      if (sub == 0) {
+        pa_e[ab.x] += ca[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) ab.x + k] += ca[1 + k];
+      } else if (sub == 1 && ab.y >= 0) {
+        pa_e[ab.y] += cb[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) ab.y + k] += cb[1 + k];
+      }
+    }
+  }
+  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+}
+
+// capacity of every pair row = master rows of both centers (8-aligned by the scan that follows)
+__global__ void __launch_bounds__(BLOCK) ljpair_cap_kernel(const int *__restrict__ cen_list, int inum, int P,
+                                                           const int *__restrict__ counts,
+                                                           const int *__restrict__ list_num, int *__restrict__ cap,
+                                                           int2 *__restrict__ ab_out)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= 2 * P) return;
+  const int E = q / P, p = q - E * P;
+  const int cnt = counts[E];
+  const int *list = cen_list + (size_t) E * (inum + 32);
+  int a = -1, b = -1, n = 0;
+  if (2 * p < cnt) {
+    a = list[2 * p];
+    n = list_num[a];
+    if (2 * p + 1 < cnt) {
+      b = list[2 * p + 1];
+      n += list_num[b];
+    }
+  }
+  cap[q] = n;
+  ab_out[q] = make_int2(a, b);
+}
+
+// union rows: one warp per pair, order-preserving ballot compaction, partners segmented by element as in lj rows.
+// pass 1: candidates of a's master row within the margin sphere of a (remembered in a per-warp hash set in shared
+// memory); pass 2: candidates of b's master row within the margin sphere of b that pass 1 did not take.  The test is
+// set membership, not geometry: after atoms have moved, an atom inside a's margin sphere need not be in a's master
+// row (it cannot reach a's cutoff before the next master rebuild, but it may reach b's), and a itself never is.
+#define LJP_BLOCK 128
+#define LJP_HT 2048
+__global__ void __launch_bounds__(LJP_BLOCK) build_ljpair_kernel(
+    const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ list_off,
+    const int *__restrict__ list_num, const int *__restrict__ list_val, int P, const int2 *__restrict__ ljp_ab,
+    const int64_t *__restrict__ ljp_off, int *__restrict__ ljp_num, int *__restrict__ lj_val, int *__restrict__ flags)
+{
+  __shared__ int s_tab[LJP_BLOCK / 32][LJP_HT];
+  const int lane = threadIdx.x & 31;
+  const int q = (int) (((size_t) blockIdx.x * LJP_BLOCK + threadIdx.x) >> 5);
+  if (q >= 2 * P) return;
+  const int2 ab = ljp_ab[q];
+  if (ab.x < 0) {
+    if (lane == 0) ljp_num[2 * q] = ljp_num[2 * q + 1] = 0;
+    return;
+  }
+  int *tab = s_tab[threadIdx.x >> 5];
+  for (int k = lane; k < LJP_HT; k += 32) tab[k] = -1;
+  __syncwarp();
+  const int ti = q / P;
+  const double4 xa = xq[ab.x];
+  const int64_t base = ljp_off[q];
+  const int cap = (int) (ljp_off[q + 1] - base);
+  const unsigned lt = (1u << lane) - 1u;
+  int nlA = 0, nlB = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int c = pass ? ab.y : ab.x;
+    if (c < 0) break;
+    const double4 xc = pass ? xq[c] : xa;
+    const int n = list_num[c];
+    const int64_t mb = list_off[c];
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      bool pl = false;
+      int j = 0, tj = 0;
+      if (e < n) {
+        j = ld_stream_int(list_val + mb + e) & B200MD_NEIGHMASK;
+        const double4 xj = xq[j];
+        tj = elem_of(xj);
+        if (tj >= 0) {
+          const double dx = xc.x - xj.x, dy = xc.y - xj.y, dz = xc.z - xj.z;
+          pl = dx * dx + dy * dy + dz * dz <= par.ljsq[ti * 2 + tj];
+        }
+        if (pl) {
+          unsigned h = ((unsigned) j * 2654435761u) >> 21;    // 11 bits
+          if (pass == 0) {
+            while (atomicCAS(&tab[h], -1, j) != -1) h = (h + 1) & (LJP_HT - 1);
+          } else {
+            int v;
+            while ((v = tab[h]) != -1) {
+              if (v == j) {
+                pl = false;
+                break;
+              }
+              h = (h + 1) & (LJP_HT - 1);
+            }
+          }
+        }
+      }
+      const unsigned mA = __ballot_sync(0xffffffffu, pl && tj == 0);
+      const unsigned mB = __ballot_sync(0xffffffffu, pl && tj == 1);
+      if (pl) {
+        if (tj == 0) lj_val[base + nlA + __popc(mA & lt)] = j;
+        else lj_val[base + cap - 1 - (nlB + __popc(mB & lt))] = j;
+      }
+      nlA += __popc(mA);
+      nlB += __popc(mB);
+      if (pass == 0 && nlA + nlB > LJP_HT * 3 / 4 - 32) {    // warp-uniform: the hash set would fill up
+        if (lane == 0) flags[0] = 1;
+        break;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    ljp_num[2 * q] = nlA;
+    ljp_num[2 * q + 1] = nlB;
+    atomicAdd(&flags[5], nlA + nlB);
+  }
+}
+
 // ================================================================== host side
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
 
@@ -917,12 +1228,15 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   set_margin(c);
   CUDA_TRY(c, c->short_idx.reserve((size_t) B200MD_SHORT_WIDTH * rows + 64));
   CUDA_TRY(c, c->short_num.reserve((size_t) rows + 32));
-  CUDA_TRY(c, c->lj_off.reserve((size_t) inum + 2));
-  CUDA_TRY(c, c->lj_num.reserve(2 * (size_t) inum + 32));
-  int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->lj_off.p, inum, 8);
-  if (rc) return rc;
+  const bool pairs = c->lj_pairs != 0;
+  const int P = inum / 2 + 2;    // pair slots per element
+  c->ljp_P = P;
+  CUDA_TRY(c, c->lj_off.reserve((size_t) (pairs ? 2 * P : inum) + 2));
+  CUDA_TRY(c, c->lj_num.reserve((size_t) (pairs ? 4 * P : 2 * inum) + 32));
+  int rc = B200MD_OK;
+  if (!pairs && (rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->lj_off.p, inum, 8))) return rc;
   // capacity bound without a host round trip: every row padded to a multiple of 8
-  const int64_t cap = c->list_entries + 8 * (int64_t) inum + 64;
+  const int64_t cap = c->list_entries + 8 * (int64_t) (pairs ? 2 * P : inum) + 64;
   CUDA_TRY(c, c->lj_val.reserve((size_t) cap));
   c->lj_capacity = cap;
   CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
@@ -930,7 +1244,7 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   if (rows > 0) {
     LaunchScope ls(c, "build_inner");
     build_inner_kernel<<<nblocks((long long) rows * 32, BLOCK), BLOCK, 0, c->stream>>>(
-        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, rows, inum,
+        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, rows, pairs ? 0 : inum,
         c->short_idx.p, c->short_num.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, c->flags.p);
     CUDA_TRY(c, cudaGetLastError());
   }
@@ -954,6 +1268,22 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
     CUDA_TRY(c, cudaGetLastError());
   } else
     CUDA_TRY(c, cudaMemsetAsync(c->cen_scan.p, 0, sizeof(int64_t), c->stream));
+  if (pairs) {
+    // LJ rows of center PAIRS (consecutive entries of the ascending center lists): capacities, offsets, union rows
+    CUDA_TRY(c, c->ljp_ab.reserve(4 * (size_t) P + 8));
+    CUDA_TRY(c, c->scan_tmp.reserve(2 * (size_t) P + 8));
+    {
+      LaunchScope ls(c, "build_inner");
+      ljpair_cap_kernel<<<nblocks(2 * P, BLOCK), BLOCK, 0, c->stream>>>(c->cen_list.p, inum, P, c->flags.p + 12,
+                                                                      c->list_num.p, c->scan_tmp.p, (int2 *) c->ljp_ab.p);
+    }
+    if ((rc = b200md_exclusive_scan_i64(c, c->scan_tmp.p, c->lj_off.p, 2 * P, 8))) return rc;
+    LaunchScope ls(c, "build_inner");
+    build_ljpair_kernel<<<nblocks((long long) 2 * P * 32, LJP_BLOCK), LJP_BLOCK, 0, c->stream>>>(
+        c->rp, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, P, (const int2 *) c->ljp_ab.p, c->lj_off.p,
+        c->lj_num.p, c->lj_val.p, c->flags.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
   c->inner_valid = true;
   c->n_inner_rebuild++;
   return B200MD_OK;
@@ -992,8 +1322,8 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   int *cnt0 = c->flags.p + 12, *cnt1 = c->flags.p + 13, *cntO = c->flags.p + 14;
   // Mo centers: 16 lanes, 16 staged bonds; S centers: 4 lanes, 8 staged bonds, overflow to 16/16.
   // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
-  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * c->rebo_ctas);
-  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * c->rebo_ctas);
+  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
+  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
 #define RC_ARGS(list, cnt, ol, oc) \
   c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
   {
@@ -1062,8 +1392,31 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   // grid: 8 lanes per center, capped (grid-stride loop); list pieces are located on the device.  Occupancy decides:
   // 2 candidates in flight per lane at 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10;
   // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
-  const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * c->lj_ctas);
+  const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * 64);
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
+  if (c->lj_pairs) {
+    const int pgrid = min(nblocks((long long) ((t_hi - t_lo) / 2 + 2) * 8, BLOCK), c->num_sms * 64);
+#define LJP_ARGS \
+  c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, c->ljp_P, \
+      (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, c->scal.p, c->pa_e, c->pa_v
+    // force-only instance: 2 position buffers per lane, 80 registers (3 CTAs/SM).  r02 sweep at 995 904 atoms: D=2/80 regs
+    // 0.634 ms; D=1 0.77; D=3/80 (spills) 0.85; D=4/118 regs (2 CTAs) 0.69; D=2/64 regs (spills) 0.78
+#define LJP_FORCE(E) lj_pair_kernel<false, E, 2, 3, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+    {
+      LaunchScope ls(c, "lj_mo");
+      if (atom) lj_pair_kernel<true, 0, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else if (eflag || vflag) lj_pair_kernel<true, 0, 2, 1, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else LJP_FORCE(0)
+    }
+    {
+      LaunchScope ls(c, "lj_s");
+      if (atom) lj_pair_kernel<true, 1, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else if (eflag || vflag) lj_pair_kernel<true, 1, 2, 1, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else LJP_FORCE(1)
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return B200MD_OK;
+  }
 #define LJ_ARGS(list) \
   c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, \
       c->scal.p, c->pa_e, c->pa_v
@@ -1086,24 +1439,6 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 {
   int rc;
-  if (c->overlap && !vflag && !c->deterministic && !c->pa_e && c->list_inum > 0) {    // fdotr must not see LJ forces
-    // LJ (bound by the L1 data pipe) beside the bond-order launches (bound by instruction issue) on a second stream;
-    // both grids are capped so that CTAs of both kinds are resident on every SM.  f is only ever added to atomically.
-    if (!c->copy_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++)
-      if (!c->copy_ev[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->copy_ev[k], cudaEventDisableTiming));
-    CUDA_TRY(c, cudaEventRecord(c->copy_ev[0], c->stream));
-    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
-    cudaStream_t main_stream = c->stream;
-    c->stream = c->copy_stream;
-    rc = rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
-    c->stream = main_stream;
-    if (rc) return rc;
-    if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
-    CUDA_TRY(c, cudaEventRecord(c->copy_ev[1], c->copy_stream));
-    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->copy_ev[1], 0));
-    return B200MD_OK;
-  }
   if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
   return rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
 }

@@ -1841,6 +1841,10 @@ static int thermo(b200md_ctx *c, SystemState *s)
   CUDA_TRY(c, cudaMemcpyAsync(h, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (fl[4] || fl[5]) {    // inner-list statistics of the latest (re)build
+    c->n_short_entries = fl[4];
+    c->n_lj_entries = fl[5];
+  }
   if (fl[0]) {
     c->fail("per-atom row overflow in the force kernels (flag " + std::to_string(fl[0]) + ")");
     return B200MD_ERR_OVERFLOW;

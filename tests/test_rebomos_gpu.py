@@ -275,7 +275,7 @@ def test_ranged_force_return_equals_single_copy(ctx, oracle_built, overwrite, ch
     ctx.set_option("d2h_chunks", chunks)
     f2, e2, v2 = ctx.rebomos_compute(*args, f=base.copy())
     ctx.set_option("f_overwrite", 0)
-    ctx.set_option("d2h_chunks", 6)
+    ctx.set_option("d2h_chunks", 4)
     ctx.set_option("d2h_min_atoms", 65536)
     assert S.rel_err(f2, f1) < 1e-14
     assert abs(e2 - e1) < 1e-13 * abs(e1) and S.rel_err(v2, v1) < 1e-13
@@ -283,4 +283,32 @@ def test_ranged_force_return_equals_single_copy(ctx, oracle_built, overwrite, ch
     f = S.fold_ghost_forces(f2 - off, snap["swaps"], snap["nlocal"])
     assert S.rel_err(f, f_ref) < FTOL
     assert abs(e2 - e_ref) < ETOL * abs(e_ref)
+    lmp.close()
+
+
+def test_lj_center_pairs_equal_single_rows(ctx, oracle_built):
+    """LJ over pairs of neighboring centers sharing one union row (default) against one row per center
+    (lj_pairs = 0) and against the oracle, on a chemically scrambled cell whose element counts are ODD (a center
+    without partner) and whose consecutive same-element centers are far apart in places (union ~ 2 spheres)."""
+    for seed in range(11, 40):
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 1, 1), displace=0.1,
+                                    extra=["set group all type/fraction 2 0.15 %d" % seed])
+        lmp.setup(1, 2)
+        snap = S.snapshot(lmp)
+        nmo = int((snap["type"][:snap["nlocal"]] == 1).sum())
+        if nmo % 2 == 1 and (snap["nlocal"] - nmo) % 2 == 1:
+            break
+        lmp.close()
+    else:
+        pytest.skip("no seed with odd element counts")
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    init_ctx(ctx)
+    out = {}
+    for pairs in (1, 0):
+        ctx.set_option("lj_pairs", pairs)
+        out[pairs] = gpu_forces(ctx, snap)
+        f, e, v = out[pairs]
+        assert S.rel_err(f, f_ref) < FTOL and abs(e - e_ref) < ETOL * abs(e_ref) and S.rel_err(v, v_ref) < FTOL
+    ctx.set_option("lj_pairs", 1)
+    assert S.rel_err(out[1][0], out[0][0]) < 1e-12
     lmp.close()

@@ -272,9 +272,9 @@ struct DetTables {
   int *nb;       // [ncen]
 };
 
-// G(cos) and dG/dcos for a compile-time element; `blend` = some lane of the calling group has cos >= 1/2
+// G(cos) and dG/dcos for a compile-time element: the base polynomial (pair_rebomos.h:104-130) ...
 template <int ELEM>
-__device__ __forceinline__ double gspline_e(const RebomosDev &par, double c, bool blend, double &dgdc)
+__device__ __forceinline__ double gspline_base(const RebomosDev &par, double c, double &dgdc)
 {
   const double *b = par.b[ELEM];
   double g = b[6];
@@ -290,55 +290,56 @@ __device__ __forceinline__ double gspline_e(const RebomosDev &par, double c, boo
   g = fma(g, c, b[1]);
   dg = fma(dg, c, b[1]);
   g = fma(g, c, b[0]);
-  if (blend) {
-    const double *bg = par.bg[ELEM];
-    double gam = bg[6];
-    double dgam = 6.0 * bg[6];
-    gam = fma(gam, c, bg[5]);
-    dgam = fma(dgam, c, 5.0 * bg[5]);
-    gam = fma(gam, c, bg[4]);
-    dgam = fma(dgam, c, 4.0 * bg[4]);
-    gam = fma(gam, c, bg[3]);
-    dgam = fma(dgam, c, 3.0 * bg[3]);
-    gam = fma(gam, c, bg[2]);
-    dgam = fma(dgam, c, 2.0 * bg[2]);
-    gam = fma(gam, c, bg[1]);
-    dgam = fma(dgam, c, bg[1]);
-    gam = fma(gam, c, bg[0]);
-    double sn, cs;
-    sincospi(2.0 * (c - 0.5), &sn, &cs);
-    const double psi = 0.5 * (1.0 - cs);
-    const double dpsi = 3.14159265358979323846 * sn;
-    if (c >= 0.5) {
-      dg = dg + dpsi * (gam - g) + psi * (dgam - dg);
-      g = g + psi * (gam - g);
-    }
-  }
   dgdc = dg;
   return g;
 }
-
-__device__ __forceinline__ int tri_index(int m, int q)
+// ... and the blend towards the gamma polynomial for cos >= 1/2 (pair_rebomos.h:131-167), applied to (g, dg) in place
+template <int ELEM>
+__device__ __forceinline__ void gspline_blend(const RebomosDev &par, double c, double &g, double &dg)
 {
-  const int hi = max(m, q), lo = min(m, q);
-  return (hi * (hi - 1)) / 2 + lo;
+  const double *bg = par.bg[ELEM];
+  double gam = bg[6];
+  double dgam = 6.0 * bg[6];
+  gam = fma(gam, c, bg[5]);
+  dgam = fma(dgam, c, 5.0 * bg[5]);
+  gam = fma(gam, c, bg[4]);
+  dgam = fma(dgam, c, 4.0 * bg[4]);
+  gam = fma(gam, c, bg[3]);
+  dgam = fma(dgam, c, 3.0 * bg[3]);
+  gam = fma(gam, c, bg[2]);
+  dgam = fma(dgam, c, 2.0 * bg[2]);
+  gam = fma(gam, c, bg[1]);
+  dgam = fma(dgam, c, bg[1]);
+  gam = fma(gam, c, bg[0]);
+  double sn, cs;
+  sincospi(2.0 * (c - 0.5), &sn, &cs);
+  const double psi = 0.5 * (1.0 - cs);
+  const double dpsi = 3.14159265358979323846 * sn;
+  dg = dg + dpsi * (gam - g) + psi * (dgam - dg);
+  g = g + psi * (gam - g);
 }
 
-template <int NT, int G, int CAP, int ELEM, bool EV, bool DET, bool ATOM>
-__global__ void __launch_bounds__(NT) rebo_center_kernel(
+template <int NT, int G, int CAP, int ELEM, bool EV, bool DET, bool ATOM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int *__restrict__ short_idx,
     const int *__restrict__ short_num, const int *__restrict__ cen_list, const int *__restrict__ cen_count_ptr,
     int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
     double *__restrict__ scal, int *__restrict__ flags, double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
   constexpr int NG = NT / G;    // groups per block
-  constexpr int NTRI = CAP * (CAP - 1) / 2;
+  // pair table in ROUND-ROBIN layout: the unordered bond pair {m, (m + k) mod nb}, 1 <= k <= nb/2, lives at [k-1][m].
+  // Indexing is an add (v2 decoded a triangular index with sqrtf per pair and min/max/mul per use: 13 % of all
+  // instructions, ncu r01 source view), lanes of a group touch consecutive words, and a lane that walks its partners
+  // q = m+1 .. m+nb-1 (mod nb) never meets q == m.  For even nb the round k = nb/2 holds every pair twice.
+  constexpr int NTRI = (CAP / 2) * CAP;
   constexpr unsigned GBITS = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
   constexpr int tb = ELEM * 2;
   __shared__ double s_dx[NG * CAP], s_dy[NG * CAP], s_dz[NG * CAP], s_ri[NG * CAP], s_w[NG * CAP], s_dw[NG * CAP],
       s_pref[NG * CAP], s_frad[NG * CAP];
   __shared__ double s_c[NG * NTRI], s_g[NG * NTRI], s_dg[NG * NTRI];
   __shared__ int s_j[NG * CAP], s_tj[NG * CAP];
+  __shared__ unsigned char s_bl[NG * NTRI];    // table slots whose cos >= 1/2 (blend towards the gamma polynomial)
+  static_assert(NTRI <= 256, "blend list stores table slots in bytes");
   const int lane = threadIdx.x & 31;
   const int sub = threadIdx.x & (G - 1);
   const int gl = threadIdx.x / G;    // group within the block
@@ -356,42 +357,61 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
     int nb = 0;
     double nM = 0.0, nS = 0.0;
     const int *row = short_idx + (size_t) i * B200MD_SHORT_WIDTH;
-    for (int e0 = 0; e0 < n; e0 += G) {
-      const int e = e0 + sub;
-      bool in = false;
-      int j = 0, tj = 0;
-      double dx = 0, dy = 0, dz = 0, rsq = 1.0;
-      if (e < n) {
-        j = row[e];
-        const double4 xj = ld_sector(xq + j);
-        tj = elem_of(xj);
-        dx = xi.x - xj.x;
-        dy = xi.y - xj.y;
-        dz = xi.z - xj.z;
-        // same operation order as the reference, no FMA contraction: membership must be bit-exact
-        rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        in = rsq < (tj ? par.rcmaxsq[tb + 1] : par.rcmaxsq[tb]);
+    // UB trips' worth of candidates are gathered before the first one is looked at (UB gathers in flight per lane:
+    // ncu r02 showed the S-center launch waiting on one gather per trip, long-scoreboard 3.6 per issue); they are then
+    // consumed in row order, so membership and bond order stay those of the reference
+    constexpr int UB = (G <= 4) ? 4 : 2;
+    for (int e0 = 0; e0 < n; e0 += G * UB) {
+      int jb[UB];
+      double4 xb[UB];
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        const int e = e0 + u * G + sub;
+        jb[u] = (e < n) ? row[e] : -1;
       }
-      const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
-      if (in) {
-        const int pos = nb + __popc(bits & ((1u << sub) - 1u));
-        const double r = sqrt(rsq);
-        double dw;
-        const double w = sp_switch(r, tj ? par.rcmin[tb + 1] : par.rcmin[tb], tj ? par.rcw[tb + 1] : par.rcw[tb], dw);
-        if (tj == 0) nM += w;
-        else nS += w;
-        if (pos < CAP) {
-          s_dx[sb + pos] = dx;
-          s_dy[sb + pos] = dy;
-          s_dz[sb + pos] = dz;
-          s_ri[sb + pos] = 1.0 / r;
-          s_w[sb + pos] = w;
-          s_dw[sb + pos] = dw;
-          s_j[sb + pos] = j;
-          s_tj[sb + pos] = tj;
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        xb[u] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (jb[u] >= 0) xb[u] = ld_sector(xq + jb[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        if (e0 + u * G >= n) break;    // group-uniform
+        bool in = false;
+        const int j = jb[u];
+        int tj = 0;
+        double dx = 0, dy = 0, dz = 0, rsq = 1.0;
+        if (j >= 0) {
+          const double4 xj = xb[u];
+          tj = elem_of(xj);
+          dx = xi.x - xj.x;
+          dy = xi.y - xj.y;
+          dz = xi.z - xj.z;
+          // same operation order as the reference, no FMA contraction: membership must be bit-exact
+          rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          in = rsq < (tj ? par.rcmaxsq[tb + 1] : par.rcmaxsq[tb]);
         }
+        const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
+        if (in) {
+          const int pos = nb + __popc(bits & ((1u << sub) - 1u));
+          const double r = sqrt(rsq);
+          double dw;
+          const double w = sp_switch(r, tj ? par.rcmin[tb + 1] : par.rcmin[tb], tj ? par.rcw[tb + 1] : par.rcw[tb], dw);
+          if (tj == 0) nM += w;
+          else nS += w;
+          if (pos < CAP) {
+            s_dx[sb + pos] = dx;
+            s_dy[sb + pos] = dy;
+            s_dz[sb + pos] = dz;
+            s_ri[sb + pos] = 1.0 / r;
+            s_w[sb + pos] = w;
+            s_dw[sb + pos] = dw;
+            s_j[sb + pos] = j;
+            s_tj[sb + pos] = tj;
+          }
+        }
+        nb += __popc(bits);
       }
-      nb += __popc(bits);
     }
     __syncwarp(gmask);
     if (nb > CAP) {
@@ -413,29 +433,48 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
     const double ex = exp(-par.a[ELEM][2] * N);
     const double dP = -par.a[ELEM][0] + par.a[ELEM][1] * par.a[ELEM][2] * ex;
     const double P = -par.a[ELEM][0] * (N - 1.0) - par.a[ELEM][1] * ex + par.a[ELEM][3];
-    // ---- P: cos, G, G' of every unordered bond pair
-    const int npairs = nb * (nb - 1) / 2;
-    for (int p0 = 0; p0 < npairs; p0 += G) {
-      const int p = p0 + sub;
-      const bool act = p < npairs;
-      int hi = (int) ((1.0f + sqrtf(1.0f + 8.0f * (float) p)) * 0.5f);
-      if ((hi * (hi - 1)) / 2 > p) hi--;
-      if (((hi + 1) * hi) / 2 <= p) hi++;
-      const int lo = p - (hi * (hi - 1)) / 2;
-      double c = 0.0;
-      if (act) {
-        c = (s_dx[sb + hi] * s_dx[sb + lo] + s_dy[sb + hi] * s_dy[sb + lo] + s_dz[sb + hi] * s_dz[sb + lo]) *
-            (s_ri[sb + hi] * s_ri[sb + lo]);
-        c = fmin(c, 1.0);
-        c = fmax(c, -1.0);
+    // ---- P: cos, G, G' of every unordered bond pair (round k: lane m takes the pair {m, m+k mod nb})
+    const int nr = nb >> 1;
+    int nbl = 0;
+    for (int k = 1; k <= nr; k++) {
+      for (int m0 = 0; m0 < nb; m0 += G) {
+        const int m = m0 + sub;
+        const bool act = m < nb;
+        int q = m + k;
+        if (q >= nb) q -= nb;
+        double c = 0.0;
+        if (act) {
+          c = (s_dx[sb + m] * s_dx[sb + q] + s_dy[sb + m] * s_dy[sb + q] + s_dz[sb + m] * s_dz[sb + q]) *
+              (s_ri[sb + m] * s_ri[sb + q]);
+          c = fmin(c, 1.0);
+          c = fmax(c, -1.0);
+        }
+        double dg;
+        const double gg = gspline_base<ELEM>(par, c, dg);
+        const bool bl = act && c >= 0.5;
+        const unsigned bits = (__ballot_sync(gmask, bl) >> gshift) & GBITS;
+        const int t = (k - 1) * CAP + m;
+        if (act) {
+          s_c[st + t] = c;
+          s_g[st + t] = gg;
+          s_dg[st + t] = dg;
+        }
+        // the blend needs a second polynomial and a sincospi; only a few pairs of a center are in it (the 60-degree
+        // Mo-Mo-Mo angles), so they are collected and fixed up in one extra trip instead of making every trip pay
+        // (v2 took the blend path on a group vote: sincospi alone was 11 % of all instructions)
+        if (bl) s_bl[st + nbl + __popc(bits & ((1u << sub) - 1u))] = (unsigned char) t;
+        nbl += __popc(bits);
       }
-      const bool blend = __any_sync(gmask, act && c >= 0.5);
-      double dg;
-      const double gg = gspline_e<ELEM>(par, c, blend, dg);
-      if (act) {
-        s_c[st + p] = c;
-        s_g[st + p] = gg;
-        s_dg[st + p] = dg;
+    }
+    __syncwarp(gmask);
+    for (int b0 = 0; b0 < nbl; b0 += G) {
+      const int b = b0 + sub;
+      if (b < nbl) {
+        const int t = st + s_bl[st + b];
+        double gg = s_g[t], dg = s_dg[t];
+        gspline_blend<ELEM>(par, s_c[t], gg, dg);
+        s_g[t] = gg;
+        s_dg[t] = dg;
       }
     }
     __syncwarp(gmask);
@@ -447,8 +486,17 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
       double pref = 0.0, frad = 0.0;
       if (wm > TOL) {
         double S = 0.0;
-        for (int q = 0; q < nb; q++)
-          if (q != m) S += s_w[sb + q] * s_g[st + tri_index(m, q)];
+        // partners q = m+k (mod nb): rounds 1..nr are this lane's own table column, the rest are the partner's
+        for (int k = 1; k <= nr; k++) {
+          int q = m + k;
+          if (q >= nb) q -= nb;
+          S += s_w[sb + q] * s_g[st + (k - 1) * CAP + m];
+        }
+        for (int k = nr + 1; k < nb; k++) {
+          int q = m + k;
+          if (q >= nb) q -= nb;
+          S += s_w[sb + q] * s_g[st + (nb - k - 1) * CAP + q];
+        }
         const double p = 1.0 / sqrt(1.0 + S + P);
         const int pt = tb + s_tj[sb + m];
         const double r = 1.0 / rinv;
@@ -483,12 +531,13 @@ __global__ void __launch_bounds__(NT) rebo_center_kernel(
       const double rinvm2 = rinvm * rinvm;
       double fx = 0.0, fy = 0.0, fz = 0.0;
       double vm[6] = {0, 0, 0, 0, 0, 0};
-      for (int q = 0; q < nb; q++) {
-        if (q == m) continue;
+      for (int k = 1; k < nb; k++) {
+        int q = m + k;
+        if (q >= nb) q -= nb;
+        const int t = st + ((k <= nr) ? (k - 1) * CAP + m : (nb - k - 1) * CAP + q);
         const double prefn = s_pref[sb + q];
         const double ca = -(prefm * s_w[sb + q] + prefn * wm);
         const double cb = prefn * dwm;
-        const int t = st + tri_index(m, q);
         const double c = s_c[t];
         const double A = ca * s_dg[t];
         const double B = cb * (s_g[t] + dP) * rinvm;
@@ -1326,17 +1375,22 @@ static void launch_centers(b200md_ctx *c, const DetTables &det)
   const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
 #define RC_ARGS(list, cnt, ol, oc) \
   c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
+  // occupancy (r02 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
+  // 4 bonds per center (bulk S has 3; more go to the overflow launch) which cuts its shared memory from 45 to 17 KB, and
+  // runs at 72 registers (7 CTAs/SM): 0.257 -> 0.210 ms; at 64 registers 0.213, at 80: 0.223, unbounded (104): 0.280
+  constexpr bool PLAIN = !EV && !DET && !ATOM;
+  constexpr int MB_MO = PLAIN ? 6 : 5, MB_S = PLAIN ? 7 : 5, CAP_S = PLAIN ? 4 : 8;
   {
     LaunchScope ls(c, "rebo_center_mo");
-    rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
+    rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM, MB_MO><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
   }
   {
     LaunchScope ls(c, "rebo_center_s");
-    rebo_center_kernel<128, 4, 8, 1, EV, DET, ATOM><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
+    rebo_center_kernel<128, 4, CAP_S, 1, EV, DET, ATOM, MB_S><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
   }
   {
     LaunchScope ls(c, "rebo_center_overflow");
-    rebo_center_kernel<128, 16, 16, 1, EV, DET, ATOM><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
+    rebo_center_kernel<128, 16, 16, 1, EV, DET, ATOM, MB_MO><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
   }
 }
 

@@ -100,3 +100,22 @@ def test_b200_plugin_fails_loudly_without_gpu(oracle_built):
     with pytest.raises(S.LammpsError, match="Cannot open the B200 device"):
         lmp.commands(["fix 1 all nve", "run 0"])
     lmp.close()
+
+
+def test_cmake_configures_in_shim_mode(tmp_path):
+    """the CMake glue mirrors the reference's plugin build (LAMMPS_SOURCE_DIR +
+    LAMMPSInterfacePlugin); without a LAMMPS tree the B200MD_USE_SHIM option must configure, and the LAMMPS branch
+    must refuse to configure without LAMMPS_SOURCE_DIR, with the reference's message."""
+    import shutil
+    import subprocess
+    cmake = shutil.which("cmake")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not cmake or not os.path.exists(nvcc):
+        pytest.skip("cmake or nvcc not available")
+    src = os.path.join(S.REPO, "lammps_plugins_b200")
+    r = subprocess.run([cmake, "-S", src, "-B", str(tmp_path / "shim"), "-DB200MD_USE_SHIM=ON",
+                        "-DCMAKE_CUDA_COMPILER=" + nvcc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([cmake, "-S", src, "-B", str(tmp_path / "real"), "-DCMAKE_CUDA_COMPILER=" + nvcc],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "Must set LAMMPS_SOURCE_DIR" in r.stderr

@@ -140,6 +140,11 @@ struct AeamHost;       // 7-coefficient spline tables kept for b200md_aeam_get_s
 struct b200md_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t up_stream = nullptr;      // plugin mode: position upload in pieces beside the bond-order launches
+  cudaEvent_t up_ev[B200MD_MAX_D2H_CHUNKS + 2] = {};
+  int h2d_chunks = 6, h2d_K = 0;
+  bool h2d_ready = false;
+  int h2d_need[B200MD_MAX_D2H_CHUNKS + 1] = {}, h2d_t[B200MD_MAX_D2H_CHUNKS + 2] = {};
   cudaStream_t copy_stream = nullptr;    // plugin mode: D2H of finished force ranges runs beside the remaining kernels
   cudaEvent_t copy_ev[B200MD_MAX_D2H_CHUNKS + 2] = {};      // "range finished on the compute stream"
   cudaEvent_t copy_done[B200MD_MAX_D2H_CHUNKS + 2] = {};    // "range has arrived on the host"
@@ -167,6 +172,7 @@ struct b200md_ctx {
   // counters
   long long n_launch = 0, n_list_upload = 0, n_inner_rebuild = 0, h2d_bytes = 0, d2h_bytes = 0;
   long long n_lj_entries = 0, n_short_entries = 0;
+  long long n_pipelined = 0, n_redo = 0;    // plugin-mode calls through the pipelined path / recomputed after a refresh
   // per-launch CUDA events while "sync_timing" is on; folded into kstat by b200md_collect_timers()
   std::vector<std::string> kname;
   std::map<std::string, int> kname_id;

@@ -59,14 +59,14 @@ extern "C" int b200md_create(int device, b200md_ctx **out)
     delete c;
     return B200MD_ERR_CUDA;
   }
-  if (c->scal.reserve(64) != cudaSuccess || c->flags.reserve(16) != cudaSuccess ||
+  if (c->scal.reserve(64) != cudaSuccess || c->flags.reserve(16 + B200MD_MAX_D2H_CHUNKS) != cudaSuccess ||
       c->pin_scal.reserve(64) != cudaSuccess) {
     g_create_error = "b200md_create: device allocation failed";
     delete c;
     return B200MD_ERR_CUDA;
   }
   cudaMemsetAsync(c->scal.p, 0, 64 * sizeof(double), c->stream);
-  cudaMemsetAsync(c->flags.p, 0, 16 * sizeof(int), c->stream);
+  cudaMemsetAsync(c->flags.p, 0, (16 + B200MD_MAX_D2H_CHUNKS) * sizeof(int), c->stream);
   cudaStreamSynchronize(c->stream);
   *out = c;
   return B200MD_OK;
@@ -103,6 +103,9 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   for (cudaEvent_t e : c->copy_done)
     if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t e : c->up_ev)
+    if (e) cudaEventDestroy(e);
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -121,6 +124,9 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
   else if (n == "lj_pairs") {
     c->lj_pairs = value ? 1 : 0;
+    c->inner_valid = false;
+  } else if (n == "h2d_chunks") {
+    c->h2d_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
     c->inner_valid = false;
   } else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;
   else if (n == "d2h_chunks") c->d2h_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
@@ -144,6 +150,8 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
   if (n == "short_entries") return c->n_short_entries;
   if (n == "num_sms") return c->num_sms;
   if (n == "p2p_exchanges") return c->n_p2p;
+  if (n == "pipelined_calls") return c->n_pipelined;
+  if (n == "pipelined_redos") return c->n_redo;
   return -1;
 }
 

@@ -119,19 +119,24 @@ __device__ __forceinline__ double gspline(const RebomosDev &par, double c, int t
   return g;
 }
 
+// cen_scan[t] packs the list positions of atom-index threshold t for both center lists: Mo-like count in the low
+// 30 bits, S-like count above
+#define CEN_SHIFT 30
+#define CEN_MASK ((1LL << CEN_SHIFT) - 1)
+
 // ================================================================== staging kernels
 __global__ void __launch_bounds__(BLOCK) pack_xq_kernel(const double *__restrict__ x,
                                                         const int *__restrict__ type,
-                                                        const int *__restrict__ map, int ntypes, int nall,
+                                                        const int *__restrict__ map, int ntypes, int lo, int hi,
                                                         double4 *__restrict__ xq, int *__restrict__ flags)
 {
-  int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (i >= nall) return;
+  int i = lo + blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= hi) return;
   int t = type[i];
   int e = -1;
   if (t >= 1 && t <= ntypes) e = map[t];
   else flags[3] = 1;    // invalid atom type
-  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (double) e);
+  xq[i] = make_double4(x[3 * (size_t) i], x[3 * (size_t) i + 1], x[3 * (size_t) i + 2], (double) e);
 }
 
 __global__ void __launch_bounds__(BLOCK) check_disp_kernel(const double4 *__restrict__ xq,
@@ -323,7 +328,7 @@ template <int NT, int G, int CAP, int ELEM, bool EV, bool DET, bool ATOM, int MI
 __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     const __grid_constant__ RebomosDev par, const double4 *__restrict__ xq, const int *__restrict__ short_idx,
     const int *__restrict__ short_num, const int *__restrict__ cen_list, const int *__restrict__ cen_count_ptr,
-    int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
+    const long long *__restrict__ cen_scan, int t_lo, int t_hi, int *__restrict__ ovf_list, int *__restrict__ ovf_count, double *__restrict__ f, const DetTables det,
     double *__restrict__ scal, int *__restrict__ flags, double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
   constexpr int NG = NT / G;    // groups per block
@@ -347,9 +352,17 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
   const unsigned gmask = GBITS << gshift;
   const int sb = gl * CAP;     // this group's staging base
   const int st = gl * NTRI;    // ... and pair-table base
-  const int count = *cen_count_ptr;
+  // centers [first, count) of the list: all of it (count read from the device), or -- plugin-mode pipelining -- the
+  // piece of the ascending list whose atom indices lie in [t_lo, t_hi)
+  int first = 0, count;
+  if (cen_scan) {
+    const long long c0 = cen_scan[t_lo], c1 = cen_scan[t_hi];
+    first = (ELEM == 0) ? (int) (c0 & CEN_MASK) : (int) (c0 >> CEN_SHIFT);
+    count = (ELEM == 0) ? (int) (c1 & CEN_MASK) : (int) (c1 >> CEN_SHIFT);
+  } else
+    count = *cen_count_ptr;
   double eacc[1] = {0.0};
-  for (int g = blockIdx.x * NG + gl; g < count; g += gridDim.x * NG) {
+  for (int g = first + blockIdx.x * NG + gl; g < count; g += gridDim.x * NG) {
     const int i = cen_list[g];
     const double4 xi = xq[i];
     const int n = short_num[i];
@@ -658,8 +671,6 @@ __global__ void __launch_bounds__(BLOCK) rebo_gather_kernel(const int *__restric
 // launch work on neighboring atoms, and an index range [t_lo, t_hi) of owned atoms maps to a contiguous piece of
 // each list -- cen_scan[t] holds the list positions of threshold t for both elements (Mo count in the low 30
 // bits, S count above), so ranged LJ launches need no host round trip.
-#define CEN_SHIFT 30
-#define CEN_MASK ((1LL << CEN_SHIFT) - 1)
 __global__ void __launch_bounds__(BLOCK) center_key_kernel(const double4 *__restrict__ xq, int ncen,
                                                            int *__restrict__ key)
 {
@@ -1158,6 +1169,30 @@ __global__ void __launch_bounds__(LJP_BLOCK) build_ljpair_kernel(
   }
 }
 
+// plugin-mode upload pipelining: for every range of owned centers, the largest OWNED atom index its bond-order
+// evaluation reads (the centers themselves and their short-row candidates; ghosts are uploaded first).  Positions
+// arrive in ascending index order, so a range may start as soon as the piece holding that index is on the device.
+struct ChunkBounds {
+  int t[B200MD_MAX_D2H_CHUNKS + 1];
+  int K;
+};
+__global__ void __launch_bounds__(BLOCK) dep_range_kernel(const int *__restrict__ short_idx,
+                                                          const int *__restrict__ short_num, int inum,
+                                                          const ChunkBounds cb, int *__restrict__ dep)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= inum) return;
+  int m = i;
+  const int n = short_num[i];
+  for (int e = 0; e < n; e++) {
+    const int j = short_idx[(size_t) i * B200MD_SHORT_WIDTH + e];
+    if (j < inum && j > m) m = j;
+  }
+  int k = 0;
+  while (k + 1 < cb.K && i >= cb.t[k + 1]) k++;
+  atomicMax(&dep[k], m);
+}
+
 // ================================================================== host side
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
 
@@ -1264,7 +1299,7 @@ int b200md_rebomos_pack(b200md_ctx *c)
   if (c->nall == 0) return B200MD_OK;
   LaunchScope ls(c, "pack");
   pack_xq_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, c->map_d.p,
-                                                                   c->ntypes, c->nall, c->xq.p, c->flags.p);
+                                                                   c->ntypes, 0, c->nall, c->xq.p, c->flags.p);
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
 }
@@ -1333,6 +1368,32 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
         c->lj_num.p, c->lj_val.p, c->flags.p);
     CUDA_TRY(c, cudaGetLastError());
   }
+  // upload pipelining (plugin mode): which piece of the position upload each range of centers has to wait for
+  c->h2d_ready = false;
+  if (c->h2d_chunks > 1 && inum >= c->d2h_min_atoms && !c->sys) {
+    const int K = c->h2d_chunks;
+    ChunkBounds cb;
+    cb.K = K;
+    for (int k = 0; k <= K; k++) cb.t[k] = (int) ((long long) inum * k / K);
+    int *dep = c->flags.p + 16;    // flags holds 16 + B200MD_MAX_D2H_CHUNKS ints
+    CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
+    {
+      LaunchScope ls(c, "build_inner");
+      dep_range_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, inum, cb, dep);
+    }
+    int *pin = (int *) (c->pin_scal.p + 48);
+    CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < K; k++) {
+      int p = k;    // a range always needs its own piece
+      while (p + 1 < K && pin[k] >= cb.t[p + 1]) p++;
+      c->h2d_need[k] = p;
+      c->h2d_t[k] = cb.t[k];
+    }
+    c->h2d_t[K] = inum;
+    c->h2d_K = K;
+    c->h2d_ready = true;
+  }
   c->inner_valid = true;
   c->n_inner_rebuild++;
   return B200MD_OK;
@@ -1364,42 +1425,48 @@ int b200md_rebomos_refresh_inner(b200md_ctx *c)
 
 // force kernels on whatever is resident: xq, inner lists.  f and scal must be zeroed by the caller.
 template <bool EV, bool DET, bool ATOM>
-static void launch_centers(b200md_ctx *c, const DetTables &det)
+static void launch_centers(b200md_ctx *c, const DetTables &det, int t_lo, int t_hi, bool overflow_pass)
 {
   const int inum = c->list_inum;
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + inum + 32, *ovf = c->cen_list.p + 2 * ((size_t) inum + 32);
   int *cnt0 = c->flags.p + 12, *cnt1 = c->flags.p + 13, *cntO = c->flags.p + 14;
-  // Mo centers: 16 lanes, 16 staged bonds; S centers: 4 lanes, 8 staged bonds, overflow to 16/16.
-  // Grids cover the worst case (every owned atom in one class); surplus groups see g >= count and leave.
-  const int grid0 = min(nblocks((long long) inum * 16, 128), c->num_sms * 48);
-  const int grid1 = min(nblocks((long long) inum * 4, 128), c->num_sms * 48);
-#define RC_ARGS(list, cnt, ol, oc) \
-  c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
+  const long long *scan = (const long long *) c->cen_scan.p;
+  // Mo centers: 16 lanes, 16 staged bonds; S centers: 4 lanes, overflow to 16/16.
+  // Grids cover the worst case (every atom of the range in one class); surplus groups see g >= count and leave.
+  const int nr = t_hi - t_lo;
+  const int grid0 = min(nblocks((long long) nr * 16, 128), c->num_sms * 48);
+  const int grid1 = min(nblocks((long long) nr * 4, 128), c->num_sms * 48);
+#define RC_ARGS(list, cnt, sc, ol, oc) \
+  c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, c->scal.p, c->flags.p, \
+      c->pa_e, c->pa_v
   // occupancy (r02 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
   // 4 bonds per center (bulk S has 3; more go to the overflow launch) which cuts its shared memory from 45 to 17 KB, and
   // runs at 72 registers (7 CTAs/SM): 0.257 -> 0.210 ms; at 64 registers 0.213, at 80: 0.223, unbounded (104): 0.280
   constexpr bool PLAIN = !EV && !DET && !ATOM;
   constexpr int MB_MO = PLAIN ? 6 : 5, MB_S = PLAIN ? 7 : 5, CAP_S = PLAIN ? 4 : 8;
-  {
-    LaunchScope ls(c, "rebo_center_mo");
-    rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM, MB_MO><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, nullptr, nullptr));
+  if (nr > 0) {
+    {
+      LaunchScope ls(c, "rebo_center_mo");
+      rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM, MB_MO><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, scan, nullptr, nullptr));
+    }
+    {
+      LaunchScope ls(c, "rebo_center_s");
+      rebo_center_kernel<128, 4, CAP_S, 1, EV, DET, ATOM, MB_S><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, scan, ovf, cntO));
+    }
   }
-  {
-    LaunchScope ls(c, "rebo_center_s");
-    rebo_center_kernel<128, 4, CAP_S, 1, EV, DET, ATOM, MB_S><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, ovf, cntO));
-  }
-  {
+  if (overflow_pass) {
     LaunchScope ls(c, "rebo_center_overflow");
-    rebo_center_kernel<128, 16, 16, 1, EV, DET, ATOM, MB_MO><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr));
+    rebo_center_kernel<128, 16, 16, 1, EV, DET, ATOM, MB_MO><<<c->num_sms * 2, 128, 0, c->stream>>>(RC_ARGS(ovf, cntO, nullptr, nullptr, nullptr));
   }
 }
 
-// many-body part (REBO_neigh + FREBO + bondorder, fdotr virial) on c->stream
-static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag)
+// many-body part (REBO_neigh + FREBO + bondorder, fdotr virial) on c->stream, for the centers with atom index in
+// [t_lo, t_hi).  first: set up this call's tables; last: overflow launch, deterministic gather, fdotr.
+static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi, bool first, bool last)
 {
   const int ncen = c->list_inum;
   const int rows = c->list_inum + c->list_gnum;
-  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 14, 0, sizeof(int), c->stream));
+  if (first) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 14, 0, sizeof(int), c->stream));
   if (ncen == 0) return B200MD_OK;
   DetTables det = {nullptr, nullptr, nullptr, nullptr};
   const bool detmode = c->deterministic != 0;
@@ -1412,24 +1479,28 @@ static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag)
     det.fi = c->det_fb.p + 3 * (size_t) ncen * B200MD_MAX_REBO;
     det.j = c->det_j.p;
     det.nb = c->det_j.p + (size_t) ncen * B200MD_MAX_REBO;
-    CUDA_TRY(c, cudaMemsetAsync(det.nb, 0, ncen * sizeof(int), c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(det.fi, 0, 3 * (size_t) ncen * sizeof(double), c->stream));
+    if (first) {
+      CUDA_TRY(c, cudaMemsetAsync(det.nb, 0, ncen * sizeof(int), c->stream));
+      CUDA_TRY(c, cudaMemsetAsync(det.fi, 0, 3 * (size_t) ncen * sizeof(double), c->stream));
+    }
   }
   const bool ev = eflag != 0;
   const bool atom = c->pa_e != nullptr;
   ARG_CHECK(c, !(atom && detmode), "per-atom energy/virial is not available in deterministic mode");
-  if (atom) launch_centers<true, false, true>(c, det);
+  if (atom) launch_centers<true, false, true>(c, det, t_lo, t_hi, last);
   else if (detmode) {
-    if (ev) launch_centers<true, true, false>(c, det);
-    else launch_centers<false, true, false>(c, det);
-    LaunchScope ls(c, "rebo_gather");
-    rebo_gather_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, rows, ncen, det,
-                                                                     c->f.p);
+    if (ev) launch_centers<true, true, false>(c, det, t_lo, t_hi, last);
+    else launch_centers<false, true, false>(c, det, t_lo, t_hi, last);
+    if (last) {
+      LaunchScope ls(c, "rebo_gather");
+      rebo_gather_kernel<<<nblocks(rows, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, rows, ncen, det,
+                                                                       c->f.p);
+    }
   } else {
-    if (ev) launch_centers<true, false, false>(c, det);
-    else launch_centers<false, false, false>(c, det);
+    if (ev) launch_centers<true, false, false>(c, det, t_lo, t_hi, last);
+    else launch_centers<false, false, false>(c, det, t_lo, t_hi, last);
   }
-  if (vflag) {
+  if (vflag && last) {
     LaunchScope ls(c, "fdotr");
     fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, c->scal.p);
   }
@@ -1493,7 +1564,7 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
 {
   int rc;
-  if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
+  if ((rc = rebomos_forces_manybody(c, eflag, vflag, 0, c->list_inum, true, true))) return rc;
   return rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
 }
 
@@ -1517,6 +1588,90 @@ static int check_flags(b200md_ctx *c, const int *fl)
   return B200MD_OK;
 }
 
+// Plugin-mode compute with the position upload, the force kernels and the force download all overlapped:
+//   upload stream : ghosts | piece 0 | piece 1 | ... (each packed into xq as it lands), displacement check, its flag
+//   compute stream: bond-order launches of center range k as soon as the piece holding the largest index it reads
+//                   has arrived (h2d_need, computed when the inner lists were built); then the LJ ranges
+//   copy stream   : ghost forces after the last bond-order launch, owned forces range by range behind the LJ launches
+// The inner lists are used SPECULATIVELY: whether an atom has moved more than margin/2 since they were derived is only
+// known once all positions are on the device.  If so (rare: every ~50+ steps at 300 K) the lists are re-derived and
+// the forces recomputed by the plain path; nothing of the speculative pass has been added to the caller's f by then.
+static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, const double *x, int eflag, int vflag,
+                                     double *f, double *eng_vdwl, double *virial, int *fl, bool *redo)
+{
+  *redo = false;
+  const int K = c->h2d_K;
+  const int nall = nlocal + nghost;
+  if (!c->up_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  for (int k = 0; k <= K; k++)
+    if (!c->up_ev[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->up_ev[k], cudaEventDisableTiming));
+  c->nlocal = nlocal;
+  c->nghost = nghost;
+  c->nall = nall;
+  const bool need_check = c->margin < c->skin;
+  int *pin_flag = (int *) (c->pin_scal.p + 56);
+  *pin_flag = 0;
+  // ---- upload stream
+  cudaStream_t compute_stream = c->stream;
+  c->stream = c->up_stream;    // LaunchScope and the helpers below enqueue on c->stream
+  int rc = B200MD_OK;
+  auto piece = [&](int lo, int hi) -> int {
+    if (hi <= lo) return B200MD_OK;
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p + 3 * (size_t) lo, x + 3 * (size_t) lo, 3 * (size_t) (hi - lo) * sizeof(double),
+                                cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long) (3 * (size_t) (hi - lo) * sizeof(double));
+    LaunchScope ls(c, "pack");
+    pack_xq_kernel<<<nblocks(hi - lo, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, c->map_d.p, c->ntypes, lo,
+                                                                    hi, c->xq.p, c->flags.p);
+    return B200MD_OK;
+  };
+  rc = piece(nlocal, nall);
+  for (int p = 0; p < K && !rc; p++) {
+    rc = piece(c->h2d_t[p], c->h2d_t[p + 1]);
+    if (!rc && cudaEventRecord(c->up_ev[p], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
+  }
+  if (!rc && need_check) {
+    const double half = 0.5 * c->margin;
+    {
+      LaunchScope ls(c, "check_disp");
+      check_disp_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, (const double4 *) c->xhold.p, nall,
+                                                                      half * half, c->flags.p);
+    }
+    if (cudaMemcpyAsync(pin_flag, c->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      rc = B200MD_ERR_CUDA;
+  }
+  if (!rc && cudaEventRecord(c->up_ev[K], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
+  c->stream = compute_stream;
+  if (rc) return rc;
+  // ---- compute stream
+  const size_t n3 = 3 * (size_t) nall;
+  CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+  for (int k = 0; k < K; k++) {
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->up_ev[c->h2d_need[k]], 0));
+    if ((rc = rebomos_forces_manybody(c, eflag, vflag, c->h2d_t[k], c->h2d_t[k + 1], k == 0, k == K - 1))) return rc;
+  }
+  if ((rc = b200md_d2h_begin(c))) return rc;
+  if ((rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, n3))) return rc;
+  const int KD = c->d2h_chunks;
+  for (int k = 0; k < KD; k++) {
+    const int t0 = (int) ((long long) nlocal * k / KD), t1 = (int) ((long long) nlocal * (k + 1) / KD);
+    if ((rc = rebomos_forces_lj(c, eflag, vflag, t0, t1))) return rc;
+    if ((rc = b200md_d2h_range(c, k + 1, f, 3 * (size_t) t0, 3 * (size_t) t1))) return rc;
+  }
+  // ---- the verdict on the lists arrives while the kernels are still running
+  CUDA_TRY(c, cudaEventSynchronize(c->up_ev[K]));
+  if (need_check && *pin_flag) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    b200md_collect_timers(c);
+    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
+    *redo = true;
+    return B200MD_OK;
+  }
+  return b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl);
+}
+
 extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, const double *x,
                                       const int *type, const int *tag, int eflag, int vflag, double *f,
                                       double *eng_vdwl, double *virial)
@@ -1535,20 +1690,31 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
   ARG_CHECK(c, c->list_inum == nlocal, "rebomos_compute: neighbor list was built for a different nlocal");
   ARG_CHECK(c, f != nullptr, "rebomos_compute: f is NULL");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag);
-  if (rc) return rc;
+  int rc;
+  int fl[16];
+  bool redo = false;
+  if (!eatom && !vatom && !c->deterministic && c->inner_valid && c->h2d_ready && c->d2h_chunks > 1 &&
+      c->type_on_device && (c->tag_on_device || !tag) && nlocal + nghost == c->ids_nall && c->nlocal == nlocal) {
+    if ((rc = rebomos_compute_pipelined(c, nlocal, nghost, x, eflag, vflag, f, eng_vdwl, virial, fl, &redo))) return rc;
+    c->n_pipelined++;
+    if (!redo) return check_flags(c, fl);
+    c->n_redo++;
+    // an atom had moved beyond the inner lists' margin: positions are on the device, re-derive and recompute
+    if ((rc = b200md_rebomos_build_inner(c))) return rc;
+  } else {
+    if ((rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag))) return rc;
+    if ((rc = b200md_rebomos_pack(c))) return rc;
+    if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
+  }
   const size_t n3 = 3 * (size_t) c->nall;
   CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
-  if ((rc = b200md_rebomos_pack(c))) return rc;
-  if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
   if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
-  int fl[16];
   if (!eatom && !vatom && c->d2h_chunks > 1 && nlocal >= c->d2h_min_atoms) {
     // Forces go home while the LJ kernels are still running: the many-body launches scatter into owned and ghost
     // entries, so they run first; ghost forces are then final and travel during the first LJ range, and every LJ
     // range [t_k, t_k+1) completes f of exactly those owned atoms, which travel during the next range.
-    if ((rc = rebomos_forces_manybody(c, eflag, vflag))) return rc;
+    if ((rc = rebomos_forces_manybody(c, eflag, vflag, 0, nlocal, true, true))) return rc;
     if ((rc = b200md_d2h_begin(c))) return rc;
     const int K = c->d2h_chunks;
     if ((rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, 3 * (size_t) c->nall))) return rc;

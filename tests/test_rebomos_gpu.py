@@ -312,3 +312,55 @@ def test_lj_center_pairs_equal_single_rows(ctx, oracle_built):
     ctx.set_option("lj_pairs", 1)
     assert S.rel_err(out[1][0], out[0][0]) < 1e-12
     lmp.close()
+
+
+@pytest.mark.parametrize("overwrite", [0, 1], ids=["accumulate", "overwrite"])
+def test_pipelined_upload_equals_plain_path(ctx, oracle_built, overwrite):
+    """Plugin-mode pipelining of the position upload (pieces of x land while the bond-order launches of earlier center
+    ranges run; the inner lists are used speculatively and the step is recomputed when the displacement check, which
+    needs all positions, says they were stale).  Forced on for a small system: (1) same forces as the plain path and
+    the oracle, (2) after a small move, (3) after a move beyond margin/2, which must take the recompute path."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), displace=0.15)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    nl, ng = snap["nlocal"], snap["nghost"]
+    init_ctx(ctx)
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    ctx.set_option("f_overwrite", overwrite)
+    ctx.set_option("d2h_min_atoms", 0)
+    ctx.set_option("d2h_chunks", 2)
+    ctx.set_option("h2d_chunks", 3)
+    base = 0.0 if overwrite else 0.5
+
+    def run(x):
+        f, e, v = ctx.rebomos_compute(nl, ng, x, snap["type"], snap["tag"], 1, 2, f=np.full((nl + ng, 3), base))
+        return f - base, e, v
+
+    try:
+        x0 = snap["x"].copy()
+        f0, e0, v0 = run(x0)                        # derives the inner lists: plain path
+        p0, r0 = ctx.counter("pipelined_calls"), ctx.counter("pipelined_redos")
+        f1, e1, v1 = run(x0)                        # pipelined
+        assert ctx.counter("pipelined_calls") == p0 + 1 and ctx.counter("pipelined_redos") == r0
+        assert S.rel_err(f1, f0) < 1e-14 and abs(e1 - e0) < 1e-13 * abs(e0) and S.rel_err(v1, v0) < 1e-13
+        assert S.rel_err(S.fold_ghost_forces(f1.copy(), snap["swaps"], nl), f_ref) < FTOL
+        assert abs(e1 - e_ref) < ETOL * abs(e_ref)
+        rng = np.random.default_rng(5)
+        x1 = x0 + rng.uniform(-0.05, 0.05, x0.shape)   # inside the margin: lists stay
+        f2, e2, v2 = run(x1)
+        assert ctx.counter("pipelined_redos") == r0
+        x2 = x1.copy()
+        x2[7] += (0.45, 0.45, 0.0)                  # |d| = 0.64 > margin/2 = 0.5 (< skin/2: the master list is still good)
+        f3, e3, v3 = run(x2)
+        assert ctx.counter("pipelined_redos") == r0 + 1
+        ctx.set_option("h2d_chunks", 1)             # plain path (re-derives the lists at the positions it is given)
+        for x, (fp, ep, vp) in ((x1, (f2, e2, v2)), (x2, (f3, e3, v3))):
+            fq, eq, vq = run(x)
+            assert S.rel_err(fp, fq) < 1e-13 and abs(ep - eq) < 1e-13 * abs(eq) and S.rel_err(vp, vq) < 1e-12
+    finally:
+        ctx.set_option("f_overwrite", 0)
+        ctx.set_option("d2h_chunks", 4)
+        ctx.set_option("h2d_chunks", 6)
+        ctx.set_option("d2h_min_atoms", 65536)
+        lmp.close()

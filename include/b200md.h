@@ -221,6 +221,12 @@ int b200md_measure_peaks(b200md_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
 /* page-locked host memory for callers that want DMA-speed x/f transfers */
 void *b200md_host_alloc(size_t bytes);
 void b200md_host_free(void *p);
+/* page-lock memory the CALLER owns (LAMMPS' atom->x / atom->f blocks, Memory::create'd: pair_rebomos.cpp reads them
+ * through the Pointers members): the piecewise x upload and ranged f download of the compute entry points only overlap
+ * with the kernels when the host side is pinned.  Returns 0 on success; a failure is not fatal (transfers are then
+ * staged by the driver).  Unregister before the block is freed or reallocated. */
+int b200md_host_register(void *p, size_t bytes);
+int b200md_host_unregister(void *p);
 
 /* =============================================================================
  * GPU-resident MD system (the benchmark driver's run loop; one per GPU/rank)

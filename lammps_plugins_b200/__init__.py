@@ -121,6 +121,8 @@ SYMBOLS = [
     ("b200md_measure_peaks", c_int, [c_void_p, _PD, _PD]),
     ("b200md_host_alloc", c_void_p, [ctypes.c_size_t]),
     ("b200md_host_free", None, [c_void_p]),
+    ("b200md_host_register", c_int, [c_void_p, ctypes.c_size_t]),
+    ("b200md_host_unregister", c_int, [c_void_p]),
     ("b200md_system_create", c_int, [c_void_p, POINTER(SystemDesc), c_int, _PD, _PD, _PI, _PI]),
     ("b200md_nccl_unique_id", c_int, [c_void_p]),
     ("b200md_system_comm_init", c_int, [c_void_p, c_void_p, c_int, c_int]),

@@ -207,6 +207,23 @@ extern "C" double b200md_event_elapsed_ms(b200md_ctx *c, int a, int b)
   return (double) ms;
 }
 
+extern "C" int b200md_host_register(void *p, size_t bytes)
+{
+  if (!p || !bytes) return B200MD_ERR_ARG;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e == cudaSuccess) return B200MD_OK;
+  cudaGetLastError();    // not sticky: the caller carries on with pageable memory
+  return (e == cudaErrorHostMemoryAlreadyRegistered) ? B200MD_OK : B200MD_ERR_CUDA;
+}
+
+extern "C" int b200md_host_unregister(void *p)
+{
+  if (!p) return B200MD_ERR_ARG;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) cudaGetLastError();
+  return e == cudaSuccess ? B200MD_OK : B200MD_ERR_CUDA;
+}
+
 extern "C" void *b200md_host_alloc(size_t bytes)
 {
   void *p = nullptr;

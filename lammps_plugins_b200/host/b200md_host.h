@@ -75,5 +75,37 @@ inline int sync_neighbor_list(b200md_ctx *ctx, LAMMPS_NS::Atom *atom, LAMMPS_NS:
                                   neighbor->skin);
 }
 
+// Page-locks LAMMPS' per-atom x and f blocks so that the library's piecewise upload / ranged download run as DMA beside
+// its kernels.  LAMMPS reallocates these blocks when nmax grows (Atom::avec->grow), so the registration is refreshed
+// whenever a base pointer or nmax changes.  B200MD_PIN_HOST=0 switches it off.
+struct PinnedAtomArrays {
+  void *seen_x = nullptr, *seen_f = nullptr;    // the blocks last looked at ...
+  int seen_nmax = 0;
+  void *reg_x = nullptr, *reg_f = nullptr;      // ... and what is actually registered (a refusal is not retried)
+  void release()
+  {
+    if (reg_x) b200md_host_unregister(reg_x);
+    if (reg_f) b200md_host_unregister(reg_f);
+    reg_x = reg_f = seen_x = seen_f = nullptr;
+    seen_nmax = 0;
+  }
+  void refresh(LAMMPS_NS::Atom *atom)
+  {
+    const char *env = getenv("B200MD_PIN_HOST");
+    if (env && atoi(env) == 0) return;
+    if (atom->nmax <= 0 || !atom->x || !atom->f) return;
+    void *px = &atom->x[0][0], *pf = &atom->f[0][0];
+    if (px == seen_x && pf == seen_f && atom->nmax == seen_nmax) return;
+    release();
+    const size_t bytes = 3 * (size_t) atom->nmax * sizeof(double);
+    if (b200md_host_register(px, bytes) == B200MD_OK) reg_x = px;
+    if (b200md_host_register(pf, bytes) == B200MD_OK) reg_f = pf;
+    seen_x = px;
+    seen_f = pf;
+    seen_nmax = atom->nmax;
+  }
+  ~PinnedAtomArrays() { release(); }
+};
+
 }    // namespace B200MDHost
 #endif

@@ -61,6 +61,7 @@ PairAEAM::~PairAEAM()
 void PairAEAM::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
+  pinned.refresh(atom);
 
   if (atom->nmax > nmax) {
     memory->destroy(rho);

@@ -20,6 +20,7 @@ PairStyle(aeam,PairAEAM);
 
 #include "b200md.h"
 #include "pair.h"
+#include "b200md_host.h"
 
 #include <string>
 #include <vector>
@@ -60,6 +61,7 @@ class PairAEAM : public Pair {
 
   b200md_ctx *ctx;
   int uploaded_nlocal, uploaded_nghost;
+  B200MDHost::PinnedAtomArrays pinned;    // atom->x / atom->f page-locked for DMA beside the kernels
 
   void allocate();
   virtual void read_file(char *);

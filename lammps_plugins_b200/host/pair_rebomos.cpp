@@ -60,6 +60,7 @@ PairREBOMoS::~PairREBOMoS()
 void PairREBOMoS::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
+  pinned.refresh(atom);
 
   const int nlocal = atom->nlocal;
   const int nghost = atom->nghost;

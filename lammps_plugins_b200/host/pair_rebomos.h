@@ -20,6 +20,7 @@ PairStyle(rebomos,PairREBOMoS);
 
 #include "b200md.h"
 #include "pair.h"
+#include "b200md_host.h"
 
 namespace LAMMPS_NS {
 
@@ -40,6 +41,7 @@ class PairREBOMoS : public Pair {
   double cut3rebo;
   bigint last_list_step;           // timestep stamp of the list now on the device
   int uploaded_nlocal, uploaded_nghost;
+  B200MDHost::PinnedAtomArrays pinned;    // atom->x / atom->f page-locked for DMA beside the kernels
 
   void read_file(char *);
   void allocate();

@@ -1530,13 +1530,13 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
     {
       LaunchScope ls(c, "lj_mo");
       if (atom) lj_pair_kernel<true, 0, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
-      else if (eflag || vflag) lj_pair_kernel<true, 0, 2, 1, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else if (eflag || vflag) lj_pair_kernel<true, 0, 2, 2, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
       else LJP_FORCE(0)
     }
     {
       LaunchScope ls(c, "lj_s");
       if (atom) lj_pair_kernel<true, 1, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
-      else if (eflag || vflag) lj_pair_kernel<true, 1, 2, 1, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      else if (eflag || vflag) lj_pair_kernel<true, 1, 2, 2, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
       else LJP_FORCE(1)
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -84,9 +84,30 @@ class Update : protected Pointers {
 class Modify : protected Pointers {
  public:
   int nve;    // 1 if "fix nve" on group all is defined
-  explicit Modify(LAMMPS *lmp) : Pointers(lmp), nve(0) {}
+  // "fix ID all nvt temp Tstart Tstop Tdamp": Nose-Hoover chain thermostat, LAMMPS defaults (tchain 3, tloop 1,
+  // drag 0), restating FixNH::setup / initial_integrate / final_integrate / nhc_temp_integrate [LAMMPS-core
+  // src/fix_nh.cpp]; needed to run USER-AEAM/sample.in:23 literally
+  int nvt;
+  double t_start, t_stop, t_period;
+  static const int MTCHAIN = 3;
+  double eta[MTCHAIN], eta_dot[MTCHAIN + 1], eta_dotdot[MTCHAIN], eta_mass[MTCHAIN];
+  double t_current, t_target, ke_target, tdof, t_freq;
+  explicit Modify(LAMMPS *lmp) : Pointers(lmp), nve(0), nvt(0), t_start(0), t_stop(0), t_period(0)
+  {
+    for (int k = 0; k < MTCHAIN; k++) eta[k] = eta_dot[k] = eta_dotdot[k] = eta_mass[k] = 0.0;
+    eta_dot[MTCHAIN] = 0.0;
+    t_current = t_target = ke_target = tdof = t_freq = 0.0;
+  }
+  void setup();    // after the setup force computation (Verlet::setup -> Modify::setup)
   void initial_integrate();
   void final_integrate();
+  double nh_energy() const;    // thermostat contribution to the conserved quantity (FixNH::compute_scalar)
+
+ private:
+  void nve_v();
+  void nve_x();
+  void compute_temp_target();
+  void nhc_temp_integrate();
 };
 
 class Output : protected Pointers {

@@ -174,6 +174,7 @@ void Update::setup_run()
   force_clear();
   force->pair->compute(eflag, vflag);
   comm->reverse_comm();
+  modify->setup();
   output->write_thermo(ntimestep);
 }
 
@@ -238,28 +239,8 @@ void Update::run(int nsteps)
 }
 
 // ================================================================== fix nve
-void Modify::initial_integrate()
+void Modify::nve_v()
 {
-  if (!nve) return;
-  double dtv = update->dt;
-  double dtf = 0.5 * update->dt * force->ftm2v;
-  double **x = atom->x, **v = atom->v, **f = atom->f;
-  double *mass = atom->mass;
-  int *type = atom->type;
-  int nlocal = atom->nlocal;
-  for (int i = 0; i < nlocal; i++) {
-    double dtfm = dtf / mass[type[i]];
-    v[i][0] += dtfm * f[i][0];
-    v[i][1] += dtfm * f[i][1];
-    v[i][2] += dtfm * f[i][2];
-    x[i][0] += dtv * v[i][0];
-    x[i][1] += dtv * v[i][1];
-    x[i][2] += dtv * v[i][2];
-  }
-}
-void Modify::final_integrate()
-{
-  if (!nve) return;
   double dtf = 0.5 * update->dt * force->ftm2v;
   double **v = atom->v, **f = atom->f;
   double *mass = atom->mass;
@@ -271,6 +252,129 @@ void Modify::final_integrate()
     v[i][1] += dtfm * f[i][1];
     v[i][2] += dtfm * f[i][2];
   }
+}
+
+void Modify::nve_x()
+{
+  double dtv = update->dt;
+  double **x = atom->x, **v = atom->v;
+  int nlocal = atom->nlocal;
+  for (int i = 0; i < nlocal; i++) {
+    x[i][0] += dtv * v[i][0];
+    x[i][1] += dtv * v[i][1];
+    x[i][2] += dtv * v[i][2];
+  }
+}
+
+void Modify::initial_integrate()
+{
+  if (nvt) {
+    // FixNH::initial_integrate: thermostat half step, then the velocity-Verlet half kick and drift
+    compute_temp_target();
+    nhc_temp_integrate();
+    nve_v();
+    nve_x();
+    return;
+  }
+  if (!nve) return;
+  nve_v();
+  nve_x();
+}
+
+void Modify::final_integrate()
+{
+  if (nvt) {
+    nve_v();
+    t_current = output->compute_temp();
+    nhc_temp_integrate();
+    return;
+  }
+  if (!nve) return;
+  nve_v();
+}
+
+// ---- fix nvt (FixNH with tstat only)
+void Modify::compute_temp_target()
+{
+  double delta = (double) (update->ntimestep - update->firststep);
+  if (delta != 0.0) delta /= (double) (update->laststep - update->firststep);
+  t_target = t_start + delta * (t_stop - t_start);
+  ke_target = tdof * force->boltz * t_target;
+}
+
+void Modify::setup()
+{
+  if (!nvt) return;
+  t_freq = 1.0 / t_period;
+  tdof = 3.0 * (double) atom->natoms - 3.0;
+  if (tdof < 0.0) tdof = 0.0;
+  t_current = output->compute_temp();
+  compute_temp_target();
+  const double boltz = force->boltz;
+  eta_mass[0] = tdof * boltz * t_target / (t_freq * t_freq);
+  for (int ich = 1; ich < MTCHAIN; ich++) eta_mass[ich] = boltz * t_target / (t_freq * t_freq);
+  for (int ich = 1; ich < MTCHAIN; ich++)
+    eta_dotdot[ich] = (eta_mass[ich - 1] * eta_dot[ich - 1] * eta_dot[ich - 1] - boltz * t_target) / eta_mass[ich];
+}
+
+void Modify::nhc_temp_integrate()
+{
+  const double boltz = force->boltz;
+  const double dt = update->dt;
+  const double dthalf = 0.5 * dt, dt4 = 0.25 * dt, dt8 = 0.125 * dt;
+  double expfac;
+  double kecurrent = tdof * boltz * t_current;
+  // eta_mass_flag = 1: masses follow the target temperature
+  eta_mass[0] = tdof * boltz * t_target / (t_freq * t_freq);
+  for (int ich = 1; ich < MTCHAIN; ich++) eta_mass[ich] = boltz * t_target / (t_freq * t_freq);
+  if (eta_mass[0] > 0.0) eta_dotdot[0] = (kecurrent - ke_target) / eta_mass[0];
+  else eta_dotdot[0] = 0.0;
+  // nc_tchain = 1, tdrag_factor = 1
+  for (int ich = MTCHAIN - 1; ich > 0; ich--) {
+    expfac = exp(-dt8 * eta_dot[ich + 1]);
+    eta_dot[ich] *= expfac;
+    eta_dot[ich] += eta_dotdot[ich] * dt4;
+    eta_dot[ich] *= expfac;
+  }
+  expfac = exp(-dt8 * eta_dot[1]);
+  eta_dot[0] *= expfac;
+  eta_dot[0] += eta_dotdot[0] * dt4;
+  eta_dot[0] *= expfac;
+  const double factor_eta = exp(-dthalf * eta_dot[0]);
+  {    // nh_v_temp
+    double **v = atom->v;
+    int nlocal = atom->nlocal;
+    for (int i = 0; i < nlocal; i++) {
+      v[i][0] *= factor_eta;
+      v[i][1] *= factor_eta;
+      v[i][2] *= factor_eta;
+    }
+  }
+  t_current *= factor_eta * factor_eta;
+  kecurrent = tdof * boltz * t_current;
+  if (eta_mass[0] > 0.0) eta_dotdot[0] = (kecurrent - ke_target) / eta_mass[0];
+  else eta_dotdot[0] = 0.0;
+  for (int ich = 0; ich < MTCHAIN; ich++) eta[ich] += dthalf * eta_dot[ich];
+  eta_dot[0] *= expfac;
+  eta_dot[0] += eta_dotdot[0] * dt4;
+  eta_dot[0] *= expfac;
+  for (int ich = 1; ich < MTCHAIN; ich++) {
+    expfac = exp(-dt8 * eta_dot[ich + 1]);
+    eta_dot[ich] *= expfac;
+    eta_dotdot[ich] = (eta_mass[ich - 1] * eta_dot[ich - 1] * eta_dot[ich - 1] - boltz * t_target) / eta_mass[ich];
+    eta_dot[ich] += eta_dotdot[ich] * dt4;
+    eta_dot[ich] *= expfac;
+  }
+}
+
+// FixNH::compute_scalar for a pure thermostat: sum_k ( kT_k eta_k + 0.5 m_k eta_dot_k^2 ), kT_0 = ke_target
+double Modify::nh_energy() const
+{
+  if (!nvt) return 0.0;
+  const double kt = force->boltz * t_target;
+  double e = ke_target * eta[0] + 0.5 * eta_mass[0] * eta_dot[0] * eta_dot[0];
+  for (int ich = 1; ich < MTCHAIN; ich++) e += kt * eta[ich] + 0.5 * eta_mass[ich] * eta_dot[ich] * eta_dot[ich];
+  return e;
 }
 
 // ================================================================== thermo
@@ -989,9 +1093,22 @@ void Input::displace_atoms(std::vector<std::string> &a)
 void Input::fix(std::vector<std::string> &a)
 {
   if (a.size() < 3) error->all(FLERR, "Illegal fix command");
+  if (a[1] == "all" && a[2] == "nvt") {
+    // fix ID all nvt temp Tstart Tstop Tdamp   (USER-AEAM/sample.in:23)
+    if (a.size() != 7 || a[3] != "temp") error->all(FLERR, "minilmp supports 'fix ID all nvt temp Tstart Tstop Tdamp' only");
+    modify->t_start = utils::numeric(FLERR, a[4], false, lmp);
+    modify->t_stop = utils::numeric(FLERR, a[5], false, lmp);
+    modify->t_period = utils::numeric(FLERR, a[6], false, lmp);
+    if (modify->t_start <= 0.0 || modify->t_stop <= 0.0) error->all(FLERR, "Target temperature for fix nvt cannot be 0.0");
+    if (modify->t_period <= 0.0) error->all(FLERR, "Fix nvt Tdamp must be > 0.0");
+    modify->nvt = 1;
+    modify->nve = 0;
+    return;
+  }
   if (a[1] != "all" || a[2] != "nve")
-    error->all(FLERR, "minilmp supports 'fix ID all nve' only (got fix {} {})", a[1], a[2]);
+    error->all(FLERR, "minilmp supports 'fix ID all nve|nvt' only (got fix {} {})", a[1], a[2]);
   modify->nve = 1;
+  modify->nvt = 0;
 }
 
 void Input::run(std::vector<std::string> &a)
@@ -1248,6 +1365,8 @@ double minilmp_get_double(void *ptr, int rank, const char *name)
   if (n == "mvv2e") return l->force->mvv2e;
   if (n == "ftm2v") return l->force->ftm2v;
   if (n == "nktv2p") return l->force->nktv2p;
+  if (n == "nh_energy") return l->modify->nh_energy();
+  if (n == "nh_t_current") return l->modify->t_current;
   if (n == "binsizex") return l->neighbor->binsizex;
   if (n == "binsizey") return l->neighbor->binsizey;
   if (n == "binsizez") return l->neighbor->binsizez;

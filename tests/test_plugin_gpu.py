@@ -49,6 +49,31 @@ def test_aeam_sample_b200_plugin_vs_reference_plugin(oracle_built, grid):
     got.close()
 
 
+@pytest.mark.parametrize("grid", [(2, 2, 2)])
+def test_sample_in_as_shipped_b200_plugin_vs_reference_plugin(oracle_built, grid):
+    """BASELINE configs[1]: USER-AEAM/sample.in AS SHIPPED -- 20^3 fcc cells = 32 000 atoms, 0.75 % Si through
+    `set type/fraction ... 7683797`, `velocity all create 863.0 1082337` (LAMMPS' RanPark streams), `fix nvt`
+    (Nose-Hoover chain), 400 steps, thermo 100 -- run literally by the engine with the reference plugin and with the
+    B200 plugin (only the potential path is rewritten).  The reference ships no log for it; the check is that
+    switching the plugin changes nothing: same rebuild count, thermo rows equal to 1e-8."""
+    pot = os.path.join(S.potential_dir(), "AlSi.aeam")
+    cmds = [("pair_coeff * * %s Al Si" % pot) if c.startswith("pair_coeff") else c for c in S.input_script("sample.in")]
+    ref = run_script(S.oracle_plugin("aeam"), cmds, grid)
+    got = run_script(S.B200_AEAM_SO, cmds, grid)
+    assert ref.get_int("natoms") == 32000
+    assert got.get_int("nbuild") == ref.get_int("nbuild")
+    rr, gg = ref.thermo(), got.thermo()
+    assert [r["step"] for r in rr] == [0, 100, 200, 300, 400] == [r["step"] for r in gg]
+    assert abs(rr[0]["temp"] - 863.0) < 1e-9
+    for r, g in zip(gg, rr):
+        for key in ("temp", "pe", "etotal", "press"):
+            assert abs(r[key] - g[key]) < 1e-8 * max(abs(g[key]), 1.0), (r["step"], key, r[key], g[key])
+    print("sample.in thermo (step temp etotal pe press):",
+          [(g["step"], round(g["temp"], 3), round(g["etotal"], 4), round(g["pe"], 4), round(g["press"], 2)) for g in rr])
+    ref.close()
+    got.close()
+
+
 def test_forces_lockstep_along_reference_trajectory(ctx, oracle_built):
     """lock-step parity (chaotic divergence makes free-running comparison meaningless):
     the reference drives the trajectory; at every sampled step the CUDA path is fed the reference's own

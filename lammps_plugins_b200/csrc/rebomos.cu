@@ -991,8 +991,8 @@ __device__ __forceinline__ void ljp_segment(const RebomosDev &par, const double4
   }
 }
 
-template <bool EV, int ELEM, int D, int MINB, bool ATOM>
-__global__ void __launch_bounds__(BLOCK, MINB) lj_pair_kernel(const __grid_constant__ RebomosDev par,
+template <bool EV, int ELEM, int D, int MINB, bool ATOM, int NT>
+__global__ void __launch_bounds__(NT, MINB) lj_pair_kernel(const __grid_constant__ RebomosDev par,
                                                               const double4 *__restrict__ xq,
                                                               const int64_t *__restrict__ ljp_off,
                                                               const int *__restrict__ ljp_num,
@@ -1010,7 +1010,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_pair_kernel(const __grid_const
   const int first = (s0 + 1) >> 1, last = (s1 + 1) >> 1;
   const int sub = threadIdx.x & 7;
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int g = first + ((blockIdx.x * BLOCK + threadIdx.x) >> 3); g < last; g += (gridDim.x * BLOCK) >> 3) {
+  for (int g = first + ((blockIdx.x * NT + threadIdx.x) >> 3); g < last; g += (gridDim.x * NT) >> 3) {
     const int q = ELEM * P + g;
     const int2 ab = ljp_ab[q];
     const double4 xa = xq[ab.x];
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_pair_kernel(const __grid_const
       }
     }
   }
-  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+  if (EV) block_accumulate<7, NT>(ev, scal);
 }
 
 // capacity of every pair row = master rows of both centers (8-aligned by the scan that follows)
@@ -1520,23 +1520,26 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * 64);
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
   if (c->lj_pairs) {
-    const int pgrid = min(nblocks((long long) ((t_hi - t_lo) / 2 + 2) * 8, BLOCK), c->num_sms * 64);
+    const long long ngroups = (t_hi - t_lo) / 2 + 2;
 #define LJP_ARGS \
   c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, c->ljp_P, \
       (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, c->scal.p, c->pa_e, c->pa_v
+#define LJP_LAUNCH(EVF, E, MB, AT, NTH) \
+  lj_pair_kernel<EVF, E, 2, MB, AT, NTH><<<min(nblocks(ngroups * 8, NTH), c->num_sms * 64 * (256 / NTH)), NTH, 0, c->stream>>>(LJP_ARGS)
     // force-only instance: 2 position buffers per lane, 80 registers (3 CTAs/SM).  r02 sweep at 995 904 atoms: D=2/80 regs
     // 0.634 ms; D=1 0.77; D=3/80 (spills) 0.85; D=4/118 regs (2 CTAs) 0.69; D=2/64 regs (spills) 0.78
-#define LJP_FORCE(E) lj_pair_kernel<false, E, 2, 3, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+    // CTAs of 128 threads at 80 registers (6 CTAs/SM): 0.605 ms; 256 threads x 3 CTAs: 0.619; 72 regs x 7 CTAs (spills): 0.683
+#define LJP_FORCE(E) LJP_LAUNCH(false, E, 6, false, 128);
     {
       LaunchScope ls(c, "lj_mo");
-      if (atom) lj_pair_kernel<true, 0, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
-      else if (eflag || vflag) lj_pair_kernel<true, 0, 2, 2, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      if (atom) LJP_LAUNCH(true, 0, 1, true, 256);
+      else if (eflag || vflag) LJP_LAUNCH(true, 0, 2, false, 256);
       else LJP_FORCE(0)
     }
     {
       LaunchScope ls(c, "lj_s");
-      if (atom) lj_pair_kernel<true, 1, 2, 1, true><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
-      else if (eflag || vflag) lj_pair_kernel<true, 1, 2, 2, false><<<pgrid, BLOCK, 0, c->stream>>>(LJP_ARGS);
+      if (atom) LJP_LAUNCH(true, 1, 1, true, 256);
+      else if (eflag || vflag) LJP_LAUNCH(true, 1, 2, false, 256);
       else LJP_FORCE(1)
     }
     CUDA_TRY(c, cudaGetLastError());

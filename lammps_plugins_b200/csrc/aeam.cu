@@ -826,7 +826,7 @@ int b200md_aeam_density(b200md_ctx *c)
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_density_ang");
-    aeam_density_ang_kernel<<<c->num_sms * 2, 128, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p,
+    aeam_density_ang_kernel<<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p,
                                                                   c->ea_val.p, rhor, c->ang_list.p,
                                                                   c->flags.p + 6, c->rho.p, c->flags.p);
   }
@@ -885,9 +885,9 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
 #define AA_ARGS \
   c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, \
       c->scal.p, c->flags.p, c->pa_v
-    if (atom) aeam_force_ang_kernel<true, true><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
-    else if (ev) aeam_force_ang_kernel<true, false><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
-    else aeam_force_ang_kernel<false, false><<<c->num_sms * 2, 128, 0, c->stream>>>(AA_ARGS);
+    if (atom) aeam_force_ang_kernel<true, true><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
+    else if (ev) aeam_force_ang_kernel<true, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
+    else aeam_force_ang_kernel<false, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;

@@ -162,6 +162,8 @@ struct b200md_ctx {
   int sync_timing = 0;
   int f_overwrite = 0;
   int peratom_opt = 0;    // AEAM two-phase API: tally per-atom energy/virial from the density phase on
+  int ang_ctas = 10;     // AEAM angular launches: CTAs (4 warps, one angular center each) per SM; latency-bound kernels:
+                         // 2 -> 10 CTAs/SM: force_ang 0.30 -> 0.16 ms, density_ang 0.086 -> 0.041 ms at 15 360 Si atoms
   int lj_pairs = 1;      // LJ over pairs of neighboring centers sharing one union row (0: one row per center)
   int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency
   int d2h_chunks = 4;    // plugin mode: owned-atom index ranges whose forces go home while the next range computes

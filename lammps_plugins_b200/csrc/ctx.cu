@@ -125,7 +125,8 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "lj_pairs") {
     c->lj_pairs = value ? 1 : 0;
     c->inner_valid = false;
-  } else if (n == "h2d_chunks") {
+  } else if (n == "ang_ctas") c->ang_ctas = (int) (value < 1 ? 1 : value);
+  else if (n == "h2d_chunks") {
     c->h2d_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
     c->inner_valid = false;
   } else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;

@@ -32,9 +32,27 @@ __device__ __forceinline__ double pin(double v)
   return v;
 }
 
+// 1/sqrt(a) for a normal, positive a in a harmless range (bond lengths, 1 + S + P): MUFU.RSQ64H seed + two Newton
+// steps, no slow path, <= 2 ulp; r = a * rsqrt(a).  The library sqrt and division each cost ~25 instructions with
+// their special-case handling (6 % of the bond-order kernel's instructions went there, ncu source view).
+__device__ __forceinline__ double rsqrt_nr(double a)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+
 // Sp cutoff (pair_rebomos.h:195-211): value and derivative
 __device__ __forceinline__ double sp_switch(double r, double rmin, double rw, double &dS)
 {
+  if (r <= rmin) {    // t <= 0 (rw > 0): most bonds of a crystal; no division spent
+    dS = 0.0;
+    return 1.0;
+  }
   const double t = (r - rmin) / rw;    // rw = rcmax - rcmin
   if (t <= 0.0) {
     dS = 0.0;
@@ -407,7 +425,8 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
         if (in) {
           const int pos = nb + __popc(bits & ((1u << sub) - 1u));
-          const double r = sqrt(rsq);
+          const double rinv = rsqrt_nr(rsq);
+          const double r = rsq * rinv;
           double dw;
           const double w = sp_switch(r, tj ? par.rcmin[tb + 1] : par.rcmin[tb], tj ? par.rcw[tb + 1] : par.rcw[tb], dw);
           if (tj == 0) nM += w;
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
             s_dx[sb + pos] = dx;
             s_dy[sb + pos] = dy;
             s_dz[sb + pos] = dz;
-            s_ri[sb + pos] = 1.0 / r;
+            s_ri[sb + pos] = rinv;
             s_w[sb + pos] = w;
             s_dw[sb + pos] = dw;
             s_j[sb + pos] = j;
@@ -510,16 +529,19 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
           if (q >= nb) q -= nb;
           S += s_w[sb + q] * s_g[st + (nb - k - 1) * CAP + q];
         }
-        const double p = 1.0 / sqrt(1.0 + S + P);
+        const double p = rsqrt_nr(1.0 + S + P);
         const int pt = tb + s_tj[sb + m];
-        const double r = 1.0 / rinv;
+        const double r = (s_dx[sb + m] * s_dx[sb + m] + s_dy[sb + m] * s_dy[sb + m] + s_dz[sb + m] * s_dz[sb + m]) * rinv;
         const double Q = par.Q[pt], al = par.alpha[pt];
-        const double pre = wm * par.A[pt] * exp(-al * r);
-        const double VR = pre * (1.0 + Q * rinv);
-        const double dVR = pre * (-al - Q * rinv * rinv - Q * al * rinv) + VR / wm * dwm;
+        // VR = wm * VR0, VA = wm * VA0: the reference's VR / wm * dwm is VR0 * dwm without the division
+        const double pre0 = par.A[pt] * exp(-al * r);
+        const double VR0 = pre0 * (1.0 + Q * rinv);
+        const double VR = wm * VR0;
+        const double dVR = wm * pre0 * (-al - Q * rinv * rinv - Q * al * rinv) + VR0 * dwm;
         const double be = par.Beta[pt];
-        const double VA = -wm * par.BIJc[pt] * exp(-be * r);
-        const double dVA = -be * VA + VA / wm * dwm;
+        const double VA0 = -par.BIJc[pt] * exp(-be * r);
+        const double VA = wm * VA0;
+        const double dVA = -be * VA + VA0 * dwm;
         pref = VA * 0.5 * (-0.5 * p * p * p);
         frad = 0.5 * (dVR + p * dVA) * rinv + pref * dP * dwm * rinv;
         if (EV) eacc[0] += 0.5 * (VR + p * VA);

@@ -1390,34 +1390,41 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
         c->lj_num.p, c->lj_val.p, c->flags.p);
     CUDA_TRY(c, cudaGetLastError());
   }
-  // upload pipelining (plugin mode): which piece of the position upload each range of centers has to wait for
-  c->h2d_ready = false;
-  if (c->h2d_chunks > 1 && inum >= c->d2h_min_atoms && !c->sys) {
-    const int K = c->h2d_chunks;
-    ChunkBounds cb;
-    cb.K = K;
-    for (int k = 0; k <= K; k++) cb.t[k] = (int) ((long long) inum * k / K);
-    int *dep = c->flags.p + 16;    // flags holds 16 + B200MD_MAX_D2H_CHUNKS ints
-    CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
-    {
-      LaunchScope ls(c, "build_inner");
-      dep_range_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, inum, cb, dep);
-    }
-    int *pin = (int *) (c->pin_scal.p + 48);
-    CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < K; k++) {
-      int p = k;    // a range always needs its own piece
-      while (p + 1 < K && pin[k] >= cb.t[p + 1]) p++;
-      c->h2d_need[k] = p;
-      c->h2d_t[k] = cb.t[k];
-    }
-    c->h2d_t[K] = inum;
-    c->h2d_K = K;
-    c->h2d_ready = true;
-  }
+  c->h2d_ready = false;    // the upload dependencies below belong to these lists (plugin mode computes them on demand)
   c->inner_valid = true;
   c->n_inner_rebuild++;
+  return B200MD_OK;
+}
+
+// upload pipelining (plugin mode): which piece of the position upload each range of centers has to wait for.  Computed
+// from the short rows the first time a plugin-mode call finds fresh inner lists (one small kernel + one host read).
+static int rebomos_prepare_pipeline(b200md_ctx *c)
+{
+  const int inum = c->list_inum;
+  c->h2d_ready = false;
+  if (c->h2d_chunks <= 1 || inum < c->d2h_min_atoms || inum == 0) return B200MD_OK;
+  const int K = c->h2d_chunks;
+  ChunkBounds cb;
+  cb.K = K;
+  for (int k = 0; k <= K; k++) cb.t[k] = (int) ((long long) inum * k / K);
+  int *dep = c->flags.p + 16;    // flags holds 16 + B200MD_MAX_D2H_CHUNKS ints
+  CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
+  {
+    LaunchScope ls(c, "build_inner");
+    dep_range_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, inum, cb, dep);
+  }
+  int *pin = (int *) (c->pin_scal.p + 48);
+  CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < K; k++) {
+    int p = k;    // a range always needs its own piece
+    while (p + 1 < K && pin[k] >= cb.t[p + 1]) p++;
+    c->h2d_need[k] = p;
+    c->h2d_t[k] = cb.t[k];
+  }
+  c->h2d_t[K] = inum;
+  c->h2d_K = K;
+  c->h2d_ready = true;
   return B200MD_OK;
 }
 
@@ -1731,6 +1738,7 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
     if ((rc = b200md_rebomos_pack(c))) return rc;
     if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
   }
+  if (!c->h2d_ready && !eatom && !vatom && !c->deterministic && (rc = rebomos_prepare_pipeline(c))) return rc;
   const size_t n3 = 3 * (size_t) c->nall;
   CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));

@@ -75,6 +75,24 @@ inline int sync_neighbor_list(b200md_ctx *ctx, LAMMPS_NS::Atom *atom, LAMMPS_NS:
                                   neighbor->skin);
 }
 
+// Is atom->f known to be all zero when Pair::compute() is entered?  Verlet::force_clear() zeroes it and only fixes with
+// a pre_force() method run between that and the pair style; a sub-style of pair hybrid may find the forces of the
+// styles before it.  When it is zero the library WRITES the forces (DMA straight into atom->f) instead of adding them
+// on the host -- at 1 M atoms the host-side add (96 MB of memory traffic on one core) costs several times the GPU
+// step.  B200MD_F_OVERWRITE=0 forces the accumulate path.
+template <class PairT, class ForceT, class ModifyT> inline bool forces_zero_on_entry(PairT *self, ForceT *force, ModifyT *modify)
+{
+  const char *env = getenv("B200MD_F_OVERWRITE");
+  if (env && atoi(env) == 0) return false;
+  if ((void *) force->pair != (void *) self) return false;    // pair hybrid and friends
+#ifdef LMPSHIM_H
+  (void) modify;    // the API shim's host application has no pre_force fixes (its Modify type is opaque here)
+  return true;
+#else
+  return modify->n_pre_force == 0;
+#endif
+}
+
 // Page-locks LAMMPS' per-atom x and f blocks so that the library's piecewise upload / ranged download run as DMA beside
 // its kernels.  LAMMPS reallocates these blocks when nmax grows (Atom::avec->grow), so the registration is refreshed
 // whenever a base pointer or nmax changes.  B200MD_PIN_HOST=0 switches it off.

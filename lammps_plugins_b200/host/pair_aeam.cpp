@@ -12,6 +12,7 @@
 
 #include "b200md_host.h"
 #include "force.h"
+#include "modify.h"
 #include "memory.h"
 #include "text_file_reader.h"
 #include "tokenizer.h"
@@ -62,6 +63,13 @@ void PairAEAM::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
   pinned.refresh(atom);
+  {
+    const int ow = B200MDHost::forces_zero_on_entry(this, force, modify) ? 1 : 0;
+    if (ow != f_overwrite) {
+      B200MDHost::check(error, ctx, b200md_set_option(ctx, "f_overwrite", ow), "option");
+      f_overwrite = ow;
+    }
+  }
 
   if (atom->nmax > nmax) {
     memory->destroy(rho);

@@ -61,6 +61,7 @@ class PairAEAM : public Pair {
 
   b200md_ctx *ctx;
   int uploaded_nlocal, uploaded_nghost;
+  int f_overwrite = -1;                   // what the library was last told (b200md_set_option "f_overwrite")
   B200MDHost::PinnedAtomArrays pinned;    // atom->x / atom->f page-locked for DMA beside the kernels
 
   void allocate();

@@ -41,6 +41,7 @@ class PairREBOMoS : public Pair {
   double cut3rebo;
   bigint last_list_step;           // timestep stamp of the list now on the device
   int uploaded_nlocal, uploaded_nghost;
+  int f_overwrite = -1;                   // what the library was last told (b200md_set_option "f_overwrite")
   B200MDHost::PinnedAtomArrays pinned;    // atom->x / atom->f page-locked for DMA beside the kernels
 
   void read_file(char *);

@@ -33,6 +33,21 @@ def test_in_rebomos_bulk_through_the_b200_plugin(oracle_built, grid, neigh, monk
     lmp.close()
 
 
+@pytest.mark.parametrize("overwrite", ["0", "1"])
+def test_plugin_force_return_modes(oracle_built, overwrite, monkeypatch):
+    """The host class lets the library WRITE atom->f when it is known to be zero on entry (top-level pair style, no
+    pre_force fix; B200MD_F_OVERWRITE=1, the default) and ADDS otherwise (forced here with =0): same golden rows."""
+    monkeypatch.setenv("B200MD_F_OVERWRITE", overwrite)
+    gold = json.load(open(os.path.join(S.GOLDEN, "log_rebomos_bulk.json")))["log.rebomos-bulk.1"]
+    pot = os.path.join(S.potential_dir(), "MoS.REBO.set5b")
+    cmds = [("pair_coeff * * %s M S" % pot) if c.startswith("pair_coeff") else c for c in S.input_script("in.rebomos-bulk")]
+    lmp = run_script(S.B200_REBOMOS_SO, cmds)
+    for r, g in zip(lmp.thermo(), gold["thermo"]):
+        assert (S.fmt8(r["temp"]), S.fmt8(r["press"]), S.fmt8(r["pe"]), S.fmt8(r["ke"])) == \
+               (S.fmt8(g[1]), S.fmt8(g[2]), S.fmt8(g[3]), S.fmt8(g[4]))
+    lmp.close()
+
+
 @pytest.mark.parametrize("grid", [(1, 1, 1), (2, 1, 2)])
 def test_aeam_sample_b200_plugin_vs_reference_plugin(oracle_built, grid):
     """sample.in-like run (fcc Al + Si, 863 K, NVE): B200 plugin tracks the reference plugin"""

@@ -246,8 +246,11 @@ def run_b200(args):
         fp64_peak, hbm_here = None, None
     traffic = None
     tpath = os.path.join(HERE, "profiles", "r01_traffic.json")
+    l1_pct = None
     if os.path.exists(tpath) and world == 1 and not args.rep:
-        traffic = json.load(open(tpath)).get(kind, {}).get(dom)
+        tj = json.load(open(tpath))
+        traffic = tj.get(kind, {}).get(dom)
+        l1_pct = tj.get("l1_data_pipe_pct", {}).get(kind, {}).get(dom)
     # bytes this implementation's kernel has to stream (its own derived rows), for comparison with `traffic`
     rows_entries = ctx.counter("lj_entries")
     own_bytes = None
@@ -259,6 +262,9 @@ def run_b200(args):
                 "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
                 "algorithmic_bytes_per_atom_step": ALGO[kind]["bytes"],
                 "own_row_bytes_per_launch_set": own_bytes,
+                # the resource a neighbor-gather kernel presses against is the L1 data pipe (one gathered 32-byte sector
+                # per cycle and SM), not HBM: its utilisation in the committed ncu capture of this kernel (profiles/)
+                "l1_data_pipe_pct_ncu": l1_pct,
                 "hbm_copy_measured_here_gbs": hbm_here,
                 "whole_step": {"hbm_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak, "fp64_tflops": step_tflops,
                                "fp64_peak_measured_tflops": fp64_peak,

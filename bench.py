@@ -296,7 +296,7 @@ def run_b200(args):
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "kernel_groups_ms_per_step": {g: round(v, 5) for g, v in gtime.items()},
         "kernel_timing_pass": {"steps": ksteps, "ms_per_step_with_event_pairs": ms_kpass / ksteps},
-        "neighbor": {"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner, "setup_s": t_setup, "atoms_migrated_total": migrated},
+        "neighbor": {"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner, "tight_row_derives_total": ctx.counter("tight_refreshes"), "setup_s": t_setup, "atoms_migrated_total": migrated},
         "thermo_last": {k: (float(v) if not isinstance(v, np.ndarray) else None) for k, v in thermo[-1].items() if k != "virial"},
     }
     emit(line)

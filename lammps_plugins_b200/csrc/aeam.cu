@@ -749,6 +749,7 @@ int b200md_aeam_pack(b200md_ctx *c)
 int b200md_aeam_build_inner(b200md_ctx *c)
 {
   const int inum = c->list_inum;
+  c->tight_valid = false;    // the third list level exists for rebomos only
   double m = (c->margin_opt > 0.0) ? c->margin_opt : 0.5 * c->skin;    // default: two-level list, inner skin = skin/2
   if (m > c->skin) m = c->skin;
   c->margin = m;

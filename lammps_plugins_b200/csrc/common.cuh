@@ -159,6 +159,7 @@ struct b200md_ctx {
   // options
   int deterministic = 0;
   double margin_opt = 0.0;    // 0 -> use skin
+  double margin_t_opt = 0.4;  // margin of the tight rows in A ("margin_tight", mA); 0 = no third level
   int sync_timing = 0;
   int f_overwrite = 0;
   int peratom_opt = 0;    // AEAM two-phase API: tally per-atom energy/virial from the density phase on
@@ -222,6 +223,14 @@ struct b200md_ctx {
   DevBuf<int> lj_num;        // [inum]
   DevBuf<int> lj_val;        // directed LJ-window rows
   int64_t lj_capacity = 0;
+  // third list level (GPU-resident loop only): the rows the force kernels actually stream, filtered from the inner
+  // ("wide") rows above to rcut + margin_t and re-derived from them -- a pass over 128 entries per atom instead of the
+  // 496 of the master rows -- whenever an atom moved margin_t/2
+  DevBuf<int> short_idx_t, short_num_t, lj_val_t, lj_num_t;
+  DevBuf<double> xhold_t;    // [nall*4] positions at the last tight derive
+  double margin_t = 0.0;
+  bool tight_valid = false;
+  long long n_tight = 0;
   DevBuf<int> ljp_ab;        // pair mode: {a, b} atom indices of every pair row, [2][P] by element
   int ljp_P = 0;             // pair slots per element
   DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow], ascending index

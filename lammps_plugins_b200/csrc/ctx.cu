@@ -85,6 +85,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->list_off.release(); c->list_num.release(); c->list_val.release(); c->xhold.release();
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release(); c->ljp_ab.release();
+  c->short_idx_t.release(); c->short_num_t.release(); c->lj_val_t.release(); c->lj_num_t.release(); c->xhold_t.release();
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
@@ -117,6 +118,9 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   if (n == "deterministic") c->deterministic = value ? 1 : 0;
   else if (n == "margin") {
     c->margin_opt = 1.0e-3 * (double) value;
+    c->inner_valid = false;
+  } else if (n == "margin_tight") {
+    c->margin_t_opt = 1.0e-3 * (double) value;
     c->inner_valid = false;
   } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
@@ -151,6 +155,7 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
   if (n == "short_entries") return c->n_short_entries;
   if (n == "num_sms") return c->num_sms;
   if (n == "p2p_exchanges") return c->n_p2p;
+  if (n == "tight_refreshes") return c->n_tight;
   if (n == "pipelined_calls") return c->n_pipelined;
   if (n == "pipelined_redos") return c->n_redo;
   return -1;

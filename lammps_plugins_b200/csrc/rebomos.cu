@@ -1215,6 +1215,108 @@ __global__ void __launch_bounds__(BLOCK) dep_range_kernel(const int *__restrict_
   atomicMax(&dep[k], m);
 }
 
+// ================================================================== tight rows (third list level)
+// The force kernels stream rows filtered to rcut + margin_t.  They are derived from the inner ("wide") rows, never from
+// the master rows: a pair that reaches the cutoff before the next tight derive is within rcut + margin_t now (each atom
+// moves less than margin_t/2 until then), and it is in the wide rows because those hold every master-list pair that
+// was within rcut + margin when they were derived and are themselves re-derived at margin/2.  Order inside a row (and
+// inside each element segment of an LJ pair row) is preserved, so results do not depend on the level structure.
+struct TightLimits {
+  double shortsq[4], ljsq[4];
+};
+__global__ void __launch_bounds__(BLOCK) derive_tight_short_kernel(const double4 *__restrict__ xq,
+                                                                   const int *__restrict__ short_idx,
+                                                                   const int *__restrict__ short_num, int inum,
+                                                                   const TightLimits lim, int *__restrict__ out_idx,
+                                                                   int *__restrict__ out_num)
+{
+  // 8 lanes per owned row, ballot compaction inside the lane group
+  const int sub = threadIdx.x & 7;
+  const int i = (blockIdx.x * BLOCK + threadIdx.x) >> 3;
+  if (i >= inum) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gshift = lane & ~7u;
+  const unsigned gmask = 0xffu << gshift;
+  const double4 xi = xq[i];
+  const int ti = elem_of(xi);
+  const int n = short_num[i];
+  const int *row = short_idx + (size_t) i * B200MD_SHORT_WIDTH;
+  int *orow = out_idx + (size_t) i * B200MD_SHORT_WIDTH;
+  int cnt = 0;
+  for (int e0 = 0; e0 < n; e0 += 8) {
+    const int e = e0 + sub;
+    bool keep = false;
+    int j = 0;
+    if (e < n && ti >= 0) {
+      j = row[e];
+      const double4 xj = ld_sector(xq + j);
+      const int tj = elem_of(xj);
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      keep = tj >= 0 && dx * dx + dy * dy + dz * dz <= lim.shortsq[ti * 2 + tj];
+    }
+    const unsigned bits = (__ballot_sync(gmask, keep) >> gshift) & 0xffu;
+    if (keep) orow[cnt + __popc(bits & ((1u << sub) - 1u))] = j;
+    cnt += __popc(bits);
+  }
+  if (sub == 0) out_num[i] = cnt;
+}
+
+__global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *__restrict__ xq,
+                                                                const int64_t *__restrict__ ljp_off,
+                                                                const int *__restrict__ ljp_num,
+                                                                const int2 *__restrict__ ljp_ab,
+                                                                const int *__restrict__ lj_val, int P,
+                                                                const TightLimits lim, int *__restrict__ out_val,
+                                                                int *__restrict__ out_num)
+{
+  const int sub = threadIdx.x & 7;
+  const int q = (blockIdx.x * BLOCK + threadIdx.x) >> 3;
+  if (q >= 2 * P) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gshift = lane & ~7u;
+  const unsigned gmask = 0xffu << gshift;
+  const int2 ab = ljp_ab[q];
+  if (ab.x < 0) {
+    if (sub == 0) out_num[2 * q] = out_num[2 * q + 1] = 0;
+    return;
+  }
+  const int ti = q / P;
+  const double4 xa = xq[ab.x];
+  double4 xb = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+  if (ab.y >= 0) xb = xq[ab.y];
+  const int64_t base = ljp_off[q];
+  const int cap = (int) (ljp_off[q + 1] - base);
+  const int nA = ljp_num[2 * q], nB = ljp_num[2 * q + 1];
+  const int *row = lj_val + base;
+  int *orow = out_val + base;
+  for (int seg = 0; seg < 2; seg++) {
+    const int n = seg ? nB : nA;
+    const double limit = lim.ljsq[ti * 2 + seg];
+    int cnt = 0;
+    for (int e0 = 0; e0 < n; e0 += 8) {
+      const int e = e0 + sub;
+      bool keep = false;
+      int j = 0;
+      if (e < n) {
+        j = seg ? row[cap - 1 - e] : row[e];    // S partners fill the slot range from its back
+        const double4 xj = ld_sector(xq + j);
+        double dx = xa.x - xj.x, dy = xa.y - xj.y, dz = xa.z - xj.z;
+        keep = dx * dx + dy * dy + dz * dz <= limit;
+        dx = xb.x - xj.x, dy = xb.y - xj.y, dz = xb.z - xj.z;
+        keep = keep || (dx * dx + dy * dy + dz * dz <= limit);
+      }
+      const unsigned bits = (__ballot_sync(gmask, keep) >> gshift) & 0xffu;
+      if (keep) {
+        const int pos = cnt + __popc(bits & ((1u << sub) - 1u));
+        if (seg) orow[cap - 1 - pos] = j;
+        else orow[pos] = j;
+      }
+      cnt += __popc(bits);
+    }
+    if (sub == 0) out_num[2 * q + seg] = cnt;
+  }
+}
+
 // ================================================================== host side
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
 
@@ -1391,8 +1493,48 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
     CUDA_TRY(c, cudaGetLastError());
   }
   c->h2d_ready = false;    // the upload dependencies below belong to these lists (plugin mode computes them on demand)
+  c->tight_valid = false;  // ... and so do the tight rows (the resident loop derives them next)
   c->inner_valid = true;
   c->n_inner_rebuild++;
+  return B200MD_OK;
+}
+
+// derive (or re-derive) the tight rows from the wide rows at the positions now on the device; GPU-resident loop only
+int b200md_rebomos_derive_tight(b200md_ctx *c)
+{
+  c->tight_valid = false;
+  if (!c->inner_valid || !c->lj_pairs || c->deterministic) return B200MD_OK;
+  const double m = c->margin_t_opt;
+  if (m <= 0.0 || m >= c->margin) return B200MD_OK;
+  const int inum = c->list_inum, P = c->ljp_P;
+  if (inum == 0) return B200MD_OK;
+  c->margin_t = m;
+  TightLimits lim;
+  for (int k = 0; k < 4; k++) {
+    const double a = c->rp.rcmax[k] + m, b = c->rp.rcLJmax[k] + m;
+    lim.shortsq[k] = a * a;
+    lim.ljsq[k] = b * b;
+  }
+  CUDA_TRY(c, c->short_idx_t.reserve((size_t) B200MD_SHORT_WIDTH * inum + 64));
+  CUDA_TRY(c, c->short_num_t.reserve((size_t) inum + 32));
+  CUDA_TRY(c, c->lj_val_t.reserve((size_t) c->lj_capacity));
+  CUDA_TRY(c, c->lj_num_t.reserve(4 * (size_t) P + 32));
+  CUDA_TRY(c, c->xhold_t.reserve(4 * (size_t) c->nall + 8));
+  {
+    LaunchScope ls(c, "derive_tight");
+    derive_tight_short_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+        c->xq.p, c->short_idx.p, c->short_num.p, inum, lim, c->short_idx_t.p, c->short_num_t.p);
+  }
+  {
+    LaunchScope ls(c, "derive_tight");
+    derive_tight_lj_kernel<<<nblocks((long long) 2 * P * 8, BLOCK), BLOCK, 0, c->stream>>>(
+        c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, P, lim, c->lj_val_t.p, c->lj_num_t.p);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(c->xhold_t.p, c->xq.p, (size_t) c->nall * sizeof(double4), cudaMemcpyDeviceToDevice,
+                              c->stream));
+  c->tight_valid = true;
+  c->n_tight++;
   return B200MD_OK;
 }
 
@@ -1465,9 +1607,10 @@ static void launch_centers(b200md_ctx *c, const DetTables &det, int t_lo, int t_
   const int nr = t_hi - t_lo;
   const int grid0 = min(nblocks((long long) nr * 16, 128), c->num_sms * 48);
   const int grid1 = min(nblocks((long long) nr * 4, 128), c->num_sms * 48);
+  const bool tight = c->tight_valid && !DET;
+  const int *sidx = tight ? c->short_idx_t.p : c->short_idx.p, *snum = tight ? c->short_num_t.p : c->short_num.p;
 #define RC_ARGS(list, cnt, sc, ol, oc) \
-  c->rp, c->xq.p, c->short_idx.p, c->short_num.p, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, c->scal.p, c->flags.p, \
-      c->pa_e, c->pa_v
+  c->rp, c->xq.p, sidx, snum, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
   // occupancy (r02 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
   // 4 bonds per center (bulk S has 3; more go to the overflow launch) which cuts its shared memory from 45 to 17 KB, and
   // runs at 72 registers (7 CTAs/SM): 0.257 -> 0.210 ms; at 64 registers 0.213, at 80: 0.223, unbounded (104): 0.280
@@ -1550,8 +1693,9 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
   if (c->lj_pairs) {
     const long long ngroups = (t_hi - t_lo) / 2 + 2;
+    const int *ljnum = c->tight_valid ? c->lj_num_t.p : c->lj_num.p, *ljval = c->tight_valid ? c->lj_val_t.p : c->lj_val.p;
 #define LJP_ARGS \
-  c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, c->ljp_P, \
+  c->rp, c->xq.p, c->lj_off.p, ljnum, (const int2 *) c->ljp_ab.p, ljval, c->ljp_P, \
       (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, c->scal.p, c->pa_e, c->pa_v
 #define LJP_LAUNCH(EVF, E, MB, AT, NTH) \
   lj_pair_kernel<EVF, E, 2, MB, AT, NTH><<<min(nblocks(ngroups * 8, NTH), c->num_sms * 64 * (256 / NTH)), NTH, 0, c->stream>>>(LJP_ARGS)
@@ -1722,6 +1866,7 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
   ARG_CHECK(c, c->list_inum == nlocal, "rebomos_compute: neighbor list was built for a different nlocal");
   ARG_CHECK(c, f != nullptr, "rebomos_compute: f is NULL");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  c->tight_valid = false;    // the tight rows belong to the GPU-resident loop, which owns their refresh schedule
   int rc;
   int fl[16];
   bool redo = false;

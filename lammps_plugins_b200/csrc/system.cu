@@ -32,6 +32,7 @@
 #define P2P_SLOTS 18    // 3 message kinds x 3 dimensions x 2 directions
 
 int b200md_rebomos_build_inner(b200md_ctx *c);
+int b200md_rebomos_derive_tight(b200md_ctx *c);
 int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag);
 int b200md_aeam_build_inner(b200md_ctx *c);
 int b200md_aeam_density(b200md_ctx *c);
@@ -535,15 +536,17 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_unpack_f(double *__restrict__ f, 
   f[3 * j + 2] += __ldcg(src + 3 * (size_t) k + 2);
 }
 
-// FixNVE::initial_integrate fused with Neighbor::check_distance.  flags[9] = 2: some atom moved more than
-// skin/2 since the master list was built (LAMMPS' rebuild rule); 1: some atom moved more than margin/2 since
-// the inner lists were derived from it (two-level Verlet list: only the cheap inner filter is redone)
+// FixNVE::initial_integrate fused with Neighbor::check_distance.  flags[9] = 3: some atom moved more than
+// skin/2 since the master list was built (LAMMPS' rebuild rule); 2: some atom moved more than margin/2 since
+// the inner lists were derived from it (only the inner filter is redone); 1: more than margin_t/2 since the tight rows
+// were derived from the inner lists (only that short pass is redone)
 __global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict__ x, double *__restrict__ v,
                                                              const double *__restrict__ f, const int *__restrict__ type,
                                                              const double *__restrict__ mass, int nlocal, double dtf,
                                                              double dtv, const double4 *__restrict__ xhold,
                                                              double triggersq, const double4 *__restrict__ xhold_inner,
-                                                             double innersq, int *__restrict__ flags)
+                                                             double innersq, const double4 *__restrict__ xhold_tight,
+                                                             double tightsq, int *__restrict__ flags)
 {
   int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= nlocal) return;
@@ -562,12 +565,19 @@ __global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict
   x[i] = p;
   const double4 h = xhold[i];
   const double dx = p.x - h.x, dy = p.y - h.y, dz = p.z - h.z;
-  if (dx * dx + dy * dy + dz * dz > triggersq) atomicMax(&flags[9], 2);
-  else if (xhold_inner) {
+  int level = 0;
+  if (dx * dx + dy * dy + dz * dz > triggersq) level = 3;
+  if (level == 0 && xhold_inner) {
     const double4 g = xhold_inner[i];
     const double ex = p.x - g.x, ey = p.y - g.y, ez = p.z - g.z;
-    if (ex * ex + ey * ey + ez * ez > innersq) atomicMax(&flags[9], 1);
+    if (ex * ex + ey * ey + ez * ez > innersq) level = 2;
   }
+  if (level == 0 && xhold_tight) {    // also when the inner lists carry the full skin and have no trigger of their own
+    const double4 t = xhold_tight[i];
+    const double tx = p.x - t.x, ty = p.y - t.y, tz = p.z - t.z;
+    if (tx * tx + ty * ty + tz * tz > tightsq) level = 1;
+  }
+  if (level) atomicMax(&flags[9], level);
 }
 __global__ void __launch_bounds__(BLOCK) k_final_integrate(double *__restrict__ v, const double *__restrict__ f,
                                                            const int *__restrict__ type, const double *__restrict__ mass,
@@ -1804,6 +1814,7 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
     return rc;
   rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
   if (rc) return rc;
+  if (s->d.style == 0 && (rc = b200md_rebomos_derive_tight(c))) return rc;
   s->ago = 0;
   if (!first) s->nbuild++;
   return B200MD_OK;
@@ -2027,9 +2038,12 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
       LaunchScope ls(c, "initial_integrate");
       const bool two_level = c->inner_valid && c->margin < s->d.skin;
       const double innersq = 0.25 * c->margin * c->margin;
+      const bool three_level = c->inner_valid && c->tight_valid;
+      const double tightsq = 0.25 * c->margin_t * c->margin_t;
       k_initial_integrate<<<nblk(n), BLOCK, 0, c->stream>>>(c->xq.p, s->v.p, c->f.p, c->type.p, s->dmass.p, n, dtf, dtv,
                                                           s->xhold.p, triggersq,
                                                           two_level ? (const double4 *) c->xhold.p : nullptr, innersq,
+                                                          three_level ? (const double4 *) c->xhold_t.p : nullptr, tightsq,
                                                           c->flags.p);
     }
     // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
@@ -2039,15 +2053,18 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (flag) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
-    if (flag >= 2) {
+    if (flag >= 3) {
       if (s->ago == 1) s->ndanger++;
       if ((rc = reneighbor(c, s, false))) return rc;
     } else {
       if ((rc = halo_forward_x(c, s))) return rc;
-      if (flag == 1) {    // master list still valid: re-derive the inner lists from it at the current positions
+      if (flag == 2) {    // master list still valid: re-derive the inner lists from it at the current positions
         rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
         if (rc) return rc;
+        if (s->d.style == 0 && (rc = b200md_rebomos_derive_tight(c))) return rc;
         s->ninner++;
+      } else if (flag == 1 && s->d.style == 0) {    // inner lists still valid: only the tight rows are re-derived
+        if ((rc = b200md_rebomos_derive_tight(c))) return rc;
       }
     }
     if ((rc = compute_forces(c, s, thermo_step ? 1 : 0, thermo_step ? 2 : 0))) return rc;

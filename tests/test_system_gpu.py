@@ -142,6 +142,32 @@ def test_two_level_list_refresh_matches_single_level(ctx, oracle_built, style):
     lmp.close()
 
 
+def test_three_level_list_matches_two_level(ctx, oracle_built):
+    """third list level (rebomos): the force kernels stream tight rows (rcut + margin_tight) that are re-derived from the
+    inner rows -- not from the master rows -- whenever an atom moved margin_tight/2.  A hot run with the level switched
+    on (several tight derives, inner refreshes and master rebuilds) equals the run without it to rounding."""
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), extra=["velocity all create 1500.0 4928459"])
+    ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    out = {}
+    for label, mt in (("off", 0), ("on", 300)):
+        ctx.set_option("margin_tight", mt)
+        t0 = ctx.counter("tight_refreshes")
+        start_system(ctx, lmp, "rebomos")
+        ctx.system_run(150, 25)
+        out[label] = (ctx.system_thermo_rows(), ctx.system_sizes(), ctx.system_download(), ctx.counter("tight_refreshes") - t0)
+    ctx.set_option("margin_tight", 400)
+    (ra, sa, da, ta), (rb, sb, db, tb) = out["off"], out["on"]
+    print("builds", sa["nbuild"], sb["nbuild"], "inner refreshes", sa["ninner"], sb["ninner"], "tight derives", ta, tb)
+    assert ta == 0 and tb > sb["nbuild"] + sb["ninner"] + 1      # derived on its own schedule, not only after rebuilds
+    assert sa["nbuild"] == sb["nbuild"] and sa["ninner"] == sb["ninner"] and sb["ninner"] > 0
+    for q, g in zip(rb, ra):
+        assert abs(q["pe"] - g["pe"]) < 1e-11 * abs(g["pe"]) and abs(q["ke"] - g["ke"]) < 1e-9 * max(g["ke"], 1.0)
+        assert abs(q["press"] - g["press"]) < 1e-8 * max(abs(g["press"]), 1.0)
+    assert S.rel_err(db["f"][:db["nlocal"]], da["f"][:da["nlocal"]]) < 1e-9
+    assert np.array_equal(db["tag"][:db["nlocal"]], da["tag"][:da["nlocal"]])
+    lmp.close()
+
+
 def test_energy_drift_1000_nve_steps_matches_reference(ctx, oracle_built):
     """north star: "energy drift over 1000 NVE steps matching the reference's".  The shipped 288-atom cell at 300 K,
     dt = 1 fs, 1000 steps on the device and in the engine with the reference plugin.  Early on the two runs are the same

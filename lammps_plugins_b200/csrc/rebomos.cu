@@ -1269,15 +1269,13 @@ __global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *_
                                                                 const TightLimits lim, int *__restrict__ out_val,
                                                                 int *__restrict__ out_num)
 {
-  const int sub = threadIdx.x & 7;
-  const int q = (blockIdx.x * BLOCK + threadIdx.x) >> 3;
+  // one warp per pair row, two candidates per lane in flight
+  const int lane = threadIdx.x & 31;
+  const int q = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
   if (q >= 2 * P) return;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned gshift = lane & ~7u;
-  const unsigned gmask = 0xffu << gshift;
   const int2 ab = ljp_ab[q];
   if (ab.x < 0) {
-    if (sub == 0) out_num[2 * q] = out_num[2 * q + 1] = 0;
+    if (lane == 0) out_num[2 * q] = out_num[2 * q + 1] = 0;
     return;
   }
   const int ti = q / P;
@@ -1289,31 +1287,41 @@ __global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *_
   const int nA = ljp_num[2 * q], nB = ljp_num[2 * q + 1];
   const int *row = lj_val + base;
   int *orow = out_val + base;
+  const unsigned lt = (1u << lane) - 1u;
   for (int seg = 0; seg < 2; seg++) {
     const int n = seg ? nB : nA;
     const double limit = lim.ljsq[ti * 2 + seg];
     int cnt = 0;
-    for (int e0 = 0; e0 < n; e0 += 8) {
-      const int e = e0 + sub;
-      bool keep = false;
-      int j = 0;
-      if (e < n) {
-        j = seg ? row[cap - 1 - e] : row[e];    // S partners fill the slot range from its back
-        const double4 xj = ld_sector(xq + j);
-        double dx = xa.x - xj.x, dy = xa.y - xj.y, dz = xa.z - xj.z;
-        keep = dx * dx + dy * dy + dz * dz <= limit;
-        dx = xb.x - xj.x, dy = xb.y - xj.y, dz = xb.z - xj.z;
-        keep = keep || (dx * dx + dy * dy + dz * dz <= limit);
+    for (int e0 = 0; e0 < n; e0 += 64) {
+      int j[2];
+      double4 xj[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = e0 + 32 * u + lane;
+        j[u] = -1;
+        if (e < n) j[u] = seg ? row[cap - 1 - e] : row[e];    // S partners fill the slot range from its back
       }
-      const unsigned bits = (__ballot_sync(gmask, keep) >> gshift) & 0xffu;
-      if (keep) {
-        const int pos = cnt + __popc(bits & ((1u << sub) - 1u));
-        if (seg) orow[cap - 1 - pos] = j;
-        else orow[pos] = j;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        xj[u] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+        if (j[u] >= 0) xj[u] = ld_sector(xq + j[u]);
       }
-      cnt += __popc(bits);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        double dx = xa.x - xj[u].x, dy = xa.y - xj[u].y, dz = xa.z - xj[u].z;
+        bool keep = dx * dx + dy * dy + dz * dz <= limit;
+        dx = xb.x - xj[u].x, dy = xb.y - xj[u].y, dz = xb.z - xj[u].z;
+        keep = (j[u] >= 0) && (keep || (dx * dx + dy * dy + dz * dz <= limit));
+        const unsigned bits = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int pos = cnt + __popc(bits & lt);
+          if (seg) orow[cap - 1 - pos] = j[u];
+          else orow[pos] = j[u];
+        }
+        cnt += __popc(bits);
+      }
     }
-    if (sub == 0) out_num[2 * q + seg] = cnt;
+    if (lane == 0) out_num[2 * q + seg] = cnt;
   }
 }
 
@@ -1527,7 +1535,7 @@ int b200md_rebomos_derive_tight(b200md_ctx *c)
   }
   {
     LaunchScope ls(c, "derive_tight");
-    derive_tight_lj_kernel<<<nblocks((long long) 2 * P * 8, BLOCK), BLOCK, 0, c->stream>>>(
+    derive_tight_lj_kernel<<<nblocks((long long) 2 * P * 32, BLOCK), BLOCK, 0, c->stream>>>(
         c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, P, lim, c->lj_val_t.p, c->lj_num_t.p);
   }
   CUDA_TRY(c, cudaGetLastError());

@@ -127,26 +127,53 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     const int xb = ib - zb * my * mx - yb * mx;
     const int64_t obase = FILL ? row_off[i] : 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int r = 0; r < g.nruns; r++) {
-      const int4 run = runs[r];
-      int x0 = xb + run.x, x1 = xb + run.y;
-      const int y = yb + run.z, z = zb + run.w;
-      {
+    // The candidates of a row are the concatenation, in stencil-run order, of the runs' slices of the bin-sorted atom
+    // array.  32 runs at a time: lane k looks up run k's slice (all bin_start lookups in flight at once instead of one
+    // dependent chain per run), a warp scan turns the slice lengths into offsets, and the warp then walks the
+    // CONCATENATED candidate sequence 32 at a time, every lane finding its (run, position) by a 5-step search over the
+    // offsets.  Same candidates in the same order as the run-by-run walk (rows stay bit-exact), but full warps per
+    // trip -- a run of fcc Al holds ~16 atoms -- and 12 instead of 25+ dependent trips per row.
+    for (int r0 = 0; r0 < g.nruns; r0 += 32) {
+      int len = 0, s0 = 0;
+      if (r0 + lane < g.nruns) {
+        const int4 run = runs[r0 + lane];
+        int x0 = xb + run.x, x1 = xb + run.y;
+        const int y = yb + run.z, z = zb + run.w;
         // ghost atoms: skip stencil bins outside the local bin grid (NPairFullBinGhost).  For owned
         // atoms the grid always covers the stencil, so the same clip is a no-op that guards memory.
-        if (y < 0 || y >= my || z < 0 || z >= mz) continue;
-        x0 = max(x0, 0);
-        x1 = min(x1, mx - 1);
-        if (x0 > x1) continue;
+        if (y >= 0 && y < my && z >= 0 && z < mz) {
+          x0 = max(x0, 0);
+          x1 = min(x1, mx - 1);
+          if (x0 <= x1) {
+            const int b0 = z * my * mx + y * mx + x0;
+            s0 = (int) bin_start[b0];
+            len = (int) bin_start[b0 + (x1 - x0) + 1] - s0;
+          }
+        }
       }
-      const int b0 = z * my * mx + y * mx + x0;
-      const int s0 = (int) bin_start[b0], s1 = (int) bin_start[b0 + (x1 - x0) + 1];
-      for (int s = s0; s < s1; s += 32) {
-        const int q = s + lane;
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, inc, 31);
+      const int exc = inc - len;
+      for (int c0 = 0; c0 < total; c0 += 32) {
+        const int cidx = c0 + lane;
+        // largest k with exc_k <= cidx (zero-length runs share their successor's offset and are skipped by "largest")
+        int k = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int probe = k + step;
+          const int e = __shfl_sync(0xffffffffu, exc, probe & 31);
+          if (probe < 32 && e <= cidx) k = probe;
+        }
+        const int sk = __shfl_sync(0xffffffffu, s0, k), ek = __shfl_sync(0xffffffffu, exc, k);
         bool keep = false;
         int j = -1;
-        if (q < s1) {
-          j = bin_atoms[q];
+        if (cidx < total) {
+          j = bin_atoms[sk + (cidx - ek)];
           if (j != i) {
             const double4 xj = xt[j];
             const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;

@@ -191,15 +191,25 @@ int b200md_aeam_force_phase_peratom(b200md_ctx *ctx, const double *rho_all, cons
 int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp);
 
 /* ---- tuning / introspection ------------------------------------------------ */
-/* option names: "deterministic" (0/1: rebomos bond forces are written to a (center, slot) table and summed by
- * destination in a fixed order instead of FP64 atomics -- forces are then bitwise reproducible run to run), "margin" (inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin),
- * "p2p_halo" (0/1, default 1: multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the sender packs
- * straight into the receiver's HBM over NVLink -- falling back to NCCL send/recv when IPC is unavailable),
- * "peratom" (0/1, AEAM two-phase API only), "sync_timing" (0/1), "f_overwrite" (0/1: f is written, not accumulated -- valid when the caller
- * guarantees f == 0 on entry, as right after LAMMPS' force_clear()) */
+/* option names (value is an integer):
+ *  "deterministic"   0/1: rebomos bond forces are written to a (center, slot) table and summed by destination in a
+ *                    fixed order instead of FP64 atomics -- forces are then bitwise reproducible run to run
+ *  "margin"          inner-list skin in 1e-3 A, 0 = default skin/2; clamped to skin
+ *  "margin_tight"    rebomos, GPU-resident loop: margin of the tight rows the force kernels stream, in 1e-3 A
+ *                    (default 400; 0 = no third list level).  Re-derived from the inner rows at margin_tight/2
+ *  "lj_pairs"        0/1 (default 1): LJ over pairs of neighboring centers sharing one union row / one row per center
+ *  "f_overwrite"     0/1: f is written, not accumulated -- valid when the caller guarantees f == 0 on entry, as right
+ *                    after LAMMPS' force_clear()
+ *  "h2d_chunks"      plugin mode: pieces of the pipelined position upload (default 6, 1 = one copy, no overlap)
+ *  "d2h_chunks"      plugin mode: atom ranges of the pipelined force download (default 4, 1 = one copy)
+ *  "d2h_min_atoms"   plugin mode: below this many owned atoms both pipelines are off (default 65536)
+ *  "p2p_halo"        0/1 (default 1): multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the
+ *                    sender packs straight into the receiver's HBM over NVLink -- falling back to NCCL send/recv
+ *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)
+ *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
-/* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
- * "lj_entries", "short_entries", "num_sms", "p2p_exchanges" */
+/* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",
+ * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos" */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
  * ("rebo_center_mo","rebo_center_s","lj","fdotr","aeam_density","aeam_force",...) */

@@ -94,8 +94,11 @@ template <class PairT, class ForceT, class ModifyT> inline bool forces_zero_on_e
 }
 
 // Page-locks LAMMPS' per-atom x and f blocks so that the library's piecewise upload / ranged download run as DMA beside
-// its kernels.  LAMMPS reallocates these blocks when nmax grows (Atom::avec->grow), so the registration is refreshed
-// whenever a base pointer or nmax changes.  B200MD_PIN_HOST=0 switches it off.
+// its kernels.  OPT-IN (B200MD_PIN_HOST=1): LAMMPS reallocates these blocks when nmax grows (Atom::avec->grow, at a
+// reneighboring step, i.e. between two compute() calls), and CUDA wants a block unregistered BEFORE it is freed -- the
+// pair style only sees the new pointer afterwards.  The registration is refreshed whenever a base pointer or nmax
+// changes, which is what current drivers tolerate, but that order could not be exercised against a real LAMMPS here.
+// Without pinning everything works the same, the driver stages the transfers.
 struct PinnedAtomArrays {
   void *seen_x = nullptr, *seen_f = nullptr;    // the blocks last looked at ...
   int seen_nmax = 0;
@@ -110,7 +113,7 @@ struct PinnedAtomArrays {
   void refresh(LAMMPS_NS::Atom *atom)
   {
     const char *env = getenv("B200MD_PIN_HOST");
-    if (env && atoi(env) == 0) return;
+    if (!env || atoi(env) == 0) return;
     if (atom->nmax <= 0 || !atom->x || !atom->f) return;
     void *px = &atom->x[0][0], *pf = &atom->f[0][0];
     if (px == seen_x && pf == seen_f && atom->nmax == seen_nmax) return;

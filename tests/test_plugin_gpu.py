@@ -33,11 +33,13 @@ def test_in_rebomos_bulk_through_the_b200_plugin(oracle_built, grid, neigh, monk
     lmp.close()
 
 
+@pytest.mark.parametrize("pin", ["0", "1"])
 @pytest.mark.parametrize("overwrite", ["0", "1"])
-def test_plugin_force_return_modes(oracle_built, overwrite, monkeypatch):
+def test_plugin_force_return_modes(oracle_built, overwrite, pin, monkeypatch):
     """The host class lets the library WRITE atom->f when it is known to be zero on entry (top-level pair style, no
     pre_force fix; B200MD_F_OVERWRITE=1, the default) and ADDS otherwise (forced here with =0): same golden rows."""
     monkeypatch.setenv("B200MD_F_OVERWRITE", overwrite)
+    monkeypatch.setenv("B200MD_PIN_HOST", pin)          # page-locking of the host application's x/f blocks is opt-in
     gold = json.load(open(os.path.join(S.GOLDEN, "log_rebomos_bulk.json")))["log.rebomos-bulk.1"]
     pot = os.path.join(S.potential_dir(), "MoS.REBO.set5b")
     cmds = [("pair_coeff * * %s M S" % pot) if c.startswith("pair_coeff") else c for c in S.input_script("in.rebomos-bulk")]

@@ -29,19 +29,22 @@ namespace LAMMPS_NS {
 
 class PairAEAM : public Pair {
  public:
-  PairAEAM(class LAMMPS *);
+  explicit PairAEAM(class LAMMPS *lmp);
   ~PairAEAM() override;
-  void compute(int, int) override;
-  void settings(int, char **) override;
-  void coeff(int, char **) override;
-  void init_style() override;
-  double init_one(int, int) override;
 
-  int pack_forward_comm(int, int *, double *, int, int *) override;
-  void unpack_forward_comm(int, int, double *) override;
-  int pack_reverse_comm(int, int, double *) override;
-  void unpack_reverse_comm(int, int *, double *) override;
+  // ---- what LAMMPS drives: the virtuals the reference overrides (USER-AEAM/pair_aeam.h:30-41), same meaning
+  void settings(int narg, char **arg) override;      // pair_style aeam   (takes no arguments)
+  void coeff(int narg, char **arg) override;         // pair_coeff * * <setfl file> <element per atom type>
+  void init_style() override;                        // newton on, full list; tables go to the device here
+  double init_one(int itype, int jtype) override;    // largest cutoff of the file
+  void compute(int eflag, int vflag) override;       // density phase | fp halo by LAMMPS' Comm | force phase
   double memory_usage() override;
+
+  // F'(rho) of ghost atoms between the two device phases (forward); rho (reverse) kept for interface parity
+  int pack_forward_comm(int n, int *list, double *buf, int pbc_flag, int *pbc) override;
+  void unpack_forward_comm(int n, int first, double *buf) override;
+  int pack_reverse_comm(int n, int first, double *buf) override;
+  void unpack_reverse_comm(int n, int *list, double *buf) override;
 
  protected:
   int nmax;             // allocated size of per-atom arrays

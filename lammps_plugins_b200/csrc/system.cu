@@ -410,6 +410,47 @@ __global__ void __launch_bounds__(BLOCK) k_reverse_f_unpack(double *__restrict__
   f[3 * j + 2] += buf[3 * (size_t) k + 2];
 }
 
+// the -d and +d self swaps of one dimension in ONE launch (single rank: 3 launches per halo instead of 6; each of these
+// kernels is a few microseconds of work behind ~5 microseconds of launch latency).  Both swaps scan the same, earlier
+// atoms and own disjoint ghost ranges, so the forward copy needs no ordering; in the reverse fold an atom that sits in
+// both send lists (a box thinner than twice the ghost cutoff) receives two adds, hence the atomics.
+__global__ void __launch_bounds__(BLOCK) k_forward_x2(double4 *__restrict__ x, const int *__restrict__ list_a, int na,
+                                                      int first_a, double ax, double ay, double az, int pbc_a,
+                                                      const int *__restrict__ list_b, int nb, int first_b, double bx,
+                                                      double by, double bz, int pbc_b)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= na + nb) return;
+  const bool second = k >= na;
+  if (second) k -= na;
+  const int src = second ? list_b[k] : list_a[k];
+  const int dst = (second ? first_b : first_a) + k;
+  const double4 p = x[src];
+  double4 q = x[dst];
+  if (second ? pbc_b : pbc_a) {
+    q.x = p.x + (second ? bx : ax);
+    q.y = p.y + (second ? by : ay);
+    q.z = p.z + (second ? bz : az);
+  } else {
+    q.x = p.x;
+    q.y = p.y;
+    q.z = p.z;
+  }
+  x[dst] = q;
+}
+__global__ void __launch_bounds__(BLOCK) k_reverse_f2(double *__restrict__ f, const int *__restrict__ list_a, int na,
+                                                      int first_a, const int *__restrict__ list_b, int nb, int first_b)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= na + nb) return;
+  const bool second = k >= na;
+  if (second) k -= na;
+  const size_t j = second ? list_b[k] : list_a[k], g = (size_t) (second ? first_b : first_a) + k;
+  atomicAdd(&f[3 * j], f[3 * g]);
+  atomicAdd(&f[3 * j + 1], f[3 * g + 1]);
+  atomicAdd(&f[3 * j + 2], f[3 * g + 2]);
+}
+
 // ------------------------------------------------------------------ peer-memory halo kernels
 // The sender packs straight into the RECEIVER's window over NVLink (no staging copy, no NCCL launch), then the last
 // block to finish publishes the epoch in the receiver's flag; the receiver's unpack kernel waits for the epoch.
@@ -1382,6 +1423,16 @@ static int halo_forward_x(b200md_ctx *c, SystemState *s)
   for (int dim = 0; dim < 3; dim++) {
     const DimSwaps d = dim_swaps(s, dim);
     if (!d.paired) {
+      if (d.count == 2 && s->swaps[d.first].sendproc == s->me && s->swaps[d.first + 1].sendproc == s->me) {
+        const Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+        if (a.nsend + b.nsend) {
+          LaunchScope ls(c, "forward_x");
+          k_forward_x2<<<nblk(a.nsend + b.nsend), BLOCK, 0, c->stream>>>(
+              c->xq.p, a.sendlist.p, a.nsend, a.firstrecv, a.fshift[0], a.fshift[1], a.fshift[2], a.pbc_flag, b.sendlist.p,
+              b.nsend, b.firstrecv, b.fshift[0], b.fshift[1], b.fshift[2], b.pbc_flag);
+        }
+        continue;
+      }
       for (int k = 0; k < d.count; k++) {
         int rc = forward_x_one(c, s, s->swaps[d.first + k]);
         if (rc) return rc;
@@ -1570,6 +1621,16 @@ static int halo_reverse_f(b200md_ctx *c, SystemState *s)
   for (int dim = 2; dim >= 0; dim--) {
     const DimSwaps d = dim_swaps(s, dim);
     if (!d.paired) {
+      if (d.count == 2 && !c->deterministic && s->swaps[d.first].sendproc == s->me &&
+          s->swaps[d.first + 1].sendproc == s->me) {
+        const Swap &a = s->swaps[d.first], &b = s->swaps[d.first + 1];
+        if (a.nsend + b.nsend) {
+          LaunchScope ls(c, "reverse_f");
+          k_reverse_f2<<<nblk(a.nsend + b.nsend), BLOCK, 0, c->stream>>>(c->f.p, a.sendlist.p, a.nsend, a.firstrecv,
+                                                                         b.sendlist.p, b.nsend, b.firstrecv);
+        }
+        continue;
+      }
       for (int k = d.count - 1; k >= 0; k--) {
         int rc = reverse_f_one(c, s, s->swaps[d.first + k]);
         if (rc) return rc;

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     double nM = 0.0, nS = 0.0;
     const int *row = short_idx + (size_t) i * B200MD_SHORT_WIDTH;
     // UB trips' worth of candidates are gathered before the first one is looked at (UB gathers in flight per lane:
-    // ncu r02 showed the S-center launch waiting on one gather per trip, long-scoreboard 3.6 per issue); they are then
+    // ncu r01 v6 showed the S-center launch waiting on one gather per trip, long-scoreboard 3.6 per issue); they are then
     // consumed in row order, so membership and bond order stay those of the reference
     constexpr int UB = (G <= 4) ? 4 : 2;
     for (int e0 = 0; e0 < n; e0 += G * UB) {
@@ -891,14 +891,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) lj_kernel(const __grid_constant__
 }
 
 // ================================================================== K5b: tapered LJ over PAIRS of centers
-// ncu (r01/r02): lj_kernel is bound by the L1 data pipe, which delivers one gathered 32-byte position sector per
+// ncu (r01 v3/v6): lj_kernel is bound by the L1 data pipe, which delivers one gathered 32-byte position sector per
 // cycle and SM -- one per (center, candidate).  Two neighboring centers of the same element share most of their
 // candidates (spheres of radius rcLJmax + margin whose centers are ~3-5 A apart: union = 1.2-1.3 x one sphere), so a
 // lane group works on a PAIR (a, b) of consecutive centers of the ascending center list and streams the UNION row:
 // one gathered sector serves two interactions, 30-40 % fewer sectors per atom for one extra distance test per
 // candidate.  Row layout, element segmentation, exact rsq window thresholds and arithmetic are those of lj_kernel.
 // A center without partner (odd count) has b = -1 and a far-away dummy position (every candidate fails the window).
-// One (center, candidate) term, BRANCH-FREE in the 12-6 regime: ncu r02 showed the branchy form bound by
+// One (center, candidate) term, BRANCH-FREE in the 12-6 regime: ncu r01 v6 showed the branchy form bound by
 // fixed-latency dependency stalls ("wait" 4.2 per issue) -- every term was its own divergent region, so the FP64 chains
 // of the 2 x U terms of a trip could not overlap.  Here a term outside the window runs the same arithmetic on a
 // harmless rsq (1.0) and contributes fpair = 0, and the compiler interleaves all chains of a trip.  The cubic-taper
@@ -971,7 +971,7 @@ __device__ __forceinline__ void lj_term_taper(const RebomosDev &par, const doubl
 
 // One row segment [lo, hi) of a union row for the two centers of a pair, software-pipelined: D position buffers per
 // lane; while the two terms of one buffer are computed the gathers of the other D-1 are in flight, and the row indices
-// run two rounds ahead of the gathers (ncu r02: with load-then-use in the same trip the kernel sat on long-scoreboard
+// run two rounds ahead of the gathers (ncu r01 v6: with load-then-use in the same trip the kernel sat on long-scoreboard
 // stalls, 6.3 per issue at 34 % occupancy).  An empty slot holds a far-away dummy position that fails every window test.
 template <bool EV, int PT, int D>
 __device__ __forceinline__ void ljp_segment(const RebomosDev &par, const double4 *__restrict__ xq,
@@ -1619,7 +1619,7 @@ static void launch_centers(b200md_ctx *c, const DetTables &det, int t_lo, int t_
   const int *sidx = tight ? c->short_idx_t.p : c->short_idx.p, *snum = tight ? c->short_num_t.p : c->short_num.p;
 #define RC_ARGS(list, cnt, sc, ol, oc) \
   c->rp, c->xq.p, sidx, snum, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
-  // occupancy (r02 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
+  // occupancy (r01 v6 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
   // 4 bonds per center (bulk S has 3; more go to the overflow launch) which cuts its shared memory from 45 to 17 KB, and
   // runs at 72 registers (7 CTAs/SM): 0.257 -> 0.210 ms; at 64 registers 0.213, at 80: 0.223, unbounded (104): 0.280
   constexpr bool PLAIN = !EV && !DET && !ATOM;
@@ -1694,11 +1694,8 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   const int ncen = c->list_inum;
   if (t_hi <= t_lo) return B200MD_OK;
   const bool atom = c->pa_e != nullptr;
-  // grid: 8 lanes per center, capped (grid-stride loop); list pieces are located on the device.  Occupancy decides:
-  // 2 candidates in flight per lane at 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10;
-  // forcing 48 or 40 registers spills and loses (1.4, 1.7 ms)  [r01, 995 904 atoms]
-  const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * 64);
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
+  // grids: 8 lanes per center (pair of centers), capped (grid-stride loops); list pieces are located on the device
   if (c->lj_pairs) {
     const long long ngroups = (t_hi - t_lo) / 2 + 2;
     const int *ljnum = c->tight_valid ? c->lj_num_t.p : c->lj_num.p, *ljval = c->tight_valid ? c->lj_val_t.p : c->lj_val.p;
@@ -1707,7 +1704,7 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
       (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, c->scal.p, c->pa_e, c->pa_v
 #define LJP_LAUNCH(EVF, E, MB, AT, NTH) \
   lj_pair_kernel<EVF, E, 2, MB, AT, NTH><<<min(nblocks(ngroups * 8, NTH), c->num_sms * 64 * (256 / NTH)), NTH, 0, c->stream>>>(LJP_ARGS)
-    // force-only instance: 2 position buffers per lane, 80 registers (3 CTAs/SM).  r02 sweep at 995 904 atoms: D=2/80 regs
+    // force-only instance: 2 position buffers per lane, 80 registers (3 CTAs/SM).  r01 v6 sweep at 995 904 atoms: D=2/80 regs
     // 0.634 ms; D=1 0.77; D=3/80 (spills) 0.85; D=4/118 regs (2 CTAs) 0.69; D=2/64 regs (spills) 0.78
     // CTAs of 128 threads at 80 registers (6 CTAs/SM): 0.605 ms; 256 threads x 3 CTAs: 0.619; 72 regs x 7 CTAs (spills): 0.683
 #define LJP_FORCE(E) LJP_LAUNCH(false, E, 6, false, 128);
@@ -1726,6 +1723,9 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
     CUDA_TRY(c, cudaGetLastError());
     return B200MD_OK;
   }
+  // one row per center (lj_pairs = 0, the r01 v3 kernel).  Occupancy decided there too: 2 candidates in flight per lane at
+  // 64 registers (4 CTAs/SM) 0.87 ms; 3 at 80: 0.94; 4 at 96 (2 CTAs): 1.10; 48 or 40 registers spill (1.4, 1.7 ms)
+  const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * 64);
 #define LJ_ARGS(list) \
   c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, \
       c->scal.p, c->pa_e, c->pa_v

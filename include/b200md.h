@@ -272,6 +272,12 @@ int b200md_exchange_plan(int n, const int *leavers, int nleave, int *order, int 
 /* advance n NVE steps entirely on the device; thermo quantities are evaluated on the last step
  * (and every thermo_every steps, retrievable with b200md_system_thermo) */
 int b200md_system_run(b200md_ctx *ctx, int nsteps, int thermo_every);
+/* `fix ID all nvt temp Tstart Tstop Tdamp` for the resident loop (USER-AEAM/sample.in:23): Nose-Hoover chain with LAMMPS'
+ * defaults (tchain 3, tloop 1, no drag), restating FixNH [LAMMPS-core src/fix_nh.cpp] setup / initial_integrate /
+ * final_integrate / nhc_temp_integrate.  The ramp runs over each b200md_system_run call like over a LAMMPS `run`.
+ * Tdamp <= 0 switches back to plain NVE.  b200md_system_nh_energy = thermostat part of the conserved quantity. */
+int b200md_system_set_nvt(b200md_ctx *ctx, double t_start, double t_stop, double t_period);
+double b200md_system_nh_energy(b200md_ctx *ctx);
 /* thermo of the most recent evaluation: out[0..11] = step, temp, press, pe, ke, vol, virial[6]
  * (global sums over ranks) */
 int b200md_system_thermo(b200md_ctx *ctx, double *out);

@@ -130,6 +130,8 @@ SYMBOLS = [
     ("b200md_system_comm_init_local", c_int, [c_void_p, c_int, c_int, c_int]),
     ("b200md_exchange_plan", c_int, [c_int, _PI, c_int, _PI, _PI, _PI, _PI]),
     ("b200md_system_run", c_int, [c_void_p, c_int, c_int]),
+    ("b200md_system_set_nvt", c_int, [c_void_p, c_double, c_double, c_double]),
+    ("b200md_system_nh_energy", c_double, [c_void_p]),
     ("b200md_system_thermo", c_int, [c_void_p, _PD]),
     ("b200md_system_thermo_count", c_int, [c_void_p]),
     ("b200md_system_thermo_row", c_int, [c_void_p, c_int, _PD]),
@@ -417,6 +419,13 @@ class Context:
 
     def system_run(self, nsteps, thermo_every=0):
         self._check(self.L.b200md_system_run(self.h, int(nsteps), int(thermo_every)))
+
+    def system_set_nvt(self, t_start, t_stop, t_period):
+        """fix nvt temp t_start t_stop t_period for the resident loop (t_period <= 0: back to NVE)"""
+        self._check(self.L.b200md_system_set_nvt(self.h, float(t_start), float(t_stop), float(t_period)))
+
+    def system_nh_energy(self):
+        return float(self.L.b200md_system_nh_energy(self.h))
 
     def system_thermo_rows(self):
         rows = []

@@ -108,6 +108,14 @@ struct SystemState {
   int ago = 0;
   std::vector<std::vector<double>> rows;    // thermo rows
   long long nmigrated = 0, ninner = 0;
+  // fix nvt (Nose-Hoover chain, LAMMPS defaults: tchain 3, tloop 1, no drag) -- FixNH restated for the resident loop
+  struct NoseHoover {
+    bool on = false;
+    double t_start = 0, t_stop = 0, t_period = 0;
+    double eta[3] = {0, 0, 0}, eta_dot[4] = {0, 0, 0, 0}, eta_dotdot[3] = {0, 0, 0}, eta_mass[3] = {0, 0, 0};
+    double t_current = 0, t_target = 0, ke_target = 0, tdof = 0, t_freq = 0;
+    long long begin = 0, end = 0;
+  } nh;
   // transport between ranks: NCCL (one process per GPU) or the in-process loopback group
   ncclComm_t nccl = nullptr;
   std::shared_ptr<LocalGroup> local;
@@ -641,6 +649,12 @@ __global__ void __launch_bounds__(BLOCK) k_ke(const double *__restrict__ v, cons
     t[0] += (vx * vx + vy * vy + vz * vz) * mass[type[i]];
   }
   block_accumulate<1, BLOCK>(t, scal + 8);
+}
+// FixNH::nh_v_temp: v *= exp(-dt/2 * eta_dot[0])
+__global__ void __launch_bounds__(BLOCK) k_scale_v(double *__restrict__ v, size_t n3, double factor)
+{
+  const size_t k = (size_t) blockIdx.x * BLOCK + threadIdx.x;
+  if (k < n3) v[k] *= factor;
 }
 // w component: potential-specific element code from the LAMMPS type
 __global__ void __launch_bounds__(BLOCK) k_set_w(double4 *__restrict__ x, const int *__restrict__ type,
@@ -2080,6 +2094,113 @@ extern "C" int b200md_system_comm_init_local(b200md_ctx *c, int group, int nrank
   return B200MD_OK;
 }
 
+// ---- fix nvt on the device loop.  The chain variables live on the host (a handful of doubles); per step the loop
+// needs the kinetic energy once (one reduction kernel, read back with the step's other host sync) and scales the
+// velocities twice (FixNH::initial_integrate / final_integrate, [LAMMPS-core] src/fix_nh.cpp).
+static int nh_temperature(b200md_ctx *c, SystemState *s, double *t_out)
+{
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p + 10, 0, sizeof(double), c->stream));
+  {
+    LaunchScope ls(c, "ke");
+    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, c->scal.p + 2);    // -> scal[10]
+  }
+  int rc = xfer_allreduce_sum(c, s, c->scal.p + 10, 1);
+  if (rc) return rc;
+  double h = 0.0;
+  CUDA_TRY(c, cudaMemcpyAsync(&h, c->scal.p + 10, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const double dof = fmax(3.0 * (double) s->natoms - 3.0, 0.0);
+  *t_out = dof > 0.0 ? h * s->d.mvv2e / (dof * s->d.boltz) : 0.0;
+  return B200MD_OK;
+}
+
+static void nh_temp_target(SystemState *s)
+{
+  SystemState::NoseHoover &n = s->nh;
+  double delta = (double) (s->step - n.begin);
+  if (delta != 0.0) delta /= (double) (n.end - n.begin);
+  n.t_target = n.t_start + delta * (n.t_stop - n.t_start);
+  n.ke_target = n.tdof * s->d.boltz * n.t_target;
+}
+
+// FixNH::nhc_temp_integrate (nc_tchain = 1, tdrag_factor = 1, eta_mass_flag = 1); returns the velocity factor
+static double nh_chain_half_step(SystemState *s)
+{
+  SystemState::NoseHoover &n = s->nh;
+  const double boltz = s->d.boltz, dt = s->d.dt;
+  const double dthalf = 0.5 * dt, dt4 = 0.25 * dt, dt8 = 0.125 * dt;
+  double expfac;
+  double kecurrent = n.tdof * boltz * n.t_current;
+  n.eta_mass[0] = n.tdof * boltz * n.t_target / (n.t_freq * n.t_freq);
+  for (int ich = 1; ich < 3; ich++) n.eta_mass[ich] = boltz * n.t_target / (n.t_freq * n.t_freq);
+  n.eta_dotdot[0] = n.eta_mass[0] > 0.0 ? (kecurrent - n.ke_target) / n.eta_mass[0] : 0.0;
+  for (int ich = 2; ich > 0; ich--) {
+    expfac = exp(-dt8 * n.eta_dot[ich + 1]);
+    n.eta_dot[ich] *= expfac;
+    n.eta_dot[ich] += n.eta_dotdot[ich] * dt4;
+    n.eta_dot[ich] *= expfac;
+  }
+  expfac = exp(-dt8 * n.eta_dot[1]);
+  n.eta_dot[0] *= expfac;
+  n.eta_dot[0] += n.eta_dotdot[0] * dt4;
+  n.eta_dot[0] *= expfac;
+  const double factor = exp(-dthalf * n.eta_dot[0]);
+  n.t_current *= factor * factor;
+  kecurrent = n.tdof * boltz * n.t_current;
+  n.eta_dotdot[0] = n.eta_mass[0] > 0.0 ? (kecurrent - n.ke_target) / n.eta_mass[0] : 0.0;
+  for (int ich = 0; ich < 3; ich++) n.eta[ich] += dthalf * n.eta_dot[ich];
+  n.eta_dot[0] *= expfac;
+  n.eta_dot[0] += n.eta_dotdot[0] * dt4;
+  n.eta_dot[0] *= expfac;
+  for (int ich = 1; ich < 3; ich++) {
+    expfac = exp(-dt8 * n.eta_dot[ich + 1]);
+    n.eta_dot[ich] *= expfac;
+    n.eta_dotdot[ich] = (n.eta_mass[ich - 1] * n.eta_dot[ich - 1] * n.eta_dot[ich - 1] - boltz * n.t_target) / n.eta_mass[ich];
+    n.eta_dot[ich] += n.eta_dotdot[ich] * dt4;
+    n.eta_dot[ich] *= expfac;
+  }
+  return factor;
+}
+
+static int nh_scale_velocities(b200md_ctx *c, SystemState *s, double factor)
+{
+  const size_t n3 = 3 * (size_t) s->nlocal;
+  if (n3) {
+    LaunchScope ls(c, "nh_scale_v");
+    k_scale_v<<<(unsigned) ((n3 + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(s->v.p, n3, factor);
+  }
+  return B200MD_OK;
+}
+
+extern "C" int b200md_system_set_nvt(b200md_ctx *c, double t_start, double t_stop, double t_period)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, c->sys, "system_set_nvt: call b200md_system_create first");
+  SystemState::NoseHoover &n = c->sys->nh;
+  if (t_period <= 0.0) {    // back to plain NVE
+    n.on = false;
+    return B200MD_OK;
+  }
+  ARG_CHECK(c, t_start > 0.0 && t_stop > 0.0, "Target temperature for fix nvt cannot be 0.0");
+  n = SystemState::NoseHoover();
+  n.on = true;
+  n.t_start = t_start;
+  n.t_stop = t_stop;
+  n.t_period = t_period;
+  return B200MD_OK;
+}
+
+// thermostat part of the conserved quantity (FixNH::compute_scalar for a pure thermostat)
+extern "C" double b200md_system_nh_energy(b200md_ctx *c)
+{
+  if (!c || !c->sys || !c->sys->nh.on) return 0.0;
+  const SystemState::NoseHoover &n = c->sys->nh;
+  const double kt = c->sys->d.boltz * n.t_target;
+  double e = n.ke_target * n.eta[0] + 0.5 * n.eta_mass[0] * n.eta_dot[0] * n.eta_dot[0];
+  for (int ich = 1; ich < 3; ich++) e += kt * n.eta[ich] + 0.5 * n.eta_mass[ich] * n.eta_dot[ich] * n.eta_dot[ich];
+  return e;
+}
+
 extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
 {
   if (!c) return B200MD_ERR_ARG;
@@ -2091,8 +2212,25 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
   const double triggersq = 0.25 * s->d.skin * s->d.skin;
   const long long last = s->step + nsteps;
   int rc;
+  if (s->nh.on && nsteps > 0) {    // FixNH::setup at the start of every run
+    SystemState::NoseHoover &n = s->nh;
+    n.begin = s->step;
+    n.end = last;
+    n.t_freq = 1.0 / n.t_period;
+    n.tdof = fmax(3.0 * (double) s->natoms - 3.0, 0.0);
+    if ((rc = nh_temperature(c, s, &n.t_current))) return rc;
+    nh_temp_target(s);
+    n.eta_mass[0] = n.tdof * s->d.boltz * n.t_target / (n.t_freq * n.t_freq);
+    for (int ich = 1; ich < 3; ich++) n.eta_mass[ich] = s->d.boltz * n.t_target / (n.t_freq * n.t_freq);
+    for (int ich = 1; ich < 3; ich++)
+      n.eta_dotdot[ich] = (n.eta_mass[ich - 1] * n.eta_dot[ich - 1] * n.eta_dot[ich - 1] - s->d.boltz * n.t_target) / n.eta_mass[ich];
+  }
   for (int it = 0; it < nsteps; it++) {
     s->step++;
+    if (s->nh.on) {    // FixNH::initial_integrate: thermostat half step before the kick
+      nh_temp_target(s);
+      if ((rc = nh_scale_velocities(c, s, nh_chain_half_step(s)))) return rc;
+    }
     const bool thermo_step = (s->step == last) || (thermo_every > 0 && s->step % thermo_every == 0);
     const int n = s->nlocal;
     if (n) {
@@ -2132,6 +2270,10 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     if (s->nlocal) {    // not `n`: migration at a reneighboring step changes the owned count
       LaunchScope ls(c, "final_integrate");
       k_final_integrate<<<nblk(s->nlocal), BLOCK, 0, c->stream>>>(s->v.p, c->f.p, c->type.p, s->dmass.p, s->nlocal, dtf);
+    }
+    if (s->nh.on) {    // FixNH::final_integrate: temperature of the kicked velocities, thermostat half step
+      if ((rc = nh_temperature(c, s, &s->nh.t_current))) return rc;
+      if ((rc = nh_scale_velocities(c, s, nh_chain_half_step(s)))) return rc;
     }
     if (thermo_step)
       if ((rc = thermo(c, s))) return rc;

@@ -168,6 +168,47 @@ def test_three_level_list_matches_two_level(ctx, oracle_built):
     lmp.close()
 
 
+@pytest.mark.parametrize("tstop", [863.0, 500.0], ids=["constant-T", "ramp"])
+def test_device_nvt_tracks_engine(ctx, oracle_built, tstop):
+    """`fix nvt` in the GPU-resident loop (USER-AEAM/sample.in:23, Nose-Hoover chain restated from FixNH) against the
+    engine's fix nvt driving the reference plugin: sample.in on 8^3 cells, 200 steps -- thermo rows and the thermostat's
+    share of the conserved quantity agree to 1e-8; also with a temperature ramp (Tstart != Tstop)."""
+    pot = os.path.join(S.potential_dir(), "AlSi.aeam")
+    lmp = S.MiniLmp((1, 1, 1))
+    lmp.command("plugin load " + S.oracle_plugin("aeam"))
+    for c in S.input_script("sample.in"):
+        w = c.split()
+        if w[0] == "run":
+            continue
+        if w[0] == "region":
+            c = "region MeSi block 0 8 0 8 0 8"
+        if w[0] == "pair_coeff":
+            c = "pair_coeff * * %s Al Si" % pot
+        if w[0] == "fix":
+            c = "fix 1 all nvt temp 863.0 %g 0.1" % tstop
+        if w[0] == "thermo":
+            c = "thermo 50"
+        lmp.command(c)
+    ctx.aeam_init(aeam_tables())
+    start_system(ctx, lmp, "aeam")
+    ctx.system_set_nvt(863.0, tstop, 0.1)
+    ctx.system_run(200, 50)
+    rows = ctx.system_thermo_rows()
+    nh = ctx.system_nh_energy()
+    ctx.system_set_nvt(0.0, 0.0, 0.0)
+    lmp.command("run 200")
+    ref = lmp.thermo()
+    assert [r["step"] for r in rows] == [g["step"] for g in ref] == [0, 50, 100, 150, 200]
+    for r, g in zip(rows, ref):
+        print(r["step"], r["temp"], g["temp"], r["pe"], g["pe"])
+        assert abs(r["temp"] - g["temp"]) < 1e-8 * max(g["temp"], 1.0)
+        assert abs(r["pe"] - g["pe"]) < 1e-9 * abs(g["pe"])
+        assert abs(r["press"] - g["press"]) < 1e-7 * max(abs(g["press"]), 1.0)
+    assert abs(rows[0]["temp"] - 863.0) < 1e-9 and abs(rows[-1]["temp"] - 863.0) > 50.0    # the run is not trivial
+    assert abs(nh - lmp.get_double("nh_energy")) < 1e-8 * max(abs(nh), 1.0)
+    lmp.close()
+
+
 def test_energy_drift_1000_nve_steps_matches_reference(ctx, oracle_built):
     """north star: "energy drift over 1000 NVE steps matching the reference's".  The shipped 288-atom cell at 300 K,
     dt = 1 fs, 1000 steps on the device and in the engine with the reference plugin.  Early on the two runs are the same

@@ -142,6 +142,7 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
       const int hi = i > j ? i : j, lo = i > j ? j : i;
       const int ntri = t->nr[hi * nel + lo];
       d.pair_off[ij] = (int) (p_pair.size() / 8);
+      d.z2r_n[ij] = ntri;
       for (int m = 0; m <= n; m++) {
         for (int k = 0; k < 4; k++) p_pair.push_back(p_rhor[4 * ((size_t) d.rhor_off[ij] + m) + k]);
         const int mz = m < ntri ? m : ntri;
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
 struct PairPar {
   double cutgt, rdr;
   int nr, off;
+  int roff, zoff, nz, pad;    // cluster form: rows of the separate rhor / z2r tables, z2r row clamp
 };
 __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, bool rhor_table = false)
 {
@@ -285,6 +287,10 @@ __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, b
     sp[threadIdx.x].rdr = par.rdr[threadIdx.x];
     sp[threadIdx.x].nr = par.nr[threadIdx.x];
     sp[threadIdx.x].off = rhor_table ? par.rhor_off[threadIdx.x] : par.pair_off[threadIdx.x];
+    sp[threadIdx.x].roff = par.rhor_off[threadIdx.x];
+    sp[threadIdx.x].zoff = par.z2r_off[threadIdx.x];
+    sp[threadIdx.x].nz = par.z2r_n[threadIdx.x];
+    sp[threadIdx.x].pad = 0;
   }
   __syncthreads();
 }
@@ -340,6 +346,411 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
   if (mine && sub == 0) rho[i] = acc;
 }
 
+
+// ================================================================== cluster form (default)
+// CL consecutive owned centers (a "cluster") share ONE union row: every gathered candidate position is tested against
+// all CL centers, so a step gathers ~38 instead of ~81 position sectors per atom (fcc Al, cut + margin = 7 A), and the
+// density pass stores f'_{ti,tj}(r) of every (entry, center) slot next to the row (one 32-byte store per entry), so the
+// force pass reads it back as a coalesced stream instead of gathering the rhor row a second time: per in-range
+// (center, candidate) the two passes gather 2 spline sectors instead of 3.  Gathers are the bound of these kernels
+// (tools/microbench/gather.cu: 0.87 random sectors per cycle and SM, whatever the width), FP64 is at 10 %.
+#define CL 4
+#define CL_SHIFT 2
+#define CL_HT 1024
+#define CL_BLOCK 128
+
+__device__ __forceinline__ void st_sector(double4 *p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ double4 ld_stream_sector(const double4 *p)
+{
+  double4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// capacity of a cluster's union row: the sum of its centers' master rows (upper bound)
+__global__ void __launch_bounds__(BLOCK) aeam_cluster_cap_kernel(const int *__restrict__ list_num, int inum, int ncl,
+                                                                 int *__restrict__ cap)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= ncl) return;
+  int s = 0;
+#pragma unroll
+  for (int c = 0; c < CL; c++)
+    if (CL * q + c < inum) s += list_num[CL * q + c];
+  cap[q] = s;
+}
+
+// one warp per cluster: union of the centers' master-row entries within max(cut_ij, cut_ji) + margin of THAT center,
+// duplicates dropped through a per-warp hash set, order of first appearance (optionally sorted by atom index)
+__global__ void __launch_bounds__(CL_BLOCK) aeam_build_cluster_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ list_off,
+    const int *__restrict__ list_num, const int *__restrict__ list_val, int inum, int ncl,
+    const int64_t *__restrict__ ec_off, int *__restrict__ ec_num, int *__restrict__ ec_val, int *__restrict__ ang_list,
+    int *__restrict__ flags, int sort_rows)
+{
+  __shared__ int s_tab[CL_BLOCK / 32][CL_HT];
+  const int lane = threadIdx.x & 31;
+  const int q = (int) (((size_t) blockIdx.x * CL_BLOCK + threadIdx.x) >> 5);
+  if (q >= ncl) return;
+  int *tab = s_tab[threadIdx.x >> 5];
+  for (int k = lane; k < CL_HT; k += 32) tab[k] = -1;
+  __syncwarp();
+  const int64_t base = ec_off[q];
+  const unsigned lt = (1u << lane) - 1u;
+  int no = 0;
+  bool full = false;
+  for (int cc = 0; cc < CL && !full; cc++) {
+    const int i = CL * q + cc;
+    if (i >= inum) break;
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    const int n = list_num[i];
+    const int64_t mb = list_off[i];
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      bool keep = false;
+      int j = 0;
+      if (e < n) {
+        j = ld_stream_int(list_val + mb + e) & B200MD_NEIGHMASK;
+        const double4 xj = xq[j];
+        const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+        keep = dx * dx + dy * dy + dz * dz <= par.cutsq_list[ti * par.nel + etype(xj)];
+      }
+      if (keep) {    // find or insert
+        unsigned h = ((unsigned) j * 2654435761u) >> 22;    // 10 bits
+        for (;;) {
+          const int v = atomicCAS(&tab[h], -1, j);
+          if (v == -1) break;
+          if (v == j) {
+            keep = false;
+            break;
+          }
+          h = (h + 1) & (CL_HT - 1);
+        }
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, keep);
+      if (keep) ec_val[base + no + __popc(mk & lt)] = j;
+      no += __popc(mk);
+      if (no > CL_HT * 3 / 4 - 32) {    // warp-uniform: the hash set would fill up
+        if (lane == 0) flags[0] = 4;
+        full = true;
+        break;
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && ti >= par.nnonangular) ang_list[atomicAdd(&flags[6], 1)] = i;
+  }
+  if (sort_rows && !full && no > 1) {
+    // bitonic sort of the row by atom index in the (now free) hash table: adjacent lanes of the compute kernels then
+    // read adjacent sectors, which share 128-byte lines
+    __syncwarp();
+    int np = 32;
+    while (np < no) np <<= 1;
+    for (int k = lane; k < np; k += 32) tab[k] = k < no ? ec_val[base + k] : 0x7fffffff;
+    __syncwarp();
+    for (int kk = 2; kk <= np; kk <<= 1)
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+        for (int t = lane; t < np; t += 32) {
+          const int u = t ^ jj;
+          if (u > t) {
+            const int a = tab[t], b = tab[u];
+            const bool up = (t & kk) == 0;
+            if ((a > b) == up) {
+              tab[t] = b;
+              tab[u] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    for (int k = lane; k < no; k += 32) ec_val[base + k] = tab[k];
+  }
+  if (lane == 0) {
+    ec_num[q] = no;
+    atomicAdd(&flags[5], no);
+  }
+}
+
+__device__ __forceinline__ double comp4(const double4 &v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+
+// A1 (cluster form): density of the non-angular centers of a cluster, 8 lanes per cluster.  Also writes
+// f'_{ti,tj}(r) of every (entry, center) slot (0 where the density pass takes nothing) for the force pass.
+template <int U>
+__global__ void __launch_bounds__(BLOCK, 2) aeam_density_cl_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ec_off,
+    const int *__restrict__ ec_num, const int *__restrict__ ec_val, const double4 *__restrict__ rhor, int inum,
+    double *__restrict__ rho, double4 *__restrict__ ec_df)
+{
+  __shared__ PairPar sp[16];
+  load_pair_par(par, sp);
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int q = tid >> 3, sub = tid & 7;
+  const int i0 = q * CL;
+  double acc[CL], cx[CL], cy[CL], cz[CL];
+  int tb[CL];    // ti * nel of a center that takes a density here, else -1 (angular center, or beyond inum)
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    acc[c] = 0.0;
+    cx[c] = cy[c] = cz[c] = 0.0;
+    tb[c] = -1;
+  }
+  if (i0 < inum) {
+#pragma unroll
+    for (int c = 0; c < CL; c++)
+      if (i0 + c < inum) {
+        const double4 xi = xq[i0 + c];
+        cx[c] = xi.x;
+        cy[c] = xi.y;
+        cz[c] = xi.z;
+        const int ti = etype(xi);
+        tb[c] = ti < par.nnonangular ? ti * par.nel : -1;
+      }
+    const int n = ec_num[q];
+    const int64_t base = ec_off[q];
+    const int *row = ec_val + base;
+    double4 *df = ec_df + base;
+    for (int e0 = 0; e0 < n; e0 += 8 * U) {
+      int jj[U];
+      double4 xj[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int e = e0 + u * 8 + sub;
+        jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (jj[u] >= 0) xj[u] = ld_sector(xq + jj[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (jj[u] < 0) continue;
+        const int tj = etype(xj[u]);
+        bool hit[CL];
+        double pp[CL], rd[CL];
+        const double4 *ra[CL];
+#pragma unroll
+        for (int c = 0; c < CL; c++) {
+          const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          const PairPar &P = sp[(tb[c] < 0 ? 0 : tb[c]) + tj];
+          // r > cut -> out; i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
+          hit[c] = tb[c] >= 0 && jj[u] != i0 + c && rsq < P.cutgt;
+          int m;
+          spl_index(rsq * rsqrt_nr(fmax(rsq, 1.0e-300)), P.rdr, P.nr, m, pp[c]);
+          rd[c] = P.rdr;
+          ra[c] = rhor + P.roff + m;
+        }
+        double4 rw[CL];
+#pragma unroll
+        for (int c = 0; c < CL; c++)
+          if (hit[c]) rw[c] = ld_sector(ra[c]);
+        double o[CL];
+#pragma unroll
+        for (int c = 0; c < CL; c++) {
+          o[c] = 0.0;
+          if (hit[c]) {
+            acc[c] += spl_val(rw[c], pp[c]);
+            o[c] = spl_der(rw[c], pp[c], rd[c]);
+          }
+        }
+        st_sector(df + (e0 + u * 8 + sub), o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CL; c++) acc[c] = group_sum<8>(acc[c]);
+  if (sub == 0) {
+#pragma unroll
+    for (int c = 0; c < CL; c++)
+      if (tb[c] >= 0) rho[i0 + c] = acc[c];
+  }
+}
+
+// B1 (cluster form): pair + embedding forces in gather form, 8 lanes per cluster.  f'_{ij} comes from the density
+// pass (ec_df); the phi row is the only spline gather of a same-element pair.
+template <bool EV, bool ATOM, int U>
+__global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ec_off,
+    const int *__restrict__ ec_num, const int *__restrict__ ec_val, const double4 *__restrict__ ec_df,
+    const double4 *__restrict__ rhor, const double4 *__restrict__ z2r, int inum, double *__restrict__ f,
+    double *__restrict__ scal, double *__restrict__ pa_e, double *__restrict__ pa_v)
+{
+  __shared__ PairPar sp[16];
+  load_pair_par(par, sp);
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int q = tid >> 3, sub = tid & 7;
+  const int i0 = q * CL;
+  const int nel = par.nel;
+  double fx[CL], fy[CL], fz[CL], cx[CL], cy[CL], cz[CL], gi[CL];
+  int ti[CL];
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  double ea[ATOM ? CL : 1];
+  double av[ATOM ? CL : 1][6];
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    fx[c] = fy[c] = fz[c] = cx[c] = cy[c] = cz[c] = gi[c] = 0.0;
+    ti[c] = -1;
+  }
+  if (ATOM) {
+#pragma unroll
+    for (int c = 0; c < CL; c++) {
+      ea[ATOM ? c : 0] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) av[ATOM ? c : 0][k] = 0.0;
+    }
+  }
+  if (i0 < inum) {
+#pragma unroll
+    for (int c = 0; c < CL; c++)
+      if (i0 + c < inum) {
+        const double4 xi = xq[i0 + c];
+        cx[c] = xi.x;
+        cy[c] = xi.y;
+        cz[c] = xi.z;
+        ti[c] = etype(xi);
+        gi[c] = w_gate(xi);
+      }
+    const int n = ec_num[q];
+    const int64_t base = ec_off[q];
+    const int *row = ec_val + base;
+    const double4 *df = ec_df + base;
+    for (int e0 = 0; e0 < n; e0 += 8 * U) {
+      int jj[U];
+      double4 xj[U], dv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int e = e0 + u * 8 + sub;
+        jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (jj[u] >= 0) {
+          xj[u] = ld_sector(xq + jj[u]);
+          dv[u] = ld_stream_sector(df + (e0 + u * 8 + sub));
+        }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (jj[u] < 0) continue;
+        const int tj = etype(xj[u]);
+        const double gj = w_gate(xj[u]);
+        // two centers at a time -- phase 1: geometry and the phi row of both; phase 2: the gathers; phase 3: the terms
+#pragma unroll
+        for (int h = 0; h < CL; h += 2) {
+          bool in_ij[2];
+          double rinv[2], pp[2];
+          int mz[2];
+          double4 zw[2];
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int c = h + k;
+            const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            const PairPar &P = sp[(ti[c] < 0 ? 0 : ti[c]) * nel + tj];
+            in_ij[k] = ti[c] >= 0 && jj[u] != i0 + c && rsq < P.cutgt;    // !(r > cut[ti][tj])
+            rinv[k] = rsqrt_nr(fmax(rsq, 1.0e-300));
+            int m;
+            spl_index(rsq * rinv[k], P.rdr, P.nr, m, pp[k]);
+            mz[k] = P.zoff + min(m, P.nz);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; k++)
+            if (in_ij[k]) zw[k] = ld_sector(z2r + mz[k]);
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int c = h + k;
+            if (ti[c] < 0 || jj[u] == i0 + c) continue;
+            const bool same = (tj == ti[c]);
+            if (same && !in_ij[k]) continue;
+            const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
+            const double recip = rinv[k];
+            double coef = 0.0;    // fpair of visit (i,j) + fpair of visit (j,i)
+            if (in_ij[k]) {
+              // visit (i,j): pair_aeam.cpp:350-393
+              const PairPar &P = sp[ti[c] * nel + tj];
+              const double dfij = comp4(dv[u], c);
+              const double phip = spl_der(zw[k], pp[k], P.rdr);
+              const double fpair = -gi[c] * dfij * recip + 0.5 * (-phip * recip);
+              coef = fpair;
+              // same element: visit (j,i) evaluates the same two splines at the same (m, p)
+              if (same) coef += -gj * dfij * recip + 0.5 * (-phip * recip);
+              if (EV) {
+                const double ph = 0.5 * spl_val(zw[k], pp[k]);
+                ev[0] += ph;
+                ev[1] += dx * dx * fpair;
+                ev[2] += dy * dy * fpair;
+                ev[3] += dz * dz * fpair;
+                ev[4] += dx * dy * fpair;
+                ev[5] += dx * dz * fpair;
+                ev[6] += dy * dz * fpair;
+                if (ATOM) ea[ATOM ? c : 0] += ph;
+              }
+            }
+            if (!same) {
+              const PairPar &Q = sp[tj * nel + ti[c]];
+              const double rsq = dx * dx + dy * dy + dz * dz;
+              if (rsq < Q.cutgt) {
+                // visit (j,i), evaluated here instead of scattering from j's row (different elements: own tables)
+                int m;
+                double p;
+                spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
+                const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
+                const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
+                coef += -gj * dfji * recip + 0.5 * (-phip * recip);
+              }
+            }
+            fx[c] -= dx * coef;
+            fy[c] -= dy * coef;
+            fz[c] -= dz * coef;
+            if (ATOM) {
+              const double hh = 0.5 * coef;
+              av[ATOM ? c : 0][0] += dx * dx * hh;
+              av[ATOM ? c : 0][1] += dy * dy * hh;
+              av[ATOM ? c : 0][2] += dz * dz * hh;
+              av[ATOM ? c : 0][3] += dx * dy * hh;
+              av[ATOM ? c : 0][4] += dx * dz * hh;
+              av[ATOM ? c : 0][5] += dy * dz * hh;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    fx[c] = group_sum<8>(fx[c]);
+    fy[c] = group_sum<8>(fy[c]);
+    fz[c] = group_sum<8>(fz[c]);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int c = 0; c < CL; c++)
+      if (ti[c] >= 0) {
+        f[3 * (size_t) (i0 + c)] += fx[c];    // one group per cluster; B2 (atomics) runs after this kernel
+        f[3 * (size_t) (i0 + c) + 1] += fy[c];
+        f[3 * (size_t) (i0 + c) + 2] += fz[c];
+      }
+  }
+  if (ATOM) {
+#pragma unroll
+    for (int c = 0; c < CL; c++) {
+      const double e1 = group_sum<8>(ea[ATOM ? c : 0]);
+      double a6[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) a6[k] = group_sum<8>(av[ATOM ? c : 0][k]);
+      if (sub == 0 && ti[c] >= 0) {
+        pa_e[i0 + c] += e1;
+#pragma unroll
+        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) (i0 + c) + k] += a6[k];
+      }
+    }
+  }
+  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+}
+
 // ================================================================== A2 / B2: angular atoms (warp per atom)
 struct AngStage {
   double dx[ANG_CAP], dy[ANG_CAP], dz[ANG_CAP], r[ANG_CAP], f[ANG_CAP], df[ANG_CAP];
@@ -351,7 +762,7 @@ struct AngStage {
 __device__ __forceinline__ int ang_stage(const AeamDev &par, const double4 *__restrict__ xq,
                                          const double4 *__restrict__ rhor, const int *row, int n,
                                          const double4 &xi, int ti, bool force_pass, AngStage &S, int lane,
-                                         int *flags)
+                                         int *flags, int self)
 {
   const unsigned lt = (1u << lane) - 1u;
   int ns = 0;
@@ -373,6 +784,7 @@ __device__ __forceinline__ int ang_stage(const AeamDev &par, const double4 *__re
       inD = !(r1 > par.cut[pt] - cutdec);
       // force pass: j-role uses the plain cutoff (pair_aeam.cpp:350), k-role the reduced one (:408-418)
       keep = force_pass ? !(r1 > par.cut[pt]) : inD;
+      if (j == self) keep = inD = false;    // union rows of a cluster hold the cluster's own centers
       if (keep) {
         int m;
         double p;
@@ -402,7 +814,7 @@ __global__ void __launch_bounds__(128) aeam_density_ang_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
     const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, double *__restrict__ rho,
-    int *__restrict__ flags)
+    int *__restrict__ flags, int rshift)
 {
   __shared__ AngStage stage[4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -412,7 +824,8 @@ __global__ void __launch_bounds__(128) aeam_density_ang_kernel(
     const double4 xi = xq[i];
     const int ti = etype(xi);
     AngStage &S = stage[wid];
-    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i], ea_num[i], xi, ti, false, S, lane, flags);
+    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i >> rshift], ea_num[i >> rshift], xi, ti, false, S, lane,
+                             flags, i);
     double acc = 0.0;
     for (int p = 0; p < ns; p++) {
       const double r1 = S.r[p], fij = S.f[p];
@@ -627,7 +1040,7 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
     const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, const double *__restrict__ rho,
     const double *__restrict__ fp, double *__restrict__ f, double *__restrict__ scal, int *__restrict__ flags,
-    double *__restrict__ pa_v)
+    double *__restrict__ pa_v, int rshift)
 {
   __shared__ AngStage stage[4];
   const double minrho = 0.0000000000001;
@@ -639,7 +1052,8 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     const double4 xi = xq[i];
     const int ti = etype(xi);
     AngStage &S = stage[wid];
-    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i], ea_num[i], xi, ti, true, S, lane, flags);
+    const int ns = ang_stage(par, xq, rhor, ea_val + ea_off[i >> rshift], ea_num[i >> rshift], xi, ti, true, S, lane,
+                             flags, i);
     // Fptmp*fp[i], Fptmp = ni*rho^(ni-1) = 0.5/sqrt(rho)   (pair_aeam.cpp:329-332)
     const double rh = rho[i];
     const double G = (rh > minrho) ? 0.5 / sqrt(rh) * fp[i] : 0.0;
@@ -759,20 +1173,43 @@ int b200md_aeam_build_inner(b200md_ctx *c)
       const double cc = fmax(c->ap.cut[i * nel + j], c->ap.cut[j * nel + i]) + m;
       c->ap.cutsq_list[i * nel + j] = cc * cc;
     }
-  CUDA_TRY(c, c->ea_off.reserve((size_t) inum + 2));
-  CUDA_TRY(c, c->ea_num.reserve((size_t) inum + 32));
   CUDA_TRY(c, c->ang_list.reserve((size_t) inum + 32));
-  int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
-  if (rc) return rc;
-  CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
   CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 4, 0, 3 * sizeof(int), c->stream));
-  if (inum > 0) {
-    LaunchScope ls(c, "build_inner");
-    aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(
-        c->ap, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, inum, c->ea_off.p, c->ea_num.p,
-        c->ea_val.p, c->ang_list.p, c->flags.p);
-    CUDA_TRY(c, cudaGetLastError());
+  if (c->aeam_cluster) {
+    const int ncl = (inum + CL - 1) / CL;
+    CUDA_TRY(c, c->ec_off.reserve((size_t) ncl + 2));
+    CUDA_TRY(c, c->ec_num.reserve((size_t) ncl + 32));
+    CUDA_TRY(c, c->ec_cap.reserve((size_t) ncl + 32));
+    if (ncl > 0) {
+      LaunchScope ls(c, "build_inner");
+      aeam_cluster_cap_kernel<<<nblocks(ncl, BLOCK), BLOCK, 0, c->stream>>>(c->list_num.p, inum, ncl, c->ec_cap.p);
+    }
+    int rc = b200md_exclusive_scan_i64(c, c->ec_cap.p, c->ec_off.p, ncl, 8);
+    if (rc) return rc;
+    const size_t cap = (size_t) (c->list_entries + 8 * (int64_t) ncl + 64);
+    CUDA_TRY(c, c->ec_val.reserve(cap));
+    CUDA_TRY(c, c->ec_df.reserve(CL * cap));
+    if (ncl > 0) {
+      LaunchScope ls(c, "build_inner");
+      aeam_build_cluster_kernel<<<nblocks((long long) ncl * 32, CL_BLOCK), CL_BLOCK, 0, c->stream>>>(
+          c->ap, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, inum, ncl, c->ec_off.p, c->ec_num.p, c->ec_val.p,
+          c->ang_list.p, c->flags.p, c->aeam_sort_rows);
+      CUDA_TRY(c, cudaGetLastError());
+    }
+  } else {
+    CUDA_TRY(c, c->ea_off.reserve((size_t) inum + 2));
+    CUDA_TRY(c, c->ea_num.reserve((size_t) inum + 32));
+    int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
+    if (rc) return rc;
+    CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
+    if (inum > 0) {
+      LaunchScope ls(c, "build_inner");
+      aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(
+          c->ap, c->xq.p, c->list_off.p, c->list_num.p, c->list_val.p, inum, c->ea_off.p, c->ea_num.p,
+          c->ea_val.p, c->ang_list.p, c->flags.p);
+      CUDA_TRY(c, cudaGetLastError());
+    }
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->xhold.p, c->xq.p, (size_t) c->nall * sizeof(double4), cudaMemcpyDeviceToDevice,
                               c->stream));
@@ -820,16 +1257,29 @@ int b200md_aeam_density(b200md_ctx *c)
   CUDA_TRY(c, c->fp.reserve((size_t) c->nall + 32));
   if (inum == 0) return B200MD_OK;
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
+  const bool cl = c->aeam_cluster != 0;
+  const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
+  const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
+  const int rshift = cl ? CL_SHIFT : 0;
   {
     LaunchScope ls(c, "aeam_density");
-    aeam_density_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
-        c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p);
+    if (cl) {
+      const int ncl = (inum + CL - 1) / CL;
+      if (c->aeam_variant & 2)
+        aeam_density_cl_kernel<1><<<nblocks((long long) ncl * 8, BLOCK), BLOCK, 0, c->stream>>>(
+            c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, rhor, inum, c->rho.p, (double4 *) c->ec_df.p);
+      else
+        aeam_density_cl_kernel<2><<<nblocks((long long) ncl * 8, BLOCK), BLOCK, 0, c->stream>>>(
+            c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, rhor, inum, c->rho.p, (double4 *) c->ec_df.p);
+    } else
+      aeam_density_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p);
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_density_ang");
-    aeam_density_ang_kernel<<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(c->ap, c->xq.p, c->ea_off.p, c->ea_num.p,
-                                                                  c->ea_val.p, rhor, c->ang_list.p,
-                                                                  c->flags.p + 6, c->rho.p, c->flags.p);
+    aeam_density_ang_kernel<<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(c->ap, c->xq.p, r_off, r_num, r_val, rhor,
+                                                                  c->ang_list.p, c->flags.p + 6, c->rho.p, c->flags.p,
+                                                                  rshift);
   }
   {
     LaunchScope ls(c, "aeam_embed");
@@ -873,7 +1323,22 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
                                                                      c->nall);
   }
   const bool atom = c->pa_e != nullptr;
-  {
+  const bool cl = c->aeam_cluster != 0;
+  const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
+  const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
+  const int rshift = cl ? CL_SHIFT : 0;
+  if (cl) {
+    LaunchScope ls(c, "aeam_force");
+    const int ncl = (inum + CL - 1) / CL;
+    const int nb = nblocks((long long) ncl * 8, BLOCK);
+#define AFC_ARGS \
+  c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, (const double4 *) c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, \
+      inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
+    if (atom) aeam_force_cl_kernel<true, true, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
+    else if (ev) aeam_force_cl_kernel<true, false, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
+    else if (c->aeam_variant & 1) aeam_force_cl_kernel<false, false, 2><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
+    else aeam_force_cl_kernel<false, false, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
+  } else {
     LaunchScope ls(c, "aeam_force");
     const int nb = nblocks((long long) inum * 8, BLOCK);
 #define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
@@ -884,8 +1349,8 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_force_ang");
 #define AA_ARGS \
-  c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, \
-      c->scal.p, c->flags.p, c->pa_v
+  c->ap, c->xq.p, r_off, r_num, r_val, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, c->scal.p, \
+      c->flags.p, c->pa_v, rshift
     if (atom) aeam_force_ang_kernel<true, true><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
     else if (ev) aeam_force_ang_kernel<true, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
     else aeam_force_ang_kernel<false, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
@@ -908,6 +1373,12 @@ static int aeam_check_flags(b200md_ctx *c, const int *fl)
             "API (b200md_aeam_density / halo exchange of fp / b200md_aeam_force)");
     cudaMemsetAsync(c->flags.p + 7, 0, sizeof(int), c->stream);
     return B200MD_ERR_ARG;
+  }
+  if (fl[0] == 4) {
+    c->fail("AEAM cluster row overflow (more than " + std::to_string(CL_HT * 3 / 4 - 32) +
+            " distinct neighbors of 4 consecutive atoms within cut + margin); set option aeam_cluster = 0");
+    cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream);
+    return B200MD_ERR_OVERFLOW;
   }
   if (fl[0]) {
     c->fail("AEAM angular-neighbor staging overflow (more than " + std::to_string(ANG_CAP) + " neighbors in range)");

@@ -119,6 +119,7 @@ struct AeamDev {
   double cutsq_list[16];    // (cut+margin)^2 for the inner list
   int pair_off[16];         // row offset (in 64-byte rows) of the fused {rhor | z2r} table of pair (i,j)
   double cut_gt_sq[16];     // smallest rsq with sqrt(rsq) > cut[i][j]: `rsq >= this` is the reference's `r > cut`
+  int z2r_n[16];            // rows of the z2r table pair (i,j) reads (the row index is clamped to it)
 };
 
 // ---------------------------------------------------------------- context
@@ -166,6 +167,10 @@ struct b200md_ctx {
   int ang_ctas = 10;     // AEAM angular launches: CTAs (4 warps, one angular center each) per SM; latency-bound kernels:
                          // 2 -> 10 CTAs/SM: force_ang 0.30 -> 0.16 ms, density_ang 0.086 -> 0.041 ms at 15 360 Si atoms
   int lj_pairs = 1;      // LJ over pairs of neighboring centers sharing one union row (0: one row per center)
+  int aeam_cluster = 1;  // AEAM: clusters of 4 consecutive centers share one union row and the density pass hands the
+                         // force pass f'(r) of every (center, candidate) (0: one row per center, the round-1 kernels)
+  int aeam_variant = 0;      // tuning experiments: bit 0 = force kernel 2 entries per lane and trip, bit 1 = density 1
+  int aeam_sort_rows = 0;    // AEAM cluster rows sorted by atom index (adjacent lanes then read adjacent sectors)
   int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency
   int d2h_chunks = 4;    // plugin mode: owned-atom index ranges whose forces go home while the next range computes
   int p2p_halo = 1;    // multi-GPU halo through peer memory (CUDA IPC) when available; 0 = NCCL send/recv only
@@ -250,6 +255,9 @@ struct b200md_ctx {
   DevBuf<int64_t> ea_off;
   DevBuf<int> ea_num, ea_val;        // inner AEAM rows (filtered to cut+margin)
   DevBuf<int> ang_list;              // owned angular atoms
+  DevBuf<int64_t> ec_off;            // cluster form: [ncl+1] 8-aligned offsets of the union rows
+  DevBuf<int> ec_num, ec_val, ec_cap;    // union row of cluster q = centers 4q..4q+3
+  DevBuf<double> ec_df;              // [4 * entries] f'_{ti,tj}(r) of (entry, center), written by the density pass
   int n_ang = 0;
 
   // ---- device-built list scratch (neigh.cu)
@@ -367,6 +375,19 @@ __device__ __forceinline__ double4 ld_sector(const double4 *p)
   double4 r;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
+}
+// 1/sqrt(a) for a normal, positive a in a harmless range (bond lengths, 1 + S + P): MUFU.RSQ64H seed + two Newton
+// steps, no slow path, <= 2 ulp; r = a * rsqrt(a).  The library sqrt and division each cost ~25 instructions with
+// their special-case handling (6 % of the bond-order kernel's instructions went there, ncu source view).
+__device__ __forceinline__ double rsqrt_nr(double a)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
 }
 __device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
 {

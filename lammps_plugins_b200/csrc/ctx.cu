@@ -90,6 +90,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
   c->ang_list.release();
+  c->ec_off.release(); c->ec_num.release(); c->ec_val.release(); c->ec_cap.release(); c->ec_df.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
   c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();
   for (int k = 0; k < 8; k++)
@@ -128,6 +129,13 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
   else if (n == "lj_pairs") {
     c->lj_pairs = value ? 1 : 0;
+    c->inner_valid = false;
+  } else if (n == "aeam_cluster") {
+    c->aeam_cluster = value ? 1 : 0;
+    c->inner_valid = false;
+  } else if (n == "aeam_variant") c->aeam_variant = (int) value;
+  else if (n == "aeam_sort_rows") {
+    c->aeam_sort_rows = value ? 1 : 0;
     c->inner_valid = false;
   } else if (n == "ang_ctas") c->ang_ctas = (int) (value < 1 ? 1 : value);
   else if (n == "h2d_chunks") {

@@ -32,20 +32,6 @@ __device__ __forceinline__ double pin(double v)
   return v;
 }
 
-// 1/sqrt(a) for a normal, positive a in a harmless range (bond lengths, 1 + S + P): MUFU.RSQ64H seed + two Newton
-// steps, no slow path, <= 2 ulp; r = a * rsqrt(a).  The library sqrt and division each cost ~25 instructions with
-// their special-case handling (6 % of the bond-order kernel's instructions went there, ncu source view).
-__device__ __forceinline__ double rsqrt_nr(double a)
-{
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double h = 0.5 * a;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  return fma(y, e, y);
-}
-
 // Sp cutoff (pair_rebomos.h:195-211): value and derivative
 __device__ __forceinline__ double sp_switch(double r, double rmin, double rw, double &dS)
 {

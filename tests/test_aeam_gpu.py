@@ -184,3 +184,36 @@ def test_per_atom_energy_and_virial(ctx, oracle_built, case):
     assert S.rel_err(va, va_ref) < 1e-10
     assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], nl), f_ref) < 1e-10
     lmp.close()
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3]], ids=[CASES[1]["id"], CASES[2]["id"], CASES[3]["id"]])
+def test_cluster_rows_equal_single_rows(ctx, oracle_built, case):
+    """Cluster form (4 consecutive centers share one union row, f' handed from the density to the force pass; the
+    default) == one row per center (the round-1 kernels, option aeam_cluster = 0), with and without index-sorted rows.
+    nlocal is not a multiple of 4 in the 5x4x6 case of test_forces_energy_virial; here the per-atom variants too."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), case["cells"], si_fraction=case["si"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    ctx.aeam_init(aeam_tables())
+    res = {}
+    try:
+        for name, opts in (("single", dict(aeam_cluster=0)), ("cluster", dict(aeam_cluster=1, aeam_sort_rows=0)),
+                           ("cluster-sorted", dict(aeam_cluster=1, aeam_sort_rows=1)),
+                           ("cluster-u2", dict(aeam_cluster=1, aeam_sort_rows=0, aeam_variant=3))):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            res[name] = gpu_forces(ctx, snap)
+            ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+            fo, eo, vo = ctx.aeam_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], 0, 0)
+            assert S.rel_err(S.fold_ghost_forces(fo, snap["swaps"], snap["nlocal"]), res[name][0]) < 1e-13
+    finally:
+        ctx.set_option("aeam_cluster", 1)
+        ctx.set_option("aeam_sort_rows", 0)
+        ctx.set_option("aeam_variant", 0)
+    for name, (f, e, v) in res.items():
+        print("\n%s %s: ferr vs reference %.2e" % (case["id"], name, S.rel_err(f, f_ref)))
+        assert S.rel_err(f, f_ref) < FTOL and abs(e - e_ref) < ETOL * abs(e_ref) and S.rel_err(v, v_ref) < FTOL
+        assert S.rel_err(f, res["single"][0]) < 1e-12
+        assert abs(e - res["single"][1]) < 1e-12 * abs(e_ref)
+    lmp.close()

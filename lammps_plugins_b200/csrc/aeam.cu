@@ -295,11 +295,55 @@ __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, b
   __syncthreads();
 }
 
+__device__ __forceinline__ void st_sector(double4 *p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ double4 ld_stream_sector(const double4 *p)
+{
+  double4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <int CPL> struct DfVec;
+template <> struct DfVec<4> {
+  static __device__ __forceinline__ void st(double *p, const double *o) { st_sector((double4 *) p, o[0], o[1], o[2], o[3]); }
+  static __device__ __forceinline__ void ld(const double *p, double *o)
+  {
+    const double4 v = ld_stream_sector((const double4 *) p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct DfVec<2> {
+  static __device__ __forceinline__ void st(double *p, const double *o)
+  {
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(o[0]), "d"(o[1]) : "memory");
+  }
+  static __device__ __forceinline__ void ld(const double *p, double *o)
+  {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
+  }
+};
+template <> struct DfVec<1> {
+  static __device__ __forceinline__ void st(double *p, const double *o)
+  {
+    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(o[0]) : "memory");
+  }
+  static __device__ __forceinline__ void ld(const double *p, double *o)
+  {
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(o[0]) : "l"(p));
+  }
+};
+
 // ================================================================== A1: density of non-angular atoms
+template <bool DF>
 __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
-    int inum, double *__restrict__ rho)
+    int inum, double *__restrict__ rho, double *__restrict__ ea_df)
 {
   __shared__ PairPar sp[16];
   load_pair_par(par, sp, true);
@@ -314,6 +358,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     if (mine) {
       const int n = ea_num[i];
       const int *row = ea_val + ea_off[i];
+      double *dfrow = DF ? ea_df + ea_off[i] : nullptr;    // f'_{ti,tj}(r) per entry, for the force pass
       const int tbase = ti * par.nel;
       for (int e0 = 0; e0 < n; e0 += 32) {
         int jj[4];
@@ -332,12 +377,17 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
           const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
           const double rsq = dx * dx + dy * dy + dz * dz;
           const PairPar pp = sp[tbase + etype(xj[u])];
-          if (rsq >= pp.cutgt) continue;    // r > cut; i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
-          const double r1 = sqrt(rsq);
-          int m;
-          double p;
-          spl_index(r1, pp.rdr, pp.nr, m, p);
-          acc += spl_val(ld_sector(rhor + pp.off + m), p);
+          double dfv = 0.0;
+          if (rsq < pp.cutgt) {    // else r > cut; i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
+            const double r1 = sqrt(rsq);
+            int m;
+            double p;
+            spl_index(r1, pp.rdr, pp.nr, m, p);
+            const double4 cf = ld_sector(rhor + pp.off + m);
+            acc += spl_val(cf, p);
+            if (DF) dfv = spl_der(cf, p, pp.rdr);
+          }
+          if (DF) DfVec<1>::st(dfrow + e0 + u * 8 + sub, &dfv);
         }
       }
     }
@@ -358,19 +408,6 @@ __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
 #define CL_SHIFT 2
 #define CL_HT 1024
 #define CL_BLOCK 128
-
-__device__ __forceinline__ void st_sector(double4 *p, double a, double b, double c, double d)
-{
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ double4 ld_stream_sector(const double4 *p)
-{
-  double4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
-               : "l"(p));
-  return r;
-}
 
 // capacity of a cluster's union row: the sum of its centers' master rows (upper bound)
 __global__ void __launch_bounds__(BLOCK) aeam_cluster_cap_kernel(const int *__restrict__ list_num, int inum, int ncl,
@@ -476,34 +513,50 @@ __global__ void __launch_bounds__(CL_BLOCK) aeam_build_cluster_kernel(
   }
 }
 
-__device__ __forceinline__ double comp4(const double4 &v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+// Lane layout of the cluster kernels: a cluster is served by 8 * LPE lanes; in one trip it takes 8 row entries, each
+// by LPE adjacent lanes ("parts") that gather the SAME position sector (the L1 serves the duplicates at register
+// write-back speed, tools/microbench/gather.cu) and test it against CPL = CL / LPE centers each.  LPE = 1 keeps all
+// four centers in one lane (fewest gathered lanes, 128 registers, 14 resident warps: latency-bound, r02 ncu v1);
+// LPE = 2 / 4 trade duplicate-lane gathers for half / a quarter of the per-lane state and 2-3x the resident warps.
+// sum over the lanes of a cluster group that hold the same part (lanes l, l + LPE, l + 2 LPE, ...: 8 of them)
+template <int LPE> __device__ __forceinline__ double part_sum(double v)
+{
+  constexpr int G = 8 * LPE;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned) (G - 1)));
+#pragma unroll
+  for (int o = 4 * LPE; o >= LPE; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
 
-// A1 (cluster form): density of the non-angular centers of a cluster, 8 lanes per cluster.  Also writes
-// f'_{ti,tj}(r) of every (entry, center) slot (0 where the density pass takes nothing) for the force pass.
-template <int U>
-__global__ void __launch_bounds__(BLOCK, 2) aeam_density_cl_kernel(
+// A1 (cluster form): density of the non-angular centers of a cluster.  Also writes f'_{ti,tj}(r) of every
+// (entry, center) slot (0 where the density pass takes nothing) for the force pass.
+template <int LPE, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) aeam_density_cl_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ec_off,
     const int *__restrict__ ec_num, const int *__restrict__ ec_val, const double4 *__restrict__ rhor, int inum,
-    double *__restrict__ rho, double4 *__restrict__ ec_df)
+    double *__restrict__ rho, double *__restrict__ ec_df)
 {
+  constexpr int CPL = CL / LPE, G = 8 * LPE;
   __shared__ PairPar sp[16];
   load_pair_par(par, sp);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
-  const int q = tid >> 3, sub = tid & 7;
-  const int i0 = q * CL;
-  double acc[CL], cx[CL], cy[CL], cz[CL];
-  int tb[CL];    // ti * nel of a center that takes a density here, else -1 (angular center, or beyond inum)
+  const int q = tid / G, gl = tid % G;
+  const int slot = gl / LPE, part = gl % LPE;
+  const int i0 = q * CL, c0 = part * CPL;
+  double acc[CPL], cx[CPL], cy[CPL], cz[CPL];
+  int tb[CPL];    // ti * nel of a center that takes a density here, else -1 (angular center, or beyond inum)
 #pragma unroll
-  for (int c = 0; c < CL; c++) {
+  for (int c = 0; c < CPL; c++) {
     acc[c] = 0.0;
     cx[c] = cy[c] = cz[c] = 0.0;
     tb[c] = -1;
   }
   if (i0 < inum) {
 #pragma unroll
-    for (int c = 0; c < CL; c++)
-      if (i0 + c < inum) {
-        const double4 xi = xq[i0 + c];
+    for (int c = 0; c < CPL; c++)
+      if (i0 + c0 + c < inum) {
+        const double4 xi = xq[i0 + c0 + c];
         cx[c] = xi.x;
         cy[c] = xi.y;
         cz[c] = xi.z;
@@ -513,13 +566,13 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_density_cl_kernel(
     const int n = ec_num[q];
     const int64_t base = ec_off[q];
     const int *row = ec_val + base;
-    double4 *df = ec_df + base;
+    double *df = ec_df + CL * base + c0;
     for (int e0 = 0; e0 < n; e0 += 8 * U) {
       int jj[U];
       double4 xj[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int e = e0 + u * 8 + sub;
+        const int e = e0 + u * 8 + slot;
         jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
       }
 #pragma unroll
@@ -529,75 +582,78 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_density_cl_kernel(
       for (int u = 0; u < U; u++) {
         if (jj[u] < 0) continue;
         const int tj = etype(xj[u]);
-        bool hit[CL];
-        double pp[CL], rd[CL];
-        const double4 *ra[CL];
+        bool hit[CPL];
+        double pp[CPL], rd[CPL];
+        const double4 *ra[CPL];
 #pragma unroll
-        for (int c = 0; c < CL; c++) {
+        for (int c = 0; c < CPL; c++) {
           const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
           const double rsq = dx * dx + dy * dy + dz * dz;
           const PairPar &P = sp[(tb[c] < 0 ? 0 : tb[c]) + tj];
           // r > cut -> out; i non-angular: CutDec = 0 (pair_aeam.cpp:187-194)
-          hit[c] = tb[c] >= 0 && jj[u] != i0 + c && rsq < P.cutgt;
-          int m;
-          spl_index(rsq * rsqrt_nr(fmax(rsq, 1.0e-300)), P.rdr, P.nr, m, pp[c]);
+          hit[c] = tb[c] >= 0 && jj[u] != i0 + c0 + c && rsq < P.cutgt;
+          int m = 0;
+          pp[c] = 0.0;
+          if (CPL == 1 ? hit[c] : true) spl_index(rsq * rsqrt_nr(fmax(rsq, 1.0e-300)), P.rdr, P.nr, m, pp[c]);
           rd[c] = P.rdr;
           ra[c] = rhor + P.roff + m;
         }
-        double4 rw[CL];
+        double4 rw[CPL];
 #pragma unroll
-        for (int c = 0; c < CL; c++)
+        for (int c = 0; c < CPL; c++)
           if (hit[c]) rw[c] = ld_sector(ra[c]);
-        double o[CL];
+        double o[CPL];
 #pragma unroll
-        for (int c = 0; c < CL; c++) {
+        for (int c = 0; c < CPL; c++) {
           o[c] = 0.0;
           if (hit[c]) {
             acc[c] += spl_val(rw[c], pp[c]);
             o[c] = spl_der(rw[c], pp[c], rd[c]);
           }
         }
-        st_sector(df + (e0 + u * 8 + sub), o[0], o[1], o[2], o[3]);
+        DfVec<CPL>::st(df + (size_t) CL * (e0 + u * 8 + slot), o);
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < CL; c++) acc[c] = group_sum<8>(acc[c]);
-  if (sub == 0) {
+  for (int c = 0; c < CPL; c++) acc[c] = part_sum<LPE>(acc[c]);
+  if (slot == 0) {
 #pragma unroll
-    for (int c = 0; c < CL; c++)
-      if (tb[c] >= 0) rho[i0 + c] = acc[c];
+    for (int c = 0; c < CPL; c++)
+      if (tb[c] >= 0) rho[i0 + c0 + c] = acc[c];
   }
 }
 
-// B1 (cluster form): pair + embedding forces in gather form, 8 lanes per cluster.  f'_{ij} comes from the density
-// pass (ec_df); the phi row is the only spline gather of a same-element pair.
-template <bool EV, bool ATOM, int U>
-__global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
+// B1 (cluster form): pair + embedding forces in gather form.  f'_{ij} comes from the density pass (ec_df); the phi
+// row is the only spline gather of a same-element pair.
+template <bool EV, bool ATOM, int LPE, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ec_off,
-    const int *__restrict__ ec_num, const int *__restrict__ ec_val, const double4 *__restrict__ ec_df,
+    const int *__restrict__ ec_num, const int *__restrict__ ec_val, const double *__restrict__ ec_df,
     const double4 *__restrict__ rhor, const double4 *__restrict__ z2r, int inum, double *__restrict__ f,
     double *__restrict__ scal, double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
+  constexpr int CPL = CL / LPE, G = 8 * LPE;
   __shared__ PairPar sp[16];
   load_pair_par(par, sp);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
-  const int q = tid >> 3, sub = tid & 7;
-  const int i0 = q * CL;
+  const int q = tid / G, gl = tid % G;
+  const int slot = gl / LPE, part = gl % LPE;
+  const int i0 = q * CL, c0 = part * CPL;
   const int nel = par.nel;
-  double fx[CL], fy[CL], fz[CL], cx[CL], cy[CL], cz[CL], gi[CL];
-  int ti[CL];
+  double fx[CPL], fy[CPL], fz[CPL], cx[CPL], cy[CPL], cz[CPL], gi[CPL];
+  int ti[CPL];
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
-  double ea[ATOM ? CL : 1];
-  double av[ATOM ? CL : 1][6];
+  double ea[ATOM ? CPL : 1];
+  double av[ATOM ? CPL : 1][6];
 #pragma unroll
-  for (int c = 0; c < CL; c++) {
+  for (int c = 0; c < CPL; c++) {
     fx[c] = fy[c] = fz[c] = cx[c] = cy[c] = cz[c] = gi[c] = 0.0;
     ti[c] = -1;
   }
   if (ATOM) {
 #pragma unroll
-    for (int c = 0; c < CL; c++) {
+    for (int c = 0; c < CPL; c++) {
       ea[ATOM ? c : 0] = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; k++) av[ATOM ? c : 0][k] = 0.0;
@@ -605,9 +661,9 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
   }
   if (i0 < inum) {
 #pragma unroll
-    for (int c = 0; c < CL; c++)
-      if (i0 + c < inum) {
-        const double4 xi = xq[i0 + c];
+    for (int c = 0; c < CPL; c++)
+      if (i0 + c0 + c < inum) {
+        const double4 xi = xq[i0 + c0 + c];
         cx[c] = xi.x;
         cy[c] = xi.y;
         cz[c] = xi.z;
@@ -617,52 +673,54 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
     const int n = ec_num[q];
     const int64_t base = ec_off[q];
     const int *row = ec_val + base;
-    const double4 *df = ec_df + base;
+    const double *df = ec_df + CL * base + c0;
     for (int e0 = 0; e0 < n; e0 += 8 * U) {
       int jj[U];
-      double4 xj[U], dv[U];
+      double4 xj[U];
+      double dv[U][CPL];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int e = e0 + u * 8 + sub;
+        const int e = e0 + u * 8 + slot;
         jj[u] = (e < n) ? ld_stream_int(row + e) : -1;
       }
 #pragma unroll
       for (int u = 0; u < U; u++)
         if (jj[u] >= 0) {
           xj[u] = ld_sector(xq + jj[u]);
-          dv[u] = ld_stream_sector(df + (e0 + u * 8 + sub));
+          DfVec<CPL>::ld(df + (size_t) CL * (e0 + u * 8 + slot), dv[u]);
         }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (jj[u] < 0) continue;
         const int tj = etype(xj[u]);
         const double gj = w_gate(xj[u]);
-        // two centers at a time -- phase 1: geometry and the phi row of both; phase 2: the gathers; phase 3: the terms
+        // at most two centers at a time -- phase 1: geometry and the phi row; phase 2: the gathers; phase 3: the terms
+        constexpr int HB = CPL < 2 ? CPL : 2;
 #pragma unroll
-        for (int h = 0; h < CL; h += 2) {
-          bool in_ij[2];
-          double rinv[2], pp[2];
-          int mz[2];
-          double4 zw[2];
+        for (int h = 0; h < CPL; h += HB) {
+          bool in_ij[HB];
+          double rinv[HB], pp[HB];
+          int mz[HB];
+          double4 zw[HB];
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
+          for (int k = 0; k < HB; k++) {
             const int c = h + k;
             const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
             const double rsq = dx * dx + dy * dy + dz * dz;
             const PairPar &P = sp[(ti[c] < 0 ? 0 : ti[c]) * nel + tj];
-            in_ij[k] = ti[c] >= 0 && jj[u] != i0 + c && rsq < P.cutgt;    // !(r > cut[ti][tj])
+            in_ij[k] = ti[c] >= 0 && jj[u] != i0 + c0 + c && rsq < P.cutgt;    // !(r > cut[ti][tj])
             rinv[k] = rsqrt_nr(fmax(rsq, 1.0e-300));
             int m;
             spl_index(rsq * rinv[k], P.rdr, P.nr, m, pp[k]);
             mz[k] = P.zoff + min(m, P.nz);
           }
 #pragma unroll
-          for (int k = 0; k < 2; k++)
+          for (int k = 0; k < HB; k++)
             if (in_ij[k]) zw[k] = ld_sector(z2r + mz[k]);
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
+          for (int k = 0; k < HB; k++) {
             const int c = h + k;
-            if (ti[c] < 0 || jj[u] == i0 + c) continue;
+            if (ti[c] < 0 || jj[u] == i0 + c0 + c) continue;
             const bool same = (tj == ti[c]);
             if (same && !in_ij[k]) continue;
             const double dx = xj[u].x - cx[c], dy = xj[u].y - cy[c], dz = xj[u].z - cz[c];
@@ -671,7 +729,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
             if (in_ij[k]) {
               // visit (i,j): pair_aeam.cpp:350-393
               const PairPar &P = sp[ti[c] * nel + tj];
-              const double dfij = comp4(dv[u], c);
+              const double dfij = dv[u][c];
               const double phip = spl_der(zw[k], pp[k], P.rdr);
               const double fpair = -gi[c] * dfij * recip + 0.5 * (-phip * recip);
               coef = fpair;
@@ -720,31 +778,31 @@ __global__ void __launch_bounds__(BLOCK, 2) aeam_force_cl_kernel(
     }
   }
 #pragma unroll
-  for (int c = 0; c < CL; c++) {
-    fx[c] = group_sum<8>(fx[c]);
-    fy[c] = group_sum<8>(fy[c]);
-    fz[c] = group_sum<8>(fz[c]);
+  for (int c = 0; c < CPL; c++) {
+    fx[c] = part_sum<LPE>(fx[c]);
+    fy[c] = part_sum<LPE>(fy[c]);
+    fz[c] = part_sum<LPE>(fz[c]);
   }
-  if (sub == 0) {
+  if (slot == 0) {
 #pragma unroll
-    for (int c = 0; c < CL; c++)
+    for (int c = 0; c < CPL; c++)
       if (ti[c] >= 0) {
-        f[3 * (size_t) (i0 + c)] += fx[c];    // one group per cluster; B2 (atomics) runs after this kernel
-        f[3 * (size_t) (i0 + c) + 1] += fy[c];
-        f[3 * (size_t) (i0 + c) + 2] += fz[c];
+        f[3 * (size_t) (i0 + c0 + c)] += fx[c];    // one lane per center; B2 (atomics) runs after this kernel
+        f[3 * (size_t) (i0 + c0 + c) + 1] += fy[c];
+        f[3 * (size_t) (i0 + c0 + c) + 2] += fz[c];
       }
   }
   if (ATOM) {
 #pragma unroll
-    for (int c = 0; c < CL; c++) {
-      const double e1 = group_sum<8>(ea[ATOM ? c : 0]);
+    for (int c = 0; c < CPL; c++) {
+      const double e1 = part_sum<LPE>(ea[ATOM ? c : 0]);
       double a6[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) a6[k] = group_sum<8>(av[ATOM ? c : 0][k]);
-      if (sub == 0 && ti[c] >= 0) {
-        pa_e[i0 + c] += e1;
+      for (int k = 0; k < 6; k++) a6[k] = part_sum<LPE>(av[ATOM ? c : 0][k]);
+      if (slot == 0 && ti[c] >= 0) {
+        pa_e[i0 + c0 + c] += e1;
 #pragma unroll
-        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) (i0 + c) + k] += a6[k];
+        for (int k = 0; k < 6; k++) pa_v[6 * (size_t) (i0 + c0 + c) + k] += a6[k];
       }
     }
   }
@@ -1033,6 +1091,163 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
   if (EV) block_accumulate<7, BLOCK>(ev, scal);
 }
 
+
+// B1 with f' handed over by the density pass (option aeam_cluster = 2): per in-range pair ONE spline gather (the phi
+// row of the separate z2r table) instead of the fused 64-byte {rho' | phi} row, i.e. 173 instead of 223 sectors per
+// atom (ncu r02).  The kernel is latency-sensitive (every trip is row indices -> positions -> spline rows), so the
+// next trip's indices are fetched a trip ahead, the phi rows of two candidates are in flight together, and bond length
+// and reciprocal come from one rsqrt; 3 CTAs per SM.
+template <bool EV, bool ATOM, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
+    const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
+    const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double *__restrict__ ea_df,
+    const double4 *__restrict__ rhor, const double4 *__restrict__ z2r, int inum, double *__restrict__ f,
+    double *__restrict__ scal, double *__restrict__ pa_e, double *__restrict__ pa_v)
+{
+  __shared__ PairPar sp[16];
+  load_pair_par(par, sp);
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int i = tid >> 3, sub = tid & 7;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  double av[6] = {0, 0, 0, 0, 0, 0};
+  if (i < inum) {
+    const double4 xi = xq[i];
+    const int ti = etype(xi);
+    const int nel = par.nel;
+    const double gi = w_gate(xi);
+    // an angular center stored nothing in the density pass (its density comes from the triplet kernel); its gate is 0
+    const bool has_df = ti < par.nnonangular;
+    const int n = ea_num[i];
+    const int64_t off = ea_off[i];
+    const int *row = ea_val + off;
+    const double *dfrow = ea_df + off;
+    const PairPar *spi = sp + ti * nel;
+    int jn[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) jn[u] = (u * 8 + sub < n) ? ld_stream_int(row + u * 8 + sub) : -1;
+    for (int e0 = 0; e0 < n; e0 += 8 * U) {
+      int jj[U];
+      double4 xj[U];
+      double dfs[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        jj[u] = jn[u];
+        const int e = e0 + 8 * U + u * 8 + sub;
+        jn[u] = (e < n) ? ld_stream_int(row + e) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        dfs[u] = 0.0;
+        if (jj[u] >= 0) {
+          xj[u] = ld_sector(xq + jj[u]);
+          if (has_df) DfVec<1>::ld(dfrow + e0 + u * 8 + sub, &dfs[u]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < U; h += 2) {
+        bool in_ij[2];
+        double rinv[2], pp[2];
+        int za[2];
+        double4 zw[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int u = h + k;
+          in_ij[k] = false;
+          rinv[k] = pp[k] = 0.0;
+          za[k] = 0;
+          if (jj[u] < 0) continue;
+          const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          const PairPar &P = spi[etype(xj[u])];
+          in_ij[k] = rsq < P.cutgt;    // !(r > cut[ti][tj])
+          rinv[k] = rsqrt_nr(rsq);
+          int m;
+          spl_index(rsq * rinv[k], P.rdr, P.nr, m, pp[k]);
+          za[k] = P.zoff + min(m, P.nz);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+          if (in_ij[k]) zw[k] = ld_sector(z2r + za[k]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int u = h + k;
+          if (jj[u] < 0) continue;
+          const int tj = etype(xj[u]);
+          const bool same = (tj == ti);
+          if (same && !in_ij[k]) continue;
+          const double dx = xj[u].x - xi.x, dy = xj[u].y - xi.y, dz = xj[u].z - xi.z;
+          const double recip = rinv[k];
+          const double gj = w_gate(xj[u]);
+          double coef = 0.0;    // fpair of visit (i,j) + fpair of visit (j,i)
+          if (in_ij[k]) {
+            // visit (i,j): pair_aeam.cpp:350-393
+            const double dfij = dfs[u];
+            const double phip = spl_der(zw[k], pp[k], spi[tj].rdr);
+            const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
+            coef = fpair;
+            // same element: visit (j,i) evaluates the same two splines at the same (m, p)
+            if (same) coef += -gj * dfij * recip + 0.5 * (-phip * recip);
+            if (EV) {
+              ev[0] += 0.5 * spl_val(zw[k], pp[k]);
+              ev[1] += dx * dx * fpair;
+              ev[2] += dy * dy * fpair;
+              ev[3] += dz * dz * fpair;
+              ev[4] += dx * dy * fpair;
+              ev[5] += dx * dz * fpair;
+              ev[6] += dy * dz * fpair;
+            }
+          }
+          if (!same) {
+            const PairPar &Q = sp[tj * nel + ti];
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            if (rsq < Q.cutgt) {
+              // visit (j,i), evaluated here instead of scattering from j's row (different elements: own tables)
+              int m;
+              double p;
+              spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
+              const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
+              const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
+              coef += -gj * dfji * recip + 0.5 * (-phip * recip);
+            }
+          }
+          fx -= dx * coef;
+          fy -= dy * coef;
+          fz -= dz * coef;
+          if (ATOM) {
+            const double hh = 0.5 * coef;
+            av[0] += dx * dx * hh;
+            av[1] += dy * dy * hh;
+            av[2] += dz * dz * hh;
+            av[3] += dx * dy * hh;
+            av[4] += dx * dz * hh;
+            av[5] += dy * dz * hh;
+          }
+        }
+      }
+    }
+  }
+  fx = group_sum<8>(fx);
+  fy = group_sum<8>(fy);
+  fz = group_sum<8>(fz);
+  if (i < inum && sub == 0) {
+    f[3 * (size_t) i] += fx;    // one group per atom; B2 (atomics) runs after this kernel
+    f[3 * (size_t) i + 1] += fy;
+    f[3 * (size_t) i + 2] += fz;
+  }
+  if (ATOM) {
+    const double ea = group_sum<8>(ev[0]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) av[k] = group_sum<8>(av[k]);
+    if (i < inum && sub == 0) {
+      pa_e[i] += ea;
+#pragma unroll
+      for (int k = 0; k < 6; k++) pa_v[6 * (size_t) i + k] += av[k];
+    }
+  }
+  if (EV) block_accumulate<7, BLOCK>(ev, scal);
+}
+
 // ================================================================== B2: 3-body forces of angular atoms
 template <bool EV, bool ATOM>
 __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
@@ -1176,7 +1391,7 @@ int b200md_aeam_build_inner(b200md_ctx *c)
   CUDA_TRY(c, c->ang_list.reserve((size_t) inum + 32));
   CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 4, 0, 3 * sizeof(int), c->stream));
-  if (c->aeam_cluster) {
+  if (c->aeam_cluster == 1) {
     const int ncl = (inum + CL - 1) / CL;
     CUDA_TRY(c, c->ec_off.reserve((size_t) ncl + 2));
     CUDA_TRY(c, c->ec_num.reserve((size_t) ncl + 32));
@@ -1203,6 +1418,7 @@ int b200md_aeam_build_inner(b200md_ctx *c)
     int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
     if (rc) return rc;
     CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
+    if (c->aeam_cluster == 2) CUDA_TRY(c, c->ec_df.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
     if (inum > 0) {
       LaunchScope ls(c, "build_inner");
       aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(
@@ -1257,7 +1473,7 @@ int b200md_aeam_density(b200md_ctx *c)
   CUDA_TRY(c, c->fp.reserve((size_t) c->nall + 32));
   if (inum == 0) return B200MD_OK;
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
-  const bool cl = c->aeam_cluster != 0;
+  const bool cl = c->aeam_cluster == 1;
   const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
   const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
   const int rshift = cl ? CL_SHIFT : 0;
@@ -1265,15 +1481,25 @@ int b200md_aeam_density(b200md_ctx *c)
     LaunchScope ls(c, "aeam_density");
     if (cl) {
       const int ncl = (inum + CL - 1) / CL;
-      if (c->aeam_variant & 2)
-        aeam_density_cl_kernel<1><<<nblocks((long long) ncl * 8, BLOCK), BLOCK, 0, c->stream>>>(
-            c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, rhor, inum, c->rho.p, (double4 *) c->ec_df.p);
-      else
-        aeam_density_cl_kernel<2><<<nblocks((long long) ncl * 8, BLOCK), BLOCK, 0, c->stream>>>(
-            c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, rhor, inum, c->rho.p, (double4 *) c->ec_df.p);
-    } else
-      aeam_density_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
-          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p);
+#define ADC_ARGS c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, rhor, inum, c->rho.p, c->ec_df.p
+#define ADC_LAUNCH(LPE, U, MINB) \
+  aeam_density_cl_kernel<LPE, U, MINB><<<nblocks((long long) ncl * 8 * LPE, BLOCK), BLOCK, 0, c->stream>>>(ADC_ARGS)
+      switch (c->aeam_variant % 10) {
+        case 1: ADC_LAUNCH(1, 2, 2); break;
+        case 2: ADC_LAUNCH(2, 1, 3); break;
+        case 3: ADC_LAUNCH(2, 2, 3); break;
+        case 4: ADC_LAUNCH(4, 1, 4); break;
+        case 5: ADC_LAUNCH(4, 2, 4); break;
+        case 6: ADC_LAUNCH(4, 4, 4); break;
+        case 7: ADC_LAUNCH(2, 2, 2); break;
+        default: ADC_LAUNCH(4, 2, 4); break;
+      }
+    } else if (c->aeam_cluster == 2)
+      aeam_density_kernel<true><<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p, c->ec_df.p);
+    else
+      aeam_density_kernel<false><<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+          c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p, nullptr);
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_density_ang");
@@ -1323,28 +1549,53 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
                                                                      c->nall);
   }
   const bool atom = c->pa_e != nullptr;
-  const bool cl = c->aeam_cluster != 0;
+  const bool cl = c->aeam_cluster == 1;
   const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
   const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
   const int rshift = cl ? CL_SHIFT : 0;
   if (cl) {
     LaunchScope ls(c, "aeam_force");
     const int ncl = (inum + CL - 1) / CL;
-    const int nb = nblocks((long long) ncl * 8, BLOCK);
 #define AFC_ARGS \
-  c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, (const double4 *) c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, \
+  c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, \
       inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
-    if (atom) aeam_force_cl_kernel<true, true, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
-    else if (ev) aeam_force_cl_kernel<true, false, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
-    else if (c->aeam_variant & 1) aeam_force_cl_kernel<false, false, 2><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
-    else aeam_force_cl_kernel<false, false, 1><<<nb, BLOCK, 0, c->stream>>>(AFC_ARGS);
+#define AFC_LAUNCH(EV, ATOM, LPE, U, MINB) \
+  aeam_force_cl_kernel<EV, ATOM, LPE, U, MINB><<<nblocks((long long) ncl * 8 * LPE, BLOCK), BLOCK, 0, c->stream>>>(AFC_ARGS)
+    if (atom) AFC_LAUNCH(true, true, 4, 1, 2);
+    else if (ev) AFC_LAUNCH(true, false, 4, 2, 3);
+    else
+      switch ((c->aeam_variant / 10) % 10) {
+        case 1: AFC_LAUNCH(false, false, 1, 1, 2); break;
+        case 2: AFC_LAUNCH(false, false, 2, 1, 3); break;
+        case 3: AFC_LAUNCH(false, false, 2, 2, 3); break;
+        case 4: AFC_LAUNCH(false, false, 4, 1, 4); break;
+        case 5: AFC_LAUNCH(false, false, 4, 2, 4); break;
+        case 6: AFC_LAUNCH(false, false, 4, 4, 4); break;
+        case 7: AFC_LAUNCH(false, false, 2, 2, 2); break;
+        default: AFC_LAUNCH(false, false, 4, 2, 4); break;
+      }
   } else {
     LaunchScope ls(c, "aeam_force");
     const int nb = nblocks((long long) inum * 8, BLOCK);
 #define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
-    if (atom) aeam_force_kernel<true, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
-    else if (ev) aeam_force_kernel<true, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
-    else aeam_force_kernel<false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+#define AFD_ARGS \
+  c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, inum, c->f.p, \
+      c->scal.p, c->pa_e, c->pa_v
+    if (c->aeam_cluster == 2) {
+      if (atom) aeam_force_df_kernel<true, true, 2, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
+      else if (ev) aeam_force_df_kernel<true, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
+      else
+        switch ((c->aeam_variant / 10) % 10) {
+          case 1: aeam_force_df_kernel<false, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
+          case 2: aeam_force_df_kernel<false, false, 4, 3><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
+          case 3: aeam_force_df_kernel<false, false, 2, 4><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
+          default: aeam_force_df_kernel<false, false, 2, 3><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
+        }
+    } else {
+      if (atom) aeam_force_kernel<true, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+      else if (ev) aeam_force_kernel<true, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+      else aeam_force_kernel<false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+    }
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_force_ang");

@@ -44,7 +44,7 @@ template <typename T> struct DevBuf {
   cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0)
   {
     if (n <= cap) return cudaSuccess;
-    size_t ncap = n + n / 8 + 256;
+    size_t ncap = n + n / 4 + 256;    // a quarter of headroom: neighbor rows grow ~20 % from a cold lattice to a hot one
     T *q = nullptr;
     cudaError_t e = cudaMalloc((void **) &q, ncap * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -167,8 +167,10 @@ struct b200md_ctx {
   int ang_ctas = 10;     // AEAM angular launches: CTAs (4 warps, one angular center each) per SM; latency-bound kernels:
                          // 2 -> 10 CTAs/SM: force_ang 0.30 -> 0.16 ms, density_ang 0.086 -> 0.041 ms at 15 360 Si atoms
   int lj_pairs = 1;      // LJ over pairs of neighboring centers sharing one union row (0: one row per center)
-  int aeam_cluster = 1;  // AEAM: clusters of 4 consecutive centers share one union row and the density pass hands the
-                         // force pass f'(r) of every (center, candidate) (0: one row per center, the round-1 kernels)
+  int aeam_cluster = 2;  // AEAM row form.  2 (default): one row per center, the density pass hands f'(r) of every entry to the
+                         // force pass (one spline gather per pair and pass).  1: clusters of 4 consecutive centers share one
+                         // union row (fewest gathered sectors, but latency-bound: slower, profiles/r02_aeam_kernels.md).
+                         // 0: one row per center, force pass re-gathers the fused {rho' | phi} row (the round-1 kernels)
   int aeam_variant = 0;      // tuning experiments: bit 0 = force kernel 2 entries per lane and trip, bit 1 = density 1
   int aeam_sort_rows = 0;    // AEAM cluster rows sorted by atom index (adjacent lanes then read adjacent sectors)
   int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency

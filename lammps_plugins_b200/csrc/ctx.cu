@@ -131,7 +131,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->lj_pairs = value ? 1 : 0;
     c->inner_valid = false;
   } else if (n == "aeam_cluster") {
-    c->aeam_cluster = value ? 1 : 0;
+    c->aeam_cluster = (int) (value < 0 ? 0 : (value > 2 ? 2 : value));
     c->inner_valid = false;
   } else if (n == "aeam_variant") c->aeam_variant = (int) value;
   else if (n == "aeam_sort_rows") {

@@ -188,9 +188,9 @@ def test_per_atom_energy_and_virial(ctx, oracle_built, case):
 
 @pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3]], ids=[CASES[1]["id"], CASES[2]["id"], CASES[3]["id"]])
 def test_cluster_rows_equal_single_rows(ctx, oracle_built, case):
-    """Cluster form (4 consecutive centers share one union row, f' handed from the density to the force pass; the
-    default) == one row per center (the round-1 kernels, option aeam_cluster = 0), with and without index-sorted rows.
-    nlocal is not a multiple of 4 in the 5x4x6 case of test_forces_energy_virial; here the per-atom variants too."""
+    """The three row forms agree: one row per center with f' handed from the density to the force pass (default,
+    aeam_cluster = 2), the round-1 kernels (0), and the cluster form (1: 4 consecutive centers share one union row) in
+    its lane layouts, with and without index-sorted rows."""
     lmp = S.make_aeam_system(S.oracle_plugin("aeam"), case["cells"], si_fraction=case["si"], displace=case["displace"])
     lmp.setup(1, 2)
     snap = S.snapshot(lmp)
@@ -200,7 +200,9 @@ def test_cluster_rows_equal_single_rows(ctx, oracle_built, case):
     try:
         for name, opts in (("single", dict(aeam_cluster=0)), ("cluster", dict(aeam_cluster=1, aeam_sort_rows=0)),
                            ("cluster-sorted", dict(aeam_cluster=1, aeam_sort_rows=1)),
-                           ("cluster-u2", dict(aeam_cluster=1, aeam_sort_rows=0, aeam_variant=3))):
+                           ("cluster-lpe1", dict(aeam_cluster=1, aeam_sort_rows=0, aeam_variant=11)),
+                           ("cluster-lpe2", dict(aeam_cluster=1, aeam_sort_rows=0, aeam_variant=33)),
+                           ("single-df", dict(aeam_cluster=2, aeam_variant=0))):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             res[name] = gpu_forces(ctx, snap)
@@ -208,7 +210,7 @@ def test_cluster_rows_equal_single_rows(ctx, oracle_built, case):
             fo, eo, vo = ctx.aeam_compute(snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], 0, 0)
             assert S.rel_err(S.fold_ghost_forces(fo, snap["swaps"], snap["nlocal"]), res[name][0]) < 1e-13
     finally:
-        ctx.set_option("aeam_cluster", 1)
+        ctx.set_option("aeam_cluster", 2)
         ctx.set_option("aeam_sort_rows", 0)
         ctx.set_option("aeam_variant", 0)
     for name, (f, e, v) in res.items():

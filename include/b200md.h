@@ -63,6 +63,9 @@ typedef struct b200md_ctx b200md_ctx;
 
 /* ---- lifecycle ----------------------------------------------------------- */
 int b200md_create(int device, b200md_ctx **out);
+/* number of visible devices this library can drive (all must be sm_100; 0 if none or a mixed box) -- what the host
+ * classes take a rank's node-local index modulo of */
+int b200md_device_count(void);
 void b200md_destroy(b200md_ctx *ctx);
 /* text of the last error on this context (ctx may be NULL: last create error) */
 const char *b200md_last_error(const b200md_ctx *ctx);
@@ -113,6 +116,12 @@ int b200md_aeam_get_spline(b200md_ctx *ctx, int kind, int index, double *out, in
  * whenever LAMMPS rebuilt the list (neighbor->ago == 0).                      */
 int b200md_set_neighbor_list(b200md_ctx *ctx, int inum, int gnum, const int *numneigh,
                              const int *const *firstneigh, double skin);
+/* the same list described the way LAMMPS' NeighList really is (neigh_list.h: numneigh[] and firstneigh[] indexed by
+ * ATOM index, ilist[0..inum+gnum) naming the atoms that have a row; pair_rebomos.cpp:304-310 walks it that way).  The
+ * list must give every owned atom -- and every ghost when gnum > 0 -- exactly one row: skip lists and the sub-style
+ * lists of pair hybrid are refused with B200MD_ERR_ARG.  ilist == NULL means the identity. */
+int b200md_set_neighbor_list_ilist(b200md_ctx *ctx, int inum, int gnum, const int *ilist, const int *numneigh,
+                                   const int *const *firstneigh, double skin);
 /* same, from a flat CSR (offsets[inum+gnum+1], values) */
 int b200md_set_neighbor_csr(b200md_ctx *ctx, int inum, int gnum, const int64_t *offsets,
                             const int *values, double skin);
@@ -205,10 +214,14 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *  "d2h_min_atoms"   plugin mode: below this many owned atoms both pipelines are off (default 65536)
  *  "p2p_halo"        0/1 (default 1): multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the
  *                    sender packs straight into the receiver's HBM over NVLink -- falling back to NCCL send/recv
+ *  "aeam_cluster"    AEAM row form: 2 (default) one row per center, the density pass hands f'(r) of every entry to the force
+ *                    pass; 1 clusters of 4 consecutive centers share one union row; 0 the force pass re-gathers rho'
+ *  "force_rebuild"   resident loop: the NEXT step takes the reneighboring path whatever the displacements (set it on
+ *                    every rank; used to time a master rebuild)
  *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)
  *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
-/* counters: "kernel_launches", "list_uploads", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",
+/* counters: "kernel_launches", "list_uploads" (master lists received: handed over or built on the device), "compute_calls", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",
  * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos" */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name

@@ -93,10 +93,12 @@ SYMBOLS = [
     ("b200md_destroy", None, [c_void_p]),
     ("b200md_last_error", c_char_p, [c_void_p]),
     ("b200md_version", c_int, []),
+    ("b200md_device_count", c_int, []),
     ("b200md_rebomos_init", c_int, [c_void_p, POINTER(RebomosParams), c_int, _PI]),
     ("b200md_aeam_init", c_int, [c_void_p, POINTER(AeamTables)]),
     ("b200md_aeam_get_spline", c_int, [c_void_p, c_int, c_int, _PD, c_int]),
     ("b200md_set_neighbor_list", c_int, [c_void_p, c_int, c_int, _PI, POINTER(_PI), c_double]),
+    ("b200md_set_neighbor_list_ilist", c_int, [c_void_p, c_int, c_int, _PI, _PI, POINTER(_PI), c_double]),
     ("b200md_set_neighbor_csr", c_int, [c_void_p, c_int, c_int, _PL, _PI, c_double]),
     ("b200md_neigh_build", c_int, [c_void_p, POINTER(Box), c_int, _PD, _PD, c_int, c_int, _PD, _PI, c_int, c_double]),
     ("b200md_neigh_size", c_int, [c_void_p, _PI, _PL]),
@@ -195,6 +197,9 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def last_error(self):
+        return self.L.b200md_last_error(self.h).decode()
 
     def _check(self, rc):
         if rc != 0:

@@ -143,6 +143,7 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
       const int ntri = t->nr[hi * nel + lo];
       d.pair_off[ij] = (int) (p_pair.size() / 8);
       d.z2r_n[ij] = ntri;
+      d.z2r_rdr[ij] = 1.0 / t->dr[hi * nel + lo];
       for (int m = 0; m <= n; m++) {
         for (int k = 0; k < 4; k++) p_pair.push_back(p_rhor[4 * ((size_t) d.rhor_off[ij] + m) + k]);
         const int mz = m < ntri ? m : ntri;
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
 struct PairPar {
   double cutgt, rdr;
   int nr, off;
-  int roff, zoff, nz, pad;    // cluster form: rows of the separate rhor / z2r tables, z2r row clamp
+  int roff, zoff, nz, pad;    // rows of the separate rhor / z2r tables, z2r row clamp
+  double zrdr;                // 1/dr the z2r table was built with: dr[max][min] (pair_aeam.cpp:836-843, 906-910)
 };
 __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, bool rhor_table = false)
 {
@@ -291,6 +293,7 @@ __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, b
     sp[threadIdx.x].zoff = par.z2r_off[threadIdx.x];
     sp[threadIdx.x].nz = par.z2r_n[threadIdx.x];
     sp[threadIdx.x].pad = 0;
+    sp[threadIdx.x].zrdr = par.z2r_rdr[threadIdx.x];
   }
   __syncthreads();
 }
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
               // visit (i,j): pair_aeam.cpp:350-393
               const PairPar &P = sp[ti[c] * nel + tj];
               const double dfij = dv[u][c];
-              const double phip = spl_der(zw[k], pp[k], P.rdr);
+              const double phip = spl_der(zw[k], pp[k], P.zrdr);
               const double fpair = -gi[c] * dfij * recip + 0.5 * (-phip * recip);
               coef = fpair;
               // same element: visit (j,i) evaluates the same two splines at the same (m, p)
@@ -756,7 +759,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
                 double p;
                 spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
                 const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
-                const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
+                const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.zrdr);
                 coef += -gj * dfji * recip + 0.5 * (-phip * recip);
               }
             }
@@ -1025,7 +1028,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
           const double4 cr = ld_sector(ptab + 2 * (size_t) (pij.off + m));
           const double4 cz = ld_sector(ptab + 2 * (size_t) (pij.off + m) + 1);
           const double dfij = spl_der(cr, p, pij.rdr);
-          const double phip = spl_der(cz, p, pij.rdr);
+          const double phip = spl_der(cz, p, pij.zrdr);
           const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
           coef = fpair;
           // same element: visit (j,i) reads the same rows with the same (m, p) -- evaluated without a
@@ -1049,7 +1052,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
             double p;
             spl_index(r1, pji.rdr, pji.nr, m, p);
             const double dfji = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m)), p, pji.rdr);
-            const double phip = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m) + 1), p, pji.rdr);
+            const double phip = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m) + 1), p, pji.zrdr);
             coef += -gj * dfji * recip + 0.5 * (-phip * recip);
           }
         }
@@ -1183,7 +1186,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
           if (in_ij[k]) {
             // visit (i,j): pair_aeam.cpp:350-393
             const double dfij = dfs[u];
-            const double phip = spl_der(zw[k], pp[k], spi[tj].rdr);
+            const double phip = spl_der(zw[k], pp[k], spi[tj].zrdr);
             const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
             coef = fpair;
             // same element: visit (j,i) evaluates the same two splines at the same (m, p)
@@ -1207,7 +1210,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
               double p;
               spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
               const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
-              const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
+              const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.zrdr);
               coef += -gj * dfji * recip + 0.5 * (-phip * recip);
             }
           }
@@ -1675,8 +1678,15 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
                                            double *virial, double *eatom, double *vatom)
 {
   if (!c) return B200MD_ERR_ARG;
-  ARG_CHECK(c, f != nullptr, "aeam_compute: f is NULL");
+  ARG_CHECK(c, f != nullptr || nlocal + nghost == 0, "aeam_compute: f is NULL");
   ARG_CHECK(c, tag != nullptr || nghost == 0, "aeam_compute: atom IDs are needed to give ghosts their fp");
+  c->n_compute++;
+  if (nlocal + nghost == 0) {    // an empty rank (vacuum brick)
+    if (eng_vdwl) *eng_vdwl = 0.0;
+    if (virial)
+      for (int k = 0; k < 6; k++) virial[k] = 0.0;
+    return B200MD_OK;
+  }
   int rc = aeam_begin(c, nlocal, nghost, x, type, tag);
   if (rc) return rc;
   if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
@@ -1700,6 +1710,7 @@ extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, 
                                          const int *type, double *rho_out, double *fp_out)
 {
   if (!c) return B200MD_ERR_ARG;
+  c->n_compute++;
   int rc = aeam_begin(c, nlocal, nghost, x, type, nullptr);
   if (rc) return rc;
   // option "peratom": the embedding energy of this phase is tallied per atom and handed out by the force phase

@@ -120,6 +120,7 @@ struct AeamDev {
   int pair_off[16];         // row offset (in 64-byte rows) of the fused {rhor | z2r} table of pair (i,j)
   double cut_gt_sq[16];     // smallest rsq with sqrt(rsq) > cut[i][j]: `rsq >= this` is the reference's `r > cut`
   int z2r_n[16];            // rows of the z2r table pair (i,j) reads (the row index is clamped to it)
+  double z2r_rdr[16];       // 1/dr of that table, dr[max(i,j)][min(i,j)]: the scale of its derivative coefficients
 };
 
 // ---------------------------------------------------------------- context
@@ -171,6 +172,7 @@ struct b200md_ctx {
                          // force pass (one spline gather per pair and pass).  1: clusters of 4 consecutive centers share one
                          // union row (fewest gathered sectors, but latency-bound: slower, profiles/r02_aeam_kernels.md).
                          // 0: one row per center, force pass re-gathers the fused {rho' | phi} row (the round-1 kernels)
+  int force_rebuild = 0;     // resident loop: the next step rebuilds the master list whatever the displacements
   int aeam_variant = 0;      // tuning experiments: bit 0 = force kernel 2 entries per lane and trip, bit 1 = density 1
   int aeam_sort_rows = 0;    // AEAM cluster rows sorted by atom index (adjacent lanes then read adjacent sectors)
   int d2h_min_atoms = 65536;    // below this the ranged path is all launch latency
@@ -182,6 +184,7 @@ struct b200md_ctx {
   // counters
   long long n_launch = 0, n_list_upload = 0, n_inner_rebuild = 0, h2d_bytes = 0, d2h_bytes = 0;
   long long n_lj_entries = 0, n_short_entries = 0;
+  long long n_compute = 0;    // force computations through the host-buffer entry points
   long long n_pipelined = 0, n_redo = 0;    // plugin-mode calls through the pipelined path / recomputed after a refresh
   // per-launch CUDA events while "sync_timing" is on; folded into kstat by b200md_collect_timers()
   std::vector<std::string> kname;

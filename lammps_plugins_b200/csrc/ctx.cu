@@ -17,6 +17,20 @@ extern "C" const char *b200md_last_error(const b200md_ctx *ctx)
   return g_create_error.c_str();
 }
 
+extern "C" int b200md_device_count(void)
+{
+  int ndev = 0, usable = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (int d = 0; d < ndev; d++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) usable++;
+  }
+  return usable == ndev ? ndev : 0;    // a mixed box: say 0 and let the caller name the device explicitly
+}
+
 extern "C" int b200md_create(int device, b200md_ctx **out)
 {
   std::lock_guard<std::mutex> lk(g_mutex);
@@ -134,6 +148,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->aeam_cluster = (int) (value < 0 ? 0 : (value > 2 ? 2 : value));
     c->inner_valid = false;
   } else if (n == "aeam_variant") c->aeam_variant = (int) value;
+  else if (n == "force_rebuild") c->force_rebuild = value ? 1 : 0;
   else if (n == "aeam_sort_rows") {
     c->aeam_sort_rows = value ? 1 : 0;
     c->inner_valid = false;
@@ -156,6 +171,7 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
   std::string n(name);
   if (n == "kernel_launches") return c->n_launch;
   if (n == "list_uploads") return c->n_list_upload;
+  if (n == "compute_calls") return c->n_compute;
   if (n == "inner_rebuilds") return c->n_inner_rebuild;
   if (n == "h2d_bytes") return c->h2d_bytes;
   if (n == "d2h_bytes") return c->d2h_bytes;
@@ -450,7 +466,7 @@ int b200md_collect_timers(b200md_ctx *c)
 int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
                         const int *tag)
 {
-  ARG_CHECK(c, nlocal >= 0 && nghost >= 0 && x && type, "upload_atoms: bad sizes or NULL arrays");
+  ARG_CHECK(c, nlocal >= 0 && nghost >= 0 && ((x && type) || nlocal + nghost == 0), "upload_atoms: bad sizes or NULL arrays");
   int nall = nlocal + nghost;
   c->nlocal = nlocal;
   c->nghost = nghost;
@@ -644,6 +660,33 @@ extern "C" int b200md_set_neighbor_list(b200md_ctx *c, int inum, int gnum, const
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // `off` is a stack-owned staging vector
   c->h2d_bytes += (long long) (total * sizeof(int) + rows * (sizeof(int) + sizeof(int64_t)));
   return finish_list(c, inum, gnum, total, skin);
+}
+
+// LAMMPS' NeighList as it really is: numneigh[] and firstneigh[] are indexed by ATOM index, ilist[0..inum+gnum) names
+// the atoms that have a row.  The device rows are indexed by atom index as well, so the list must give every owned atom
+// (and, with ghost rows, every ghost) exactly one row: skip lists / sub-style lists of pair hybrid are refused.
+extern "C" int b200md_set_neighbor_list_ilist(b200md_ctx *c, int inum, int gnum, const int *ilist, const int *numneigh,
+                                              const int *const *firstneigh, double skin)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, inum >= 0 && gnum >= 0 && numneigh && firstneigh && skin >= 0.0, "set_neighbor_list_ilist");
+  const int rows = inum + gnum;
+  if (!ilist) return b200md_set_neighbor_list(c, inum, gnum, numneigh, firstneigh, skin);
+  bool identity = true;
+  for (int ii = 0; ii < rows && identity; ii++) identity = ilist[ii] == ii;
+  if (identity) return b200md_set_neighbor_list(c, inum, gnum, numneigh, firstneigh, skin);
+  // a permuted ilist: gather the row descriptors by atom index
+  std::vector<int> num((size_t) rows, -1);
+  std::vector<const int *> first((size_t) rows, nullptr);
+  for (int ii = 0; ii < rows; ii++) {
+    const int i = ilist[ii];
+    ARG_CHECK(c, i >= 0 && i < rows && num[i] < 0 && (ii < inum) == (i < inum),
+              "set_neighbor_list_ilist: the list must hold one row for every owned atom (and every ghost, for ghost "
+              "rows): skip lists and sub-style lists are not supported");
+    num[i] = numneigh[i];
+    first[i] = firstneigh[i];
+  }
+  return b200md_set_neighbor_list(c, inum, gnum, num.data(), first.data(), skin);
 }
 
 extern "C" int b200md_set_neighbor_csr(b200md_ctx *c, int inum, int gnum, const int64_t *offsets,

@@ -420,6 +420,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
   c->skin = skin;
   c->list_valid = true;
   c->inner_valid = false;
+  c->n_list_upload++;    // counts every master list the context received, built here or handed over
   return B200MD_OK;
 }
 

@@ -1858,8 +1858,15 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
   ARG_CHECK(c, c->rebomos_ready, "rebomos_compute: call b200md_rebomos_init first");
   ARG_CHECK(c, c->list_valid, "rebomos_compute: no neighbor list (b200md_set_neighbor_list / b200md_neigh_build)");
   ARG_CHECK(c, c->list_inum == nlocal, "rebomos_compute: neighbor list was built for a different nlocal");
-  ARG_CHECK(c, f != nullptr, "rebomos_compute: f is NULL");
+  ARG_CHECK(c, f != nullptr || nlocal + nghost == 0, "rebomos_compute: f is NULL");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  c->n_compute++;
+  if (nlocal + nghost == 0) {    // an empty rank (vacuum brick): nothing to upload, nothing to add
+    if (eng_vdwl) *eng_vdwl = 0.0;
+    if (virial)
+      for (int k = 0; k < 6; k++) virial[k] = 0.0;
+    return B200MD_OK;
+  }
   c->tight_valid = false;    // the tight rows belong to the GPU-resident loop, which owns their refresh schedule
   int rc;
   int fl[16];

@@ -2252,6 +2252,10 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (flag) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+    if (c->force_rebuild) {    // option "force_rebuild": this step takes the reneighboring path (measurement; collective)
+      c->force_rebuild = 0;
+      flag = 3;
+    }
     if (flag >= 3) {
       if (s->ago == 1) s->ndanger++;
       if ((rc = reneighbor(c, s, false))) return rc;

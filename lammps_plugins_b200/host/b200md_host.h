@@ -17,19 +17,49 @@
 #include "neigh_list.h"
 #include "neighbor.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 namespace B200MDHost {
 
-// which GPU this rank drives: B200MD_DEVICE if set, else rank modulo the visible device count
+// which GPU this rank drives: B200MD_DEVICE if set, else the NODE-LOCAL rank (as the MPI launcher exports it; the
+// global rank if it exports nothing) modulo the number of visible sm_100 devices (B200MD_DEVICES_PER_NODE overrides
+// the count).  Returns -1 when no usable device is visible: b200md_create then reports why.
 inline int pick_device(int me)
 {
   const char *env = getenv("B200MD_DEVICE");
   if (env) return atoi(env);
+  int local = me;
+  static const char *const local_rank_vars[] = {"OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID",
+                                                "PMI_LOCAL_RANK", "SLURM_LOCALID", "LOCAL_RANK"};
+  for (const char *v : local_rank_vars) {
+    const char *e = getenv(v);
+    if (e && *e) {
+      local = atoi(e);
+      break;
+    }
+  }
   const char *vis = getenv("B200MD_DEVICES_PER_NODE");
-  int per = vis ? atoi(vis) : 0;
-  return per > 0 ? me % per : 0;
+  int per = vis ? atoi(vis) : b200md_device_count();
+  if (per <= 0) return vis ? 0 : -1;
+  return local % per;
+}
+
+// B200MD_STATS_FILE=<path>: when the pair style is destroyed, append one JSON line with the library's counters
+// (what the benchmark's drop-in leg reads: pipelined calls / recomputes, list hand-overs, bytes moved)
+inline void write_stats(b200md_ctx *ctx, const char *style, int me)
+{
+  const char *path = getenv("B200MD_STATS_FILE");
+  if (!ctx || !path || !*path) return;
+  FILE *fp = fopen(path, "a");
+  if (!fp) return;
+  static const char *const names[] = {"kernel_launches", "list_uploads", "inner_rebuilds", "h2d_bytes", "d2h_bytes",
+                                      "pipelined_calls", "pipelined_redos", "compute_calls"};
+  fprintf(fp, "{\"style\": \"%s\", \"rank\": %d", style, me);
+  for (const char *n : names) fprintf(fp, ", \"%s\": %lld", n, b200md_get_counter(ctx, n));
+  fprintf(fp, "}\n");
+  fclose(fp);
 }
 
 // true -> rebuild the list on the device from LAMMPS' positions (default);
@@ -71,8 +101,9 @@ inline int sync_neighbor_list(b200md_ctx *ctx, LAMMPS_NS::Atom *atom, LAMMPS_NS:
                               &neighbor->cutneighghostsq[0][0], atom->nlocal, atom->nghost, &atom->x[0][0],
                               atom->type, ghost_rows, neighbor->skin);
   }
-  return b200md_set_neighbor_list(ctx, list->inum, ghost_rows ? list->gnum : 0, list->numneigh, list->firstneigh,
-                                  neighbor->skin);
+  // LAMMPS indexes numneigh[] / firstneigh[] by ATOM index and names the atoms that have a row in ilist[]
+  return b200md_set_neighbor_list_ilist(ctx, list->inum, ghost_rows ? list->gnum : 0, list->ilist, list->numneigh,
+                                        list->firstneigh, neighbor->skin);
 }
 
 // Is atom->f known to be all zero when Pair::compute() is entered?  Verlet::force_clear() zeroes it and only fixes with

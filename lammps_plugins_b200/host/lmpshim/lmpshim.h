@@ -690,7 +690,7 @@ class Pair : protected Pointers {
 
   int comm_forward, comm_reverse, comm_reverse_off;
   int single_enable, born_matrix_enable, single_hessian_enable, restartinfo, respa_enable, one_coeff,
-      manybody_flag, unit_convert_flag, no_virial_fdotr, writedata, finitecutflag, ghostneigh;
+      manybody_flag, unit_convert_flag, no_virial_fdotr_compute, writedata, finitecutflag, ghostneigh;
   double **cutghost;
   int ewaldflag, pppmflag, msmflag, dispersionflag, tip4pflag, dipoleflag, spinflag, reinitflag;
   int centroidstressflag;

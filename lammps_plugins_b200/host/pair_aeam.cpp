@@ -33,6 +33,9 @@ PairAEAM::PairAEAM(LAMMPS *lmp) : Pair(lmp)
   restartinfo = 0;
   manybody_flag = 1;
   one_coeff = 1;
+  // gather-form kernels: the global virial must come from the device, never from somebody else's sum(x . f) over
+  // atom->f (see pair_rebomos.cpp)
+  no_virial_fdotr_compute = 1;
 
   nmax = 0;
   rho = fp = nullptr;
@@ -47,6 +50,7 @@ PairAEAM::PairAEAM(LAMMPS *lmp) : Pair(lmp)
 
 PairAEAM::~PairAEAM()
 {
+  B200MDHost::write_stats(ctx, "aeam", comm->me);
   if (ctx) b200md_destroy(ctx);
   memory->destroy(rho);
   memory->destroy(fp);
@@ -82,6 +86,12 @@ void PairAEAM::compute(int eflag, int vflag)
   const int nlocal = atom->nlocal;
   const int nghost = atom->nghost;
   const int nall = nlocal + nghost;
+  // a rank without owned and ghost atoms still takes part in the forward communication (it is collective)
+  if (nall == 0) {
+    comm->forward_comm(this);
+    vflag_fdotr = 0;
+    return;
+  }
 
   if (neighbor->ago == 0 || uploaded_nlocal != nlocal || uploaded_nghost != nghost) {
     int rc = B200MDHost::sync_neighbor_list(ctx, atom, neighbor, comm, domain, list, 0);

@@ -34,6 +34,11 @@ PairREBOMoS::PairREBOMoS(LAMMPS *lmp) : Pair(lmp)
   ghostneigh = 1;
   manybody_flag = 1;
   centroidstressflag = CENTROID_NOTAVAIL;
+  // The kernels evaluate every pair from both ends (gather form) and give a ghost partner nothing, so sum(x . f) over
+  // owned + ghost atoms taken by SOMEBODY ELSE (PairHybrid::compute calls virial_fdotr_compute() itself after clearing
+  // VIRIAL_FDOTR for its sub-styles) is not this style's virial.  With this flag the caller asks for VIRIAL_PAIR
+  // instead and receives the virial the device computed.
+  no_virial_fdotr_compute = 1;
 
   ctx = nullptr;
   cut3rebo = 0.0;
@@ -48,6 +53,7 @@ PairREBOMoS::PairREBOMoS(LAMMPS *lmp) : Pair(lmp)
 
 PairREBOMoS::~PairREBOMoS()
 {
+  B200MDHost::write_stats(ctx, "rebomos", comm->me);
   if (ctx) b200md_destroy(ctx);
   if (allocated) {
     memory->destroy(setflag);
@@ -72,6 +78,12 @@ void PairREBOMoS::compute(int eflag, int vflag)
 
   const int nlocal = atom->nlocal;
   const int nghost = atom->nghost;
+  // a rank whose brick holds no owned and no ghost atoms (vacuum in a slab run, many ranks): nothing to do, and
+  // atom->x / atom->f need not even be allocated
+  if (nlocal + nghost == 0) {
+    vflag_fdotr = 0;
+    return;
+  }
 
   // LAMMPS rebuilt its neighbor list on this step (or atom counts changed): refresh the device list
   if (neighbor->ago == 0 || uploaded_nlocal != nlocal || uploaded_nghost != nghost) {

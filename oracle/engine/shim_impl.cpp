@@ -370,7 +370,7 @@ Pair::Pair(LAMMPS *l) : Pointers(l)
   restartinfo = 1;
   respa_enable = 0;
   one_coeff = 0;
-  no_virial_fdotr = 0;
+  no_virial_fdotr_compute = 0;
   writedata = 0;
   finitecutflag = 0;
   ghostneigh = 0;
@@ -497,7 +497,7 @@ void Pair::ev_setup(int eflag, int vflag, int alloc)
 
   // if vflag_global = VIRIAL_FDOTR and pair::compute() calls virial_fdotr_compute()
   // compute global virial via (F dot r) instead of via pairwise summation
-  if (vflag_global == VIRIAL_FDOTR && no_virial_fdotr == 0) {
+  if (vflag_global == VIRIAL_FDOTR && no_virial_fdotr_compute == 0) {
     vflag_fdotr = 1;
     vflag_global = 0;
     if (vflag_atom == 0 && cvflag_atom == 0) vflag_either = 0;

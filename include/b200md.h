@@ -222,7 +222,9 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads" (master lists received: handed over or built on the device), "compute_calls", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",
- * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos" */
+ * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos";
+ * row statistics summed on the device when asked (measurement): "master_entries", "lj_entries_tight",
+ * "short_entries_tight", "short_entries_owned", "aeam_entries" (-1 while those rows do not exist) */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);
 /* device time of the kernels of the last compute call, ms, by name
  * ("rebo_center_mo","rebo_center_s","lj","fdotr","aeam_density","aeam_force",...) */
@@ -241,6 +243,9 @@ double b200md_event_elapsed_ms(b200md_ctx *ctx, int slot_a, int slot_b);
 /* roofline denominators measured in place on this context's device: a DFMA-saturating kernel (TFLOP/s FP64) and
  * a 2 GiB device-to-device copy (GB/s, read + write bytes).  Either pointer may be NULL. */
 int b200md_measure_peaks(b200md_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
+/* one plain copy of `bytes` between a host block and device staging memory, timed with CUDA events (ms): what the link
+ * alone needs for a per-step position upload (to_device = 1) or force download (0) */
+int b200md_copy_probe(b200md_ctx *ctx, void *host, size_t bytes, int to_device, double *ms);
 /* page-locked host memory for callers that want DMA-speed x/f transfers */
 void *b200md_host_alloc(size_t bytes);
 void b200md_host_free(void *p);

@@ -121,6 +121,7 @@ SYMBOLS = [
     ("b200md_event_record", c_int, [c_void_p, c_int]),
     ("b200md_event_elapsed_ms", c_double, [c_void_p, c_int, c_int]),
     ("b200md_measure_peaks", c_int, [c_void_p, _PD, _PD]),
+    ("b200md_copy_probe", c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_int, _PD]),
     ("b200md_host_alloc", c_void_p, [ctypes.c_size_t]),
     ("b200md_host_free", None, [c_void_p]),
     ("b200md_host_register", c_int, [c_void_p, ctypes.c_size_t]),
@@ -197,6 +198,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def copy_probe(self, host_array, to_device):
+        """ms of one plain H2D (to_device) / D2H copy of a host array"""
+        ms = c_double()
+        self._check(self.L.b200md_copy_probe(self.h, host_array.ctypes.data_as(c_void_p), host_array.nbytes,
+                                             1 if to_device else 0, ctypes.byref(ms)))
+        return ms.value
 
     def last_error(self):
         return self.L.b200md_last_error(self.h).decode()

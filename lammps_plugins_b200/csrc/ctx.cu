@@ -165,10 +165,42 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   return B200MD_OK;
 }
 
+// on-demand sums of per-row counts (measurement queries, never on the step path)
+__global__ void count_sum_kernel(const int *__restrict__ v, long long n, unsigned long long *__restrict__ out)
+{
+  unsigned long long s = 0;
+  for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+    s += (unsigned long long) v[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+static long long device_sum(b200md_ctx *c, const int *v, long long n)
+{
+  if (!v || n <= 0) return 0;
+  cudaSetDevice(c->device);
+  unsigned long long *acc = (unsigned long long *) (c->scal.p + 60);
+  unsigned long long h = 0;
+  cudaMemsetAsync(acc, 0, sizeof(h), c->stream);
+  count_sum_kernel<<<c->num_sms * 2, 256, 0, c->stream>>>(v, n, acc);
+  cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  return (long long) h;
+}
+
 extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
 {
   if (!c || !name) return -1;
   std::string n(name);
+  // entries of the rows the force kernels stream right now (summed on the device when asked)
+  if (n == "lj_entries_tight")
+    return (c->tight_valid && c->lj_pairs) ? device_sum(c, c->lj_num_t.p, 4LL * c->ljp_P) : -1;
+  if (n == "short_entries_tight") return c->tight_valid ? device_sum(c, c->short_num_t.p, c->list_inum) : -1;
+  if (n == "short_entries_owned") return c->inner_valid && c->rebomos_ready ? device_sum(c, c->short_num.p, c->list_inum) : -1;
+  if (n == "aeam_entries")
+    return (c->inner_valid && c->aeam_ready)
+               ? (c->aeam_cluster == 1 ? device_sum(c, c->ec_num.p, (c->list_inum + 3) / 4) : device_sum(c, c->ea_num.p, c->list_inum))
+               : -1;
+  if (n == "master_entries") return c->list_valid ? (long long) c->list_entries : -1;
   if (n == "kernel_launches") return c->n_launch;
   if (n == "list_uploads") return c->n_list_upload;
   if (n == "compute_calls") return c->n_compute;
@@ -718,6 +750,30 @@ extern "C" int b200md_set_neighbor_csr(b200md_ctx *c, int inum, int gnum, const 
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->h2d_bytes += (long long) (total * sizeof(int) + rows * (sizeof(int) + sizeof(int64_t)));
   return finish_list(c, inum, gnum, total, skin);
+}
+
+// one plain copy between a host block and the context's device staging, timed with CUDA events on the context's stream
+// (measurement: what the link alone needs for the per-step position upload / force download)
+extern "C" int b200md_copy_probe(b200md_ctx *c, void *host, size_t bytes, int to_device, double *ms_out)
+{
+  if (!c) return B200MD_ERR_ARG;
+  ARG_CHECK(c, host && bytes > 0 && ms_out, "copy_probe: bad arguments");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, c->x_aos.reserve(bytes / sizeof(double) + 8));
+  cudaEvent_t a, b;
+  CUDA_TRY(c, cudaEventCreate(&a));
+  CUDA_TRY(c, cudaEventCreate(&b));
+  CUDA_TRY(c, cudaEventRecord(a, c->stream));
+  if (to_device) CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  else CUDA_TRY(c, cudaMemcpyAsync(host, c->x_aos.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaEventRecord(b, c->stream));
+  CUDA_TRY(c, cudaEventSynchronize(b));
+  float ms = 0.f;
+  CUDA_TRY(c, cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *ms_out = ms;
+  return B200MD_OK;
 }
 
 extern "C" int b200md_neigh_size(b200md_ctx *c, int *nrows, int64_t *nentries)

@@ -233,7 +233,8 @@ void PairAEAM::init_style()
   B200MDHost::check(error, ctx, rc, "table upload");
   uploaded_nlocal = uploaded_nghost = -1;
 
-  neighbor->add_request(this, NeighConst::REQ_FULL);
+  // LAMMPS' own full list is requested only when it is the one handed over (B200MD_NEIGH=host); see pair_rebomos.cpp
+  if (!B200MDHost::device_neighbor_build()) neighbor->add_request(this, NeighConst::REQ_FULL);
 }
 
 double PairAEAM::init_one(int i, int j)

@@ -184,8 +184,11 @@ void PairREBOMoS::init_style()
   if (force->newton_pair == 0) error->all(FLERR, "Pair style REBOMoS requires newton pair on");
   if (atom->ntypes > 8) error->all(FLERR, "Pair style rebomos (B200) supports at most 8 atom types");
 
-  // a full neighbor list, including neighbors of ghosts (same request as the reference)
-  neighbor->add_request(this, NeighConst::REQ_FULL | NeighConst::REQ_GHOST);
+  // a full neighbor list, including neighbors of ghosts (same request as the reference) -- but only when LAMMPS' own
+  // list is the one handed over (B200MD_NEIGH=host).  By default the list is rebuilt on the device from LAMMPS'
+  // positions, bins and cutoffs, so the host need not spend its cores on 496-entry rows: no request, like the GPU
+  // package's styles when the neighbor build runs on the device; Neighbor still decides WHEN to rebuild
+  if (!B200MDHost::device_neighbor_build()) neighbor->add_request(this, NeighConst::REQ_FULL | NeighConst::REQ_GHOST);
 
   if (!ctx) {
     int rc = b200md_create(B200MDHost::pick_device(comm->me), &ctx);

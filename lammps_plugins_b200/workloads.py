@@ -202,3 +202,37 @@ def single_rank_box(w, cutneighmax):
         b.sublo[d], b.subhi[d], b.cutghost[d] = lo[d], hi[d], cg[d]
     b.cutneighmax = cutneighmax
     return b
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The same workloads as LAMMPS input commands (for a host application that loads the plugin: LAMMPS itself, or the
+# mini engine the benchmark's CPU arm and drop-in leg use).  They restate the two shipped inputs:
+# USER-REBOMOS/in.rebomos-bulk:1-22 and USER-AEAM/sample.in:1-19.
+def rebomos_bulk_script(potential_file, replicate=(1, 1, 1), cells=None):
+    """in.rebomos-bulk up to (not including) thermo/fix/run.  `replicate` appends LAMMPS' replicate command;
+    `cells` = (rx, ry, rz) instead builds one box of rx x ry x rz shipped cells (region prism scaled, tilt kept
+    proportional) -- what the CPU arm uses so that a brick grid divides the box evenly."""
+    b = "basis 0.0000000000 0.000000000 $(3.0/4.0) basis 0.0000000000 0.000000000 $(1.0/4.0) " \
+        "basis $(2.0/3.0) $(1.0/3.0) 0.862008989 basis $(1.0/3.0) $(2.0/3.0) 0.137990996 " \
+        "basis $(1.0/3.0) $(2.0/3.0) 0.362008989 basis $(2.0/3.0) $(1.0/3.0) 0.637991011"
+    region = "region box prism 0 4 0 8 0 1 -2.0 0.0 0.0"
+    if cells is not None:
+        rx, ry, rz = cells
+        region = "region box prism 0 %d 0 %d 0 %d %g 0.0 0.0" % (4 * rx, 8 * ry, rz, -2.0 * ry)
+    cmds = ["units metal",
+            "lattice custom 1.0 a1 3.1903157234 0.0000000000 0.0000000000 a2 -1.5964590311 2.7651481541 0.0000000000 "
+            "a3 0.0000000000 0.0000000000 13.9827680588 " + b + " origin 0.1 0.1 0.1",
+            region, "create_box 2 box",
+            "create_atoms 2 box basis 1 1 basis 2 1 basis 3 2 basis 4 2 basis 5 2 basis 6 2"]
+    if tuple(replicate) != (1, 1, 1):
+        cmds.append("replicate %d %d %d" % tuple(replicate))
+    cmds += ["mass 1 95.95", "mass 2 32.065", "pair_style rebomos", "pair_coeff * * %s M S" % potential_file]
+    return cmds
+
+
+def aeam_script(potential_file, cells=(20, 20, 20), si_fraction=0.0075, seed=7683797, skin=1.0):
+    """sample.in up to (not including) fix/thermo/velocity/run"""
+    return ["units metal", "atom_style atomic", "dimension 3", "boundary p p p", "lattice fcc 4.045",
+            "region MeSi block 0 %d 0 %d 0 %d" % tuple(cells), "create_box 2 MeSi", "create_atoms 1 region MeSi",
+            "pair_style aeam", "pair_coeff * * %s Al Si" % potential_file, "neighbor %g bin" % skin,
+            "neigh_modify every 1 delay 1 check yes", "set region MeSi type/fraction 2 %g %d" % (si_fraction, seed)]

@@ -91,8 +91,15 @@ void Neighbor::init()
         cutneighghostsq[i][j] = cut * cut;
     }
 
-  // (re)create the one perpetual list from the pair style's request
-  if (request == nullptr) error->all(FLERR, "Pair style made no neighbor list request");
+  // (re)create the one perpetual list from the pair style's request.  A pair style that builds its own list on the
+  // device makes none (like the GPU package's styles with neighbor builds on the device): bins, xhold and the rebuild
+  // decision still run, no host list is built
+  if (request == nullptr) {
+    delete list;
+    list = nullptr;
+    ago = -1;
+    return;
+  }
   if (!request->full) error->all(FLERR, "minilmp only builds full neighbor lists");
   delete list;
   list = new NeighList(lmp);
@@ -375,6 +382,8 @@ void Neighbor::build(int)
       xhold[i][2] = x[i][2];
     }
   }
+
+  if (!list) return;    // no request: nothing to build on the host
 
   bin_atoms();
 

@@ -435,6 +435,9 @@ void Pair::init()
   for (i = 1; i <= atom->ntypes; i++)
     if (setflag[i][i] == 0 && !manybody_flag) error->all(FLERR, "All pair coeffs are not set");
 
+  // requests are made anew by every init (Neighbor::init_pair drops the old ones in LAMMPS)
+  delete neighbor->request;
+  neighbor->request = nullptr;
   init_style();
 
   cutforce = 0.0;

@@ -43,10 +43,13 @@ ALGO = {
 }
 FP64_NOMINAL_TFLOPS = 37.0
 LONG_RUN_STEPS = {"rebomos": 1000, "aeam": 300}
-GROUPS = {"rebomos": {"lj": ["lj_mo", "lj_s"],
-                      "rebo_center": ["rebo_center_mo", "rebo_center_s", "rebo_center_overflow", "rebo_gather"]},
-          "aeam": {"aeam_force": ["aeam_force"], "aeam_density": ["aeam_density"],
-                   "aeam_angular": ["aeam_force_ang", "aeam_density_ang"]}}
+# kernel templates, each with the launches that belong to it (one per center element; "_ev" = the energy/virial
+# instances that run on thermo steps only -- one step per system_run call -- and are averaged in)
+GROUPS = {"rebomos": {"lj": ["lj_mo", "lj_s", "lj_mo_ev", "lj_s_ev"],
+                      "rebo_center": ["rebo_center_mo", "rebo_center_s", "rebo_center_mo_ev", "rebo_center_s_ev",
+                                      "rebo_center_overflow", "rebo_gather"]},
+          "aeam": {"aeam_force": ["aeam_force", "aeam_force_ev"], "aeam_density": ["aeam_density"],
+                   "aeam_angular": ["aeam_force_ang", "aeam_force_ang_ev", "aeam_density_ang"]}}
 
 
 def measured_peaks():
@@ -348,6 +351,7 @@ def measure(kind, args, grp, sampler, scaling="weak", legs=("e2e", "cpu", "long"
     # ---- roofline: per kernel its own bytes and flops, bound = the larger fraction; whole_step = headline
     hbm_peak, peak_src = measured_peaks()
     per_step = {k: v[0] / ksteps for k, v in kstats.items()}
+    per_launch = {k: v[0] / max(v[1], 1) for k, v in kstats.items()}
     groups = GROUPS[kind]
     gtime = {g: sum(per_step.get(k, 0.0) for k in ks) for g, ks in groups.items()}
     prof = load_profile_model().get(kind, {})
@@ -428,6 +432,7 @@ def measure(kind, args, grp, sampler, scaling="weak", legs=("e2e", "cpu", "long"
                  "transport": "cuda-ipc peer windows over NVLink" if p2p_ex > 0 else ("nccl send/recv" if world > 1 else "self (periodic images)")},
         "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "kernel_groups_ms_per_step": {g: round(v, 5) for g, v in gtime.items()},
+        "kernels_ms_per_launch": {k: round(v, 5) for k, v in sorted(per_launch.items(), key=lambda kv: -kv[1])[:12]},
         "kernel_timing_pass": {"steps": ksteps, "ms_per_step_with_event_pairs": ms_kpass / ksteps},
         "neighbor": dict({"rebuilds_in_timed_region": builds, "inner_list_refreshes_in_timed_region": inner,
                           "master_rebuild_ms": rebuild_ms, "step_without_rebuild_ms": plain_ms,

@@ -143,7 +143,8 @@ extern "C" int b200md_aeam_init(b200md_ctx *c, const b200md_aeam_tables *t)
       const int ntri = t->nr[hi * nel + lo];
       d.pair_off[ij] = (int) (p_pair.size() / 8);
       d.z2r_n[ij] = ntri;
-      d.z2r_rdr[ij] = 1.0 / t->dr[hi * nel + lo];
+      d.z2r_k[ij] = t->dr[ij] / t->dr[hi * nel + lo];
+      if (d.z2r_k[ij] != 1.0) d.asym_dr = 1;
       for (int m = 0; m <= n; m++) {
         for (int k = 0; k < 4; k++) p_pair.push_back(p_rhor[4 * ((size_t) d.rhor_off[ij] + m) + k]);
         const int mz = m < ntri ? m : ntri;
@@ -280,8 +281,13 @@ struct PairPar {
   double cutgt, rdr;
   int nr, off;
   int roff, zoff, nz, pad;    // rows of the separate rhor / z2r tables, z2r row clamp
-  double zrdr;                // 1/dr the z2r table was built with: dr[max][min] (pair_aeam.cpp:836-843, 906-910)
 };
+// The z2r table of an unlike pair is built with dr[max][min] (pair_aeam.cpp:836-843, 906-910) but indexed with m, p from
+// dr[i][j] (:352-372): its derivative carries 1/dr[max][min], i.e. rdr[i][j] * zk with zk = dr[i][j] / dr[max][min] -- 1
+// for like pairs and for files with symmetric dr, such as AlSi.aeam.  The hot loops run at their register limit (a few
+// bytes of spill cost 5-20 % of a kernel), so the factor exists only in the ZK instances of the round-1 force kernel,
+// which a file with asymmetric dr is routed to (AeamDev::asym_dr).
+__device__ __forceinline__ double z_scale(const AeamDev &par, int pair) { return par.z2r_k[pair]; }
 __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, bool rhor_table = false)
 {
   if (threadIdx.x < 16) {
@@ -293,7 +299,6 @@ __device__ __forceinline__ void load_pair_par(const AeamDev &par, PairPar *sp, b
     sp[threadIdx.x].zoff = par.z2r_off[threadIdx.x];
     sp[threadIdx.x].nz = par.z2r_n[threadIdx.x];
     sp[threadIdx.x].pad = 0;
-    sp[threadIdx.x].zrdr = par.z2r_rdr[threadIdx.x];
   }
   __syncthreads();
 }
@@ -342,6 +347,9 @@ template <> struct DfVec<1> {
 };
 
 // ================================================================== A1: density of non-angular atoms
+// Register-count sensitive (check -Xptxas -v after every change): the DF instance compiles to 64 registers without spill
+// = 4 CTAs per SM, 1.27 ms at 2 M atoms; at 72 registers (3 CTAs) it takes 1.50 ms, forced to 64 with 12 bytes of
+// spill 1.35 ms
 template <bool DF>
 __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
               // visit (i,j): pair_aeam.cpp:350-393
               const PairPar &P = sp[ti[c] * nel + tj];
               const double dfij = dv[u][c];
-              const double phip = spl_der(zw[k], pp[k], P.zrdr);
+              const double phip = spl_der(zw[k], pp[k], P.rdr);    // symmetric dr only (asym_dr -> round-1 kernel)
               const double fpair = -gi[c] * dfij * recip + 0.5 * (-phip * recip);
               coef = fpair;
               // same element: visit (j,i) evaluates the same two splines at the same (m, p)
@@ -759,7 +767,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
                 double p;
                 spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
                 const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
-                const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.zrdr);
+                const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
                 coef += -gj * dfji * recip + 0.5 * (-phip * recip);
               }
             }
@@ -974,7 +982,7 @@ __global__ void __launch_bounds__(BLOCK) aeam_gate_kernel(double4 *__restrict__ 
 }
 
 // ================================================================== B1: pair + embedding forces (gather)
-template <bool EV, bool ATOM>
+template <bool EV, bool ATOM, bool ZK>
 __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ ptab,
@@ -1028,7 +1036,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
           const double4 cr = ld_sector(ptab + 2 * (size_t) (pij.off + m));
           const double4 cz = ld_sector(ptab + 2 * (size_t) (pij.off + m) + 1);
           const double dfij = spl_der(cr, p, pij.rdr);
-          const double phip = spl_der(cz, p, pij.zrdr);
+          double phip = spl_der(cz, p, pij.rdr);
+          if (ZK && !same) phip *= z_scale(par, ti * nel + tj);
           const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
           coef = fpair;
           // same element: visit (j,i) reads the same rows with the same (m, p) -- evaluated without a
@@ -1052,7 +1061,8 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
             double p;
             spl_index(r1, pji.rdr, pji.nr, m, p);
             const double dfji = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m)), p, pji.rdr);
-            const double phip = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m) + 1), p, pji.zrdr);
+            double phip = spl_der(ld_sector(ptab + 2 * (size_t) (pji.off + m) + 1), p, pji.rdr);
+            if (ZK) phip *= z_scale(par, tj * nel + ti);
             coef += -gj * dfji * recip + 0.5 * (-phip * recip);
           }
         }
@@ -1186,7 +1196,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
           if (in_ij[k]) {
             // visit (i,j): pair_aeam.cpp:350-393
             const double dfij = dfs[u];
-            const double phip = spl_der(zw[k], pp[k], spi[tj].zrdr);
+            const double phip = spl_der(zw[k], pp[k], spi[tj].rdr);    // symmetric dr only (asym_dr -> round-1 kernel)
             const double fpair = -gi * dfij * recip + 0.5 * (-phip * recip);
             coef = fpair;
             // same element: visit (j,i) evaluates the same two splines at the same (m, p)
@@ -1210,7 +1220,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
               double p;
               spl_index(rsq * recip, Q.rdr, Q.nr, m, p);
               const double dfji = (gj != 0.0) ? spl_der(ld_sector(rhor + Q.roff + m), p, Q.rdr) : 0.0;
-              const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.zrdr);
+              const double phip = spl_der(ld_sector(z2r + Q.zoff + min(m, Q.nz)), p, Q.rdr);
               coef += -gj * dfji * recip + 0.5 * (-phip * recip);
             }
           }
@@ -1367,6 +1377,9 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
 
 // ================================================================== host side
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
+// row form actually used: a potential file with asymmetric dr takes the round-1 kernels (the only ones with the
+// dr[i][j] / dr[max][min] factor on the phi' of unlike pairs)
+static inline int aeam_row_mode(const b200md_ctx *c) { return c->ap.asym_dr ? 0 : c->aeam_cluster; }
 
 int b200md_aeam_pack(b200md_ctx *c)
 {
@@ -1394,7 +1407,8 @@ int b200md_aeam_build_inner(b200md_ctx *c)
   CUDA_TRY(c, c->ang_list.reserve((size_t) inum + 32));
   CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 4, 0, 3 * sizeof(int), c->stream));
-  if (c->aeam_cluster == 1) {
+  const int mode = aeam_row_mode(c);
+  if (mode == 1) {
     const int ncl = (inum + CL - 1) / CL;
     CUDA_TRY(c, c->ec_off.reserve((size_t) ncl + 2));
     CUDA_TRY(c, c->ec_num.reserve((size_t) ncl + 32));
@@ -1421,7 +1435,7 @@ int b200md_aeam_build_inner(b200md_ctx *c)
     int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
     if (rc) return rc;
     CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
-    if (c->aeam_cluster == 2) CUDA_TRY(c, c->ec_df.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
+    if (mode == 2) CUDA_TRY(c, c->ec_df.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
     if (inum > 0) {
       LaunchScope ls(c, "build_inner");
       aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(
@@ -1476,7 +1490,8 @@ int b200md_aeam_density(b200md_ctx *c)
   CUDA_TRY(c, c->fp.reserve((size_t) c->nall + 32));
   if (inum == 0) return B200MD_OK;
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
-  const bool cl = c->aeam_cluster == 1;
+  const int mode = aeam_row_mode(c);
+  const bool cl = mode == 1;
   const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
   const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
   const int rshift = cl ? CL_SHIFT : 0;
@@ -1497,7 +1512,7 @@ int b200md_aeam_density(b200md_ctx *c)
         case 7: ADC_LAUNCH(2, 2, 2); break;
         default: ADC_LAUNCH(4, 2, 4); break;
       }
-    } else if (c->aeam_cluster == 2)
+    } else if (mode == 2)
       aeam_density_kernel<true><<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
           c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p, c->ec_df.p);
     else
@@ -1552,12 +1567,13 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
                                                                      c->nall);
   }
   const bool atom = c->pa_e != nullptr;
-  const bool cl = c->aeam_cluster == 1;
+  const int mode = aeam_row_mode(c);
+  const bool cl = mode == 1;
   const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
   const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
   const int rshift = cl ? CL_SHIFT : 0;
   if (cl) {
-    LaunchScope ls(c, "aeam_force");
+    LaunchScope ls(c, (atom || ev) ? "aeam_force_ev" : "aeam_force");
     const int ncl = (inum + CL - 1) / CL;
 #define AFC_ARGS \
   c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, \
@@ -1578,13 +1594,13 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
         default: AFC_LAUNCH(false, false, 4, 2, 4); break;
       }
   } else {
-    LaunchScope ls(c, "aeam_force");
+    LaunchScope ls(c, (atom || ev) ? "aeam_force_ev" : "aeam_force");    // thermo steps: the energy/virial instance
     const int nb = nblocks((long long) inum * 8, BLOCK);
 #define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
 #define AFD_ARGS \
   c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, inum, c->f.p, \
       c->scal.p, c->pa_e, c->pa_v
-    if (c->aeam_cluster == 2) {
+    if (mode == 2) {
       if (atom) aeam_force_df_kernel<true, true, 2, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
       else if (ev) aeam_force_df_kernel<true, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
       else
@@ -1595,13 +1611,19 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
           default: aeam_force_df_kernel<false, false, 2, 3><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
         }
     } else {
-      if (atom) aeam_force_kernel<true, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
-      else if (ev) aeam_force_kernel<true, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
-      else aeam_force_kernel<false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+      if (c->ap.asym_dr) {
+        if (atom) aeam_force_kernel<true, true, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+        else if (ev) aeam_force_kernel<true, false, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+        else aeam_force_kernel<false, false, true><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+      } else {
+        if (atom) aeam_force_kernel<true, true, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+        else if (ev) aeam_force_kernel<true, false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+        else aeam_force_kernel<false, false, false><<<nb, BLOCK, 0, c->stream>>>(AF_ARGS);
+      }
     }
   }
   if (c->ap.nnonangular < c->ap.nel) {
-    LaunchScope ls(c, "aeam_force_ang");
+    LaunchScope ls(c, (atom || ev) ? "aeam_force_ang_ev" : "aeam_force_ang");
 #define AA_ARGS \
   c->ap, c->xq.p, r_off, r_num, r_val, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, c->scal.p, \
       c->flags.p, c->pa_v, rshift

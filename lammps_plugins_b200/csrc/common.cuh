@@ -120,7 +120,8 @@ struct AeamDev {
   int pair_off[16];         // row offset (in 64-byte rows) of the fused {rhor | z2r} table of pair (i,j)
   double cut_gt_sq[16];     // smallest rsq with sqrt(rsq) > cut[i][j]: `rsq >= this` is the reference's `r > cut`
   int z2r_n[16];            // rows of the z2r table pair (i,j) reads (the row index is clamped to it)
-  double z2r_rdr[16];       // 1/dr of that table, dr[max(i,j)][min(i,j)]: the scale of its derivative coefficients
+  double z2r_k[16];         // dr[i][j] / dr[max(i,j)][min(i,j)]: the z2r derivative is scaled with the lower-triangle dr
+  int asym_dr;              // some z2r_k != 1: the file's dr matrix is not symmetric
 };
 
 // ---------------------------------------------------------------- context
@@ -407,6 +408,30 @@ __device__ __forceinline__ int ld_stream_int(const int *p)
   int r;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
+}
+// L2 evict-first policy for data that is streamed once per kernel (neighbor rows, per-entry scratch): the gathered
+// data -- positions and spline tables, ~80 MB -- should own the 126 MB L2, not the gigabytes that pass through
+__device__ __forceinline__ unsigned long long policy_evict_first()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_stream_int_ef(const int *p, unsigned long long pol)
+{
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ double ld_stream_f64_ef(const double *p, unsigned long long pol)
+{
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f64_ef(double *p, double v, unsigned long long pol)
+{
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 #endif
 

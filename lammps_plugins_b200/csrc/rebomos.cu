@@ -1612,11 +1612,11 @@ static void launch_centers(b200md_ctx *c, const DetTables &det, int t_lo, int t_
   constexpr int MB_MO = PLAIN ? 6 : 5, MB_S = PLAIN ? 7 : 5, CAP_S = PLAIN ? 4 : 8;
   if (nr > 0) {
     {
-      LaunchScope ls(c, "rebo_center_mo");
+      LaunchScope ls(c, PLAIN ? "rebo_center_mo" : "rebo_center_mo_ev");
       rebo_center_kernel<128, 16, 16, 0, EV, DET, ATOM, MB_MO><<<grid0, 128, 0, c->stream>>>(RC_ARGS(list0, cnt0, scan, nullptr, nullptr));
     }
     {
-      LaunchScope ls(c, "rebo_center_s");
+      LaunchScope ls(c, PLAIN ? "rebo_center_s" : "rebo_center_s_ev");
       rebo_center_kernel<128, 4, CAP_S, 1, EV, DET, ATOM, MB_S><<<grid1, 128, 0, c->stream>>>(RC_ARGS(list1, cnt1, scan, ovf, cntO));
     }
   }
@@ -1694,14 +1694,15 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
     // 0.634 ms; D=1 0.77; D=3/80 (spills) 0.85; D=4/118 regs (2 CTAs) 0.69; D=2/64 regs (spills) 0.78
     // CTAs of 128 threads at 80 registers (6 CTAs/SM): 0.605 ms; 256 threads x 3 CTAs: 0.619; 72 regs x 7 CTAs (spills): 0.683
 #define LJP_FORCE(E) LJP_LAUNCH(false, E, 6, false, 128);
+    const bool lj_ev = atom || eflag || vflag;    // thermo steps run the energy/virial instances: their own names
     {
-      LaunchScope ls(c, "lj_mo");
+      LaunchScope ls(c, lj_ev ? "lj_mo_ev" : "lj_mo");
       if (atom) LJP_LAUNCH(true, 0, 1, true, 256);
       else if (eflag || vflag) LJP_LAUNCH(true, 0, 2, false, 256);
       else LJP_FORCE(0)
     }
     {
-      LaunchScope ls(c, "lj_s");
+      LaunchScope ls(c, lj_ev ? "lj_s_ev" : "lj_s");
       if (atom) LJP_LAUNCH(true, 1, 1, true, 256);
       else if (eflag || vflag) LJP_LAUNCH(true, 1, 2, false, 256);
       else LJP_FORCE(1)

@@ -218,6 +218,8 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *                    pass; 1 clusters of 4 consecutive centers share one union row; 0 the force pass re-gathers rho'
  *  "force_rebuild"   resident loop: the NEXT step takes the reneighboring path whatever the displacements (set it on
  *                    every rank; used to time a master rebuild)
+ *  "overlap_halo"    0/1 (default 1), resident loop: the owned centers are split into interior and boundary ones and the
+ *                    halos run on a stream of their own beside the interior kernels
  *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)
  *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
@@ -303,7 +305,7 @@ int b200md_system_thermo_count(b200md_ctx *ctx);
 int b200md_system_thermo_row(b200md_ctx *ctx, int i, double *out);
 /* sizes: out[0]=nlocal, out[1]=nghost, out[2]=neighbor builds, out[3]=dangerous builds,
  * out[4]=atoms this rank sent away in CommBrick::exchange so far, out[5]=global atom count,
- * out[6]=inner-list refreshes between master rebuilds; out[7] */
+ * out[6]=inner-list refreshes between master rebuilds, out[7]=force evaluations with the halos overlapped (out[8]) */
 int b200md_system_sizes(b200md_ctx *ctx, long long *out);
 /* download owned+ghost state (any pointer may be NULL) */
 int b200md_system_download(b200md_ctx *ctx, double *x, double *v, double *f, int *type, int *tag);

@@ -450,10 +450,10 @@ class Context:
         return rows
 
     def system_sizes(self):
-        out = (c_longlong * 7)()
+        out = (c_longlong * 8)()
         self._check(self.L.b200md_system_sizes(self.h, out))
         return dict(nlocal=out[0], nghost=out[1], nbuild=out[2], ndanger=out[3], nmigrated=out[4], natoms=out[5],
-                    ninner=out[6])
+                    ninner=out[6], noverlap=out[7])
 
     def comm_init_nccl(self, id128: bytes, nranks, rank):
         self._check(self.L.b200md_system_comm_init(self.h, id128, nranks, rank))

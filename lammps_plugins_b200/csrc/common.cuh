@@ -134,6 +134,15 @@ struct KernelStat {
   long long count = 0;
 };
 
+// Interior/boundary split of the owned centers (resident multi-stream loop): a center is INTERIOR when it is farther
+// than `r` from every face of this rank's sub-domain, so that none of its list candidates is a ghost and its forces
+// can be computed while the forward halo is still in flight.  lo/hi/r are in lamda units for a triclinic box.
+struct SplitGeom {
+  int on = 0, triclinic = 0;
+  double boxlo[3] = {0, 0, 0}, h_inv[6] = {0, 0, 0, 0, 0, 0};
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+};
+
 struct SystemState;    // resident MD system (system.cu)
 struct NeighScratch;   // device-build scratch (neigh.cu)
 struct AeamHost;       // 7-coefficient spline tables kept for b200md_aeam_get_spline (aeam.cu)
@@ -247,6 +256,17 @@ struct b200md_ctx {
   DevBuf<int> cen_list;              // owned centers by element: [Mo-like | S-like | overflow], ascending index
   DevBuf<int> cen_key;               // scan input: 1 per Mo-like center, 2^30 per S-like center
   DevBuf<int64_t> cen_scan;          // [inum+1] exclusive scan of cen_key: list position of every index threshold
+  // resident loop with halo overlap: the LJ pair rows sit in [interior | boundary] order per element (interior = both
+  // centers far from the faces of the sub-domain: no ghost among the candidates); ljp_split[0..2] = packed list
+  // positions {0, end of the interior part, end} plays cen_scan's role for the "index ranges" [0,1) and [1,2)
+  SplitGeom split;
+  bool split_valid = false;          // the pair rows on the device are in split order
+  DevBuf<int> ljp_tmp;
+  DevBuf<int64_t> ljp_scan;
+  int64_t *ljp_split = nullptr;
+  cudaStream_t halo_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_fwd = nullptr, ev_reb = nullptr, ev_rev = nullptr;
+  int overlap_halo = 1;              // option "overlap_halo": halos on their own stream beside the interior kernels
   DevBuf<double> nM, nS;             // parity API (b200md_rebomos_neigh)
   DevBuf<double> det_fb;             // deterministic mode: per-bond and per-center forces
   DevBuf<int> det_j;

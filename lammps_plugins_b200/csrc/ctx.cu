@@ -100,6 +100,10 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->map_d.release(); c->short_idx.release(); c->short_num.release();
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release(); c->ljp_ab.release();
   c->short_idx_t.release(); c->short_num_t.release(); c->lj_val_t.release(); c->lj_num_t.release(); c->xhold_t.release();
+  c->ljp_tmp.release(); c->ljp_scan.release();
+  if (c->halo_stream) cudaStreamDestroy(c->halo_stream);
+  for (cudaEvent_t e : {c->ev_ready, c->ev_fwd, c->ev_reb, c->ev_rev})
+    if (e) cudaEventDestroy(e);
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
@@ -146,6 +150,9 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->inner_valid = false;
   } else if (n == "aeam_cluster") {
     c->aeam_cluster = (int) (value < 0 ? 0 : (value > 2 ? 2 : value));
+    c->inner_valid = false;
+  } else if (n == "overlap_halo") {
+    c->overlap_halo = (int) (value < 0 ? 0 : value);
     c->inner_valid = false;
   } else if (n == "aeam_variant") c->aeam_variant = (int) value;
   else if (n == "force_rebuild") c->force_rebuild = value ? 1 : 0;

@@ -1091,6 +1091,74 @@ __global__ void __launch_bounds__(BLOCK) ljpair_cap_kernel(const int *__restrict
   ab_out[q] = make_int2(a, b);
 }
 
+
+// ---- halo overlap (resident loop): the PAIR ROWS are put in [interior | boundary] order per element before the union
+// rows are built -- pairs keep their composition (consecutive centers of the ascending lists), only their slot changes.
+// A pair is interior when both centers are farther than g.r from every face of the sub-domain (lamda space if
+// triclinic), so that no candidate of its union row is a ghost: its LJ launch may run while the forward halo is in flight.
+__device__ __forceinline__ bool split_interior(const SplitGeom &g, const double4 &p)
+{
+  double c0 = p.x, c1 = p.y, c2 = p.z;
+  if (g.triclinic) {
+    const double d0 = p.x - g.boxlo[0], d1 = p.y - g.boxlo[1], d2 = p.z - g.boxlo[2];
+    c0 = g.h_inv[0] * d0 + g.h_inv[5] * d1 + g.h_inv[4] * d2;
+    c1 = g.h_inv[1] * d1 + g.h_inv[3] * d2;
+    c2 = g.h_inv[2] * d2;
+  }
+  return c0 - g.lo[0] > g.r[0] && g.hi[0] - c0 > g.r[0] && c1 - g.lo[1] > g.r[1] && g.hi[1] - c1 > g.r[1] &&
+         c2 - g.lo[2] > g.r[2] && g.hi[2] - c2 > g.r[2];
+}
+// scan keys of the two parts: element 0 counts in the low CEN_SHIFT bits, element 1 above (as in cen_key)
+__global__ void __launch_bounds__(BLOCK) ljpair_split_key_kernel(const int2 *__restrict__ ab, int P,
+                                                                 const double4 *__restrict__ xq,
+                                                                 const __grid_constant__ SplitGeom g,
+                                                                 int *__restrict__ keyI, int *__restrict__ keyB)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= 2 * P) return;
+  const int2 p = ab[q];
+  int kI = 0, kB = 0;
+  if (p.x >= 0) {
+    bool interior = split_interior(g, xq[p.x]);
+    if (interior && p.y >= 0) interior = split_interior(g, xq[p.y]);
+    const int key = (q < P) ? 1 : (1 << CEN_SHIFT);
+    if (interior) kI = key;
+    else kB = key;
+  }
+  keyI[q] = kI;
+  keyB[q] = kB;
+}
+__global__ void __launch_bounds__(BLOCK) ljpair_split_permute_kernel(const int2 *__restrict__ ab, const int *__restrict__ cap,
+                                                                     int P, const int *__restrict__ keyI,
+                                                                     const int *__restrict__ keyB,
+                                                                     const long long *__restrict__ scanI,
+                                                                     const long long *__restrict__ scanB,
+                                                                     int2 *__restrict__ ab_out, int *__restrict__ cap_out,
+                                                                     long long *__restrict__ split)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= 2 * P) return;
+  const long long totI = scanI[2 * P], totB = scanB[2 * P];    // exclusive scans carry the totals in the last entry
+  const int nI0 = (int) (totI & CEN_MASK), nI1 = (int) (totI >> CEN_SHIFT);
+  const int E = q < P ? 0 : 1;
+  if (keyI[q]) {
+    const int pos = E ? (int) (scanI[q] >> CEN_SHIFT) : (int) (scanI[q] & CEN_MASK);
+    ab_out[E * P + pos] = ab[q];
+    cap_out[E * P + pos] = cap[q];
+  } else if (keyB[q]) {
+    const int pos = (E ? nI1 : nI0) + (E ? (int) (scanB[q] >> CEN_SHIFT) : (int) (scanB[q] & CEN_MASK));
+    ab_out[E * P + pos] = ab[q];
+    cap_out[E * P + pos] = cap[q];
+  }
+  if (q == 0) {
+    // lj_pair_kernel turns list positions [s0, s1) into pairs [(s0+1)/2, (s1+1)/2): positions = 2 x pair slots
+    const int n0 = nI0 + (int) (totB & CEN_MASK), n1 = nI1 + (int) (totB >> CEN_SHIFT);
+    split[0] = 0;
+    split[1] = (long long) (2 * nI0) | ((long long) (2 * nI1) << CEN_SHIFT);
+    split[2] = (long long) (2 * n0) | ((long long) (2 * n1) << CEN_SHIFT);
+  }
+}
+
 // union rows: one warp per pair, order-preserving ballot compaction, partners segmented by element as in lj rows.
 // pass 1: candidates of a's master row within the margin sphere of a (remembered in a per-warp hash set in shared
 // memory); pass 2: candidates of b's master row within the margin sphere of b that pass 1 did not take.  The test is
@@ -1479,6 +1547,34 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
       ljpair_cap_kernel<<<nblocks(2 * P, BLOCK), BLOCK, 0, c->stream>>>(c->cen_list.p, inum, P, c->flags.p + 12,
                                                                       c->list_num.p, c->scan_tmp.p, (int2 *) c->ljp_ab.p);
     }
+    c->split_valid = false;
+    if (c->split.on) {
+      // [interior | boundary] order of the pair slots: flags -> two scans -> permuted (a, b) and capacities
+      CUDA_TRY(c, c->ljp_tmp.reserve(2 * (size_t) (4 * P) + 2 * (size_t) (2 * P) + 64));
+      CUDA_TRY(c, c->ljp_scan.reserve(2 * ((size_t) 2 * P + 2) + 8));
+      int *keyI = c->ljp_tmp.p, *keyB = keyI + 2 * P, *cap2 = keyB + 2 * P;
+      int2 *ab2 = (int2 *) (cap2 + 2 * P + (2 * P & 1));
+      int64_t *scanI = c->ljp_scan.p, *scanB = scanI + 2 * P + 2, *split = scanB + 2 * P + 2;
+      {
+        LaunchScope ls(c, "build_inner");
+        ljpair_split_key_kernel<<<nblocks(2 * P, BLOCK), BLOCK, 0, c->stream>>>((const int2 *) c->ljp_ab.p, P, c->xq.p, c->split,
+                                                                              keyI, keyB);
+      }
+      if ((rc = b200md_exclusive_scan_i64(c, keyI, scanI, 2 * P, 1))) return rc;
+      if ((rc = b200md_exclusive_scan_i64(c, keyB, scanB, 2 * P, 1))) return rc;
+      CUDA_TRY(c, cudaMemsetAsync(ab2, 0xff, 2 * (size_t) P * sizeof(int2), c->stream));
+      CUDA_TRY(c, cudaMemsetAsync(cap2, 0, 2 * (size_t) P * sizeof(int), c->stream));
+      {
+        LaunchScope ls(c, "build_inner");
+        ljpair_split_permute_kernel<<<nblocks(2 * P, BLOCK), BLOCK, 0, c->stream>>>(
+            (const int2 *) c->ljp_ab.p, c->scan_tmp.p, P, keyI, keyB, (const long long *) scanI, (const long long *) scanB, ab2,
+            cap2, (long long *) split);
+      }
+      CUDA_TRY(c, cudaMemcpyAsync(c->ljp_ab.p, ab2, 2 * (size_t) P * sizeof(int2), cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_TRY(c, cudaMemcpyAsync(c->scan_tmp.p, cap2, 2 * (size_t) P * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+      c->ljp_split = split;
+      c->split_valid = true;
+    }
     if ((rc = b200md_exclusive_scan_i64(c, c->scan_tmp.p, c->lj_off.p, 2 * P, 8))) return rc;
     LaunchScope ls(c, "build_inner");
     build_ljpair_kernel<<<nblocks((long long) 2 * P * 32, LJP_BLOCK), LJP_BLOCK, 0, c->stream>>>(
@@ -1675,7 +1771,7 @@ static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag, int t_lo
 }
 
 // tapered LJ for the owned atoms with index in [t_lo, t_hi) on c->stream: completes f of exactly those atoms
-static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi)
+static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi, int part = -1)
 {
   const int ncen = c->list_inum;
   if (t_hi <= t_lo) return B200MD_OK;
@@ -1683,11 +1779,18 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   int *list0 = c->cen_list.p, *list1 = c->cen_list.p + ncen + 32;
   // grids: 8 lanes per center (pair of centers), capped (grid-stride loops); list pieces are located on the device
   if (c->lj_pairs) {
-    const long long ngroups = (t_hi - t_lo) / 2 + 2;
+    // split order (halo overlap): part 0 = interior pair rows, 1 = boundary rows, -1 = all; ljp_split plays cen_scan's role
+    const long long ngroups = (c->split_valid ? ncen : t_hi - t_lo) / 2 + 2;
     const int *ljnum = c->tight_valid ? c->lj_num_t.p : c->lj_num.p, *ljval = c->tight_valid ? c->lj_val_t.p : c->lj_val.p;
+    const long long *ljscan = (const long long *) c->cen_scan.p;
+    if (c->split_valid) {
+      ljscan = (const long long *) c->ljp_split;
+      t_lo = part == 1 ? 1 : 0;
+      t_hi = part == 0 ? 1 : 2;
+    }
 #define LJP_ARGS \
-  c->rp, c->xq.p, c->lj_off.p, ljnum, (const int2 *) c->ljp_ab.p, ljval, c->ljp_P, \
-      (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, c->scal.p, c->pa_e, c->pa_v
+  c->rp, c->xq.p, c->lj_off.p, ljnum, (const int2 *) c->ljp_ab.p, ljval, c->ljp_P, ljscan, t_lo, t_hi, c->f.p, c->scal.p, \
+      c->pa_e, c->pa_v
 #define LJP_LAUNCH(EVF, E, MB, AT, NTH) \
   lj_pair_kernel<EVF, E, 2, MB, AT, NTH><<<min(nblocks(ngroups * 8, NTH), c->num_sms * 64 * (256 / NTH)), NTH, 0, c->stream>>>(LJP_ARGS)
     // force-only instance: 2 position buffers per lane, 80 registers (3 CTAs/SM).  r01 v6 sweep at 995 904 atoms: D=2/80 regs
@@ -1737,6 +1840,15 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag)
   int rc;
   if ((rc = rebomos_forces_manybody(c, eflag, vflag, 0, c->list_inum, true, true))) return rc;
   return rebomos_forces_lj(c, eflag, vflag, 0, c->list_inum);
+}
+
+// resident loop with halo overlap, force-only steps.  which = 0: the bond-order launches (all centers); which = 1: the LJ
+// launches over the interior (part 0: no ghost among the candidates) or the boundary (part 1) pair rows
+int b200md_rebomos_forces_part(b200md_ctx *c, int part, int which)
+{
+  ARG_CHECK(c, c->split_valid && c->lj_pairs, "rebomos_forces_part: the pair rows are not in split order");
+  if (which == 0) return rebomos_forces_manybody(c, 0, 0, 0, c->list_inum, true, true);
+  return rebomos_forces_lj(c, 0, 0, 0, c->list_inum, part);
 }
 
 static int check_flags(b200md_ctx *c, const int *fl)
@@ -1869,6 +1981,10 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
     return B200MD_OK;
   }
   c->tight_valid = false;    // the tight rows belong to the GPU-resident loop, which owns their refresh schedule
+  if (c->split.on || c->split_valid) {    // ... and so does the interior/boundary order of the pair rows
+    c->split.on = 0;
+    if (c->split_valid) c->inner_valid = false;
+  }
   int rc;
   int fl[16];
   bool redo = false;

@@ -454,45 +454,66 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     // ---- P: cos, G, G' of every unordered bond pair (round k: lane m takes the pair {m, m+k mod nb})
     const int nr = nb >> 1;
     int nbl = 0;
-    for (int k = 1; k <= nr; k++) {
-      for (int m0 = 0; m0 < nb; m0 += G) {
-        const int m = m0 + sub;
-        const bool act = m < nb;
-        int q = m + k;
-        if (q >= nb) q -= nb;
-        double c = 0.0;
-        if (act) {
-          c = (s_dx[sb + m] * s_dx[sb + q] + s_dy[sb + m] * s_dy[sb + q] + s_dz[sb + m] * s_dz[sb + q]) *
-              (s_ri[sb + m] * s_ri[sb + q]);
-          c = fmin(c, 1.0);
-          c = fmax(c, -1.0);
-        }
-        double dg;
-        const double gg = gspline_base<ELEM>(par, c, dg);
-        const bool bl = act && c >= 0.5;
-        const unsigned bits = (__ballot_sync(gmask, bl) >> gshift) & GBITS;
-        const int t = (k - 1) * CAP + m;
-        if (act) {
-          s_c[st + t] = c;
-          s_g[st + t] = gg;
-          s_dg[st + t] = dg;
-        }
-        // the blend needs a second polynomial and a sincospi; only a few pairs of a center are in it (the 60-degree
-        // Mo-Mo-Mo angles), so they are collected and fixed up in one extra trip instead of making every trip pay
-        // (v2 took the blend path on a group vote: sincospi alone was 11 % of all instructions)
-        if (bl) s_bl[st + nbl + __popc(bits & ((1u << sub) - 1u))] = (unsigned char) t;
-        nbl += __popc(bits);
+    // The nb (nb - 1) / 2 unordered pairs are dealt to ALL G lanes as one flat sequence p = (k - 1) nb + m: full rounds
+    // k < nb/2 hold nb pairs each, the last round of an even nb only its first nb/2 (the other half are the same pairs
+    // again: their table slots are filled by the lane that has the pair).  12 bonds on 16 lanes: 5 trips of 16 instead
+    // of 6 trips of 12 with 6 pairs evaluated twice.
+    const bool even = (nb & 1) == 0;
+    const int npairs = (nb * (nb - 1)) >> 1;
+    const unsigned inv_nb = nb > 0 ? (65536u + (unsigned) nb - 1u) / (unsigned) nb : 0u;    // p / nb for p < 256
+    for (int p0 = 0; p0 < npairs; p0 += G) {
+      const int p = p0 + sub;
+      const bool act = p < npairs;
+      const int k = act ? (int) (((unsigned) p * inv_nb) >> 16) + 1 : 1;
+      const int m = act ? p - (k - 1) * nb : 0;
+      int q = m + k;
+      if (q >= nb) q -= nb;
+      double c = 0.0;
+      if (act) {
+        c = (s_dx[sb + m] * s_dx[sb + q] + s_dy[sb + m] * s_dy[sb + q] + s_dz[sb + m] * s_dz[sb + q]) *
+            (s_ri[sb + m] * s_ri[sb + q]);
+        c = fmin(c, 1.0);
+        c = fmax(c, -1.0);
       }
+      double dg;
+      const double gg = gspline_base<ELEM>(par, c, dg);
+      const bool bl = act && c >= 0.5;
+      const unsigned bits = (__ballot_sync(gmask, bl) >> gshift) & GBITS;
+      const int t = (k - 1) * CAP + m;
+      const bool twin = act && even && k == nr;    // the pair's second slot, [nr-1][q]
+      if (act) {
+        s_c[st + t] = c;
+        s_g[st + t] = gg;
+        s_dg[st + t] = dg;
+        if (twin) {
+          const int t2 = (k - 1) * CAP + q;
+          s_c[st + t2] = c;
+          s_g[st + t2] = gg;
+          s_dg[st + t2] = dg;
+        }
+      }
+      // the blend needs a second polynomial and a sincospi; only a few pairs of a center are in it (the 60-degree
+      // Mo-Mo-Mo angles), so they are collected and fixed up in one extra trip instead of making every trip pay
+      // (v2 took the blend path on a group vote: sincospi alone was 11 % of all instructions)
+      if (bl) s_bl[st + nbl + __popc(bits & ((1u << sub) - 1u))] = (unsigned char) t;
+      nbl += __popc(bits);
     }
     __syncwarp(gmask);
     for (int b0 = 0; b0 < nbl; b0 += G) {
       const int b = b0 + sub;
       if (b < nbl) {
-        const int t = st + s_bl[st + b];
+        const int tl = s_bl[st + b];
+        const int t = st + tl;
         double gg = s_g[t], dg = s_dg[t];
         gspline_blend<ELEM>(par, s_c[t], gg, dg);
         s_g[t] = gg;
         s_dg[t] = dg;
+        const int kr = tl / CAP;    // round index k - 1 of the slot
+        if (even && kr == nr - 1) {    // last round of an even nb: the twin slot [nr-1][q], q = m + nr
+          const int t2 = st + kr * CAP + (tl - kr * CAP) + nr;
+          s_g[t2] = gg;
+          s_dg[t2] = dg;
+        }
       }
     }
     __syncwarp(gmask);

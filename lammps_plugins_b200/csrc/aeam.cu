@@ -1262,15 +1262,40 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
 }
 
 // ================================================================== B2: 3-body forces of angular atoms
+// force on atom j from an angular center: FP64 atomics, or -- deterministic mode -- fixed point (2^-44 eV/A resolution,
+// range +-5e5 eV/A) into an int64 shadow array, where the order of the adds does not matter
+#define AEAM_FIX_SCALE 17592186044416.0
+__device__ __forceinline__ void force_add(double *f, unsigned long long *ffix, int j, double ax, double ay, double az)
+{
+  if (ffix) {
+    atomicAdd(&ffix[3 * (size_t) j], (unsigned long long) __double2ll_rn(ax * AEAM_FIX_SCALE));
+    atomicAdd(&ffix[3 * (size_t) j + 1], (unsigned long long) __double2ll_rn(ay * AEAM_FIX_SCALE));
+    atomicAdd(&ffix[3 * (size_t) j + 2], (unsigned long long) __double2ll_rn(az * AEAM_FIX_SCALE));
+  } else {
+    atomicAdd(&f[3 * (size_t) j], ax);
+    atomicAdd(&f[3 * (size_t) j + 1], ay);
+    atomicAdd(&f[3 * (size_t) j + 2], az);
+  }
+}
+__global__ void __launch_bounds__(BLOCK) aeam_fold_fixed_kernel(const long long *__restrict__ ffix, size_t n3,
+                                                                double *__restrict__ f)
+{
+  const size_t k = (size_t) blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n3) return;
+  const long long v = ffix[k];
+  if (v) f[k] += (double) v * (1.0 / AEAM_FIX_SCALE);
+}
+
 template <bool EV, bool ATOM>
 __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
     const int *__restrict__ ang_list, const int *__restrict__ n_ang_ptr, const double *__restrict__ rho,
     const double *__restrict__ fp, double *__restrict__ f, double *__restrict__ scal, int *__restrict__ flags,
-    double *__restrict__ pa_v, int rshift)
+    double *__restrict__ pa_v, int rshift, unsigned long long *__restrict__ ffix)
 {
   __shared__ AngStage stage[4];
+  __shared__ double fstage[4][3][ANG_CAP];
   const double minrho = 0.0000000000001;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n_ang = *n_ang_ptr;
@@ -1287,6 +1312,11 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     const double G = (rh > minrho) ? 0.5 / sqrt(rh) * fp[i] : 0.0;
     const double ci = 2.0;
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    // forces on the staged neighbors are collected in shared memory and leave the warp ONCE per neighbor (the
+    // reference scatters f[j], f[k] per triplet, pair_aeam.cpp:462-470: ~2400 triplets for a center with 70 neighbors):
+    // 3 x 70 instead of 3 x 2500 FP64 atomics per center, and a fixed summation order inside the center
+    for (int q = lane; q < ns; q += 32) fstage[wid][0][q] = fstage[wid][1][q] = fstage[wid][2][q] = 0.0;
+    __syncwarp();
     for (int p = 0; p < ns; p++) {
       const double r1 = S.r[p], fij = S.f[p], dfij = S.df[p];
       const double d1x = S.dx[p], d1y = S.dy[p], d1z = S.dz[p];
@@ -1317,11 +1347,12 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
         const double fk0 = d2x * FFik + d3x * FFjk, fk1 = d2y * FFik + d3y * FFjk, fk2 = d2z * FFik + d3z * FFjk;
         fjx += fj0; fjy += fj1; fjz += fj2;
         fix -= fj0 + fk0; fiy -= fj1 + fk1; fiz -= fj2 + fk2;
-        const int k = S.j[q];
-        atomicAdd(&f[3 * (size_t) k], fk0);
-        atomicAdd(&f[3 * (size_t) k + 1], fk1);
-        atomicAdd(&f[3 * (size_t) k + 2], fk2);
+        // a lane owns slot q within this p (distinct q per lane), and the p iterations are ordered by the __syncwarp below
+        fstage[wid][0][q] += fk0;
+        fstage[wid][1][q] += fk1;
+        fstage[wid][2][q] += fk2;
         if (ATOM) {    // ev_tally3: thirds to i, j, k
+          const int k = S.j[q];
           const double t[6] = {(d1x * fj0 + d2x * fk0) * (1.0 / 3.0), (d1y * fj1 + d2y * fk1) * (1.0 / 3.0),
                                (d1z * fj2 + d2z * fk2) * (1.0 / 3.0), (d1x * fj1 + d2x * fk1) * (1.0 / 3.0),
                                (d1x * fj2 + d2x * fk2) * (1.0 / 3.0), (d1y * fj2 + d2y * fk2) * (1.0 / 3.0)};
@@ -1345,21 +1376,24 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
       fjx = warp_sum(fjx);
       fjy = warp_sum(fjy);
       fjz = warp_sum(fjz);
-      if (lane == 0 && (fjx != 0.0 || fjy != 0.0 || fjz != 0.0)) {
-        const int j = S.j[p];
-        atomicAdd(&f[3 * (size_t) j], fjx);
-        atomicAdd(&f[3 * (size_t) j + 1], fjy);
-        atomicAdd(&f[3 * (size_t) j + 2], fjz);
+      __syncwarp();
+      if (lane == 0) {
+        fstage[wid][0][p] += fjx;
+        fstage[wid][1][p] += fjy;
+        fstage[wid][2][p] += fjz;
       }
+      __syncwarp();
     }
     fix = warp_sum(fix);
     fiy = warp_sum(fiy);
     fiz = warp_sum(fiz);
-    if (lane == 0) {
-      atomicAdd(&f[3 * (size_t) i], fix);
-      atomicAdd(&f[3 * (size_t) i + 1], fiy);
-      atomicAdd(&f[3 * (size_t) i + 2], fiz);
+    // one update per staged neighbor and one for the center; in deterministic mode in fixed point (integer atomics are
+    // associative), folded into f by aeam_fold_fixed_kernel afterwards
+    for (int q = lane; q < ns; q += 32) {
+      const double ax = fstage[wid][0][q], ay = fstage[wid][1][q], az = fstage[wid][2][q];
+      if (ax != 0.0 || ay != 0.0 || az != 0.0) force_add(f, ffix, S.j[q], ax, ay, az);
     }
+    if (lane == 0) force_add(f, ffix, i, fix, fiy, fiz);
     __syncwarp();
   }
   if (EV) {
@@ -1370,8 +1404,8 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
       if (lane == 0) sh[k][wid] = s;
     }
     __syncthreads();
-    if (threadIdx.x < 6) atomicAdd(&scal[1 + threadIdx.x], sh[threadIdx.x][0] + sh[threadIdx.x][1] +
-                                                                 sh[threadIdx.x][2] + sh[threadIdx.x][3]);
+    if (threadIdx.x < 6)
+      accumulate_global(scal, 1 + threadIdx.x, sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3]);
   }
 }
 
@@ -1528,7 +1562,7 @@ int b200md_aeam_density(b200md_ctx *c)
   {
     LaunchScope ls(c, "aeam_embed");
     aeam_embed_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->ap, c->xq.p, (const double4 *) c->spl_frho.p,
-                                                                   c->rho.p, inum, c->fp.p, c->scal.p, c->pa_e);
+                                                                   c->rho.p, inum, c->fp.p, b200md_scal_arg(c), c->pa_e);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
@@ -1577,7 +1611,7 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
     const int ncl = (inum + CL - 1) / CL;
 #define AFC_ARGS \
   c->ap, c->xq.p, c->ec_off.p, c->ec_num.p, c->ec_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, \
-      inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
+      inum, c->f.p, b200md_scal_arg(c), c->pa_e, c->pa_v
 #define AFC_LAUNCH(EV, ATOM, LPE, U, MINB) \
   aeam_force_cl_kernel<EV, ATOM, LPE, U, MINB><<<nblocks((long long) ncl * 8 * LPE, BLOCK), BLOCK, 0, c->stream>>>(AFC_ARGS)
     if (atom) AFC_LAUNCH(true, true, 4, 1, 2);
@@ -1596,10 +1630,10 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
   } else {
     LaunchScope ls(c, (atom || ev) ? "aeam_force_ev" : "aeam_force");    // thermo steps: the energy/virial instance
     const int nb = nblocks((long long) inum * 8, BLOCK);
-#define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, c->scal.p, c->pa_e, c->pa_v
+#define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, b200md_scal_arg(c), c->pa_e, c->pa_v
 #define AFD_ARGS \
   c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, inum, c->f.p, \
-      c->scal.p, c->pa_e, c->pa_v
+      b200md_scal_arg(c), c->pa_e, c->pa_v
     if (mode == 2) {
       if (atom) aeam_force_df_kernel<true, true, 2, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
       else if (ev) aeam_force_df_kernel<true, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
@@ -1624,12 +1658,20 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
   }
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, (atom || ev) ? "aeam_force_ang_ev" : "aeam_force_ang");
+    unsigned long long *ffix = nullptr;
+    const size_t n3 = 3 * (size_t) c->nall;
+    if (c->deterministic) {
+      CUDA_TRY(c, c->det_ffix.reserve(n3 + 8));
+      CUDA_TRY(c, cudaMemsetAsync(c->det_ffix.p, 0, n3 * sizeof(long long), c->stream));
+      ffix = (unsigned long long *) c->det_ffix.p;
+    }
 #define AA_ARGS \
-  c->ap, c->xq.p, r_off, r_num, r_val, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, c->scal.p, \
-      c->flags.p, c->pa_v, rshift
+  c->ap, c->xq.p, r_off, r_num, r_val, rhor, c->ang_list.p, c->flags.p + 6, c->rho.p, c->fp.p, c->f.p, b200md_scal_arg(c), \
+      c->flags.p, c->pa_v, rshift, ffix
     if (atom) aeam_force_ang_kernel<true, true><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
     else if (ev) aeam_force_ang_kernel<true, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
     else aeam_force_ang_kernel<false, false><<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(AA_ARGS);
+    if (ffix) aeam_fold_fixed_kernel<<<nblocks((long long) n3, BLOCK), BLOCK, 0, c->stream>>>(c->det_ffix.p, n3, c->f.p);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;

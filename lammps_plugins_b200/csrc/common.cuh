@@ -222,6 +222,8 @@ struct b200md_ctx {
   // ---- master neighbor list (dense CSR on device)
   int list_inum = 0, list_gnum = 0;
   int64_t list_entries = 0;
+  int list_maxnum = 0;       // longest row of the last device build: stride hint of the next one-pass build
+  int one_pass_neigh = 1;    // option "one_pass_neigh": resident-loop rebuilds walk the stencil once (fixed-stride rows)
   double skin = 0.0;
   double margin = 0.0;       // margin actually used by the inner lists
   bool list_valid = false, inner_valid = false;
@@ -281,6 +283,8 @@ struct b200md_ctx {
   DevBuf<int64_t> ea_off;
   DevBuf<int> ea_num, ea_val;        // inner AEAM rows (filtered to cut+margin)
   DevBuf<int> ang_list;              // owned angular atoms
+  DevBuf<long long> det_ffix;        // deterministic mode: fixed-point forces of the angular triplets [nall*3]
+  DevBuf<double> det_part;           // deterministic mode: per-block partial sums of the global accumulators
   DevBuf<int64_t> ec_off;            // cluster form: [ncl+1] 8-aligned offsets of the union rows
   DevBuf<int> ec_num, ec_val, ec_cap;    // union row of cluster q = centers 4q..4q+3
   DevBuf<double> ec_df;              // [4 * entries] f'_{ti,tj}(r) of (entry, center), written by the density pass
@@ -375,6 +379,21 @@ template <int W> __device__ __forceinline__ double group_sum(double v)
   for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
+// Global accumulators (energy, virial, kinetic energy).  Default: one FP64 atomic per block and value -- the sum then
+// depends on the order in which blocks retire.  Deterministic mode: the kernels are handed a TAGGED pointer (bit 0 set)
+// into a table of per-block partial sums, partial[blockIdx.x][16]; kernels of one stream run one after the other, so a
+// block's slot is updated by one thread at a time, and b200md_det_fold() adds the table up in a fixed order (a fixed
+// two-level tree) into scal[] before it is used: bitwise reproducible whatever the order in which blocks retire.
+#define B200MD_DET_BLOCKS (1 << 18)    // rows of the table: enough for 8 M atoms per GPU at 8 lanes per atom
+__device__ __forceinline__ void accumulate_global(double *out, int k, double s)
+{
+  const unsigned long long u = (unsigned long long) out;
+  if (u & 1ull) {
+    double *part = (double *) (u & ~7ull);
+    part[(size_t) blockIdx.x * 16 + k] += s;
+  } else
+    atomicAdd(&out[k], s);
+}
 // block-level sum of `n` doubles per thread into global accumulators (one atomic per block per value)
 template <int N, int BLOCK> __device__ __forceinline__ void block_accumulate(double (&v)[N], double *out)
 {
@@ -390,7 +409,7 @@ template <int N, int BLOCK> __device__ __forceinline__ void block_accumulate(dou
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < BLOCK / 32; w++) s += sh[threadIdx.x][w];
-    atomicAdd(&out[threadIdx.x], s);
+    accumulate_global(out, threadIdx.x, s);
   }
 }
 // One 32-byte sector with ONE instruction (LDG.E.ENL2.256, sm_100+): a double4 gather written as `p[j]`
@@ -456,6 +475,12 @@ __device__ __forceinline__ void st_stream_f64_ef(double *p, double v, unsigned l
 #endif
 
 // shared internal entry points
+// accumulator pointer handed to the kernels: scal[], or the tagged fixed-point accumulators in deterministic mode
+static inline double *b200md_scal_arg(b200md_ctx *c)
+{
+  return (c->deterministic && c->det_part.p) ? (double *) (((unsigned long long) c->det_part.p) | 1ull) : c->scal.p;
+}
+int b200md_det_fold(b200md_ctx *c);    // deterministic mode: per-block partial sums -> scal[0..15] in a fixed order (and zeroed)
 int b200md_peratom_begin(b200md_ctx *c, bool wanted);                      // zeroed device arrays, sets pa_e / pa_v
 int b200md_peratom_finish(b200md_ctx *c, double *eatom, double *vatom);    // D2H + accumulate into the host arrays
 int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,

@@ -107,7 +107,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
-  c->ang_list.release();
+  c->ang_list.release(); c->det_ffix.release(); c->det_part.release();
   c->ec_off.release(); c->ec_num.release(); c->ec_val.release(); c->ec_cap.release(); c->ec_df.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
   c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();
@@ -134,7 +134,18 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
 {
   if (!c || !name) return B200MD_ERR_ARG;
   std::string n(name);
-  if (n == "deterministic") c->deterministic = value ? 1 : 0;
+  if (n == "deterministic") {
+    c->deterministic = value ? 1 : 0;
+    if (c->deterministic && !c->det_part.p) {    // table of per-block partial sums of the global accumulators
+      cudaSetDevice(c->device);
+      if (c->det_part.reserve((size_t) B200MD_DET_BLOCKS * 16) != cudaSuccess) {
+        c->fail("deterministic mode: cannot allocate the partial-sum table");
+        c->deterministic = 0;
+        return B200MD_ERR_CUDA;
+      }
+      cudaMemsetAsync(c->det_part.p, 0, (size_t) B200MD_DET_BLOCKS * 16 * sizeof(double), c->stream);
+    }
+  }
   else if (n == "margin") {
     c->margin_opt = 1.0e-3 * (double) value;
     c->inner_valid = false;
@@ -154,7 +165,8 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   } else if (n == "overlap_halo") {
     c->overlap_halo = (int) (value < 0 ? 0 : value);
     c->inner_valid = false;
-  } else if (n == "aeam_variant") c->aeam_variant = (int) value;
+  } else if (n == "one_pass_neigh") c->one_pass_neigh = value ? 1 : 0;
+  else if (n == "aeam_variant") c->aeam_variant = (int) value;
   else if (n == "force_rebuild") c->force_rebuild = value ? 1 : 0;
   else if (n == "aeam_sort_rows") {
     c->aeam_sort_rows = value ? 1 : 0;
@@ -370,12 +382,46 @@ extern "C" int b200md_measure_peaks(b200md_ctx *c, double *fp64_tflops, double *
   return B200MD_OK;
 }
 
+// slot k = blockIdx.x: 256 threads sum contiguous chunks of the table rows in ascending order, thread 0 adds the 256
+// chunk sums in ascending order -- a fixed tree -- and the rows are zeroed for the next evaluation
+__global__ void __launch_bounds__(256) det_fold_kernel(double *__restrict__ part, int rows, double *__restrict__ scal)
+{
+  __shared__ double sh[256];
+  const int k = blockIdx.x;
+  const int per = (rows + 255) / 256;
+  const int lo = threadIdx.x * per, hi = min(rows, lo + per);
+  double s = 0.0;
+  for (int b = lo; b < hi; b++) {
+    const double v = part[(size_t) b * 16 + k];
+    if (v != 0.0) {
+      s += v;
+      part[(size_t) b * 16 + k] = 0.0;
+    }
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 256; w++) t += sh[w];
+    scal[k] += t;
+  }
+}
+int b200md_det_fold(b200md_ctx *c)
+{
+  if (!c->deterministic || !c->det_part.p) return B200MD_OK;
+  det_fold_kernel<<<16, 256, 0, c->stream>>>(c->det_part.p, B200MD_DET_BLOCKS, c->scal.p);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
 // forces + scalars + flags back to the host; f accumulated (default) or overwritten
 int b200md_finish_compute(b200md_ctx *c, int eflag, int vflag, double *f, double *eng_vdwl, double *virial,
                           int *flags_out)
 {
   const size_t n3 = 3 * (size_t) c->nall;
   int *pin_flags = (int *) (c->pin_scal.p + 32);
+  int rcf = b200md_det_fold(c);
+  if (rcf) return rcf;
   if (c->f_overwrite) {
     if (n3) CUDA_TRY(c, cudaMemcpyAsync(f, c->f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   } else {
@@ -427,6 +473,8 @@ int b200md_d2h_finish(b200md_ctx *c, int eflag, int vflag, double *f_host, doubl
                       int *flags_out)
 {
   int *pin_flags = (int *) (c->pin_scal.p + 32);
+  int rcf = b200md_det_fold(c);
+  if (rcf) return rcf;
   CUDA_TRY(c, cudaMemcpyAsync(c->pin_scal.p, c->scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(pin_flags, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (!c->f_overwrite) {
@@ -507,6 +555,8 @@ int b200md_upload_atoms(b200md_ctx *c, int nlocal, int nghost, const double *x, 
 {
   ARG_CHECK(c, nlocal >= 0 && nghost >= 0 && ((x && type) || nlocal + nghost == 0), "upload_atoms: bad sizes or NULL arrays");
   int nall = nlocal + nghost;
+  ARG_CHECK(c, !c->deterministic || nall <= 32 * (B200MD_DET_BLOCKS - 64),
+            "deterministic mode holds per-block partial sums for at most 8.3 M atoms per GPU");
   c->nlocal = nlocal;
   c->nghost = nghost;
   c->nall = nall;

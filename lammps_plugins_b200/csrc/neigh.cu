@@ -104,13 +104,19 @@ __global__ void __launch_bounds__(BLOCK) bin_sort_kernel(const int64_t *__restri
 
 // ---------------------------------------------------------------- K2: rows
 // A stencil "run" = maximal set of stencil bins with equal (j,k) and consecutive i: run[4] = {i0, i1, j, k}.
-template <bool FILL>
+// MODE 0: count the rows (row_num).  MODE 1: fill them at the offsets of the scan in between (dense CSR, two stencil
+// walks).  MODE 2: ONE walk into rows of a fixed stride (row i at i * stride; the stride comes from the longest row of
+// the previous build of the same system): rows, counts and offsets in one pass -- a row longer than the stride raises
+// flags[15] and the caller falls back to the two-pass build.  Row contents are identical in all modes.
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     const __grid_constant__ BinGeom g, const double4 *__restrict__ xt, const int *__restrict__ bin_of,
     const int64_t *__restrict__ bin_start, const int *__restrict__ bin_atoms, const int4 *__restrict__ runs,
     const double *__restrict__ cutsq, const double *__restrict__ cutghostsq, int nlocal, int nrows,
-    const int64_t *__restrict__ row_off, int *__restrict__ row_num, int *__restrict__ row_val)
+    int64_t *__restrict__ row_off, int *__restrict__ row_num, int *__restrict__ row_val, int stride,
+    int *__restrict__ flags)
 {
+  constexpr bool FILL = MODE != 0;
   const int lane = threadIdx.x & 31;
   const int i = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
   if (i >= nrows) return;
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     const int zb = ib / (my * mx);
     const int yb = (ib - zb * my * mx) / mx;
     const int xb = ib - zb * my * mx - yb * mx;
-    const int64_t obase = FILL ? row_off[i] : 0;
+    const int64_t obase = MODE == 1 ? row_off[i] : (MODE == 2 ? (int64_t) i * stride : 0);
     const unsigned lt = (1u << lane) - 1u;
     // The candidates of a row are the concatenation, in stencil-run order, of the runs' slices of the bin-sorted atom
     // array.  32 runs at a time: lane k looks up run k's slice (all bin_start lookups in flight at once instead of one
@@ -182,12 +188,22 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
           }
         }
         const unsigned mk = __ballot_sync(0xffffffffu, keep);
-        if (FILL && keep) row_val[obase + n + __popc(mk & lt)] = j;
+        if (FILL && keep && (MODE == 1 || n + __popc(mk & lt) < stride)) row_val[obase + n + __popc(mk & lt)] = j;
         n += __popc(mk);
       }
     }
   }
-  if (!FILL && lane == 0) row_num[i] = n;
+  if (lane == 0) {
+    if (MODE != 1) {
+      row_num[i] = n;
+      atomicMax(&flags[10], n);    // longest row: the stride hint of the next build
+    }
+    if (MODE == 2) {
+      row_off[i] = (int64_t) i * stride;
+      if (i == nrows - 1) row_off[nrows] = (int64_t) nrows * stride;
+      if (n > stride) flags[15] = 1;
+    }
+  }
 }
 
 // ---------------------------------------------------------------- host: bins + stencil (NBinStandard / NStencil)
@@ -341,7 +357,7 @@ static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / 
 // c->list_{off,num,val}.  The only host round trip is the total entry count (to size the value array).
 int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, const double *cutneighsq_h,
                               const double *cutneighghostsq_h, int nlocal, int nghost, const double4 *xt,
-                              int ghost_rows, double skin)
+                              int ghost_rows, double skin, bool one_pass)
 {
   NeighScratch &S = scratch_of(c);
   BinGeom g;
@@ -386,19 +402,50 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     }
   }
   int64_t total = 0;
-  if (nrows) {
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 15, 0, sizeof(int), c->stream));
+  bool done = false;
+  if (nrows && one_pass && c->list_maxnum > 0) {
+    // resident loop, second and later builds: one stencil walk into rows of a fixed stride
+    const int stride = ((int) (c->list_maxnum * 1.2) + 24) & ~7;
+    CUDA_TRY(c, c->list_val.reserve((size_t) nrows * stride + 64));
+    {
+      LaunchScope ls(c, "neigh_fill");
+      neigh_rows_kernel<2><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
+          g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
+          c->list_off.p, c->list_num.p, c->list_val.p, stride, c->flags.p);
+    }
+    int fl[8];
+    CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p + 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (fl[0]) {
+      c->fail("neighbor build: atom outside the bin grid (lost atom or non-numeric position)");
+      return B200MD_ERR_ARG;
+    }
+    c->list_maxnum = fl[2];
+    if (!fl[7]) {
+      total = (int64_t) nrows * stride;    // capacity the rows occupy (derived lists size themselves from it)
+      done = true;
+    } else {
+      CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 15, 0, sizeof(int), c->stream));
+      CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
+    }
+  }
+  if (nrows && !done) {
     {
       LaunchScope ls(c, "neigh_count");
-      neigh_rows_kernel<false><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
+      neigh_rows_kernel<0><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
           g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
-          nullptr, c->list_num.p, nullptr);
+          nullptr, c->list_num.p, nullptr, 0, c->flags.p);
     }
     rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->list_off.p, nrows, 1);
     if (rc) return rc;
-    int flag8 = 0;
+    int flag8 = 0, maxnum = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&total, c->list_off.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&flag8, c->flags.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&maxnum, c->flags.p + 10, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->list_maxnum = maxnum;
     if (flag8) {
       c->fail("neighbor build: atom outside the bin grid (lost atom or non-numeric position)");
       return B200MD_ERR_ARG;
@@ -406,12 +453,12 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     CUDA_TRY(c, c->list_val.reserve((size_t) total + 64));
     {
       LaunchScope ls(c, "neigh_fill");
-      neigh_rows_kernel<true><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
+      neigh_rows_kernel<1><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
           g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
-          c->list_off.p, c->list_num.p, c->list_val.p);
+          c->list_off.p, c->list_num.p, c->list_val.p, 0, c->flags.p);
     }
     CUDA_TRY(c, cudaGetLastError());
-  } else {
+  } else if (!nrows) {
     CUDA_TRY(c, cudaMemsetAsync(c->list_off.p, 0, sizeof(int64_t), c->stream));
   }
   c->list_inum = nlocal;
@@ -443,7 +490,7 @@ extern "C" int b200md_neigh_build(b200md_ctx *c, const b200md_box *box, int ntyp
     LaunchScope ls(c, "nb_pack");
     nb_pack_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, nall, S.xt.p);
   }
-  rc = b200md_neigh_build_device(c, *box, ntypes, cutneighsq, cutneighghostsq, nlocal, nghost, S.xt.p, ghost_rows, skin);
+  rc = b200md_neigh_build_device(c, *box, ntypes, cutneighsq, cutneighghostsq, nlocal, nghost, S.xt.p, ghost_rows, skin, false);
   if (rc) return rc;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return B200MD_OK;

@@ -1721,7 +1721,7 @@ static void launch_centers(b200md_ctx *c, const DetTables &det, int t_lo, int t_
   const bool tight = c->tight_valid && !DET;
   const int *sidx = tight ? c->short_idx_t.p : c->short_idx.p, *snum = tight ? c->short_num_t.p : c->short_num.p;
 #define RC_ARGS(list, cnt, sc, ol, oc) \
-  c->rp, c->xq.p, sidx, snum, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, c->scal.p, c->flags.p, c->pa_e, c->pa_v
+  c->rp, c->xq.p, sidx, snum, list, cnt, sc, t_lo, t_hi, ol, oc, c->f.p, det, b200md_scal_arg(c), c->flags.p, c->pa_e, c->pa_v
   // occupancy (r01 v6 sweeps at 995 904 atoms): force-only Mo launch 80 registers (6 CTAs/SM); force-only S launch stages
   // 4 bonds per center (bulk S has 3; more go to the overflow launch) which cuts its shared memory from 45 to 17 KB, and
   // runs at 72 registers (7 CTAs/SM): 0.257 -> 0.210 ms; at 64 registers 0.213, at 80: 0.223, unbounded (104): 0.280
@@ -1785,7 +1785,7 @@ static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag, int t_lo
   }
   if (vflag && last) {
     LaunchScope ls(c, "fdotr");
-    fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, c->scal.p);
+    fdotr_kernel<<<c->num_sms * 4, BLOCK, 0, c->stream>>>(c->xq.p, c->f.p, c->nall, b200md_scal_arg(c));
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200MD_OK;
@@ -1810,7 +1810,7 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
       t_hi = part == 0 ? 1 : 2;
     }
 #define LJP_ARGS \
-  c->rp, c->xq.p, c->lj_off.p, ljnum, (const int2 *) c->ljp_ab.p, ljval, c->ljp_P, ljscan, t_lo, t_hi, c->f.p, c->scal.p, \
+  c->rp, c->xq.p, c->lj_off.p, ljnum, (const int2 *) c->ljp_ab.p, ljval, c->ljp_P, ljscan, t_lo, t_hi, c->f.p, b200md_scal_arg(c), \
       c->pa_e, c->pa_v
 #define LJP_LAUNCH(EVF, E, MB, AT, NTH) \
   lj_pair_kernel<EVF, E, 2, MB, AT, NTH><<<min(nblocks(ngroups * 8, NTH), c->num_sms * 64 * (256 / NTH)), NTH, 0, c->stream>>>(LJP_ARGS)
@@ -1839,7 +1839,7 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
   const int grid = min(nblocks((long long) (t_hi - t_lo) * 8, BLOCK), c->num_sms * 64);
 #define LJ_ARGS(list) \
   c->rp, c->xq.p, c->lj_off.p, c->lj_num.p, c->lj_val.p, list, (const long long *) c->cen_scan.p, t_lo, t_hi, c->f.p, \
-      c->scal.p, c->pa_e, c->pa_v
+      b200md_scal_arg(c), c->pa_e, c->pa_v
   {
     LaunchScope ls(c, "lj_mo");
     if (atom) lj_kernel<true, 0, 2, 2, true><<<grid, BLOCK, 0, c->stream>>>(LJ_ARGS(list0));

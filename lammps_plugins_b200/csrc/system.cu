@@ -40,7 +40,7 @@ int b200md_aeam_density(b200md_ctx *c);
 int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag);
 int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, const double *cutneighsq_h,
                               const double *cutneighghostsq_h, int nlocal, int nghost, const double4 *xt,
-                              int ghost_rows, double skin);
+                              int ghost_rows, double skin, bool one_pass);
 void b200md_neigh_forget(b200md_ctx *c);
 void b200md_aeam_forget(b200md_ctx *c);
 
@@ -1948,7 +1948,7 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
   }
   box.cutneighmax = s->cutneighmax;
   if ((rc = b200md_neigh_build_device(c, box, s->d.ntypes, s->cutneighsq.data(), s->cutneighghostsq.data(), s->nlocal,
-                                      s->nghost, s->xt.p, s->ghost_rows, s->d.skin)))
+                                      s->nghost, s->xt.p, s->ghost_rows, s->d.skin, !first && c->one_pass_neigh)))
     return rc;
   set_split_geometry(c, s);
   rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
@@ -1961,6 +1961,8 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
 
 static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
 {
+  ARG_CHECK(c, !c->deterministic || c->nall <= 32 * (B200MD_DET_BLOCKS - 64),
+            "deterministic mode holds per-block partial sums for at most 8.3 M atoms per GPU");
   const size_t n3 = 3 * (size_t) c->nall;
   CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
@@ -2056,7 +2058,11 @@ static int thermo(b200md_ctx *c, SystemState *s)
 {
   {
     LaunchScope ls(c, "ke");
-    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, c->scal.p);
+    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, b200md_scal_arg(c));
+  }
+  {
+    int rc = b200md_det_fold(c);
+    if (rc) return rc;
   }
   {
     int rc = xfer_allreduce_sum(c, s, c->scal.p, 9);
@@ -2242,7 +2248,11 @@ static int nh_temperature(b200md_ctx *c, SystemState *s, double *t_out)
   CUDA_TRY(c, cudaMemsetAsync(c->scal.p + 10, 0, sizeof(double), c->stream));
   {
     LaunchScope ls(c, "ke");
-    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, c->scal.p + 2);    // -> scal[10]
+    k_ke<<<c->num_sms * 2, BLOCK, 0, c->stream>>>(s->v.p, c->type.p, s->dmass.p, s->nlocal, b200md_scal_arg(c) + 2);    // -> scal[10]
+  }
+  {
+    int rcf = b200md_det_fold(c);
+    if (rcf) return rcf;
   }
   int rc = xfer_allreduce_sum(c, s, c->scal.p + 10, 1);
   if (rc) return rc;

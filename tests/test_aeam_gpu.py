@@ -219,3 +219,32 @@ def test_cluster_rows_equal_single_rows(ctx, oracle_built, case):
         assert S.rel_err(f, res["single"][0]) < 1e-12
         assert abs(e - res["single"][1]) < 1e-12 * abs(e_ref)
     lmp.close()
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[3]], ids=[CASES[1]["id"], CASES[3]["id"]])
+def test_deterministic_mode(ctx, oracle_built, case):
+    """option "deterministic" for pair_style aeam: the angular triplet forces (pair_aeam.cpp:438-473) leave the warp once
+    per staged neighbor and are added in fixed point (integer atomics: order-independent), the global energy / virial
+    sums likewise.  Forces (owned and ghost), energy and virial are bitwise identical over repeated calls, meet the
+    parity bar against the reference, and agree with the default path to rounding."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), case["cells"], si_fraction=case["si"], displace=case["displace"])
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    ctx.aeam_init(aeam_tables())
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    args = (snap["nlocal"], snap["nghost"], snap["x"], snap["type"], snap["tag"], 1, 2)
+    fa, ea, va = ctx.aeam_compute(*args)
+    try:
+        ctx.set_option("deterministic", 1)
+        runs = [ctx.aeam_compute(*args) for _ in range(4)]
+    finally:
+        ctx.set_option("deterministic", 0)
+    for f, e, v in runs[1:]:
+        assert np.array_equal(f, runs[0][0]), "deterministic forces differ between calls"
+        assert e == runs[0][1] and np.array_equal(v, runs[0][2]), "deterministic energy / virial differ between calls"
+    f, e, v = runs[0]
+    assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], snap["nlocal"]), f_ref) < FTOL
+    assert abs(e - e_ref) / abs(e_ref) < ETOL and S.rel_err(v, v_ref) < FTOL
+    assert S.rel_err(f, fa) < 1e-12
+    lmp.close()

@@ -185,6 +185,8 @@ def test_deterministic_mode(ctx, oracle_built, case):
         ctx.set_option("deterministic", 0)
     for f, e, v in runs[1:]:
         assert np.array_equal(f, runs[0][0]), "deterministic forces differ between calls"
+        # global sums too: block partial sums are added in fixed point (integer atomics are associative)
+        assert e == runs[0][1] and np.array_equal(v, runs[0][2]), "deterministic energy / virial differ between calls"
     f, e, v = runs[0]
     assert S.rel_err(S.fold_ghost_forces(f, snap["swaps"], snap["nlocal"]), f_ref) < FTOL
     assert abs(e - e_ref) / abs(e_ref) < ETOL and S.rel_err(v, v_ref) < FTOL

@@ -363,13 +363,14 @@ def measure(kind, args, grp, sampler, scaling="weak", legs=("e2e", "cpu", "long"
         if mk.get("bytes") and t_ms > 0:
             rec["hbm_gbs"] = mk["bytes"] / (t_ms * 1e-3) / 1e9
             rec["hbm_frac"] = rec["hbm_gbs"] / hbm_peak
-        fl = pk.get("flops_per_atom_step")
-        if fl and t_ms > 0:
-            rec["flops_per_atom_step_ncu"] = fl
-            rec["fp64_tflops"] = fl * sz0["nlocal"] / (t_ms * 1e-3) / 1e12
+        # FP64 side: the share of the FP64 pipe's issue rate the kernel's instructions take (ncu sm__inst_executed_pipe_fp64 of the
+        # committed capture of the same kernel on the same workload: a property of the SASS and the rows, not of this run)
+        if pk.get("fp64_pipe_pct_ncu") is not None:
+            rec["fp64_frac"] = pk["fp64_pipe_pct_ncu"] / 100.0
             if fp64_peak:
-                rec["fp64_frac"] = rec["fp64_tflops"] / fp64_peak
-        for k in ("dram_bytes_per_step_ncu", "fp64_pipe_pct_ncu", "issue_active_pct_ncu", "l1_data_pipe_pct_ncu", "lanes_active_ncu"):
+                rec["fp64_tflops_equiv"] = rec["fp64_frac"] * fp64_peak
+        for k in ("dram_bytes_per_step_ncu", "fp64_pipe_pct_ncu", "issue_active_pct_ncu", "l1_data_pipe_pct_ncu", "lanes_active_ncu",
+                  "gathered_sectors_per_step_ncu", "ms_per_step_ncu"):
             if k in pk:
                 rec[k] = pk[k]
         fr = [(rec.get("hbm_frac") or 0.0, "hbm"), (rec.get("fp64_frac") or 0.0, "fp64")]
@@ -381,13 +382,15 @@ def measure(kind, args, grp, sampler, scaling="weak", legs=("e2e", "cpu", "long"
     step_tflops = ALGO[kind]["flops"] * natoms / world / (ms_per_step * 1e-3) / 1e12
     use_fp64 = d.get("bound") == "fp64"
     roofline = {"bound": "hbm" if not use_fp64 else "fp64", "kernel": dom,
-                "achieved": d.get("fp64_tflops") if use_fp64 else d.get("hbm_gbs"),
+                "achieved": d.get("fp64_tflops_equiv") if use_fp64 else d.get("hbm_gbs"),
                 "peak": fp64_peak if use_fp64 else hbm_peak, "unit": "TFLOP/s" if use_fp64 else "GB/s",
                 "frac": d.get("fp64_frac") if use_fp64 else d.get("hbm_frac"),
                 "traffic": d.get("dram_bytes_per_step_ncu"),
                 "peak_source": ("DFMA-saturating kernel timed in place (MEASURED_PEAKS.json has no FP64 entry)" if use_fp64 else peak_src),
-                "achieved_note": "the kernel's OWN algorithmic bytes / flops (rows it streams + x/f; flops of its SASS), not the "
-                                 "reference formulation's; `whole_step` holds the headline fractions",
+                "achieved_note": "per kernel: HBM side = its OWN algorithmic bytes (the rows it streams + x/f) / live kernel time; FP64 side "
+                                 "= share of the FP64 pipe its instructions take (ncu, profiles/r02_kernel_model.json); bound = the larger. "
+                                 "These gather kernels are limited by neither: see l1_data_pipe_pct_ncu / issue_active_pct_ncu in per_kernel. "
+                                 "`whole_step` holds the headline fractions (reference formulation)",
                 "kernel_ms_per_step": gtime[dom], "kernel_share_of_step": gtime[dom] / ms_per_step,
                 "launches_per_step": len([k for k in groups[dom] if k in per_step]),
                 "hbm_copy_measured_here_gbs": hbm_here, "per_kernel": per_kernel,

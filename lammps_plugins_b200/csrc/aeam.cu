@@ -1244,9 +1244,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
   fy = group_sum<8>(fy);
   fz = group_sum<8>(fz);
   if (i < inum && sub == 0) {
-    f[3 * (size_t) i] += fx;    // one group per atom; B2 (atomics) runs after this kernel
-    f[3 * (size_t) i + 1] += fy;
-    f[3 * (size_t) i + 2] += fz;
+    // one add per atom from this kernel; atomic because the angular kernel and -- with halo overlap -- the reverse-halo
+    // folds on another stream add to the same atoms
+    atomicAdd(&f[3 * (size_t) i], fx);
+    atomicAdd(&f[3 * (size_t) i + 1], fy);
+    atomicAdd(&f[3 * (size_t) i + 2], fz);
   }
   if (ATOM) {
     const double ea = group_sum<8>(ev[0]);
@@ -1588,14 +1590,17 @@ int b200md_aeam_fill_ghosts_by_tag(b200md_ctx *c, int maxtag)
 }
 
 // forces; needs rho/fp of owned AND ghost atoms
-int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
+// part 0: everything (gate, pair + embedding forces, angular forces).  Halo overlap (force-only steps, default row form):
+// part 1 = gate + angular forces -- the only kernels that write ghost forces -- and part 2 = the pair kernel, which then
+// runs beside the reverse halo (every kernel adds to f with atomics, so the order between them is free)
+int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag, int part)
 {
   const int inum = c->list_inum;
   if (inum == 0) return B200MD_OK;
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
   const double4 *ptab = (const double4 *) c->spl_pair.p;
   const bool ev = eflag || vflag;
-  {
+  if (part != 2) {
     LaunchScope ls(c, "aeam_gate");
     aeam_gate_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, c->rho.p, c->fp.p, c->ap.nnonangular,
                                                                      c->nall);
@@ -1606,7 +1611,9 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
   const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
   const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
   const int rshift = cl ? CL_SHIFT : 0;
-  if (cl) {
+  if (part == 1) {
+    // pair kernel later (part 2)
+  } else if (cl) {
     LaunchScope ls(c, (atom || ev) ? "aeam_force_ev" : "aeam_force");
     const int ncl = (inum + CL - 1) / CL;
 #define AFC_ARGS \
@@ -1656,7 +1663,7 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag)
       }
     }
   }
-  if (c->ap.nnonangular < c->ap.nel) {
+  if (part != 2 && c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, (atom || ev) ? "aeam_force_ang_ev" : "aeam_force_ang");
     unsigned long long *ffix = nullptr;
     const size_t n3 = 3 * (size_t) c->nall;
@@ -1760,7 +1767,7 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
     for (int i = 0; i < nlocal; i++) maxtag = tag[i] > maxtag ? tag[i] : maxtag;
     rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag);
   }
-  if (!rc) rc = b200md_aeam_forces(c, eflag, vflag);
+  if (!rc) rc = b200md_aeam_forces(c, eflag, vflag, 0);
   if (rc) {
     c->pa_e = c->pa_v = nullptr;
     return rc;
@@ -1813,7 +1820,7 @@ extern "C" int b200md_aeam_force_phase_peratom(b200md_ctx *c, const double *rho_
     CUDA_TRY(c, cudaMemcpyAsync(c->fp.p + c->nlocal, fp_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += 2LL * ng * sizeof(double);
   }
-  int rc = b200md_aeam_forces(c, eflag, vflag);
+  int rc = b200md_aeam_forces(c, eflag, vflag, 0);
   if (rc) {
     c->pa_e = c->pa_v = nullptr;
     return rc;

@@ -37,7 +37,7 @@ int b200md_rebomos_forces(b200md_ctx *c, int eflag, int vflag);
 int b200md_rebomos_forces_part(b200md_ctx *c, int part, int which);
 int b200md_aeam_build_inner(b200md_ctx *c);
 int b200md_aeam_density(b200md_ctx *c);
-int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag);
+int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag, int part);
 int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, const double *cutneighsq_h,
                               const double *cutneighghostsq_h, int nlocal, int nghost, const double4 *xt,
                               int ghost_rows, double skin, bool one_pass);
@@ -1959,6 +1959,20 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
   return B200MD_OK;
 }
 
+// the halo stream (highest priority: its small kernels take the SM slots that compute CTAs free) and its events
+static int ensure_halo_stream(b200md_ctx *c)
+{
+  if (c->halo_stream) return B200MD_OK;
+  int lo = 0, hi = 0;
+  CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_TRY(c, cudaStreamCreateWithPriority(&c->halo_stream, cudaStreamNonBlocking, hi));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fwd, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_reb, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_rev, cudaEventDisableTiming));
+  return B200MD_OK;
+}
+
 static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
 {
   ARG_CHECK(c, !c->deterministic || c->nall <= 32 * (B200MD_DET_BLOCKS - 64),
@@ -1972,7 +1986,28 @@ static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
   } else {
     if ((rc = b200md_aeam_density(c))) return rc;
     if ((rc = halo_forward_rho_fp(c, s))) return rc;
-    if ((rc = b200md_aeam_forces(c, eflag, vflag))) return rc;
+    // force-only steps on more than one rank: the reverse halo runs on its own stream beside the pair kernel (only the
+    // angular kernel writes ghost forces)
+    if (!eflag && !vflag && s->nranks > 1 && c->overlap_halo && !c->deterministic && !c->sync_timing && c->aeam_cluster == 2 &&
+        !c->ap.asym_dr) {
+      if ((rc = ensure_halo_stream(c))) return rc;
+      cudaStream_t main = c->stream, halo = c->halo_stream;
+      if ((rc = b200md_aeam_forces(c, 0, 0, 1))) return rc;
+      CUDA_TRY(c, cudaEventRecord(c->ev_reb, main));
+      CUDA_TRY(c, cudaStreamWaitEvent(halo, c->ev_reb, 0));
+      c->stream = halo;
+      s->fold_atomic = true;
+      rc = halo_reverse_f(c, s);
+      s->fold_atomic = false;
+      c->stream = main;
+      if (rc) return rc;
+      CUDA_TRY(c, cudaEventRecord(c->ev_rev, halo));
+      if ((rc = b200md_aeam_forces(c, 0, 0, 2))) return rc;
+      CUDA_TRY(c, cudaStreamWaitEvent(main, c->ev_rev, 0));
+      s->noverlap++;
+      return B200MD_OK;
+    }
+    if ((rc = b200md_aeam_forces(c, eflag, vflag, 0))) return rc;
   }
   return halo_reverse_f(c, s);
 }
@@ -1989,17 +2024,9 @@ static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
 // derive: the tight rows are re-derived first (that needs the ghosts, so only the reverse halo is hidden).
 static int forces_overlapped(b200md_ctx *c, SystemState *s, bool derive)
 {
-  if (!c->halo_stream) {
-    int lo = 0, hi = 0;
-    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CUDA_TRY(c, cudaStreamCreateWithPriority(&c->halo_stream, cudaStreamNonBlocking, hi));
-    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
-    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fwd, cudaEventDisableTiming));
-    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_reb, cudaEventDisableTiming));
-    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_rev, cudaEventDisableTiming));
-  }
+  int rc = ensure_halo_stream(c);
+  if (rc) return rc;
   cudaStream_t main = c->stream, halo = c->halo_stream;
-  int rc;
   // B200MD_OVERLAP_TRACE=1: device timestamps of one step's phases on both streams (diagnostic)
   static const bool trace_on = getenv("B200MD_OVERLAP_TRACE") != nullptr;
   const bool trace = trace_on && s->noverlap == 60;

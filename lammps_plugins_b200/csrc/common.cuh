@@ -252,6 +252,9 @@ struct b200md_ctx {
   DevBuf<double> xhold_t;    // [nall*4] positions at the last tight derive
   double margin_t = 0.0;
   bool tight_valid = false;
+  bool sys_owns_tight = false;       // the tight rows on the device were derived by the resident loop
+  bool tight_derive_pending = false; // plugin mode: a deferred derive is in flight on the compute stream (ev_tight)
+  cudaEvent_t ev_tight = nullptr;
   long long n_tight = 0;
   DevBuf<int> ljp_ab;        // pair mode: {a, b} atom indices of every pair row, [2][P] by element
   int ljp_P = 0;             // pair slots per element

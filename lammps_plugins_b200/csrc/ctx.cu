@@ -101,6 +101,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release(); c->ljp_ab.release();
   c->short_idx_t.release(); c->short_num_t.release(); c->lj_val_t.release(); c->lj_num_t.release(); c->xhold_t.release();
   c->ljp_tmp.release(); c->ljp_scan.release();
+  if (c->ev_tight) cudaEventDestroy(c->ev_tight);
   if (c->halo_stream) cudaStreamDestroy(c->halo_stream);
   for (cudaEvent_t e : {c->ev_ready, c->ev_fwd, c->ev_reb, c->ev_rev})
     if (e) cudaEventDestroy(e);

@@ -143,15 +143,27 @@ __global__ void __launch_bounds__(BLOCK) pack_xq_kernel(const double *__restrict
   xq[i] = make_double4(x[3 * (size_t) i], x[3 * (size_t) i + 1], x[3 * (size_t) i + 2], (double) e);
 }
 
+// flags[1] = 1: an atom moved more than margin/2 since the inner (wide) rows were derived.  Plugin mode with tight rows
+// (xhold_t != NULL): flags[2] = 2 when an atom moved more than margin_t/2 since the tight rows were derived (they may
+// miss a pair now), 1 when more than soon_sq (they are re-derived after this call, before they can miss one)
 __global__ void __launch_bounds__(BLOCK) check_disp_kernel(const double4 *__restrict__ xq,
                                                            const double4 *__restrict__ xhold, int nall,
-                                                           double thresh_sq, int *__restrict__ flags)
+                                                           double thresh_sq, int *__restrict__ flags,
+                                                           const double4 *__restrict__ xhold_t = nullptr,
+                                                           double tight_sq = 0.0, double soon_sq = 0.0)
 {
   int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= nall) return;
   double4 a = xq[i], b = xhold[i];
   double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
   if (dx * dx + dy * dy + dz * dz > thresh_sq) flags[1] = 1;
+  if (xhold_t) {
+    b = xhold_t[i];
+    dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    const double d = dx * dx + dy * dy + dz * dz;
+    if (d > tight_sq) atomicMax(&flags[2], 2);
+    else if (d > soon_sq) atomicMax(&flags[2], 1);
+  }
 }
 
 // inner lists from the master rows: one warp per row, order-preserving ballot compaction
@@ -1901,9 +1913,10 @@ static int check_flags(b200md_ctx *c, const int *fl)
 // known once all positions are on the device.  If so (rare: every ~50+ steps at 300 K) the lists are re-derived and
 // the forces recomputed by the plain path; nothing of the speculative pass has been added to the caller's f by then.
 static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, const double *x, int eflag, int vflag,
-                                     double *f, double *eng_vdwl, double *virial, int *fl, bool *redo)
+                                     double *f, double *eng_vdwl, double *virial, int *fl, bool *redo, int *redo_level)
 {
   *redo = false;
+  *redo_level = 0;
   const int K = c->h2d_K;
   const int nall = nlocal + nghost;
   if (!c->up_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
@@ -1912,9 +1925,16 @@ static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, cons
   c->nlocal = nlocal;
   c->nghost = nghost;
   c->nall = nall;
-  const bool need_check = c->margin < c->skin;
+  const bool tight = c->tight_valid;
+  const bool need_check = c->margin < c->skin || tight;
   int *pin_flag = (int *) (c->pin_scal.p + 56);
-  *pin_flag = 0;
+  pin_flag[0] = pin_flag[1] = 0;
+  // the tight rows may still be being re-derived from the previous call's positions (deferred derive, below): the
+  // upload must not overwrite xq before that is done
+  if (c->tight_derive_pending) {
+    CUDA_TRY(c, cudaStreamWaitEvent(c->up_stream, c->ev_tight, 0));
+    c->tight_derive_pending = false;
+  }
   // ---- upload stream
   cudaStream_t compute_stream = c->stream;
   c->stream = c->up_stream;    // LaunchScope and the helpers below enqueue on c->stream
@@ -1935,13 +1955,16 @@ static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, cons
     if (!rc && cudaEventRecord(c->up_ev[p], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
   }
   if (!rc && need_check) {
-    const double half = 0.5 * c->margin;
+    const double half = c->margin < c->skin ? 0.5 * c->margin : 1.0e10;
+    const double th = 0.5 * c->margin_t, soon = 0.8 * th;
     {
       LaunchScope ls(c, "check_disp");
       check_disp_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, (const double4 *) c->xhold.p, nall,
-                                                                      half * half, c->flags.p);
+                                                                      half * half, c->flags.p,
+                                                                      tight ? (const double4 *) c->xhold_t.p : nullptr,
+                                                                      th * th, soon * soon);
     }
-    if (cudaMemcpyAsync(pin_flag, c->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(pin_flag, c->flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
       rc = B200MD_ERR_CUDA;
   }
   if (!rc && cudaEventRecord(c->up_ev[K], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
@@ -1965,15 +1988,26 @@ static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, cons
   }
   // ---- the verdict on the lists arrives while the kernels are still running
   CUDA_TRY(c, cudaEventSynchronize(c->up_ev[K]));
-  if (need_check && *pin_flag) {
+  if (need_check && (pin_flag[0] || pin_flag[1] == 2)) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     b200md_collect_timers(c);
-    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 1, 0, 2 * sizeof(int), c->stream));
     *redo = true;
+    *redo_level = pin_flag[0] ? 2 : 1;    // 2: re-derive the inner rows; 1: only the tight rows were overtaken
     return B200MD_OK;
   }
-  return b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl);
+  rc = b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl);
+  if (!rc && need_check && pin_flag[1] == 1) {
+    // an atom is 80 % of the way to the tight rows' limit: re-derive them now, after this call's work, from the positions
+    // on the device -- the host integrates in the meantime, the next call's upload waits for the event
+    CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
+    if ((rc = b200md_rebomos_derive_tight(c))) return rc;
+    if (!c->ev_tight) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_tight, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventRecord(c->ev_tight, c->stream));
+    c->tight_derive_pending = true;
+  }
+  return rc;
 }
 
 extern "C" int b200md_rebomos_compute(b200md_ctx *c, int nlocal, int nghost, const double *x,
@@ -2001,7 +2035,12 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
       for (int k = 0; k < 6; k++) virial[k] = 0.0;
     return B200MD_OK;
   }
-  c->tight_valid = false;    // the tight rows belong to the GPU-resident loop, which owns their refresh schedule
+  // plugin mode keeps tight rows of its own (derived after every inner-list build, checked with the positions of every
+  // call, re-derived one call ahead of need); a resident system's tight rows follow another schedule
+  if (c->sys_owns_tight) {
+    c->tight_valid = false;
+    c->sys_owns_tight = false;
+  }
   if (c->split.on || c->split_valid) {    // ... and so does the interior/boundary order of the pair rows
     c->split.on = 0;
     if (c->split_valid) c->inner_valid = false;
@@ -2011,16 +2050,24 @@ extern "C" int b200md_rebomos_compute_peratom(b200md_ctx *c, int nlocal, int ngh
   bool redo = false;
   if (!eatom && !vatom && !c->deterministic && c->inner_valid && c->h2d_ready && c->d2h_chunks > 1 &&
       c->type_on_device && (c->tag_on_device || !tag) && nlocal + nghost == c->ids_nall && c->nlocal == nlocal) {
-    if ((rc = rebomos_compute_pipelined(c, nlocal, nghost, x, eflag, vflag, f, eng_vdwl, virial, fl, &redo))) return rc;
+    int level = 0;
+    if ((rc = rebomos_compute_pipelined(c, nlocal, nghost, x, eflag, vflag, f, eng_vdwl, virial, fl, &redo, &level))) return rc;
     c->n_pipelined++;
     if (!redo) return check_flags(c, fl);
     c->n_redo++;
-    // an atom had moved beyond the inner lists' margin: positions are on the device, re-derive and recompute
-    if ((rc = b200md_rebomos_build_inner(c))) return rc;
+    // an atom had moved beyond the inner lists' margin (level 2) or beyond the tight rows' (level 1): positions are on
+    // the device, re-derive and recompute
+    if (level == 2 && (rc = b200md_rebomos_build_inner(c))) return rc;
+    if ((rc = b200md_rebomos_derive_tight(c))) return rc;
   } else {
+    if (c->tight_derive_pending) {
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      c->tight_derive_pending = false;
+    }
     if ((rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag))) return rc;
     if ((rc = b200md_rebomos_pack(c))) return rc;
     if ((rc = b200md_rebomos_refresh_inner(c))) return rc;
+    if ((rc = b200md_rebomos_derive_tight(c))) return rc;    // tight rows at these positions (0.5 ms per 1 M atoms)
   }
   if (!c->h2d_ready && !eatom && !vatom && !c->deterministic && (rc = rebomos_prepare_pipeline(c))) return rc;
   const size_t n3 = 3 * (size_t) c->nall;

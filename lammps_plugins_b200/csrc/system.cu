@@ -1951,6 +1951,7 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
                                       s->nghost, s->xt.p, s->ghost_rows, s->d.skin, !first && c->one_pass_neigh)))
     return rc;
   set_split_geometry(c, s);
+  c->sys_owns_tight = true;
   rc = (s->d.style == 0) ? b200md_rebomos_build_inner(c) : b200md_aeam_build_inner(c);
   if (rc) return rc;
   if (s->d.style == 0 && (rc = b200md_rebomos_derive_tight(c))) return rc;

@@ -194,6 +194,60 @@ def test_deterministic_mode(ctx, oracle_built, case):
     lmp.close()
 
 
+def test_plugin_mode_tight_rows(ctx, oracle_built):
+    """Plugin mode keeps tight rows (rcut + 0.4 A) of its own: the force kernels stream them, the displacement check of
+    every call covers them, they are re-derived AFTER a call in which an atom came within 80 % of their limit (the next
+    upload waits for that), and a call that finds an atom beyond the limit recomputes with rows derived on the spot.
+    Every call must equal the plain path (no pipeline, no tight rows) on the same positions."""
+    import lammps_plugins_b200 as b2
+    lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), displace=0.1)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    nl, ng = snap["nlocal"], snap["nghost"]
+    init_ctx(ctx)
+    plain = b2.Context(0)
+    plain.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    for c in (ctx, plain):
+        c.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    ctx.set_option("d2h_min_atoms", 0)
+    ctx.set_option("d2h_chunks", 2)
+    ctx.set_option("h2d_chunks", 3)
+    plain.set_option("h2d_chunks", 1)
+    plain.set_option("d2h_chunks", 1)
+    plain.set_option("margin_tight", 0)
+    try:
+        rng = np.random.default_rng(11)
+        x = snap["x"].copy()
+        redo0 = None
+        for call in range(8):
+            if call == 0:
+                pass
+            elif call in (1, 2):
+                x = x + rng.uniform(-0.02, 0.02, x.shape)            # small moves: tight rows stay
+            elif call == 3:
+                x[11] += (0.17, 0.0, 0.0)                             # > 0.8 * 0.2: derived after this call
+            elif call == 4:
+                x[11] += (0.10, 0.0, 0.0)                             # 0.27 from the ORIGINAL derive, 0.10 from the new one
+            elif call == 5:
+                x[23] += (0.0, 0.3, 0.0)                              # beyond margin_t/2 = 0.2 at once: recompute (level 1)
+            else:
+                x = x + rng.uniform(-0.03, 0.03, x.shape)
+            f, e, v = ctx.rebomos_compute(nl, ng, x, snap["type"], snap["tag"], 1, 2)
+            fq, eq, vq = plain.rebomos_compute(nl, ng, x, snap["type"], snap["tag"], 1, 2)
+            assert S.rel_err(f, fq) < 1e-12 and abs(e - eq) < 1e-12 * abs(eq) and S.rel_err(v, vq) < 1e-11, call
+            if call == 4:
+                redo0 = ctx.counter("pipelined_redos")
+            if call == 5:
+                assert ctx.counter("pipelined_redos") == redo0 + 1
+        assert ctx.counter("pipelined_calls") >= 6 and ctx.counter("tight_refreshes") >= 3
+    finally:
+        ctx.set_option("d2h_chunks", 4)
+        ctx.set_option("h2d_chunks", 6)
+        ctx.set_option("d2h_min_atoms", 65536)
+        plain.close()
+    lmp.close()
+
+
 def test_many_rebo_neighbors_overflow_path(ctx, oracle_built):
     """a compressed cell gives S atoms more than 8 REBO neighbors: those centers leave the narrow launch through
     the overflow list and are evaluated by the wide one -- same parity bar"""

@@ -253,19 +253,31 @@ __global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
   const int64_t base = list_off[i], obase = ea_off[i];
   const unsigned lt = (1u << lane) - 1u;
   int no = 0;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int e = e0 + lane;
-    bool keep = false;
-    int j = 0;
-    if (e < n) {
-      j = ld_stream_int(list_val + base + e) & B200MD_NEIGHMASK;
-      const double4 xj = xq[j];
-      const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
-      keep = dx * dx + dy * dy + dz * dz <= par.cutsq_list[ti * par.nel + etype(xj)];
+  // 4 trips of 32 entries in flight per lane (index -> position -> test is a dependent chain: one trip at a time the
+  // kernel ran at the latency of 2 x 4 round trips per row, 1.8 ms per 2 M rows)
+  constexpr int NU = 4;
+  for (int e0 = 0; e0 < n; e0 += 32 * NU) {
+    int jv[NU];
+    double4 xv[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+      const int e = e0 + u * 32 + lane;
+      jv[u] = (e < n) ? (ld_stream_int(list_val + base + e) & B200MD_NEIGHMASK) : -1;
     }
-    const unsigned mk = __ballot_sync(0xffffffffu, keep);
-    if (keep) ea_val[obase + no + __popc(mk & lt)] = j;
-    no += __popc(mk);
+#pragma unroll
+    for (int u = 0; u < NU; u++)
+      if (jv[u] >= 0) xv[u] = ld_sector(xq + jv[u]);
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+      bool keep = false;
+      if (jv[u] >= 0) {
+        const double dx = xv[u].x - xi.x, dy = xv[u].y - xi.y, dz = xv[u].z - xi.z;
+        keep = dx * dx + dy * dy + dz * dz <= par.cutsq_list[ti * par.nel + etype(xv[u])];
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, keep);
+      if (keep) ea_val[obase + no + __popc(mk & lt)] = jv[u];
+      no += __popc(mk);
+    }
   }
   if (lane == 0) {
     ea_num[i] = no;
@@ -915,8 +927,9 @@ __global__ void __launch_bounds__(128) aeam_density_ang_kernel(
 }
 
 // ================================================================== A3: embedding
+// Also gates the atom's own F' into xq.w (what aeam_gate_kernel does for the ghosts once the halo has brought their fp).
 __global__ void __launch_bounds__(BLOCK) aeam_embed_kernel(const __grid_constant__ AeamDev par,
-                                                           const double4 *__restrict__ xq,
+                                                           double4 *xq,
                                                            const double4 *__restrict__ frho,
                                                            const double *__restrict__ rho, int inum,
                                                            double *__restrict__ fp, double *__restrict__ scal,
@@ -935,7 +948,9 @@ __global__ void __launch_bounds__(BLOCK) aeam_embed_kernel(const __grid_constant
     p -= m;
     p = fmin(p, 1.0);
     const double4 cf = frho[par.frho_off[ti] + m];
-    fp[i] = spl_der(cf, p, par.rdrho[ti]);
+    const double fpi = spl_der(cf, p, par.rdrho[ti]);
+    fp[i] = fpi;
+    xq[i].w = w_encode((ti < par.nnonangular && rh > 0.0000000000001) ? fpi : 0.0, ti);
     e[0] = spl_val(cf, p);
     // pair_aeam.cpp:295-300: an angular atom's own share of its embedding energy is one third
     if (pa_e) pa_e[i] += (ti < par.nnonangular) ? e[0] : e[0] * (1.0 / 3.0);
@@ -972,10 +987,11 @@ __global__ void __launch_bounds__(BLOCK) aeam_ghost_fill_kernel(const int *__res
 
 // (1-del) * Fptmp * fp of every owned and ghost atom in one array: zero for angular atoms and for
 // rho <= minrho (pair_aeam.cpp:128,329-332), so the force kernel gathers ONE double per neighbor
+// (atoms [first, nall): the ghosts -- owned atoms are gated by aeam_embed_kernel)
 __global__ void __launch_bounds__(BLOCK) aeam_gate_kernel(double4 *__restrict__ xq, const double *__restrict__ rho,
-                                                          const double *__restrict__ fp, int nna, int nall)
+                                                          const double *__restrict__ fp, int nna, int first, int nall)
 {
-  const int a = blockIdx.x * BLOCK + threadIdx.x;
+  const int a = first + blockIdx.x * BLOCK + threadIdx.x;
   if (a >= nall) return;
   const int t = (int) (__double_as_longlong(xq[a].w) & 3LL);
   xq[a].w = w_encode((t < nna && rho[a] > 0.0000000000001) ? fp[a] : 0.0, t);
@@ -1600,10 +1616,10 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag, int part)
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
   const double4 *ptab = (const double4 *) c->spl_pair.p;
   const bool ev = eflag || vflag;
-  if (part != 2) {
+  if (part != 2 && c->nall > inum) {
     LaunchScope ls(c, "aeam_gate");
-    aeam_gate_kernel<<<nblocks(c->nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, c->rho.p, c->fp.p, c->ap.nnonangular,
-                                                                     c->nall);
+    aeam_gate_kernel<<<nblocks(c->nall - inum, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, c->rho.p, c->fp.p,
+                                                                            c->ap.nnonangular, inum, c->nall);
   }
   const bool atom = c->pa_e != nullptr;
   const int mode = aeam_row_mode(c);

@@ -167,6 +167,8 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
     c->overlap_halo = (int) (value < 0 ? 0 : value);
     c->inner_valid = false;
   } else if (n == "one_pass_neigh") c->one_pass_neigh = value ? 1 : 0;
+  else if (n == "fuse_integrate") c->fuse_integrate = value ? 1 : 0;
+  else if (n == "neigh_unroll") c->neigh_unroll = (int) value;
   else if (n == "aeam_variant") c->aeam_variant = (int) value;
   else if (n == "force_rebuild") c->force_rebuild = value ? 1 : 0;
   else if (n == "aeam_sort_rows") {
@@ -622,18 +624,34 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums(const int *__restri
   }
 }
 
-__global__ void scan_tile_offsets(long long *tile_sum, int ntiles)
+// one block: thread t owns a contiguous chunk of tiles (a single thread walking 1000 tiles of a 2 M-row list took
+// 0.1-0.5 ms of dependent global loads per scan, 1 ms per AEAM rebuild: r02 launch list)
+#define SCAN_OFF_BLOCK 1024
+__global__ void __launch_bounds__(SCAN_OFF_BLOCK) scan_tile_offsets(long long *tile_sum, int ntiles)
 {
-  // single thread: ntiles is small (n / 2048); runs once per list build
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long run = 0;
-    for (int t = 0; t < ntiles; t++) {
-      long long v = tile_sum[t];
-      tile_sum[t] = run;
-      run += v;
-    }
-    tile_sum[ntiles] = run;
+  __shared__ long long sh[SCAN_OFF_BLOCK / 32];
+  const int per = (ntiles + SCAN_OFF_BLOCK - 1) / SCAN_OFF_BLOCK;
+  const int t0 = min(ntiles, (int) threadIdx.x * per), t1 = min(ntiles, t0 + per);
+  long long s = 0;
+  for (int t = t0; t < t1; t++) s += tile_sum[t];
+  long long inc = s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
   }
+  if (lane == 31) sh[wid] = inc;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; w++) woff += sh[w];
+  long long run = woff + inc - s;
+  for (int t = t0; t < t1; t++) {
+    const long long v = tile_sum[t];
+    tile_sum[t] = run;
+    run += v;
+  }
+  if (threadIdx.x == SCAN_OFF_BLOCK - 1) tile_sum[ntiles] = run;
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_apply(const int *__restrict__ in, int n, int align,
@@ -685,7 +703,7 @@ int b200md_exclusive_scan_i64(b200md_ctx *c, const int *in, int64_t *out, int n,
   }
   {
     LaunchScope ls(c, "scan");
-    scan_tile_offsets<<<1, 32, 0, c->stream>>>((long long *) c->scan_tmp64.p, ntiles);
+    scan_tile_offsets<<<1, SCAN_OFF_BLOCK, 0, c->stream>>>((long long *) c->scan_tmp64.p, ntiles);
   }
   {
     LaunchScope ls(c, "scan");

@@ -26,6 +26,9 @@ struct BinGeom {
   int mbins;
   int nruns;
   int ntypes;
+  // per-row stencil clipping: origin of bin (0,0,0) of the local grid, bin size, padded largest cutoff squared, slack
+  double org[3], bsz[3];
+  double clipsq, eps;
 };
 
 // ---------------------------------------------------------------- device: coord2bin
@@ -84,6 +87,17 @@ __global__ void __launch_bounds__(BLOCK) bin_fill_kernel(const int *__restrict__
   bin_atoms[bin_start[b] + pos] = i;
 }
 
+// positions in bin order: the row kernels stream their candidates from it
+__global__ void __launch_bounds__(BLOCK) bin_gather_kernel(const double4 *__restrict__ xt,
+                                                           const int *__restrict__ bin_atoms, int n,
+                                                           double4 *__restrict__ xs)
+{
+  int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = bin_atoms[k];    // the tail is unwritten when an atom fell outside the grid (the build fails then)
+  if ((unsigned) j < (unsigned) n) xs[k] = xt[j];
+}
+
 // ascending local index inside every bin (insertion sort; bins hold ~15 atoms)
 __global__ void __launch_bounds__(BLOCK) bin_sort_kernel(const int64_t *__restrict__ bin_start, int mbins,
                                                          int *__restrict__ bin_atoms)
@@ -108,23 +122,29 @@ __global__ void __launch_bounds__(BLOCK) bin_sort_kernel(const int64_t *__restri
 // walks).  MODE 2: ONE walk into rows of a fixed stride (row i at i * stride; the stride comes from the longest row of
 // the previous build of the same system): rows, counts and offsets in one pass -- a row longer than the stride raises
 // flags[15] and the caller falls back to the two-pass build.  Row contents are identical in all modes.
-template <int MODE>
+template <int MODE, int NU, bool UNI>
 __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
-    const __grid_constant__ BinGeom g, const double4 *__restrict__ xt, const int *__restrict__ bin_of,
-    const int64_t *__restrict__ bin_start, const int *__restrict__ bin_atoms, const int4 *__restrict__ runs,
+    const __grid_constant__ BinGeom g, const double4 *__restrict__ xt, const double4 *__restrict__ xs,
+    const int *__restrict__ bin_of, const int64_t *__restrict__ bin_start, const int *__restrict__ bin_atoms,
+    const int4 *__restrict__ runs,
     const double *__restrict__ cutsq, const double *__restrict__ cutghostsq, int nlocal, int nrows,
     int64_t *__restrict__ row_off, int *__restrict__ row_num, int *__restrict__ row_val, int stride,
     int *__restrict__ flags)
 {
   constexpr bool FILL = MODE != 0;
-  const int lane = threadIdx.x & 31;
+  __shared__ int s_max;
+  __shared__ int2 s_run[BLOCK / 32][32];
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
-  if (i >= nrows) return;
-  const double4 xi = xt[i];
+  const bool live = i < nrows;
+  const double4 xi = xt[live ? i : 0];
   const int itype = __double2int_rn(xi.w);
   const bool owned = i < nlocal;
   const double *cut = (owned ? cutsq : cutghostsq) + (size_t) itype * (g.ntypes + 1);
-  const int ib = bin_of[i];
+  const double cut_uni = UNI ? cut[1] : 0.0;    // UNI: every type pair has the same list cutoff (both pair styles here)
+  const int ib = live ? bin_of[i] : -1;
   int n = 0;
   if (ib >= 0) {
     const int mx = g.mbin[0], my = g.mbin[1], mz = g.mbin[2];
@@ -132,13 +152,18 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     const int yb = (ib - zb * my * mx) / mx;
     const int xb = ib - zb * my * mx - yb * mx;
     const int64_t obase = MODE == 1 ? row_off[i] : (MODE == 2 ? (int64_t) i * stride : 0);
-    const unsigned lt = (1u << lane) - 1u;
+    const unsigned lt = (1u << lane) - 1u, le = 0xffffffffu >> (31 - lane);
+    // position inside the own bin, single precision: the clip below is conservative by epsf = 1e-3 bin sizes
+    const float fx = (float) (xi.x - (g.org[0] + xb * g.bsz[0])), fy = (float) (xi.y - (g.org[1] + yb * g.bsz[1])),
+                fz = (float) (xi.z - (g.org[2] + zb * g.bsz[2]));
+    const float bx = (float) g.bsz[0], by = (float) g.bsz[1], bz = (float) g.bsz[2], epsf = (float) g.eps;
+    const float clipf = (float) g.clipsq * 1.0001f;
     // The candidates of a row are the concatenation, in stencil-run order, of the runs' slices of the bin-sorted atom
     // array.  32 runs at a time: lane k looks up run k's slice (all bin_start lookups in flight at once instead of one
-    // dependent chain per run), a warp scan turns the slice lengths into offsets, and the warp then walks the
-    // CONCATENATED candidate sequence 32 at a time, every lane finding its (run, position) by a 5-step search over the
-    // offsets.  Same candidates in the same order as the run-by-run walk (rows stay bit-exact), but full warps per
-    // trip -- a run of fcc Al holds ~16 atoms -- and 12 instead of 25+ dependent trips per row.
+    // dependent chain per run), the non-empty slices are compacted, a warp scan turns their lengths into offsets, and the
+    // warp then walks the CONCATENATED candidate sequence 32 at a time.  A lane finds its (run, position) from a bit mask
+    // of the run starts inside the 32-candidate window (one REDUX + one POPC; a 5-step search over the offsets cost 30 of
+    // the ~60 instructions of a trip).  Same candidates in the same order as the run-by-run walk (rows stay bit-exact).
     for (int r0 = 0; r0 < g.nruns; r0 += 32) {
       int len = 0, s0 = 0;
       if (r0 + lane < g.nruns) {
@@ -148,6 +173,24 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
         // ghost atoms: skip stencil bins outside the local bin grid (NPairFullBinGhost).  For owned
         // atoms the grid always covers the stencil, so the same clip is a no-op that guards memory.
         if (y >= 0 && y < my && z >= 0 && z < mz) {
+          // Clip the run to the bins this atom's cutoff sphere can reach (the stencil is the union over all positions
+          // inside the atom's bin: 125 bins against ~85 for one position).  Skipped bins hold no neighbor, so the row
+          // keeps its members and their order.  Bin y covers [org + y b, org + (y + 1) b) up to the rounding of
+          // coord2bin; epsf (1e-3 b) covers that and the single-precision arithmetic here.
+          float gy = 0.0f, gz = 0.0f;
+          if (run.z > 0) gy = run.z * by - fy;
+          else if (run.z < 0) gy = fy + (-run.z - 1) * by;
+          if (run.w > 0) gz = run.w * bz - fz;
+          else if (run.w < 0) gz = fz + (-run.w - 1) * bz;
+          gy = fmaxf(gy - epsf, 0.0f);
+          gz = fmaxf(gz - epsf, 0.0f);
+          const float rem = clipf - gy * gy - gz * gz;
+          if (rem < 0.0f) x1 = x0 - 1;
+          else {
+            const float rx = sqrtf(rem) + epsf;
+            x0 = max(x0, xb + (int) floorf((fx - rx) / bx));
+            x1 = min(x1, xb + (int) floorf((fx + rx) / bx));
+          }
           x0 = max(x0, 0);
           x1 = min(x1, mx - 1);
           if (x0 <= x1) {
@@ -157,6 +200,17 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
           }
         }
       }
+      // compact the non-empty slices (their start offsets are then strictly increasing)
+      const unsigned ne = __ballot_sync(0xffffffffu, len > 0);
+      const int nrun = __popc(ne);
+      if (len > 0) s_run[wid][__popc(ne & lt)] = make_int2(s0, len);
+      __syncwarp();
+      s0 = 0, len = 0;
+      if (lane < nrun) {
+        const int2 r = s_run[wid][lane];
+        s0 = r.x, len = r.y;
+      }
+      __syncwarp();
       int inc = len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -165,44 +219,56 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
       }
       const int total = __shfl_sync(0xffffffffu, inc, 31);
       const int exc = inc - len;
-      for (int c0 = 0; c0 < total; c0 += 32) {
-        const int cidx = c0 + lane;
-        // largest k with exc_k <= cidx (zero-length runs share their successor's offset and are skipped by "largest")
-        int k = 0;
+      int kb = 0;    // slices that start before the window
+      for (int c0 = 0; c0 < total; c0 += 32 * NU) {
+        int jv[NU];
+        double4 xv[NU];
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const int probe = k + step;
-          const int e = __shfl_sync(0xffffffffu, exc, probe & 31);
-          if (probe < 32 && e <= cidx) k = probe;
-        }
-        const int sk = __shfl_sync(0xffffffffu, s0, k), ek = __shfl_sync(0xffffffffu, exc, k);
-        bool keep = false;
-        int j = -1;
-        if (cidx < total) {
-          j = bin_atoms[sk + (cidx - ek)];
-          if (j != i) {
-            const double4 xj = xt[j];
-            const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            keep = rsq <= cut[__double2int_rn(xj.w)];
+        for (int u = 0; u < NU; u++) {
+          const int w0 = c0 + u * 32, cidx = w0 + lane;
+          const int rel = exc - w0;
+          const unsigned starts = __reduce_or_sync(0xffffffffu, (lane < nrun && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+          const int k = kb + __popc(starts & le) - 1;    // last slice that starts at or before cidx
+          kb += __popc(starts);
+          const int sk = __shfl_sync(0xffffffffu, s0, k & 31), ek = __shfl_sync(0xffffffffu, exc, k & 31);
+          jv[u] = -1;
+          if (cidx < total) {
+            // candidates are consecutive entries of the bin-sorted arrays: both loads are coalesced streams (xs =
+            // positions in bin order; gathering xt[j] cost one L1 wavefront per lane)
+            const int pos = sk + (cidx - ek);
+            jv[u] = bin_atoms[pos];
+            xv[u] = ld_sector(xs + pos);
           }
         }
-        const unsigned mk = __ballot_sync(0xffffffffu, keep);
-        if (FILL && keep && (MODE == 1 || n + __popc(mk & lt) < stride)) row_val[obase + n + __popc(mk & lt)] = j;
-        n += __popc(mk);
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+          bool keep = false;
+          if (jv[u] >= 0 && jv[u] != i) {
+            const double dx = xi.x - xv[u].x, dy = xi.y - xv[u].y, dz = xi.z - xv[u].z;
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            keep = rsq <= (UNI ? cut_uni : cut[__double2int_rn(xv[u].w)]);
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, keep);
+          if (FILL && keep && (MODE == 1 || n + __popc(mk & lt) < stride)) row_val[obase + n + __popc(mk & lt)] = jv[u];
+          n += __popc(mk);
+        }
       }
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && live) {
     if (MODE != 1) {
       row_num[i] = n;
-      atomicMax(&flags[10], n);    // longest row: the stride hint of the next build
+      atomicMax(&s_max, n);
     }
     if (MODE == 2) {
       row_off[i] = (int64_t) i * stride;
       if (i == nrows - 1) row_off[nrows] = (int64_t) nrows * stride;
       if (n > stride) flags[15] = 1;
     }
+  }
+  if (MODE != 1) {    // longest row (the stride hint of the next build): one global atomic per block, not per row
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&flags[10], s_max);
   }
 }
 
@@ -282,6 +348,12 @@ int b200md_neigh_setup_bins(b200md_ctx *c, const b200md_box &box, int ntypes, Bi
   ARG_CHECK(c, bbin < 2000000000LL, "Too many neighbor bins");
   g.mbins = (int) bbin;
   g.ntypes = ntypes;
+  for (int d = 0; d < 3; d++) {
+    g.bsz[d] = binsize[d];
+    g.org[d] = g.bboxlo[d] + g.mbinlo[d] * binsize[d];
+  }
+  g.eps = 1.0e-6 * fmax(binsize[0], fmax(binsize[1], binsize[2]));
+  g.clipsq = box.cutneighmax * box.cutneighmax;    // raised to the largest list cutoff by the caller
 
   // stencil (NStencil::create_setup + NStencilFull[Ghost]Bin3d::create), grouped into x-runs
   int s[3];
@@ -326,7 +398,7 @@ int b200md_neigh_setup_bins(b200md_ctx *c, const b200md_box &box, int ntypes, Bi
 }
 
 struct NeighScratch {
-  DevBuf<double4> xt;
+  DevBuf<double4> xt, xs;
   DevBuf<int4> runs;
   DevBuf<double> cutsq, cutghostsq;
   DevBuf<int64_t> bin_start;
@@ -343,6 +415,7 @@ void b200md_neigh_forget(b200md_ctx *c)
   if (!c->neigh_scratch) return;
   NeighScratch &S = *c->neigh_scratch;
   S.xt.release();
+  S.xs.release();
   S.runs.release();
   S.cutsq.release();
   S.cutghostsq.release();
@@ -352,6 +425,14 @@ void b200md_neigh_forget(b200md_ctx *c)
 }
 
 static inline int nblocks(long long n, int per) { return (int) ((n + per - 1) / per); }
+// option "neigh_unroll": trips of 32 candidates a lane keeps in flight (A/B knob; default 1)
+#define NEIGH_LAUNCH(MODE, ...)                                                                                     \
+  do {                                                                                                              \
+    const int nb_ = nblocks((long long) nrows * 32, BLOCK);                                                         \
+    if (uniform_cut) neigh_rows_kernel<MODE, 1, true><<<nb_, BLOCK, 0, c->stream>>>(__VA_ARGS__);                   \
+    else if (c->neigh_unroll >= 2) neigh_rows_kernel<MODE, 2, false><<<nb_, BLOCK, 0, c->stream>>>(__VA_ARGS__);    \
+    else neigh_rows_kernel<MODE, 1, false><<<nb_, BLOCK, 0, c->stream>>>(__VA_ARGS__);                              \
+  } while (0)
 
 // Build from device-resident positions xt = {x,y,z,(double) type}.  Leaves the dense CSR master list in
 // c->list_{off,num,val}.  The only host round trip is the total entry count (to size the value array).
@@ -367,6 +448,21 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
   const int nall = nlocal + nghost;
   const int nrows = ghost_rows ? nall : nlocal;
   const size_t nt2 = (size_t) (ntypes + 1) * (ntypes + 1);
+  for (size_t k = 0; k < nt2; k++) {    // the clip radius covers every cutoff a row is filtered with
+    g.clipsq = fmax(g.clipsq, cutneighsq_h[k]);
+    if (cutneighghostsq_h) g.clipsq = fmax(g.clipsq, cutneighghostsq_h[k]);
+  }
+  g.clipsq *= 1.0 + 1.0e-12;
+  g.eps = 1.0e-3 * fmax(g.bsz[0], fmax(g.bsz[1], g.bsz[2]));
+  // one cutoff for every type pair (owned and ghost rows alike)?  Then the rows are filtered without the table lookup.
+  bool uniform_cut = true;
+  for (int a = 1; a <= ntypes; a++)
+    for (int b = 1; b <= ntypes; b++) {
+      const size_t k = (size_t) a * (ntypes + 1) + b;
+      if (cutneighsq_h[k] != cutneighsq_h[(size_t) ntypes + 2]) uniform_cut = false;
+      if (cutneighghostsq_h && cutneighghostsq_h[k] != cutneighsq_h[(size_t) ntypes + 2]) uniform_cut = false;
+    }
+  CUDA_TRY(c, S.xs.reserve((size_t) nall + 8));
   CUDA_TRY(c, S.runs.reserve(runs.size() + 8));
   CUDA_TRY(c, S.cutsq.reserve(nt2 + 8));
   CUDA_TRY(c, S.cutghostsq.reserve(nt2 + 8));
@@ -400,6 +496,10 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
       LaunchScope ls(c, "bin_sort");
       bin_sort_kernel<<<nblocks(g.mbins, BLOCK), BLOCK, 0, c->stream>>>(S.bin_start.p, g.mbins, c->bin_atoms.p);
     }
+    {
+      LaunchScope ls(c, "bin_gather");
+      bin_gather_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(xt, c->bin_atoms.p, nall, S.xs.p);
+    }
   }
   int64_t total = 0;
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
@@ -411,8 +511,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     CUDA_TRY(c, c->list_val.reserve((size_t) nrows * stride + 64));
     {
       LaunchScope ls(c, "neigh_fill");
-      neigh_rows_kernel<2><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
-          g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
+      NEIGH_LAUNCH(2, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
           c->list_off.p, c->list_num.p, c->list_val.p, stride, c->flags.p);
     }
     int fl[8];
@@ -434,8 +533,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
   if (nrows && !done) {
     {
       LaunchScope ls(c, "neigh_count");
-      neigh_rows_kernel<0><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
-          g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
+      NEIGH_LAUNCH(0, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
           nullptr, c->list_num.p, nullptr, 0, c->flags.p);
     }
     rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->list_off.p, nrows, 1);
@@ -453,8 +551,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     CUDA_TRY(c, c->list_val.reserve((size_t) total + 64));
     {
       LaunchScope ls(c, "neigh_fill");
-      neigh_rows_kernel<1><<<nblocks((long long) nrows * 32, BLOCK), BLOCK, 0, c->stream>>>(
-          g, xt, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
+      NEIGH_LAUNCH(1, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
           c->list_off.p, c->list_num.p, c->list_val.p, 0, c->flags.p);
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -1356,7 +1356,8 @@ __global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *_
                                                                 const TightLimits lim, int *__restrict__ out_val,
                                                                 int *__restrict__ out_num)
 {
-  // one warp per pair row, two candidates per lane in flight
+  // one warp per pair row, TU candidates per lane in flight (latency-bound: index -> position -> test)
+  constexpr int TU = 2;
   const int lane = threadIdx.x & 31;
   const int q = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
   if (q >= 2 * P) return;
@@ -1379,22 +1380,22 @@ __global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *_
     const int n = seg ? nB : nA;
     const double limit = lim.ljsq[ti * 2 + seg];
     int cnt = 0;
-    for (int e0 = 0; e0 < n; e0 += 64) {
-      int j[2];
-      double4 xj[2];
+    for (int e0 = 0; e0 < n; e0 += 32 * TU) {
+      int j[TU];
+      double4 xj[TU];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
+      for (int u = 0; u < TU; u++) {
         const int e = e0 + 32 * u + lane;
         j[u] = -1;
         if (e < n) j[u] = seg ? row[cap - 1 - e] : row[e];    // S partners fill the slot range from its back
       }
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
+      for (int u = 0; u < TU; u++) {
         xj[u] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
         if (j[u] >= 0) xj[u] = ld_sector(xq + j[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
+      for (int u = 0; u < TU; u++) {
         double dx = xa.x - xj[u].x, dy = xa.y - xj[u].y, dz = xa.z - xj[u].z;
         bool keep = dx * dx + dy * dy + dz * dz <= limit;
         dx = xb.x - xj[u].x, dy = xb.y - xj[u].y, dz = xb.z - xj[u].z;

@@ -623,16 +623,22 @@ __global__ void __launch_bounds__(BLOCK) k_initial_integrate(double4 *__restrict
                                                              double dtv, const double4 *__restrict__ xhold,
                                                              double triggersq, const double4 *__restrict__ xhold_inner,
                                                              double innersq, const double4 *__restrict__ xhold_tight,
-                                                             double tightsq, int *__restrict__ flags)
+                                                             double tightsq, int *__restrict__ flags, int fuse_final)
 {
   int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= nlocal) return;
   const double dtfm = dtf / mass[type[i]];
   double4 p = x[i];
   double vx = v[3 * (size_t) i], vy = v[3 * (size_t) i + 1], vz = v[3 * (size_t) i + 2];
-  vx += dtfm * f[3 * (size_t) i];
-  vy += dtfm * f[3 * (size_t) i + 1];
-  vz += dtfm * f[3 * (size_t) i + 2];
+  const double fx = f[3 * (size_t) i], fy = f[3 * (size_t) i + 1], fz = f[3 * (size_t) i + 2];
+  if (fuse_final) {    // FixNVE::final_integrate of the previous step, same operations in the same order (v, f read once)
+    vx += dtfm * fx;
+    vy += dtfm * fy;
+    vz += dtfm * fz;
+  }
+  vx += dtfm * fx;
+  vy += dtfm * fy;
+  vz += dtfm * fz;
   p.x += dtv * vx;
   p.y += dtv * vy;
   p.z += dtv * vz;
@@ -2403,6 +2409,7 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     for (int ich = 1; ich < 3; ich++)
       n.eta_dotdot[ich] = (n.eta_mass[ich - 1] * n.eta_dot[ich - 1] * n.eta_dot[ich - 1] - s->d.boltz * n.t_target) / n.eta_mass[ich];
   }
+  bool final_pending = false;
   for (int it = 0; it < nsteps; it++) {
     s->step++;
     if (s->nh.on) {    // FixNH::initial_integrate: thermostat half step before the kick
@@ -2421,7 +2428,8 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
                                                           s->xhold.p, triggersq,
                                                           two_level ? (const double4 *) c->xhold.p : nullptr, innersq,
                                                           three_level ? (const double4 *) c->xhold_t.p : nullptr, tightsq,
-                                                          c->flags.p);
+                                                          c->flags.p, final_pending ? 1 : 0);
+      final_pending = false;
     }
     // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
     s->ago++;
@@ -2453,7 +2461,9 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
       }
     }
     if (!forces_done && (rc = compute_forces(c, s, thermo_step ? 1 : 0, thermo_step ? 2 : 0))) return rc;
-    if (s->nlocal) {    // not `n`: migration at a reneighboring step changes the owned count
+    // the second half kick moves into the next step's initial_integrate launch when nothing reads v in between
+    if (s->nlocal && it + 1 < nsteps && !thermo_step && !s->nh.on && c->fuse_integrate) final_pending = true;
+    else if (s->nlocal) {    // not `n`: migration at a reneighboring step changes the owned count
       LaunchScope ls(c, "final_integrate");
       k_final_integrate<<<nblk(s->nlocal), BLOCK, 0, c->stream>>>(s->v.p, c->f.p, c->type.p, s->dmass.p, s->nlocal, dtf);
     }

@@ -355,8 +355,10 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
   constexpr int NTRI = (CAP / 2) * CAP;
   constexpr unsigned GBITS = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
   constexpr int tb = ELEM * 2;
-  __shared__ double s_dx[NG * CAP], s_dy[NG * CAP], s_dz[NG * CAP], s_ri[NG * CAP], s_w[NG * CAP], s_dw[NG * CAP],
-      s_pref[NG * CAP], s_frad[NG * CAP];
+  // staged bonds: UNIT vector u = d / r (the angular terms need nothing else: cos = u_m . u_q, and every force of the
+  // angular part is a combination of unit vectors), r, 1/r, switch w and w'
+  __shared__ double s_dx[NG * CAP], s_dy[NG * CAP], s_dz[NG * CAP], s_ri[NG * CAP], s_r[NG * CAP], s_w[NG * CAP],
+      s_dw[NG * CAP], s_pref[NG * CAP], s_frad[NG * CAP];
   __shared__ double s_c[NG * NTRI], s_g[NG * NTRI], s_dg[NG * NTRI];
   __shared__ int s_j[NG * CAP], s_tj[NG * CAP];
   __shared__ unsigned char s_bl[NG * NTRI];    // table slots whose cos >= 1/2 (blend towards the gamma polynomial)
@@ -365,7 +367,11 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
   const int sub = threadIdx.x & (G - 1);
   const int gl = threadIdx.x / G;    // group within the block
   const int gshift = lane & ~(G - 1);
-  const unsigned gmask = GBITS << gshift;
+  // Every vote, shuffle and warp barrier below runs on the FULL warp: the loops that contain them take the warp's
+  // largest trip count (groups with less work are predicated off).  With per-group masks each of them was a WARPSYNC +
+  // vote pair on a run-time mask: 8 % of the instructions and 17 % of the stall samples of the S-center launch sat on
+  // the ballot of phase A (ncu source view, r02).
+  constexpr unsigned FULL = 0xffffffffu;
   const int sb = gl * CAP;     // this group's staging base
   const int st = gl * NTRI;    // ... and pair-table base
   // centers [first, count) of the list: all of it (count read from the device), or -- plugin-mode pipelining -- the
@@ -378,10 +384,13 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
   } else
     count = *cen_count_ptr;
   double eacc[1] = {0.0};
-  for (int g = first + blockIdx.x * NG + gl; g < count; g += gridDim.x * NG) {
-    const int i = cen_list[g];
+  for (int g0 = first + blockIdx.x * NG + (gl & ~(32 / G - 1)); g0 < count; g0 += gridDim.x * NG) {    // warp-uniform
+    const int g = g0 + (gl & (32 / G - 1));
+    const bool valid = g < count;
+    const int i = valid ? cen_list[g] : 0;
     const double4 xi = xq[i];
-    const int n = short_num[i];
+    const int n = valid ? short_num[i] : 0;
+    const int nmax = __reduce_max_sync(FULL, n);
     // ---- A: ordered REBO sub-list (pair_rebomos.cpp:328-343)
     int nb = 0;
     double nM = 0.0, nS = 0.0;
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     // ncu r01 v6 showed the S-center launch waiting on one gather per trip, long-scoreboard 3.6 per issue); they are then
     // consumed in row order, so membership and bond order stay those of the reference
     constexpr int UB = (G <= 4) ? 4 : 2;
-    for (int e0 = 0; e0 < n; e0 += G * UB) {
+    for (int e0 = 0; e0 < nmax; e0 += G * UB) {
       int jb[UB];
       double4 xb[UB];
 #pragma unroll
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
       }
 #pragma unroll
       for (int u = 0; u < UB; u++) {
-        if (e0 + u * G >= n) break;    // group-uniform
+        if (e0 + u * G >= nmax) break;    // warp-uniform
         bool in = false;
         const int j = jb[u];
         int tj = 0;
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
           rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
           in = rsq < (tj ? par.rcmaxsq[tb + 1] : par.rcmaxsq[tb]);
         }
-        const unsigned bits = (__ballot_sync(gmask, in) >> gshift) & GBITS;
+        const unsigned bits = (__ballot_sync(FULL, in) >> gshift) & GBITS;
         if (in) {
           const int pos = nb + __popc(bits & ((1u << sub) - 1u));
           const double rinv = rsqrt_nr(rsq);
@@ -430,10 +439,11 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
           if (tj == 0) nM += w;
           else nS += w;
           if (pos < CAP) {
-            s_dx[sb + pos] = dx;
-            s_dy[sb + pos] = dy;
-            s_dz[sb + pos] = dz;
+            s_dx[sb + pos] = dx * rinv;
+            s_dy[sb + pos] = dy * rinv;
+            s_dz[sb + pos] = dz * rinv;
             s_ri[sb + pos] = rinv;
+            s_r[sb + pos] = r;
             s_w[sb + pos] = w;
             s_dw[sb + pos] = dw;
             s_j[sb + pos] = j;
@@ -443,20 +453,21 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         nb += __popc(bits);
       }
     }
-    __syncwarp(gmask);
+    __syncwarp();
+    bool deferred = false;
     if (nb > CAP) {
       // more bonds than this launch class stages: hand the center to the wide launch, or fail at the cap
       if (sub == 0) {
         if (CAP < B200MD_MAX_REBO) ovf_list[atomicAdd(ovf_count, 1)] = i;
         else flags[0] = 1;
       }
-      nb = 0;
-      if (CAP < B200MD_MAX_REBO) continue;
+      nb = 0;    // nothing more happens for this center in this launch (no `continue`: the warp stays together)
+      deferred = CAP < B200MD_MAX_REBO;
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
-      nM += __shfl_xor_sync(gmask, nM, o);
-      nS += __shfl_xor_sync(gmask, nS, o);
+      nM += __shfl_xor_sync(FULL, nM, o);
+      nS += __shfl_xor_sync(FULL, nS, o);
     }
     // PijSpline (pair_rebomos.h:173-179); N_i includes j (pair_rebomos.cpp:596-599)
     const double N = nM + nS;
@@ -473,7 +484,8 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     const bool even = (nb & 1) == 0;
     const int npairs = (nb * (nb - 1)) >> 1;
     const unsigned inv_nb = nb > 0 ? (65536u + (unsigned) nb - 1u) / (unsigned) nb : 0u;    // p / nb for p < 256
-    for (int p0 = 0; p0 < npairs; p0 += G) {
+    const int npmax = __reduce_max_sync(FULL, npairs);
+    for (int p0 = 0; p0 < npmax; p0 += G) {
       const int p = p0 + sub;
       const bool act = p < npairs;
       const int k = act ? (int) (((unsigned) p * inv_nb) >> 16) + 1 : 1;
@@ -482,15 +494,14 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
       if (q >= nb) q -= nb;
       double c = 0.0;
       if (act) {
-        c = (s_dx[sb + m] * s_dx[sb + q] + s_dy[sb + m] * s_dy[sb + q] + s_dz[sb + m] * s_dz[sb + q]) *
-            (s_ri[sb + m] * s_ri[sb + q]);
+        c = s_dx[sb + m] * s_dx[sb + q] + s_dy[sb + m] * s_dy[sb + q] + s_dz[sb + m] * s_dz[sb + q];
         c = fmin(c, 1.0);
         c = fmax(c, -1.0);
       }
       double dg;
       const double gg = gspline_base<ELEM>(par, c, dg);
       const bool bl = act && c >= 0.5;
-      const unsigned bits = (__ballot_sync(gmask, bl) >> gshift) & GBITS;
+      const unsigned bits = (__ballot_sync(FULL, bl) >> gshift) & GBITS;
       const int t = (k - 1) * CAP + m;
       const bool twin = act && even && k == nr;    // the pair's second slot, [nr-1][q]
       if (act) {
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
       if (bl) s_bl[st + nbl + __popc(bits & ((1u << sub) - 1u))] = (unsigned char) t;
       nbl += __popc(bits);
     }
-    __syncwarp(gmask);
+    __syncwarp();
     for (int b0 = 0; b0 < nbl; b0 += G) {
       const int b = b0 + sub;
       if (b < nbl) {
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         }
       }
     }
-    __syncwarp(gmask);
+    __syncwarp();
     // ---- B: bond order and pair terms of bond m
     double ei_atom = 0.0;
     for (int m = sub; m < nb; m += G) {
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         }
         const double p = rsqrt_nr(1.0 + S + P);
         const int pt = tb + s_tj[sb + m];
-        const double r = (s_dx[sb + m] * s_dx[sb + m] + s_dy[sb + m] * s_dy[sb + m] + s_dz[sb + m] * s_dz[sb + m]) * rinv;
+        const double r = s_r[sb + m];
         const double Q = par.Q[pt], al = par.alpha[pt];
         // VR = wm * VR0, VA = wm * VA0: the reference's VR / wm * dwm is VR0 * dwm without the division
         const double pre0 = par.A[pt] * exp(-al * r);
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         const double VA = wm * VA0;
         const double dVA = -be * VA + VA0 * dwm;
         pref = VA * 0.5 * (-0.5 * p * p * p);
-        frad = 0.5 * (dVR + p * dVA) * rinv + pref * dP * dwm * rinv;
+        frad = 0.5 * (dVR + p * dVA) + pref * dP * dwm;    // multiplies the unit vector u_m
         if (EV) eacc[0] += 0.5 * (VR + p * VA);
         if (ATOM) {
           // ev_tally (pair_rebomos.cpp:443-444): the half-bond energy VR + bbar*VA goes half to i, half to j;
@@ -575,33 +586,42 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
       s_pref[sb + m] = pref;
       s_frad[sb + m] = frad;
     }
-    __syncwarp(gmask);
-    // ---- C: forces
+    __syncwarp();
+    // ---- C: forces.  With unit vectors the force bond m receives from its pairing with q is
+    //   A (c u_m - u_q) / r_m + pref_q w'_m (G + P') u_m,   A = -(pref_m w_q + pref_q w_m) G'   (symmetric in m, q)
+    // so the partner loop only accumulates sum A c, sum A u_q and sum pref_q (G + P'): 9 FP64 operations and 8 shared
+    // loads per (m, q) instead of 19 and 9; 1/r_m, w'_m and u_m are applied once per bond.
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
     double vi[6] = {0, 0, 0, 0, 0, 0};    // ATOM: this lane's share of the center's per-atom virial
     for (int m = sub; m < nb; m += G) {
-      const double mx = s_dx[sb + m], my = s_dy[sb + m], mz = s_dz[sb + m], rinvm = s_ri[sb + m];
+      const double ux = s_dx[sb + m], uy = s_dy[sb + m], uz = s_dz[sb + m], rinvm = s_ri[sb + m];
       const double wm = s_w[sb + m], dwm = s_dw[sb + m], prefm = s_pref[sb + m];
-      const double rinvm2 = rinvm * rinvm;
+      double sAc = 0.0, sB = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
       double fx = 0.0, fy = 0.0, fz = 0.0;
       double vm[6] = {0, 0, 0, 0, 0, 0};
+      const double rm = ATOM ? s_r[sb + m] : 0.0;
+      const double mx = ux * rm, my = uy * rm, mz = uz * rm;    // ATOM: d_m
       for (int k = 1; k < nb; k++) {
         int q = m + k;
         if (q >= nb) q -= nb;
         const int t = st + ((k <= nr) ? (k - 1) * CAP + m : (nb - k - 1) * CAP + q);
         const double prefn = s_pref[sb + q];
         const double ca = -(prefm * s_w[sb + q] + prefn * wm);
-        const double cb = prefn * dwm;
-        const double c = s_c[t];
         const double A = ca * s_dg[t];
-        const double B = cb * (s_g[t] + dP) * rinvm;
-        const double cm = A * c * rinvm2 + B;          // multiplies d_m
-        const double cn = -A * (rinvm * s_ri[sb + q]);    // multiplies d_q
-        const double qx = cm * mx + cn * s_dx[sb + q], qy = cm * my + cn * s_dy[sb + q], qz = cm * mz + cn * s_dz[sb + q];
-        fx += qx;
-        fy += qy;
-        fz += qz;
-        if (ATOM) {
+        const double gp = s_g[t] + dP;
+        if (!ATOM) {
+          sAc = fma(A, s_c[t], sAc);
+          sB = fma(prefn, gp, sB);
+          vx = fma(A, s_dx[sb + q], vx);
+          vy = fma(A, s_dy[sb + q], vy);
+          vz = fma(A, s_dz[sb + q], vz);
+        } else {
+          const double cmu = A * s_c[t] * rinvm + prefn * dwm * gp;    // multiplies u_m
+          const double cnu = -A * rinvm;                                // multiplies u_q
+          const double qx = cmu * ux + cnu * s_dx[sb + q], qy = cmu * uy + cnu * s_dy[sb + q], qz = cmu * uz + cnu * s_dz[sb + q];
+          fx += qx;
+          fy += qy;
+          fz += qz;
           // v_tally3 (pair_rebomos.cpp:707-711): each (bond, k) triplet's r_ji (x) f_j + r_ki (x) f_k goes in thirds
           // to i, j, k.  (qx,qy,qz) is what bond m receives from its pairing with q -- once as the triplet's j, once
           // as the other triplet's k -- so (-d_m) (x) q is this lane's part of both; thirds to i, m, q.
@@ -614,13 +634,18 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
           atomicAdd(vq + 3, t3); atomicAdd(vq + 4, t4); atomicAdd(vq + 5, t5);
         }
       }
-      const double fr = s_frad[sb + m];
-      fx += fr * mx;
-      fy += fr * my;
-      fz += fr * mz;
-      if (ATOM) {
+      const double fru = s_frad[sb + m];    // radial part, multiplies u_m
+      if (!ATOM) {
+        const double cu = rinvm * sAc + dwm * sB + fru;
+        fx = cu * ux - rinvm * vx;
+        fy = cu * uy - rinvm * vy;
+        fz = cu * uz - rinvm * vz;
+      } else {
+        fx += fru * ux;
+        fy += fru * uy;
+        fz += fru * uz;
         // radial part: ev_tally (:444) and v_tally2 (:725): -d (x) (fr d), half to i, half to j
-        const double h = -0.5 * fr;
+        const double h = -0.5 * fru * rinvm;
         const double r0 = h * mx * mx, r1 = h * my * my, r2 = h * mz * mz, r3 = h * mx * my, r4 = h * mx * mz, r5 = h * my * mz;
         vi[0] += r0; vi[1] += r1; vi[2] += r2; vi[3] += r3; vi[4] += r4; vi[5] += r5;
         double *vj = pa_v + 6 * (size_t) s_j[sb + m];
@@ -645,11 +670,11 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
-      fix += __shfl_xor_sync(gmask, fix, o);
-      fiy += __shfl_xor_sync(gmask, fiy, o);
-      fiz += __shfl_xor_sync(gmask, fiz, o);
+      fix += __shfl_xor_sync(FULL, fix, o);
+      fiy += __shfl_xor_sync(FULL, fiy, o);
+      fiz += __shfl_xor_sync(FULL, fiz, o);
     }
-    if (sub == 0) {
+    if (sub == 0 && valid && !deferred) {
       if (DET) {
         det.nb[i] = nb;
         det.fi[3 * (size_t) i] = fix;
@@ -661,12 +686,12 @@ __global__ void __launch_bounds__(NT, MINB) rebo_center_kernel(
         atomicAdd(&f[3 * (size_t) i + 2], fiz);
       }
     }
-    if (ATOM) {
+    if (ATOM && valid && !deferred) {
       atomicAdd(&pa_e[i], ei_atom);
 #pragma unroll
       for (int k = 0; k < 6; k++) atomicAdd(&pa_v[6 * (size_t) i + k], vi[k]);
     }
-    __syncwarp(gmask);
+    __syncwarp();
   }
   if (EV) block_accumulate<1, NT>(eacc, scal);
 }

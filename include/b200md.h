@@ -220,6 +220,9 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *                    every rank; used to time a master rebuild)
  *  "overlap_halo"    0/1 (default 1), resident loop: the owned centers are split into interior and boundary ones and the
  *                    halos run on a stream of their own beside the interior kernels
+ *  "peer_vote"       0/1 (default 1), resident loop: the per-step reneighbor vote is exchanged through the peer-memory
+ *                    windows and reported to a mapped host word (no ncclAllReduce, no stream synchronisation per step);
+ *                    0, or no peer windows: ncclAllReduce of one int + copy + cudaStreamSynchronize
  *  "fuse_integrate"  0/1 (default 1), resident loop: the second half kick of a step that is followed by another step (no
  *                    thermo output, no thermostat in between) is applied by the next step's first integrate launch
  *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)

@@ -30,6 +30,7 @@
 #define BIGSLAB 1.0e20
 #define LOCAL_TIMEOUT_S 120
 #define P2P_SLOTS 18    // 3 message kinds x 3 dimensions x 2 directions
+#define VOTE_MAXR 64    // ranks the peer-memory reneighbor vote is laid out for (flag words after the halo slots)
 
 int b200md_rebomos_build_inner(b200md_ctx *c);
 int b200md_rebomos_derive_tight(b200md_ctx *c);
@@ -127,13 +128,16 @@ struct SystemState {
     bool ok = false;
     int want = 1;                  // option "p2p_halo"
     double *win = nullptr;         // [P2P_SLOTS * 2 parities * slot_cap]
-    int *flag = nullptr;           // [P2P_SLOTS * 2] epoch of the last completed write
+    int *flag = nullptr;           // [P2P_SLOTS * 2] epoch of the last completed write, then [2 parities][VOTE_MAXR] votes
+    DevBuf<int *> vote_peers;      // every rank's vote area (own included), index = rank
     int *done = nullptr;           // block-completion counter of the push kernels
     size_t slot_cap = 0;           // doubles per slot
     std::vector<double *> pwin;    // peers' windows mapped here (index = rank)
     std::vector<int *> pflag;
     int epoch[3] = {0, 0, 0};      // forward x, forward rho/fp, reverse f
   } p2p;
+  int *vote_host = nullptr;        // mapped pinned word the vote kernel reports to: (epoch << 3) | level
+  int vote_epoch = 0;
 };
 
 // ================================================================== kernels
@@ -611,6 +615,39 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_unpack_f(double *__restrict__ f, 
   const int k = blockIdx.x * BLOCK + threadIdx.x;
   if (k >= n) return;
   fold3(f, list[k], __ldcg(src + 3 * (size_t) k), __ldcg(src + 3 * (size_t) k + 1), __ldcg(src + 3 * (size_t) k + 2), atomic);
+}
+
+// Reneighbor vote without NCCL and without a stream synchronisation: thread r stores this rank's level
+// (flags[9], set by k_initial_integrate) into rank r's vote area over NVLink, waits for rank r's vote of the same epoch
+// in its own area, and thread 0 reports the maximum to a mapped host word the run loop spins on.  The ncclAllReduce of one
+// int + cudaMemcpyAsync + cudaStreamSynchronize it replaces left the GPU idle for ~30 us per step at 2 ranks (step
+// trace).  Two parities: a rank can be at most one vote ahead of a peer (it needs that peer's vote to go on).  One rank:
+// only the report.  Level 7 = a peer's vote did not arrive (the host fails the run).
+__global__ void __launch_bounds__(VOTE_MAXR) k_vote(int *__restrict__ flag9, int *const *__restrict__ peers, int me,
+                                                    int nranks, int epoch, int *host_word)
+{
+  __shared__ int s_lvl[VOTE_MAXR];
+  const int t = threadIdx.x;
+  const int level = *flag9;
+  int lvl = (t == 0) ? level : 0;
+  if (nranks > 1 && t < nranks) {
+    const int off = (epoch & 1) * VOTE_MAXR;
+    st_release_sys(peers[t] + off + me, (epoch << 3) | level);
+    const int *mine = peers[me] + off + t;
+    int v = 0;
+    long long spins = 0;
+    while (((v = ld_acquire_sys(mine)) >> 3) != epoch && ++spins < (1LL << 27)) {}
+    lvl = ((v >> 3) == epoch) ? (v & 7) : 7;
+  }
+  s_lvl[t] = lvl;
+  __syncthreads();
+  if (t == 0) {
+    int m = 0;
+    for (int r = 0; r < (nranks > 1 ? nranks : 1); r++) m = max(m, s_lvl[r]);
+    *flag9 = 0;
+    *((volatile int *) host_word) = (epoch << 3) | m;
+    __threadfence_system();
+  }
 }
 
 // FixNVE::initial_integrate fused with Neighbor::check_distance.  flags[9] = 3: some atom moved more than
@@ -1348,6 +1385,7 @@ static void p2p_release(SystemState *s)
   }
   P.pwin.clear();
   P.pflag.clear();
+  P.vote_peers.release();
   if (P.win) cudaFree(P.win);
   if (P.flag) cudaFree(P.flag);
   if (P.done) cudaFree(P.done);
@@ -1382,7 +1420,7 @@ static int p2p_setup(b200md_ctx *c, SystemState *s)
   const size_t cap = (want_cap + want_cap / 4 + 1) & ~(size_t) 1;    // even: every slot starts on a 16-byte boundary
   double okv = 1.0;
   if (cudaMalloc((void **) &P.win, (size_t) P2P_SLOTS * 2 * cap * sizeof(double)) != cudaSuccess ||
-      cudaMalloc((void **) &P.flag, P2P_SLOTS * 2 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **) &P.flag, (P2P_SLOTS * 2 + 2 * VOTE_MAXR) * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void **) &P.done, 4 * sizeof(int)) != cudaSuccess)
     okv = 0.0;
   struct Handles {
@@ -1390,7 +1428,7 @@ static int p2p_setup(b200md_ctx *c, SystemState *s)
   } mine;
   memset(&mine, 0, sizeof(mine));
   if (okv > 0.0) {
-    cudaMemsetAsync(P.flag, 0, P2P_SLOTS * 2 * sizeof(int), c->stream);
+    cudaMemsetAsync(P.flag, 0, (P2P_SLOTS * 2 + 2 * VOTE_MAXR) * sizeof(int), c->stream);
     cudaMemsetAsync(P.done, 0, 4 * sizeof(int), c->stream);
     if (cudaIpcGetMemHandle(&mine.win, P.win) != cudaSuccess || cudaIpcGetMemHandle(&mine.flag, P.flag) != cudaSuccess)
       okv = 0.0;
@@ -1423,6 +1461,14 @@ static int p2p_setup(b200md_ctx *c, SystemState *s)
   NCCL_TRY(c, ncclAllReduce(dn, dn, 1, ncclDouble, ncclMin, s->nccl, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(&okv, dn, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (okv > 0.0 && s->nranks <= VOTE_MAXR) {
+    std::vector<int *> vp(s->nranks);
+    for (int r = 0; r < s->nranks; r++) vp[r] = (r == s->me ? P.flag : P.pflag[r]) + P2P_SLOTS * 2;
+    if (P.vote_peers.reserve((size_t) s->nranks + 1) != cudaSuccess ||
+        cudaMemcpyAsync(P.vote_peers.p, vp.data(), s->nranks * sizeof(int *), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+      P.vote_peers.release();
+  }
   if (okv > 0.0) {
     P.ok = true;
     P.slot_cap = cap;
@@ -2144,6 +2190,7 @@ void b200md_system_free(b200md_ctx *c)
   s->x4tmp.release(); s->dtmp.release(); s->scan64.release(); s->sendbuf.release(); s->recvbuf.release();
   s->xbuf.release();
   p2p_release(s);
+  if (s->vote_host) cudaFreeHost(s->vote_host);
   if (s->nccl) ncclCommDestroy(s->nccl);
   delete s;
   c->sys = nullptr;
@@ -2182,11 +2229,17 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
     old->recvbuf.release();
     old->xbuf.release();
     p2p_release(old);
+    if (old->vote_host) cudaFreeHost(old->vote_host);
     delete old;
     c->sys = nullptr;
   }
   SystemState *s = new SystemState();
   c->sys = s;
+  if (cudaHostAlloc((void **) &s->vote_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) *s->vote_host = 0;
+  else {
+    s->vote_host = nullptr;    // the vote then goes through the copy + synchronise path
+    cudaGetLastError();
+  }
   s->nccl = keep;
   s->local = keep_local;
   s->d = *d;
@@ -2410,8 +2463,19 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
       n.eta_dotdot[ich] = (n.eta_mass[ich - 1] * n.eta_dot[ich - 1] * n.eta_dot[ich - 1] - s->d.boltz * n.t_target) / n.eta_mass[ich];
   }
   bool final_pending = false;
+  // B200MD_STEP_TRACE=1: device timestamps at the start of a step, after the reneighbor vote has reached the host, and at
+  // the end of the step, for steps 60-67 of a run (diagnostic: what the vote costs, what the halos leave exposed)
+  static const bool step_trace_on = getenv("B200MD_STEP_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
   for (int it = 0; it < nsteps; it++) {
     s->step++;
+    const bool tr = step_trace_on && it >= 60 && it < 68;
+    if (tr) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, c->stream);
+      tev.push_back(e);
+    }
     if (s->nh.on) {    // FixNH::initial_integrate: thermostat half step before the kick
       nh_temp_target(s);
       if ((rc = nh_scale_velocities(c, s, nh_chain_half_step(s)))) return rc;
@@ -2434,10 +2498,46 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     // Neighbor::decide (every 1, delay 0, check yes): rebuild if any owned atom moved more than skin/2
     s->ago++;
     int flag = 0;
-    if ((rc = xfer_allreduce_max_int(c, s, c->flags.p + 9))) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (flag) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+    s->vote_epoch++;
+    const bool peer_vote = c->peer_vote && s->vote_host && !c->sync_timing &&
+        (s->nranks == 1 || (s->p2p.ok && s->p2p.vote_peers.p && !s->local));
+    if (peer_vote) {
+      {
+        LaunchScope ls(c, "vote");
+        k_vote<<<1, VOTE_MAXR, 0, c->stream>>>(c->flags.p + 9, s->nranks > 1 ? s->p2p.vote_peers.p : nullptr, s->me, s->nranks,
+                                              s->vote_epoch, s->vote_host);
+      }
+      volatile int *hw = s->vote_host;
+      int v;
+      long long spins = 0;
+      const auto t0 = std::chrono::steady_clock::now();
+      while (((v = *hw) >> 3) != s->vote_epoch) {
+        if ((++spins & 0xfffff) == 0) {    // now and then: has the stream died, or has a peer stopped?
+          const cudaError_t q = cudaStreamQuery(c->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) CUDA_TRY(c, q);
+          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0) {
+            c->fail("reneighbor vote: no report from the device within 60 s");
+            return B200MD_ERR_NCCL;
+          }
+        }
+      }
+      flag = v & 7;
+      if (flag == 7) {
+        c->fail("reneighbor vote: a peer rank's vote did not arrive (peer stopped?)");
+        return B200MD_ERR_NCCL;
+      }
+    } else {
+      if ((rc = xfer_allreduce_max_int(c, s, c->flags.p + 9))) return rc;
+      CUDA_TRY(c, cudaMemcpyAsync(&flag, c->flags.p + 9, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if (flag) CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 9, 0, sizeof(int), c->stream));
+    }
+    if (tr) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, c->stream);
+      tev.push_back(e);
+    }
     if (c->force_rebuild) {    // option "force_rebuild": this step takes the reneighboring path (measurement; collective)
       c->force_rebuild = 0;
       flag = 3;
@@ -2473,6 +2573,20 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     }
     if (thermo_step)
       if ((rc = thermo(c, s))) return rc;
+  }
+  if (!tev.empty()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    tev.push_back(e);
+    cudaStreamSynchronize(c->stream);
+    for (size_t k = 0; k + 2 < tev.size(); k += 2) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+      cudaEventElapsedTime(&b, tev[k], tev[k + 2]);
+      fprintf(stderr, "[step trace rank %d] integrate + vote + host %.3f ms | step %.3f ms\n", s->me, a, b);
+    }
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaGetLastError());

@@ -1471,7 +1471,7 @@ int b200md_aeam_build_inner(b200md_ctx *c)
     }
     int rc = b200md_exclusive_scan_i64(c, c->ec_cap.p, c->ec_off.p, ncl, 8);
     if (rc) return rc;
-    const size_t cap = (size_t) (c->list_entries + 8 * (int64_t) ncl + 64);
+    const size_t cap = (size_t) (c->list_entries_used + 8 * (int64_t) ncl + 64);
     CUDA_TRY(c, c->ec_val.reserve(cap));
     CUDA_TRY(c, c->ec_df.reserve(CL * cap));
     if (ncl > 0) {
@@ -1486,8 +1486,8 @@ int b200md_aeam_build_inner(b200md_ctx *c)
     CUDA_TRY(c, c->ea_num.reserve((size_t) inum + 32));
     int rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->ea_off.p, inum, 8);
     if (rc) return rc;
-    CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
-    if (mode == 2) CUDA_TRY(c, c->ec_df.reserve((size_t) (c->list_entries + 8 * (int64_t) inum + 64)));
+    CUDA_TRY(c, c->ea_val.reserve((size_t) (c->list_entries_used + 8 * (int64_t) inum + 64)));
+    if (mode == 2) CUDA_TRY(c, c->ec_df.reserve((size_t) (c->list_entries_used + 8 * (int64_t) inum + 64)));
     if (inum > 0) {
       LaunchScope ls(c, "build_inner");
       aeam_build_inner_kernel<<<nblocks((long long) inum * 32, BLOCK), BLOCK, 0, c->stream>>>(

@@ -45,6 +45,8 @@ template <typename T> struct DevBuf {
   {
     if (n <= cap) return cudaSuccess;
     size_t ncap = n + n / 4 + 256;    // a quarter of headroom: neighbor rows grow ~20 % from a cold lattice to a hot one
+    static const bool trace = getenv("B200MD_ALLOC_TRACE") != nullptr;    // diagnostic: growth inside a timed region?
+    if (trace) fprintf(stderr, "[alloc] %zu -> %zu elements of %zu bytes (%.1f MB)\n", cap, ncap, sizeof(T), ncap * sizeof(T) / 1.0e6);
     T *q = nullptr;
     cudaError_t e = cudaMalloc((void **) &q, ncap * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -221,7 +223,9 @@ struct b200md_ctx {
 
   // ---- master neighbor list (dense CSR on device)
   int list_inum = 0, list_gnum = 0;
-  int64_t list_entries = 0;
+  int64_t list_entries = 0;          // extent of list_val the rows occupy (dense CSR: their sum; strided rows: rows x stride)
+  int64_t list_entries_used = 0;     // entries the rows hold
+  int list_stride = 0;               // sticky stride of the one-pass builds
   int list_maxnum = 0;       // longest row of the last device build: stride hint of the next one-pass build
   int one_pass_neigh = 1;    // option "one_pass_neigh": resident-loop rebuilds walk the stencil once (fixed-stride rows)
   double skin = 0.0;

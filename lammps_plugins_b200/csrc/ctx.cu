@@ -223,7 +223,7 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
     return (c->inner_valid && c->aeam_ready)
                ? (c->aeam_cluster == 1 ? device_sum(c, c->ec_num.p, (c->list_inum + 3) / 4) : device_sum(c, c->ea_num.p, c->list_inum))
                : -1;
-  if (n == "master_entries") return c->list_valid ? (long long) c->list_entries : -1;
+  if (n == "master_entries") return c->list_valid ? (long long) c->list_entries_used : -1;
   if (n == "kernel_launches") return c->n_launch;
   if (n == "list_uploads") return c->n_list_upload;
   if (n == "compute_calls") return c->n_compute;
@@ -721,6 +721,7 @@ static int finish_list(b200md_ctx *c, int inum, int gnum, int64_t total, double 
   c->list_inum = inum;
   c->list_gnum = gnum;
   c->list_entries = total;
+  c->list_entries_used = total;
   c->skin = skin;
   c->list_valid = true;
   c->inner_valid = false;

@@ -129,12 +129,12 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     const int4 *__restrict__ runs,
     const double *__restrict__ cutsq, const double *__restrict__ cutghostsq, int nlocal, int nrows,
     int64_t *__restrict__ row_off, int *__restrict__ row_num, int *__restrict__ row_val, int stride,
-    int *__restrict__ flags)
+    int *__restrict__ flags, unsigned long long *__restrict__ total_used)
 {
   constexpr bool FILL = MODE != 0;
-  __shared__ int s_max;
+  __shared__ int s_max, s_sum;
   __shared__ int2 s_run[BLOCK / 32][32];
-  if (threadIdx.x == 0) s_max = 0;
+  if (threadIdx.x == 0) s_max = s_sum = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
     if (MODE != 1) {
       row_num[i] = n;
       atomicMax(&s_max, n);
+      if (MODE == 2) atomicAdd(&s_sum, n);
     }
     if (MODE == 2) {
       row_off[i] = (int64_t) i * stride;
@@ -268,7 +269,10 @@ __global__ void __launch_bounds__(BLOCK) neigh_rows_kernel(
   }
   if (MODE != 1) {    // longest row (the stride hint of the next build): one global atomic per block, not per row
     __syncthreads();
-    if (threadIdx.x == 0) atomicMax(&flags[10], s_max);
+    if (threadIdx.x == 0) {
+      atomicMax(&flags[10], s_max);
+      if (MODE == 2) atomicAdd(total_used, (unsigned long long) s_sum);    // entries the strided rows really hold
+    }
   }
 }
 
@@ -399,6 +403,7 @@ int b200md_neigh_setup_bins(b200md_ctx *c, const b200md_box &box, int ntypes, Bi
 
 struct NeighScratch {
   DevBuf<double4> xt, xs;
+  DevBuf<unsigned long long> used;
   DevBuf<int4> runs;
   DevBuf<double> cutsq, cutghostsq;
   DevBuf<int64_t> bin_start;
@@ -416,6 +421,7 @@ void b200md_neigh_forget(b200md_ctx *c)
   NeighScratch &S = *c->neigh_scratch;
   S.xt.release();
   S.xs.release();
+  S.used.release();
   S.runs.release();
   S.cutsq.release();
   S.cutghostsq.release();
@@ -463,6 +469,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
       if (cutneighghostsq_h && cutneighghostsq_h[k] != cutneighsq_h[(size_t) ntypes + 2]) uniform_cut = false;
     }
   CUDA_TRY(c, S.xs.reserve((size_t) nall + 8));
+  CUDA_TRY(c, S.used.reserve(2));
   CUDA_TRY(c, S.runs.reserve(runs.size() + 8));
   CUDA_TRY(c, S.cutsq.reserve(nt2 + 8));
   CUDA_TRY(c, S.cutghostsq.reserve(nt2 + 8));
@@ -501,20 +508,27 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
       bin_gather_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(xt, c->bin_atoms.p, nall, S.xs.p);
     }
   }
-  int64_t total = 0;
+  int64_t total = 0, used = -1;
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 10, 0, sizeof(int), c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 15, 0, sizeof(int), c->stream));
   bool done = false;
   if (nrows && one_pass && c->list_maxnum > 0) {
     // resident loop, second and later builds: one stencil walk into rows of a fixed stride
-    const int stride = ((int) (c->list_maxnum * 1.2) + 24) & ~7;
+    // sticky and generous: rows of a lattice that is still heating up keep growing (fcc Al at 863 K: 98 -> 131 entries),
+    // and a stride that follows the latest maximum re-allocates GB-sized buffers inside somebody's timed region
+    int stride = ((int) (c->list_maxnum * (c->list_stride ? 1.25 : 1.5)) + 32) & ~7;    // first time: a cold lattice
+    if (stride < c->list_stride) stride = c->list_stride;
+    c->list_stride = stride;
+    CUDA_TRY(c, cudaMemsetAsync(S.used.p, 0, sizeof(unsigned long long), c->stream));
     CUDA_TRY(c, c->list_val.reserve((size_t) nrows * stride + 64));
     {
       LaunchScope ls(c, "neigh_fill");
       NEIGH_LAUNCH(2, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
-          c->list_off.p, c->list_num.p, c->list_val.p, stride, c->flags.p);
+          c->list_off.p, c->list_num.p, c->list_val.p, stride, c->flags.p, S.used.p);
     }
     int fl[8];
+    unsigned long long used_h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&used_h, S.used.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p + 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (fl[0]) {
@@ -523,7 +537,8 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     }
     c->list_maxnum = fl[2];
     if (!fl[7]) {
-      total = (int64_t) nrows * stride;    // capacity the rows occupy (derived lists size themselves from it)
+      total = (int64_t) nrows * stride;    // capacity the rows occupy
+      used = (int64_t) used_h;             // entries they hold (derived lists size themselves from it)
       done = true;
     } else {
       CUDA_TRY(c, cudaMemsetAsync(c->flags.p + 15, 0, sizeof(int), c->stream));
@@ -534,7 +549,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     {
       LaunchScope ls(c, "neigh_count");
       NEIGH_LAUNCH(0, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
-          nullptr, c->list_num.p, nullptr, 0, c->flags.p);
+          nullptr, c->list_num.p, nullptr, 0, c->flags.p, nullptr);
     }
     rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->list_off.p, nrows, 1);
     if (rc) return rc;
@@ -552,7 +567,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
     {
       LaunchScope ls(c, "neigh_fill");
       NEIGH_LAUNCH(1, g, xt, S.xs.p, c->bin_of.p, S.bin_start.p, c->bin_atoms.p, S.runs.p, S.cutsq.p, S.cutghostsq.p, nlocal, nrows,
-          c->list_off.p, c->list_num.p, c->list_val.p, 0, c->flags.p);
+          c->list_off.p, c->list_num.p, c->list_val.p, 0, c->flags.p, nullptr);
     }
     CUDA_TRY(c, cudaGetLastError());
   } else if (!nrows) {
@@ -561,6 +576,7 @@ int b200md_neigh_build_device(b200md_ctx *c, const b200md_box &box, int ntypes, 
   c->list_inum = nlocal;
   c->list_gnum = ghost_rows ? nghost : 0;
   c->list_entries = total;
+  c->list_entries_used = used >= 0 ? used : total;
   c->skin = skin;
   c->list_valid = true;
   c->inner_valid = false;

@@ -1565,7 +1565,7 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   int rc = B200MD_OK;
   if (!pairs && (rc = b200md_exclusive_scan_i64(c, c->list_num.p, c->lj_off.p, inum, 8))) return rc;
   // capacity bound without a host round trip: every row padded to a multiple of 8
-  const int64_t cap = c->list_entries + 8 * (int64_t) (pairs ? 2 * P : inum) + 64;
+  const int64_t cap = c->list_entries_used + 8 * (int64_t) (pairs ? 2 * P : inum) + 64;
   CUDA_TRY(c, c->lj_val.reserve((size_t) cap));
   c->lj_capacity = cap;
   CUDA_TRY(c, c->xhold.reserve(4 * (size_t) c->nall + 8));

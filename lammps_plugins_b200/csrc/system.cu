@@ -19,7 +19,9 @@
 
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <cmath>
 #include <condition_variable>
 #include <memory>
@@ -1999,6 +2001,7 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
     box.cutghost[d] = s->cutghost[d];
   }
   box.cutneighmax = s->cutneighmax;
+  if (first) c->list_stride = 0;    // a new system: the sticky stride of the one-pass builds starts over
   if ((rc = b200md_neigh_build_device(c, box, s->d.ntypes, s->cutneighsq.data(), s->cutneighghostsq.data(), s->nlocal,
                                       s->nghost, s->xt.p, s->ghost_rows, s->d.skin, !first && c->one_pass_neigh)))
     return rc;
@@ -2466,10 +2469,12 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
   // B200MD_STEP_TRACE=1: device timestamps at the start of a step, after the reneighbor vote has reached the host, and at
   // the end of the step, for steps 60-67 of a run (diagnostic: what the vote costs, what the halos leave exposed)
   static const bool step_trace_on = getenv("B200MD_STEP_TRACE") != nullptr;
+  static const bool step_trace_slow = step_trace_on && !strcmp(getenv("B200MD_STEP_TRACE"), "slow");    // every step; slow ones printed
   std::vector<cudaEvent_t> tev;
+  std::vector<int> tflag;
   for (int it = 0; it < nsteps; it++) {
     s->step++;
-    const bool tr = step_trace_on && it >= 60 && it < 68;
+    const bool tr = step_trace_on && (step_trace_slow || (it >= 60 && it < 68));
     if (tr) {
       cudaEvent_t e;
       cudaEventCreate(&e);
@@ -2537,6 +2542,7 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
       cudaEventCreate(&e);
       cudaEventRecord(e, c->stream);
       tev.push_back(e);
+      tflag.push_back(flag);
     }
     if (c->force_rebuild) {    // option "force_rebuild": this step takes the reneighboring path (measurement; collective)
       c->force_rebuild = 0;
@@ -2580,11 +2586,22 @@ extern "C" int b200md_system_run(b200md_ctx *c, int nsteps, int thermo_every)
     cudaEventRecord(e, c->stream);
     tev.push_back(e);
     cudaStreamSynchronize(c->stream);
+    std::vector<float> dur;
     for (size_t k = 0; k + 2 < tev.size(); k += 2) {
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+      float b = 0;
       cudaEventElapsedTime(&b, tev[k], tev[k + 2]);
-      fprintf(stderr, "[step trace rank %d] integrate + vote + host %.3f ms | step %.3f ms\n", s->me, a, b);
+      dur.push_back(b);
+    }
+    std::vector<float> sorted = dur;
+    std::sort(sorted.begin(), sorted.end());
+    const float med = sorted.empty() ? 0.f : sorted[sorted.size() / 2];
+    if (step_trace_slow) fprintf(stderr, "[step trace rank %d] %zu steps, median %.3f ms\n", s->me, dur.size(), med);
+    for (size_t k = 0; k + 2 < tev.size(); k += 2) {
+      float a = 0;
+      cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+      if (!step_trace_slow || dur[k / 2] > 1.5f * med)
+        fprintf(stderr, "[step trace rank %d] step %zu (vote %d): integrate + vote + host %.3f ms | step %.3f ms\n", s->me,
+                k / 2, tflag[k / 2], a, dur[k / 2]);
     }
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }

@@ -1339,102 +1339,137 @@ struct TightLimits {
 __global__ void __launch_bounds__(BLOCK) derive_tight_short_kernel(const double4 *__restrict__ xq,
                                                                    const int *__restrict__ short_idx,
                                                                    const int *__restrict__ short_num, int inum,
-                                                                   const TightLimits lim, int *__restrict__ out_idx,
-                                                                   int *__restrict__ out_num)
+                                                                   const __grid_constant__ TightLimits lim,
+                                                                   int *__restrict__ out_idx, int *__restrict__ out_num)
 {
-  // 8 lanes per owned row, ballot compaction inside the lane group
+  // 8 lanes per owned row, ballot compaction inside the lane group.  All candidates of a row (<= 64) are fetched before
+  // the first is tested -- 4 gathers in flight per lane; one at a time the kernel ran at the latency of 3 dependent round
+  // trips per row -- and the trip count is the warp's largest, so the votes run on the full warp.  The limits are a
+  // __grid_constant__: passed by value and indexed at run time they were copied to local memory by every thread
+  // (64 M local-store sectors per launch of the LJ pass, ncu r02).
   const int sub = threadIdx.x & 7;
   const int i = (blockIdx.x * BLOCK + threadIdx.x) >> 3;
-  if (i >= inum) return;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned gshift = lane & ~7u;
-  const unsigned gmask = 0xffu << gshift;
-  const double4 xi = xq[i];
+  const bool live = i < inum;
+  const double4 xi = xq[live ? i : 0];
   const int ti = elem_of(xi);
-  const int n = short_num[i];
-  const int *row = short_idx + (size_t) i * B200MD_SHORT_WIDTH;
-  int *orow = out_idx + (size_t) i * B200MD_SHORT_WIDTH;
+  const int n = (live && ti >= 0) ? short_num[i] : 0;
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  const int *row = short_idx + (size_t) (live ? i : 0) * B200MD_SHORT_WIDTH;
+  int *orow = out_idx + (size_t) (live ? i : 0) * B200MD_SHORT_WIDTH;
   int cnt = 0;
-  for (int e0 = 0; e0 < n; e0 += 8) {
-    const int e = e0 + sub;
-    bool keep = false;
-    int j = 0;
-    if (e < n && ti >= 0) {
-      j = row[e];
-      const double4 xj = ld_sector(xq + j);
-      const int tj = elem_of(xj);
-      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-      keep = tj >= 0 && dx * dx + dy * dy + dz * dz <= lim.shortsq[ti * 2 + tj];
+  constexpr int U = 4;
+  for (int e0 = 0; e0 < nmax; e0 += 8 * U) {
+    int j[U];
+    double4 xj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = e0 + u * 8 + sub;
+      j[u] = (e < n) ? row[e] : -1;
     }
-    const unsigned bits = (__ballot_sync(gmask, keep) >> gshift) & 0xffu;
-    if (keep) orow[cnt + __popc(bits & ((1u << sub) - 1u))] = j;
-    cnt += __popc(bits);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (j[u] >= 0) xj[u] = ld_sector(xq + j[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (e0 + u * 8 >= nmax) break;    // warp-uniform
+      bool keep = false;
+      if (j[u] >= 0) {
+        const int tj = elem_of(xj[u]);
+        const double dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+        keep = tj >= 0 && dx * dx + dy * dy + dz * dz <= lim.shortsq[ti * 2 + (tj & 1)];
+      }
+      const unsigned bits = (__ballot_sync(0xffffffffu, keep) >> gshift) & 0xffu;
+      if (keep) orow[cnt + __popc(bits & ((1u << sub) - 1u))] = j[u];
+      cnt += __popc(bits);
+    }
   }
-  if (sub == 0) out_num[i] = cnt;
+  if (sub == 0 && live) out_num[i] = cnt;
 }
 
-__global__ void __launch_bounds__(BLOCK) derive_tight_lj_kernel(const double4 *__restrict__ xq,
-                                                                const int64_t *__restrict__ ljp_off,
-                                                                const int *__restrict__ ljp_num,
-                                                                const int2 *__restrict__ ljp_ab,
-                                                                const int *__restrict__ lj_val, int P,
-                                                                const TightLimits lim, int *__restrict__ out_val,
-                                                                int *__restrict__ out_num)
+template <int TU, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) derive_tight_lj_kernel(const double4 *__restrict__ xq,
+                                                                      const int64_t *__restrict__ ljp_off,
+                                                                      const int *__restrict__ ljp_num,
+                                                                      const int2 *__restrict__ ljp_ab,
+                                                                      const int *__restrict__ lj_val, int P,
+                                                                      const int *__restrict__ cen_counts,
+                                                                      const __grid_constant__ TightLimits lim,
+                                                                      int *__restrict__ out_val, int *__restrict__ out_num)
 {
-  // one warp per pair row, TU candidates per lane in flight (latency-bound: index -> position -> test)
-  constexpr int TU = 2;
+  // One warp per pair row.  The row is walked as ONE sequence -- the Mo partners from the front of the slot range, then
+  // the S partners from its back -- TU x 32 entries per trip, and the indices of the next trip are fetched before the
+  // positions of this one are waited for: the kernel is bound by the chain index -> position -> vote (ncu r02: 17.7
+  // long-scoreboard stalls per issue, 0.77 ms per 1 M atoms with one segment and one trip at a time).
+  // Only the slots that hold a pair get a warp: ceil(nMo / 2) from slot 0 and ceil(nS / 2) from slot P (a warp per slot
+  // of the 2 P, half of them empty, spent 13 % of the kernel's stall samples waiting to learn that its slot was empty)
   const int lane = threadIdx.x & 31;
-  const int q = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
-  if (q >= 2 * P) return;
+  const int w = (int) (((size_t) blockIdx.x * BLOCK + threadIdx.x) >> 5);
+  const int p0 = (cen_counts[0] + 1) >> 1, p1 = (cen_counts[1] + 1) >> 1;
+  if (w >= p0 + p1) return;
+  const int q = w < p0 ? w : P + (w - p0);
   const int2 ab = ljp_ab[q];
   if (ab.x < 0) {
     if (lane == 0) out_num[2 * q] = out_num[2 * q + 1] = 0;
     return;
   }
+  const int64_t base = ljp_off[q];
+  const int cap = (int) (ljp_off[q + 1] - base);
+  const int nA = ljp_num[2 * q], nB = ljp_num[2 * q + 1];
+  const int ntot = nA + nB;
+  const int *row = lj_val + base;
+  int *orow = out_val + base;
+  // entry e of the sequence sits at row[e] (e < nA) or row[cap - 1 - (e - nA)] (S partners fill the slot range from its back)
+  int jn[TU];
+#pragma unroll
+  for (int u = 0; u < TU; u++) {
+    const int e = 32 * u + lane;
+    jn[u] = (e < ntot) ? row[e < nA ? e : cap - 1 - (e - nA)] : -1;
+  }
   const int ti = q / P;
   const double4 xa = xq[ab.x];
   double4 xb = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
   if (ab.y >= 0) xb = xq[ab.y];
-  const int64_t base = ljp_off[q];
-  const int cap = (int) (ljp_off[q + 1] - base);
-  const int nA = ljp_num[2 * q], nB = ljp_num[2 * q + 1];
-  const int *row = lj_val + base;
-  int *orow = out_val + base;
+  const double limA = lim.ljsq[ti * 2], limB = lim.ljsq[ti * 2 + 1];
   const unsigned lt = (1u << lane) - 1u;
-  for (int seg = 0; seg < 2; seg++) {
-    const int n = seg ? nB : nA;
-    const double limit = lim.ljsq[ti * 2 + seg];
-    int cnt = 0;
-    for (int e0 = 0; e0 < n; e0 += 32 * TU) {
-      int j[TU];
-      double4 xj[TU];
+  int cntA = 0, cntB = 0;
+  for (int e0 = 0; e0 < ntot; e0 += 32 * TU) {
+    int j[TU];
+    double4 xj[TU];
 #pragma unroll
-      for (int u = 0; u < TU; u++) {
-        const int e = e0 + 32 * u + lane;
-        j[u] = -1;
-        if (e < n) j[u] = seg ? row[cap - 1 - e] : row[e];    // S partners fill the slot range from its back
-      }
-#pragma unroll
-      for (int u = 0; u < TU; u++) {
-        xj[u] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
-        if (j[u] >= 0) xj[u] = ld_sector(xq + j[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < TU; u++) {
-        double dx = xa.x - xj[u].x, dy = xa.y - xj[u].y, dz = xa.z - xj[u].z;
-        bool keep = dx * dx + dy * dy + dz * dz <= limit;
-        dx = xb.x - xj[u].x, dy = xb.y - xj[u].y, dz = xb.z - xj[u].z;
-        keep = (j[u] >= 0) && (keep || (dx * dx + dy * dy + dz * dz <= limit));
-        const unsigned bits = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const int pos = cnt + __popc(bits & lt);
-          if (seg) orow[cap - 1 - pos] = j[u];
-          else orow[pos] = j[u];
-        }
-        cnt += __popc(bits);
-      }
+    for (int u = 0; u < TU; u++) {
+      j[u] = jn[u];
+      xj[u] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+      if (j[u] >= 0) xj[u] = ld_sector(xq + j[u]);
     }
-    if (lane == 0) out_num[2 * q + seg] = cnt;
+#pragma unroll
+    for (int u = 0; u < TU; u++) {
+      const int e = e0 + 32 * (TU + u) + lane;
+      jn[u] = (e < ntot) ? row[e < nA ? e : cap - 1 - (e - nA)] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < TU; u++) {
+      if (e0 + 32 * u >= ntot) break;    // warp-uniform
+      const bool isA = e0 + 32 * u + lane < nA;
+      double dx = xa.x - xj[u].x, dy = xa.y - xj[u].y, dz = xa.z - xj[u].z;
+      const double ra = dx * dx + dy * dy + dz * dz;
+      dx = xb.x - xj[u].x, dy = xb.y - xj[u].y, dz = xb.z - xj[u].z;
+      const double rb = dx * dx + dy * dy + dz * dz;
+      const double limit = isA ? limA : limB;
+      const bool keep = (j[u] >= 0) && (ra <= limit || rb <= limit);
+      const unsigned bA = __ballot_sync(0xffffffffu, keep && isA), bB = __ballot_sync(0xffffffffu, keep && !isA);
+      if (keep) {
+        if (isA) orow[cntA + __popc(bA & lt)] = j[u];
+        else orow[cap - 1 - (cntB + __popc(bB & lt))] = j[u];
+      }
+      cntA += __popc(bA);
+      cntB += __popc(bB);
+    }
+  }
+  if (lane == 0) {
+    out_num[2 * q] = cntA;
+    out_num[2 * q + 1] = cntB;
   }
 }
 
@@ -1648,6 +1683,8 @@ int b200md_rebomos_build_inner(b200md_ctx *c)
   return B200MD_OK;
 }
 
+int b200md_ensure_halo_stream(b200md_ctx *c);    // system.cu
+
 // derive (or re-derive) the tight rows from the wide rows at the positions now on the device; GPU-resident loop only
 int b200md_rebomos_derive_tight(b200md_ctx *c)
 {
@@ -1669,16 +1706,29 @@ int b200md_rebomos_derive_tight(b200md_ctx *c)
   CUDA_TRY(c, c->lj_val_t.reserve((size_t) c->lj_capacity));
   CUDA_TRY(c, c->lj_num_t.reserve(4 * (size_t) P + 32));
   CUDA_TRY(c, c->xhold_t.reserve(4 * (size_t) c->nall + 8));
+  // the two passes are independent and neither fills the machine (gather latency): the short rows go to the side stream
+  const bool side = !c->sync_timing && b200md_ensure_halo_stream(c) == B200MD_OK;
+  cudaStream_t s_short = c->stream;
+  if (side) {
+    CUDA_TRY(c, cudaEventRecord(c->ev_ready, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->halo_stream, c->ev_ready, 0));
+    s_short = c->halo_stream;
+  }
   {
-    LaunchScope ls(c, "derive_tight");
-    derive_tight_short_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+    LaunchScope ls(c, "derive_tight_short");
+    derive_tight_short_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, s_short>>>(
         c->xq.p, c->short_idx.p, c->short_num.p, inum, lim, c->short_idx_t.p, c->short_num_t.p);
   }
+  if (side) CUDA_TRY(c, cudaEventRecord(c->ev_fwd, c->halo_stream));
   {
-    LaunchScope ls(c, "derive_tight");
-    derive_tight_lj_kernel<<<nblocks((long long) 2 * P * 32, BLOCK), BLOCK, 0, c->stream>>>(
-        c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, P, lim, c->lj_val_t.p, c->lj_num_t.p);
+    LaunchScope ls(c, "derive_tight_lj");
+    CUDA_TRY(c, cudaMemsetAsync(c->lj_num_t.p, 0, 4 * (size_t) P * sizeof(int), c->stream));    // slots without a pair
+    const int nwarps = inum / 2 + 2;    // pairs of both elements together: ceil(nMo / 2) + ceil(nS / 2) <= inum / 2 + 1
+#define DTL_ARGS c->xq.p, c->lj_off.p, c->lj_num.p, (const int2 *) c->ljp_ab.p, c->lj_val.p, P, c->flags.p + 12, lim, c->lj_val_t.p, c->lj_num_t.p
+    // 4 trips in flight at 64 registers: 0.646 ms per 1 M atoms; 2 trips at 56 registers 0.675, at 40 (spills) 0.683
+    derive_tight_lj_kernel<4, 4><<<nblocks((long long) nwarps * 32, BLOCK), BLOCK, 0, c->stream>>>(DTL_ARGS);
   }
+  if (side) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_fwd, 0));
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaMemcpyAsync(c->xhold_t.p, c->xq.p, (size_t) c->nall * sizeof(double4), cudaMemcpyDeviceToDevice,
                               c->stream));

@@ -2016,7 +2016,7 @@ static int reneighbor(b200md_ctx *c, SystemState *s, bool first)
 }
 
 // the halo stream (highest priority: its small kernels take the SM slots that compute CTAs free) and its events
-static int ensure_halo_stream(b200md_ctx *c)
+int b200md_ensure_halo_stream(b200md_ctx *c)
 {
   if (c->halo_stream) return B200MD_OK;
   int lo = 0, hi = 0;
@@ -2046,7 +2046,7 @@ static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
     // angular kernel writes ghost forces)
     if (!eflag && !vflag && s->nranks > 1 && c->overlap_halo && !c->deterministic && !c->sync_timing && c->aeam_cluster == 2 &&
         !c->ap.asym_dr) {
-      if ((rc = ensure_halo_stream(c))) return rc;
+      if ((rc = b200md_ensure_halo_stream(c))) return rc;
       cudaStream_t main = c->stream, halo = c->halo_stream;
       if ((rc = b200md_aeam_forces(c, 0, 0, 1))) return rc;
       CUDA_TRY(c, cudaEventRecord(c->ev_reb, main));
@@ -2080,7 +2080,7 @@ static int compute_forces(b200md_ctx *c, SystemState *s, int eflag, int vflag)
 // derive: the tight rows are re-derived first (that needs the ghosts, so only the reverse halo is hidden).
 static int forces_overlapped(b200md_ctx *c, SystemState *s, bool derive)
 {
-  int rc = ensure_halo_stream(c);
+  int rc = b200md_ensure_halo_stream(c);
   if (rc) return rc;
   cudaStream_t main = c->stream, halo = c->halo_stream;
   // B200MD_OVERLAP_TRACE=1: device timestamps of one step's phases on both streams (diagnostic)

@@ -168,6 +168,43 @@ def test_three_level_list_matches_two_level(ctx, oracle_built):
     lmp.close()
 
 
+@pytest.mark.parametrize("style", ["rebomos", "aeam"])
+def test_run_loop_options_do_not_change_the_trajectory(ctx, oracle_built, style):
+    """round-2 run-loop changes -- the second half kick riding in the next step's integrate launch ("fuse_integrate"),
+    the reneighbor vote through a mapped host word instead of copy + synchronise ("peer_vote"), master rebuilds in one
+    stencil walk over clipped, bin-sorted candidates ("one_pass_neigh") -- reorder no arithmetic: in deterministic mode
+    (no atomics anywhere) a hot run with rebuilds is BITWISE the same with each of them off."""
+    if style == "rebomos":
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), extra=["velocity all create 1500.0 4928459"])
+        ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
+    else:
+        lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.02,
+                                 extra=["velocity all create 1500.0 1082337"])
+        ctx.aeam_init(aeam_tables())
+    ctx.set_option("deterministic", 1)
+    runs = {}
+    try:
+        for label, opts in (("default", {}), ("plain", {"fuse_integrate": 0, "peer_vote": 0, "one_pass_neigh": 0})):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            start_system(ctx, lmp, style)
+            ctx.system_run(360 if style == "rebomos" else 90, 15)
+            runs[label] = (ctx.system_thermo_rows(), ctx.system_sizes(), ctx.system_download())
+    finally:
+        for k in ("fuse_integrate", "peer_vote", "one_pass_neigh"):
+            ctx.set_option(k, 1)
+        ctx.set_option("deterministic", 0)
+    (ra, sa, da), (rb, sb, db) = runs["default"], runs["plain"]
+    print(style, "builds", sa["nbuild"], sb["nbuild"])
+    assert sa["nbuild"] == sb["nbuild"] and sa["nbuild"] >= 1
+    for q, g in zip(ra, rb):
+        assert q["pe"] == g["pe"] and q["ke"] == g["ke"] and q["press"] == g["press"], (q, g)
+    for key in ("x", "v", "f"):
+        assert np.array_equal(da[key][:da["nlocal"]], db[key][:db["nlocal"]]), key
+    assert np.array_equal(da["tag"][:da["nlocal"]], db["tag"][:db["nlocal"]])
+    lmp.close()
+
+
 @pytest.mark.parametrize("tstop", [863.0, 500.0], ids=["constant-T", "ramp"])
 def test_device_nvt_tracks_engine(ctx, oracle_built, tstop):
     """`fix nvt` in the GPU-resident loop (USER-AEAM/sample.in:23, Nose-Hoover chain restated from FixNH) against the

@@ -334,7 +334,11 @@ def measure(kind, args, grp, sampler, scaling="weak", legs=("e2e", "cpu", "long"
                "frames": part["frames"], "pipelined_calls": part["pipelined_calls"], "pipelined_redos": part["pipelined_redos"],
                "neighbor_handover_ms": grp.reduce_scalar(part["handover_ms"], "max"),
                "h2d_ms_alone": grp.reduce_scalar(part["h2d_ms"], "max"), "d2h_ms_alone": grp.reduce_scalar(part["d2h_ms"], "max"),
-               "checksum_f": part["checksum_f"]}
+               "checksum_f": part["checksum_f"],
+               "ms_per_call_median": grp.reduce_scalar(part["ms_per_call_median"], "max"),
+               "ms_per_call_min": grp.reduce_scalar(part["ms_per_call_min"], "max"),
+               "ms_per_call_max": grp.reduce_scalar(part["ms_per_call_max"], "max"),
+               "tight_row_derives_total": part["tight_row_derives"]}
         if between or long_rec:
             every = between or long_rec["steps"]
             e2e["value_with_handover_amortised"] = atoms_steps / (t_max + part["steps"] * 1e-3 * e2e["neighbor_handover_ms"] / every)
@@ -549,11 +553,16 @@ def run_e2e(ctx_sys, kind, w, args, device=0, rank=0, world=1):
     h0, d0 = ctx.counter("h2d_bytes"), ctx.counter("d2h_bytes")
     p0, r0 = ctx.counter("pipelined_calls"), ctx.counter("pipelined_redos")
     n = max(5, min(args.steps, args.e2e_steps))
+    per_call = []
     t0 = time.perf_counter()
     for k in range(n):
+        ta = time.perf_counter()
         one(frames[order[(k + 3) % len(order)]])
+        per_call.append((time.perf_counter() - ta) * 1e3)
     dt = time.perf_counter() - t0
     out = {"value": nl * n / dt, "unit": "atom-steps/s", "steps": n, "ms_per_step": dt / n * 1e3, "seconds": dt, "nlocal": nl,
+           "ms_per_call_median": float(np.median(per_call)), "ms_per_call_min": float(np.min(per_call)),
+           "ms_per_call_max": float(np.max(per_call)), "tight_row_derives": ctx.counter("tight_refreshes"),
            "h2d_bytes_per_step": (ctx.counter("h2d_bytes") - h0) // n, "d2h_bytes_per_step": (ctx.counter("d2h_bytes") - d0) // n,
            "path": "b200md_%s_compute via ctypes, pinned host x/f, atoms moving along %d frames of the resident trajectory, "
                    "device-built neighbor list reused" % (kind, len(frames)),

@@ -229,7 +229,8 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads" (master lists received: handed over or built on the device), "compute_calls", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",
- * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos";
+ * "lj_entries", "short_entries", "num_sms", "p2p_exchanges", "pipelined_calls", "pipelined_redos", "upload_stragglers"
+ * (atoms whose positions travel ahead of the pieces of the pipelined upload);
  * row statistics summed on the device when asked (measurement): "master_entries", "lj_entries_tight",
  * "short_entries_tight", "short_entries_owned", "aeam_entries" (-1 while those rows do not exist) */
 long long b200md_get_counter(b200md_ctx *ctx, const char *name);

@@ -159,6 +159,13 @@ struct b200md_ctx {
   int h2d_chunks = 6, h2d_K = 0;
   bool h2d_ready = false;
   int h2d_need[B200MD_MAX_D2H_CHUNKS + 1] = {}, h2d_t[B200MD_MAX_D2H_CHUNKS + 2] = {};
+  // stragglers of the upload pipeline: atoms named by the short rows of a range from more than one piece away (wrapped
+  // through a periodic face since the last sort); their positions travel ahead of the pieces
+  int n_strag = 0;
+  DevBuf<int> strag_flag, strag_list;
+  DevBuf<double> strag_dev;
+  PinBuf<double> strag_pin;
+  std::vector<int> strag_host;
   cudaStream_t copy_stream = nullptr;    // plugin mode: D2H of finished force ranges runs beside the remaining kernels
   cudaEvent_t copy_ev[B200MD_MAX_D2H_CHUNKS + 2] = {};      // "range finished on the compute stream"
   cudaEvent_t copy_done[B200MD_MAX_D2H_CHUNKS + 2] = {};    // "range has arrived on the host"

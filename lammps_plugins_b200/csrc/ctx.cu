@@ -101,6 +101,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->lj_off.release(); c->lj_num.release(); c->lj_val.release(); c->ljp_ab.release();
   c->short_idx_t.release(); c->short_num_t.release(); c->lj_val_t.release(); c->lj_num_t.release(); c->xhold_t.release();
   c->ljp_tmp.release(); c->ljp_scan.release();
+  c->strag_flag.release(); c->strag_list.release(); c->strag_dev.release(); c->strag_pin.release();
   if (c->ev_tight) cudaEventDestroy(c->ev_tight);
   if (c->halo_stream) cudaStreamDestroy(c->halo_stream);
   for (cudaEvent_t e : {c->ev_ready, c->ev_fwd, c->ev_reb, c->ev_rev})
@@ -223,6 +224,7 @@ extern "C" long long b200md_get_counter(b200md_ctx *c, const char *name)
     return (c->inner_valid && c->aeam_ready)
                ? (c->aeam_cluster == 1 ? device_sum(c, c->ec_num.p, (c->list_inum + 3) / 4) : device_sum(c, c->ea_num.p, c->list_inum))
                : -1;
+  if (n == "upload_stragglers") return c->n_strag;
   if (n == "master_entries") return c->list_valid ? (long long) c->list_entries_used : -1;
   if (n == "kernel_launches") return c->n_launch;
   if (n == "list_uploads") return c->n_list_upload;

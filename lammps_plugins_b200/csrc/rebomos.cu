@@ -1310,21 +1310,49 @@ struct ChunkBounds {
   int t[B200MD_MAX_D2H_CHUNKS + 1];
   int K;
 };
+// dep[k] = largest atom index the short rows of range k name.  With a straggler list (strag_flag != NULL) a range is
+// allowed its own piece and the next one; atoms named from farther away -- the neighbors of an atom that was wrapped
+// through a periodic face since the last Atom::sort keeps its index and now sits at the other end of the box -- go to the
+// list instead (each once), and their positions travel ahead of the pieces.  Without it ONE such atom made range 0 wait
+// for the last piece: the whole upload in front of the first kernel, 1.77 -> 2.12 ms per call after 1000 steps.
 __global__ void __launch_bounds__(BLOCK) dep_range_kernel(const int *__restrict__ short_idx,
                                                           const int *__restrict__ short_num, int inum,
-                                                          const ChunkBounds cb, int *__restrict__ dep)
+                                                          const __grid_constant__ ChunkBounds cb, int *__restrict__ dep,
+                                                          int *__restrict__ strag_flag, int *__restrict__ strag_list,
+                                                          int *__restrict__ strag_count, int strag_cap)
 {
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= inum) return;
+  int k = 0;
+  while (k + 1 < cb.K && i >= cb.t[k + 1]) k++;
+  const int far = strag_flag ? cb.t[min(k + 2, cb.K)] : inum;    // first index beyond the pieces range k may wait for
   int m = i;
   const int n = short_num[i];
   for (int e = 0; e < n; e++) {
     const int j = short_idx[(size_t) i * B200MD_SHORT_WIDTH + e];
-    if (j < inum && j > m) m = j;
+    if (j >= inum) continue;    // ghosts travel first
+    if (j >= far) {
+      if (atomicExch(&strag_flag[j], 1) == 0) {
+        const int pos = atomicAdd(strag_count, 1);
+        if (pos < strag_cap) strag_list[pos] = j;
+      }
+    } else if (j > m)
+      m = j;
   }
-  int k = 0;
-  while (k + 1 < cb.K && i >= cb.t[k + 1]) k++;
   atomicMax(&dep[k], m);
+}
+// stragglers: positions gathered on the host into a small pinned buffer, scattered into xq here
+__global__ void __launch_bounds__(BLOCK) strag_scatter_kernel(const double *__restrict__ buf, const int *__restrict__ list,
+                                                              int n, const int *__restrict__ type,
+                                                              const int *__restrict__ map, int ntypes,
+                                                              double4 *__restrict__ xq)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= n) return;
+  const int j = list[q];
+  const int t = type[j];
+  const int e = (t >= 1 && t <= ntypes) ? map[t] : -1;
+  xq[j] = make_double4(buf[3 * (size_t) q], buf[3 * (size_t) q + 1], buf[3 * (size_t) q + 2], (double) e);
 }
 
 // ================================================================== tight rows (third list level)
@@ -1749,14 +1777,37 @@ static int rebomos_prepare_pipeline(b200md_ctx *c)
   cb.K = K;
   for (int k = 0; k <= K; k++) cb.t[k] = (int) ((long long) inum * k / K);
   int *dep = c->flags.p + 16;    // flags holds 16 + B200MD_MAX_D2H_CHUNKS ints
-  CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
-  {
-    LaunchScope ls(c, "build_inner");
-    dep_range_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, inum, cb, dep);
-  }
   int *pin = (int *) (c->pin_scal.p + 48);
-  CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  int *pin_cnt = (int *) (c->pin_scal.p + 60);
+  const int cap = inum / 32 + 1024;    // more stragglers than this: the atom order is not spatial, nothing to gain
+  c->n_strag = 0;
+  CUDA_TRY(c, c->strag_flag.reserve((size_t) inum + 8));
+  CUDA_TRY(c, c->strag_list.reserve((size_t) cap + 8));
+  for (int pass = 0; pass < 2; pass++) {    // pass 0 with the straggler list, pass 1 (only if it overflowed) without
+    CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->strag_flag.p, 0, ((size_t) inum + 1) * sizeof(int), c->stream));
+    int *cnt = c->strag_flag.p + inum;
+    {
+      LaunchScope ls(c, "build_inner");
+      dep_range_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->short_idx.p, c->short_num.p, inum, cb, dep,
+                                                                     pass == 0 ? c->strag_flag.p : nullptr, c->strag_list.p,
+                                                                     cnt, cap);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(pin_cnt, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (pass == 0 && *pin_cnt <= cap) {
+      c->n_strag = *pin_cnt;
+      break;
+    }
+  }
+  if (c->n_strag) {
+    c->strag_host.resize((size_t) c->n_strag);
+    CUDA_TRY(c, cudaMemcpyAsync(c->strag_host.data(), c->strag_list.p, c->n_strag * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, c->strag_pin.reserve(3 * (size_t) c->n_strag + 8));
+    CUDA_TRY(c, c->strag_dev.reserve(3 * (size_t) c->n_strag + 8));
+  }
   for (int k = 0; k < K; k++) {
     int p = k;    // a range always needs its own piece
     while (p + 1 < K && pin[k] >= cb.t[p + 1]) p++;
@@ -2025,6 +2076,21 @@ static int rebomos_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, cons
                                                                     hi, c->xq.p, c->flags.p);
     return B200MD_OK;
   };
+  if (c->n_strag) {    // stragglers first (see dep_range_kernel): a few KB gathered on the host
+    const int ns = c->n_strag;
+    double *sp = c->strag_pin.p;
+    for (int q = 0; q < ns; q++) {
+      const size_t j = (size_t) c->strag_host[q];
+      sp[3 * (size_t) q] = x[3 * j];
+      sp[3 * (size_t) q + 1] = x[3 * j + 1];
+      sp[3 * (size_t) q + 2] = x[3 * j + 2];
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->strag_dev.p, sp, 3 * (size_t) ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long) (3 * (size_t) ns * sizeof(double));
+    LaunchScope ls(c, "pack");
+    strag_scatter_kernel<<<nblocks(ns, BLOCK), BLOCK, 0, c->stream>>>(c->strag_dev.p, c->strag_list.p, ns, c->type.p,
+                                                                     c->map_d.p, c->ntypes, c->xq.p);
+  }
   rc = piece(nlocal, nall);
   for (int p = 0; p < K && !rc; p++) {
     rc = piece(c->h2d_t[p], c->h2d_t[p + 1]);

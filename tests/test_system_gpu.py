@@ -175,11 +175,12 @@ def test_run_loop_options_do_not_change_the_trajectory(ctx, oracle_built, style)
     stencil walk over clipped, bin-sorted candidates ("one_pass_neigh") -- reorder no arithmetic: in deterministic mode
     (no atomics anywhere) a hot run with rebuilds is BITWISE the same with each of them off."""
     if style == "rebomos":
-        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1), extra=["velocity all create 1500.0 4928459"])
+        lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1),
+                                    extra=["velocity all create 2000.0 4928459", "neighbor 0.5 bin"])
         ctx.rebomos_init(S.rebomos_params_struct(), [0, 1])
     else:
         lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.02,
-                                 extra=["velocity all create 1500.0 1082337"])
+                                 extra=["velocity all create 2000.0 1082337", "neighbor 0.4 bin"])
         ctx.aeam_init(aeam_tables())
     ctx.set_option("deterministic", 1)
     runs = {}
@@ -188,7 +189,7 @@ def test_run_loop_options_do_not_change_the_trajectory(ctx, oracle_built, style)
             for k, v in opts.items():
                 ctx.set_option(k, v)
             start_system(ctx, lmp, style)
-            ctx.system_run(360 if style == "rebomos" else 90, 15)
+            ctx.system_run(90, 15)
             runs[label] = (ctx.system_thermo_rows(), ctx.system_sizes(), ctx.system_download())
     finally:
         for k in ("fuse_integrate", "peer_vote", "one_pass_neigh"):

@@ -210,6 +210,8 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *  "f_overwrite"     0/1: f is written, not accumulated -- valid when the caller guarantees f == 0 on entry, as right
  *                    after LAMMPS' force_clear()
  *  "h2d_chunks"      plugin mode: pieces of the pipelined position upload (default 6, 1 = one copy, no overlap)
+ *  "h2d_ramp"        plugin mode: piece k of the upload holds (ramp + k) / sum_j (ramp + j) of the atoms (default 4: the
+ *                    first kernels start sooner, the later launches are longer); 0 = equal pieces
  *  "d2h_chunks"      plugin mode: atom ranges of the pipelined force download (default 4, 1 = one copy)
  *  "d2h_min_atoms"   plugin mode: below this many owned atoms both pipelines are off (default 65536)
  *  "p2p_halo"        0/1 (default 1): multi-GPU halos go through peer-memory windows mapped with CUDA IPC -- the

@@ -156,7 +156,7 @@ struct b200md_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t up_stream = nullptr;      // plugin mode: position upload in pieces beside the bond-order launches
   cudaEvent_t up_ev[B200MD_MAX_D2H_CHUNKS + 2] = {};
-  int h2d_chunks = 6, h2d_K = 0;
+  int h2d_chunks = 6, h2d_K = 0, h2d_ramp = 4;
   bool h2d_ready = false;
   int h2d_need[B200MD_MAX_D2H_CHUNKS + 1] = {}, h2d_t[B200MD_MAX_D2H_CHUNKS + 2] = {};
   // stragglers of the upload pipeline: atoms named by the short rows of a range from more than one piece away (wrapped

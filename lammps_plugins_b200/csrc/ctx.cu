@@ -180,6 +180,9 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "h2d_chunks") {
     c->h2d_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
     c->inner_valid = false;
+  } else if (n == "h2d_ramp") {
+    c->h2d_ramp = (int) value;
+    c->inner_valid = false;
   } else if (n == "d2h_min_atoms") c->d2h_min_atoms = (int) value;
   else if (n == "d2h_chunks") c->d2h_chunks = (int) (value < 1 ? 1 : (value > B200MD_MAX_D2H_CHUNKS ? B200MD_MAX_D2H_CHUNKS : value));
   else {

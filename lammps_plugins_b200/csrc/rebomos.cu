@@ -1775,7 +1775,19 @@ static int rebomos_prepare_pipeline(b200md_ctx *c)
   const int K = c->h2d_chunks;
   ChunkBounds cb;
   cb.K = K;
-  for (int k = 0; k <= K; k++) cb.t[k] = (int) ((long long) inum * k / K);
+  // option "h2d_ramp": piece k is (ramp + k) / sum(ramp + j) of the atoms -- small pieces first (the first kernels start
+  // sooner), big ones last (fewer, longer launches once the upload is ahead of the kernels); 0 = equal pieces
+  {
+    const double r = c->h2d_ramp > 0 ? (double) c->h2d_ramp : 0.0;
+    double tot = 0.0, acc = 0.0;
+    for (int k = 0; k < K; k++) tot += r > 0.0 ? r + k : 1.0;
+    cb.t[0] = 0;
+    for (int k = 0; k < K; k++) {
+      acc += r > 0.0 ? r + k : 1.0;
+      cb.t[k + 1] = (int) ((double) inum * (acc / tot));
+    }
+    cb.t[K] = inum;
+  }
   int *dep = c->flags.p + 16;    // flags holds 16 + B200MD_MAX_D2H_CHUNKS ints
   int *pin = (int *) (c->pin_scal.p + 48);
   int *pin_cnt = (int *) (c->pin_scal.p + 60);

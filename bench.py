@@ -530,7 +530,10 @@ def run_e2e(ctx_sys, kind, w, args, device=0, rank=0, world=1):
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    rho_all, fp_all = np.ones(nall), np.zeros(nall)
+    # two-phase form: the host application's own rho / fp arrays (page-locked, as with B200MD_PIN_HOST=1)
+    rho_all, fp_all = ctx.pinned_array((nall,)), ctx.pinned_array((nall,))
+    rho_all[:] = 1.0
+    fp_all[:] = 0.0
 
     def one(x):
         if kind == "rebomos":
@@ -540,8 +543,7 @@ def run_e2e(ctx_sys, kind, w, args, device=0, rank=0, world=1):
         else:
             # two-phase form (PairAEAM::compute with the host's halo in between); the ghost fp values a host halo
             # would deliver are held at placeholders here -- same work, same transfers
-            rho, fp = ctx.aeam_density_phase(nl, ng, x, typ)
-            fp_all[:nl] = fp[:nl]
+            ctx.aeam_density_phase(nl, ng, x, typ, rho=rho_all, fp=fp_all)
             ctx.aeam_force_phase(rho_all, fp_all, 0, 0, f=f)
 
     order = list(range(len(frames))) + list(range(len(frames) - 2, 0, -1))      # forth and back along the trajectory

@@ -380,11 +380,15 @@ class Context:
                                                        _dp(f), ctypes.byref(eng), _dp(vir), _dp(ea), _dp(va)))
         return f, eng.value, vir, ea, va
 
-    def aeam_density_phase(self, nlocal, nghost, x, type_):
+    def aeam_density_phase(self, nlocal, nghost, x, type_, rho=None, fp=None):
+        """rho, fp: optional caller-owned output arrays of nlocal + nghost doubles (e.g. pinned_array), as a host
+        application hands its own atom->rho / atom->fp"""
         x = np.ascontiguousarray(x, dtype=np.float64)
         type_ = np.ascontiguousarray(type_, dtype=np.int32)
-        rho = np.zeros(nlocal + nghost)
-        fp = np.zeros(nlocal + nghost)
+        if rho is None:
+            rho = np.zeros(nlocal + nghost)
+        if fp is None:
+            fp = np.zeros(nlocal + nghost)
         self._check(self.L.b200md_aeam_density_phase(self.h, nlocal, nghost, _dp(x), _ip(type_), _dp(rho), _dp(fp)))
         return rho, fp
 

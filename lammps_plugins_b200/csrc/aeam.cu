@@ -1126,17 +1126,20 @@ __global__ void __launch_bounds__(BLOCK) aeam_force_kernel(
 // atom (ncu r02).  The kernel is latency-sensitive (every trip is row indices -> positions -> spline rows), so the
 // next trip's indices are fetched a trip ahead, the phi rows of two candidates are in flight together, and bond length
 // and reciprocal come from one rsqrt; 3 CTAs per SM.
-template <bool EV, bool ATOM, int U, int MINB>
+template <bool EV, bool ATOM, int U, int MINB, bool RANGED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_df_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double *__restrict__ ea_df,
-    const double4 *__restrict__ rhor, const double4 *__restrict__ z2r, int inum, double *__restrict__ f,
+    const double4 *__restrict__ rhor, const double4 *__restrict__ z2r, int first, int inum, double *__restrict__ f,
     double *__restrict__ scal, double *__restrict__ pa_e, double *__restrict__ pa_v)
 {
+  // centers [first, inum): all owned atoms, or -- plugin mode, RANGED -- one range of them (the forces of a range are
+  // complete when its launch is, and travel to the host behind it while the next range computes).  An instance of its
+  // own: the one more live value costs the resident loop's instance 4 bytes of spill and 1 % (hardware fact 7).
   __shared__ PairPar sp[16];
   load_pair_par(par, sp);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
-  const int i = tid >> 3, sub = tid & 7;
+  const int i = (RANGED ? first : 0) + (tid >> 3), sub = tid & 7;
   double fx = 0.0, fy = 0.0, fz = 0.0;
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
   double av[6] = {0, 0, 0, 0, 0, 0};
@@ -1652,14 +1655,19 @@ int b200md_aeam_forces(b200md_ctx *c, int eflag, int vflag, int part)
       }
   } else {
     LaunchScope ls(c, (atom || ev) ? "aeam_force_ev" : "aeam_force");    // thermo steps: the energy/virial instance
-    const int nb = nblocks((long long) inum * 8, BLOCK);
+    // the default row form takes a range of centers (plugin mode: force download range by range)
+    const bool ranged = mode == 2 && c->aeam_range_hi > c->aeam_range_lo;
+    const int r_lo = ranged ? c->aeam_range_lo : 0, r_hi = ranged ? c->aeam_range_hi : inum;
+    const int nb = nblocks((long long) (mode == 2 ? r_hi - r_lo : inum) * 8, BLOCK);
 #define AF_ARGS c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, ptab, inum, c->f.p, b200md_scal_arg(c), c->pa_e, c->pa_v
 #define AFD_ARGS \
-  c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, inum, c->f.p, \
-      b200md_scal_arg(c), c->pa_e, c->pa_v
+  c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, c->ec_df.p, rhor, (const double4 *) c->spl_z2r.p, r_lo, r_hi, \
+      c->f.p, b200md_scal_arg(c), c->pa_e, c->pa_v
     if (mode == 2) {
       if (atom) aeam_force_df_kernel<true, true, 2, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
+      else if (ev && ranged) aeam_force_df_kernel<true, false, 4, 2, true><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
       else if (ev) aeam_force_df_kernel<true, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
+      else if (ranged) aeam_force_df_kernel<false, false, 2, 3, true><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS);
       else
         switch ((c->aeam_variant / 10) % 10) {
           case 1: aeam_force_df_kernel<false, false, 4, 2><<<nb, BLOCK, 0, c->stream>>>(AFD_ARGS); break;
@@ -1782,6 +1790,29 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
     int maxtag = 0;
     for (int i = 0; i < nlocal; i++) maxtag = tag[i] > maxtag ? tag[i] : maxtag;
     rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag);
+  }
+  // force download pipelined with the pair kernel (force-only calls, default row form): the angular kernel -- the only one
+  // that writes ghost forces and forces of other centers -- runs first, the ghost forces leave, then the pair kernel runs
+  // over d2h_chunks ranges of centers and every range's forces leave behind its launch
+  const int KD = c->d2h_chunks;
+  if (!rc && KD > 1 && nlocal >= c->d2h_min_atoms && !eatom && !vatom && !c->deterministic && aeam_row_mode(c) == 2) {
+    const size_t n3 = 3 * (size_t) c->nall;
+    if (!(rc = b200md_aeam_forces(c, eflag, vflag, 1)) && !(rc = b200md_d2h_begin(c)) &&
+        !(rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, n3))) {
+      for (int k = 0; k < KD && !rc; k++) {
+        c->aeam_range_lo = (int) ((long long) nlocal * k / KD);
+        c->aeam_range_hi = (int) ((long long) nlocal * (k + 1) / KD);
+        if (c->aeam_range_hi <= c->aeam_range_lo) continue;
+        if (!(rc = b200md_aeam_forces(c, eflag, vflag, 2)))
+          rc = b200md_d2h_range(c, k + 1, f, 3 * (size_t) c->aeam_range_lo, 3 * (size_t) c->aeam_range_hi);
+      }
+    }
+    c->aeam_range_lo = c->aeam_range_hi = 0;
+    if (rc) return rc;
+    int fl[16];
+    if ((rc = b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+    c->n_pipelined++;
+    return aeam_check_flags(c, fl);
   }
   if (!rc) rc = b200md_aeam_forces(c, eflag, vflag, 0);
   if (rc) {

@@ -292,6 +292,7 @@ struct b200md_ctx {
 
   // ---- AEAM
   bool aeam_ready = false;
+  int aeam_range_lo = 0, aeam_range_hi = 0;    // plugin mode: the range of centers the next pair-kernel launch takes
   AeamDev ap;
   DevBuf<double> spl_frho, spl_rhor, spl_z2r;    // {c3,c4,c5,c6} per row
   DevBuf<double> spl_pair;                       // fused rows {rhor c3..c6 | z2r c3..c6} per ordered type pair

@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(BLOCK) aeam_build_inner_kernel(
   if (lane == 0) {
     ea_num[i] = no;
     atomicAdd(&flags[5], no);
-    if (ti >= par.nnonangular) ang_list[atomicAdd(&flags[6], 1)] = i;
   }
 }
 
@@ -503,7 +502,6 @@ __global__ void __launch_bounds__(CL_BLOCK) aeam_build_cluster_kernel(
       }
     }
     __syncwarp();
-    if (lane == 0 && ti >= par.nnonangular) ang_list[atomicAdd(&flags[6], 1)] = i;
   }
   if (sort_rows && !full && no > 1) {
     // bitonic sort of the row by atom index in the (now free) hash table: adjacent lanes of the compute kernels then
@@ -834,7 +832,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) aeam_force_cl_kernel(
 
 // ================================================================== A2 / B2: angular atoms (warp per atom)
 struct AngStage {
-  double dx[ANG_CAP], dy[ANG_CAP], dz[ANG_CAP], r[ANG_CAP], f[ANG_CAP], df[ANG_CAP];
+  double dx[ANG_CAP], dy[ANG_CAP], dz[ANG_CAP], ri[ANG_CAP], f[ANG_CAP], df[ANG_CAP];    // ri = 1 / r
   int j[ANG_CAP];
   unsigned char inD[ANG_CAP];    // passes the density-pass cutoff (cut - CutDec)
 };
@@ -879,7 +877,7 @@ __device__ __forceinline__ int ang_stage(const AeamDev &par, const double4 *__re
     if (keep) {
       const int pos = ns + __popc(mk & lt);
       if (pos < ANG_CAP) {
-        S.dx[pos] = dx; S.dy[pos] = dy; S.dz[pos] = dz; S.r[pos] = r1; S.f[pos] = fv; S.df[pos] = dfv;
+        S.dx[pos] = dx; S.dy[pos] = dy; S.dz[pos] = dz; S.ri[pos] = 1.0 / r1; S.f[pos] = fv; S.df[pos] = dfv;
         S.j[pos] = j;
         S.inD[pos] = inD ? 1 : 0;
       } else
@@ -909,13 +907,13 @@ __global__ void __launch_bounds__(128) aeam_density_ang_kernel(
                              flags, i);
     double acc = 0.0;
     for (int p = 0; p < ns; p++) {
-      const double r1 = S.r[p], fij = S.f[p];
+      const double ri1 = S.ri[p], fij = S.f[p];
       const double rsq1 = S.dx[p] * S.dx[p] + S.dy[p] * S.dy[p] + S.dz[p] * S.dz[p];
       for (int q = p + 1 + lane; q < ns; q += 32) {
         const double ex = S.dx[q] - S.dx[p], ey = S.dy[q] - S.dy[p], ez = S.dz[q] - S.dz[p];
         const double rsq3 = ex * ex + ey * ey + ez * ez;
         const double rsq2 = S.dx[q] * S.dx[q] + S.dy[q] * S.dy[q] + S.dz[q] * S.dz[q];
-        const double cs = (rsq1 + rsq2 - rsq3) / (2 * r1 * S.r[q]);
+        const double cs = 0.5 * (rsq1 + rsq2 - rsq3) * (ri1 * S.ri[q]);
         const double delcs = cs + (1.0 / 3.0);
         acc += 2 * fij * S.f[q] * (delcs * delcs);
       }
@@ -1339,31 +1337,35 @@ __global__ void __launch_bounds__(128) aeam_force_ang_kernel(
     for (int q = lane; q < ns; q += 32) fstage[wid][0][q] = fstage[wid][1][q] = fstage[wid][2][q] = 0.0;
     __syncwarp();
     for (int p = 0; p < ns; p++) {
-      const double r1 = S.r[p], fij = S.f[p], dfij = S.df[p];
+      // every 1/r comes from the stage (one division per staged neighbor) or, for r_jk, from one rsqrt: the triplet loop
+      // had 8 divisions and a sqrt per (j, k) -- most of its FP64 instructions
+      const double ri1 = S.ri[p], fij = S.f[p], dfij = S.df[p];
       const double d1x = S.dx[p], d1y = S.dy[p], d1z = S.dz[p];
       const double rsq1 = d1x * d1x + d1y * d1y + d1z * d1z;
       double fjx = 0.0, fjy = 0.0, fjz = 0.0;
       for (int q = p + 1 + lane; q < ns; q += 32) {
         if (!S.inD[q]) continue;
-        const double r2 = S.r[q], fik = S.f[q], dfik = S.df[q];
+        const double ri2 = S.ri[q], fik = S.f[q], dfik = S.df[q];
         const double d2x = S.dx[q], d2y = S.dy[q], d2z = S.dz[q];
         const double d3x = d2x - d1x, d3y = d2y - d1y, d3z = d2z - d1z;
         const double rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
         const double rsq3 = d3x * d3x + d3y * d3y + d3z * d3z;
-        const double r3 = sqrt(rsq3);
-        const double cs = (rsq1 + rsq2 - rsq3) / (2 * r1 * r2);
-        const double dcosij = 1 / r2 - cs / r1;
-        const double dcosik = 1 / r1 - cs / r2;
-        const double dcosjk = -r3 / (r1 * r2);
+        const double ri3 = rsqrt_nr(rsq3);
+        const double r3 = rsq3 * ri3;
+        const double i12 = ri1 * ri2;
+        const double cs = 0.5 * (rsq1 + rsq2 - rsq3) * i12;
+        const double dcosij = ri2 - cs * ri1;
+        const double dcosik = ri1 - cs * ri2;
+        const double dcosjk = -r3 * i12;
         const double delcs = cs + (1.0 / 3.0);
         const double ftet = delcs * delcs;
         const double delcs2 = 2 * delcs;
         const double DFij = ci * (fik * dfij * ftet + fij * fik * delcs2 * dcosij);
         const double DFik = ci * (fij * dfik * ftet + fij * fik * delcs2 * dcosik);
         const double DFjk = ci * fij * fik * delcs2 * dcosjk;
-        const double FFij = -G * DFij / r1;
-        const double FFik = -G * DFik / r2;
-        const double FFjk = -G * DFjk / r3;
+        const double FFij = -G * DFij * ri1;
+        const double FFik = -G * DFik * ri2;
+        const double FFjk = -G * DFjk * ri3;
         const double fj0 = d1x * FFij - d3x * FFjk, fj1 = d1y * FFij - d3y * FFjk, fj2 = d1z * FFij - d3z * FFjk;
         const double fk0 = d2x * FFik + d3x * FFjk, fk1 = d2y * FFik + d3y * FFjk, fk2 = d2z * FFik + d3z * FFjk;
         fjx += fj0; fjy += fj1; fjz += fj2;
@@ -1446,6 +1448,40 @@ int b200md_aeam_pack(b200md_ctx *c)
   return B200MD_OK;
 }
 
+// The list of angular centers in ASCENDING atom order (a scan, not an atomic append): the order decides which warp sums
+// which center's virial, so an append made deterministic mode depend on the launch that built the list.
+__global__ void __launch_bounds__(BLOCK) aeam_ang_key_kernel(const double4 *__restrict__ xq, int inum, int nna,
+                                                             int *__restrict__ key)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i < inum) key[i] = etype(xq[i]) >= nna ? 1 : 0;
+}
+__global__ void __launch_bounds__(BLOCK) aeam_ang_list_kernel(const int *__restrict__ key, const long long *__restrict__ pos,
+                                                              int inum, int *__restrict__ ang_list, int *__restrict__ count)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= inum) return;
+  if (key[i]) ang_list[pos[i]] = i;
+  if (i == inum - 1) *count = (int) (pos[i] + key[i]);
+}
+static int aeam_build_ang_list(b200md_ctx *c, int inum)
+{
+  if (inum <= 0) return B200MD_OK;
+  CUDA_TRY(c, c->ang_key.reserve((size_t) inum + 8));
+  CUDA_TRY(c, c->ang_scan.reserve((size_t) inum + 2));
+  {
+    LaunchScope ls(c, "build_inner");
+    aeam_ang_key_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, inum, c->ap.nnonangular, c->ang_key.p);
+  }
+  int rc = b200md_exclusive_scan_i64(c, c->ang_key.p, c->ang_scan.p, inum, 1);
+  if (rc) return rc;
+  LaunchScope ls(c, "build_inner");
+  aeam_ang_list_kernel<<<nblocks(inum, BLOCK), BLOCK, 0, c->stream>>>(c->ang_key.p, (const long long *) c->ang_scan.p, inum,
+                                                                     c->ang_list.p, c->flags.p + 6);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200MD_OK;
+}
+
 int b200md_aeam_build_inner(b200md_ctx *c)
 {
   const int inum = c->list_inum;
@@ -1498,6 +1534,10 @@ int b200md_aeam_build_inner(b200md_ctx *c)
           c->ea_val.p, c->ang_list.p, c->flags.p);
       CUDA_TRY(c, cudaGetLastError());
     }
+  }
+  {
+    int rc = aeam_build_ang_list(c, inum);
+    if (rc) return rc;
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->xhold.p, c->xq.p, (size_t) c->nall * sizeof(double4), cudaMemcpyDeviceToDevice,
                               c->stream));

@@ -301,6 +301,8 @@ struct b200md_ctx {
   DevBuf<int64_t> ea_off;
   DevBuf<int> ea_num, ea_val;        // inner AEAM rows (filtered to cut+margin)
   DevBuf<int> ang_list;              // owned angular atoms
+  DevBuf<int> ang_key;               // scan input / output of the ordered angular-center list
+  DevBuf<int64_t> ang_scan;
   DevBuf<long long> det_ffix;        // deterministic mode: fixed-point forces of the angular triplets [nall*3]
   DevBuf<double> det_part;           // deterministic mode: per-block partial sums of the global accumulators
   DevBuf<int64_t> ec_off;            // cluster form: [ncl+1] 8-aligned offsets of the union rows

@@ -109,7 +109,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
-  c->ang_list.release(); c->det_ffix.release(); c->det_part.release();
+  c->ang_list.release(); c->ang_key.release(); c->ang_scan.release(); c->det_ffix.release(); c->det_part.release();
   c->ec_off.release(); c->ec_num.release(); c->ec_val.release(); c->ec_cap.release(); c->ec_df.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
   c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();

@@ -152,6 +152,44 @@ def test_flags_and_accumulate(ctx, oracle_built):
     lmp.close()
 
 
+@pytest.mark.parametrize("overwrite", [0, 1], ids=["accumulate", "overwrite"])
+def test_pipelined_force_download_equals_plain_path(ctx, oracle_built, overwrite):
+    """Plugin mode: the force download is pipelined with the pair kernel (angular kernel first, ghost forces leave, then
+    ranges of centers through the RANGED instance of the force kernel, every range's forces behind its launch).  Forced
+    on for a small system with angular atoms: same forces, energy and virial as the plain path and as the oracle."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.2, displace=0.2)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    ctx.aeam_init(aeam_tables())
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    nl, ng = snap["nlocal"], snap["nghost"]
+    base = 0.0 if overwrite else 1.5
+
+    def run(eflag, vflag):
+        f, e, v = ctx.aeam_compute(nl, ng, snap["x"], snap["type"], snap["tag"], eflag, vflag, f=np.full((nl + ng, 3), base))
+        return f - base, e, v
+
+    try:
+        ctx.set_option("f_overwrite", overwrite)
+        f0, e0, v0 = run(1, 2)                       # plain path (below d2h_min_atoms)
+        ctx.set_option("d2h_min_atoms", 0)
+        ctx.set_option("d2h_chunks", 3)
+        p0 = ctx.counter("pipelined_calls")
+        f1, e1, v1 = run(1, 2)
+        f2, _, _ = run(0, 0)
+        assert ctx.counter("pipelined_calls") == p0 + 2
+        assert S.rel_err(f1, f0) < 1e-13 and abs(e1 - e0) < 1e-13 * abs(e0) and S.rel_err(v1, v0) < 1e-12
+        assert S.rel_err(f2, f0) < 1e-13
+        assert S.rel_err(S.fold_ghost_forces(f1.copy(), snap["swaps"], nl), f_ref) < FTOL
+        assert abs(e1 - e_ref) < ETOL * abs(e_ref) and S.rel_err(v1, v_ref) < FTOL
+    finally:
+        ctx.set_option("f_overwrite", 0)
+        ctx.set_option("d2h_min_atoms", 65536)
+        ctx.set_option("d2h_chunks", 4)
+    lmp.close()
+
+
 def fold_ghost_rows(a, swaps, nlocal):
     a = np.array(a, dtype=np.float64, copy=True)
     for s in reversed(swaps):

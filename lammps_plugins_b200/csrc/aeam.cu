@@ -225,9 +225,9 @@ __device__ __forceinline__ double spl_der(const double4 &c, double p, double rdx
 // positions + 0-based element packed into one 32-byte sector
 __global__ void __launch_bounds__(BLOCK) aeam_pack_kernel(const double *__restrict__ x,
                                                           const int *__restrict__ type, int nel, int nall,
-                                                          double4 *__restrict__ xq, int *__restrict__ flags)
+                                                          double4 *__restrict__ xq, int *__restrict__ flags, int lo = 0)
 {
-  int i = blockIdx.x * BLOCK + threadIdx.x;
+  int i = lo + blockIdx.x * BLOCK + threadIdx.x;    // atoms [lo, nall)
   if (i >= nall) return;
   int t = type[i];
   if (t < 1 || t > nel) {
@@ -361,16 +361,17 @@ template <> struct DfVec<1> {
 // Register-count sensitive (check -Xptxas -v after every change): the DF instance compiles to 64 registers without spill
 // = 4 CTAs per SM, 1.27 ms at 2 M atoms; at 72 registers (3 CTAs) it takes 1.50 ms, forced to 64 with 12 bytes of
 // spill 1.35 ms
-template <bool DF>
+// RANGED (plugin mode): centers [first, inum) -- an instance of its own, the resident loop's sits at its register limit.
+template <bool DF, bool RANGED = false>
 __global__ void __launch_bounds__(BLOCK) aeam_density_kernel(
     const __grid_constant__ AeamDev par, const double4 *__restrict__ xq, const int64_t *__restrict__ ea_off,
     const int *__restrict__ ea_num, const int *__restrict__ ea_val, const double4 *__restrict__ rhor,
-    int inum, double *__restrict__ rho, double *__restrict__ ea_df)
+    int inum, double *__restrict__ rho, double *__restrict__ ea_df, int first = 0)
 {
   __shared__ PairPar sp[16];
   load_pair_par(par, sp, true);
   const int tid = blockIdx.x * BLOCK + threadIdx.x;
-  const int i = tid >> 3, sub = tid & 7;
+  const int i = (RANGED ? first : 0) + (tid >> 3), sub = tid & 7;
   double acc = 0.0;
   bool mine = false;
   if (i < inum) {
@@ -1577,6 +1578,8 @@ int b200md_aeam_refresh_inner(b200md_ctx *c)
   return B200MD_OK;
 }
 
+static int aeam_density_tail(b200md_ctx *c);
+
 // density + embedding for owned atoms (rho, fp valid for [0,inum) afterwards)
 int b200md_aeam_density(b200md_ctx *c)
 {
@@ -1587,9 +1590,6 @@ int b200md_aeam_density(b200md_ctx *c)
   const double4 *rhor = (const double4 *) c->spl_rhor.p;
   const int mode = aeam_row_mode(c);
   const bool cl = mode == 1;
-  const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
-  const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
-  const int rshift = cl ? CL_SHIFT : 0;
   {
     LaunchScope ls(c, "aeam_density");
     if (cl) {
@@ -1614,6 +1614,18 @@ int b200md_aeam_density(b200md_ctx *c)
       aeam_density_kernel<false><<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
           c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, inum, c->rho.p, nullptr);
   }
+  return aeam_density_tail(c);
+}
+
+// density of the angular atoms + embedding (after the pair densities of all owned atoms)
+static int aeam_density_tail(b200md_ctx *c)
+{
+  const int inum = c->list_inum;
+  const double4 *rhor = (const double4 *) c->spl_rhor.p;
+  const bool cl = aeam_row_mode(c) == 1;
+  const int64_t *r_off = cl ? c->ec_off.p : c->ea_off.p;
+  const int *r_num = cl ? c->ec_num.p : c->ea_num.p, *r_val = cl ? c->ec_val.p : c->ea_val.p;
+  const int rshift = cl ? CL_SHIFT : 0;
   if (c->ap.nnonangular < c->ap.nel) {
     LaunchScope ls(c, "aeam_density_ang");
     aeam_density_ang_kernel<<<c->num_sms * c->ang_ctas, 128, 0, c->stream>>>(c->ap, c->xq.p, r_off, r_num, r_val, rhor,
@@ -1783,6 +1795,10 @@ static int aeam_begin(b200md_ctx *c, int nlocal, int nghost, const double *x, co
   ARG_CHECK(c, c->list_valid, "aeam: no neighbor list (b200md_set_neighbor_list / b200md_neigh_build)");
   ARG_CHECK(c, c->list_inum == nlocal, "aeam: neighbor list was built for a different nlocal");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->tight_derive_pending) {    // a deferred re-derive of the pipelined path (it reads xq) is still in flight
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->tight_derive_pending = false;
+  }
   int rc = b200md_upload_atoms(c, nlocal, nghost, x, type, tag);
   if (rc) return rc;
   const size_t n3 = 3 * (size_t) c->nall;
@@ -1800,6 +1816,270 @@ static int aeam_finish(b200md_ctx *c, int eflag, int vflag, double *f, double *e
   return aeam_check_flags(c, fl);
 }
 
+
+// ================================================================== plugin mode: upload pipelined with the density pass
+// The positions arrive in h2d_chunks pieces (ghosts first); the density launch of center range k starts as soon as the
+// piece holding the largest atom index its rows name has landed.  The dependence is computed from the MASTER rows when a
+// list is handed over (valid for every inner list derived from it; the inner rows are re-derived every ~12 calls at 863 K),
+// with the straggler list of rebomos.cu's dep_range_kernel: atoms named from more than one piece away travel first.
+struct AeamChunks {
+  int t[B200MD_MAX_D2H_CHUNKS + 1];
+  int K;
+};
+__global__ void __launch_bounds__(BLOCK) aeam_dep_kernel(const int64_t *__restrict__ list_off,
+                                                         const int *__restrict__ list_num,
+                                                         const int *__restrict__ list_val, int inum,
+                                                         const __grid_constant__ AeamChunks cb, int *__restrict__ dep,
+                                                         int *__restrict__ strag_flag, int *__restrict__ strag_list,
+                                                         int *__restrict__ strag_count, int strag_cap)
+{
+  const int tid = blockIdx.x * BLOCK + threadIdx.x;
+  const int i = tid >> 3, sub = tid & 7;
+  if (i >= inum) return;
+  int k = 0;
+  while (k + 1 < cb.K && i >= cb.t[k + 1]) k++;
+  const int far = strag_flag ? cb.t[min(k + 2, cb.K)] : inum;
+  int m = i;
+  const int n = list_num[i];
+  const int *row = list_val + list_off[i];
+  for (int e = sub; e < n; e += 8) {
+    const int j = row[e] & B200MD_NEIGHMASK;
+    if (j >= inum) continue;    // ghosts travel first
+    if (j >= far) {
+      if (atomicExch(&strag_flag[j], 1) == 0) {
+        const int pos = atomicAdd(strag_count, 1);
+        if (pos < strag_cap) strag_list[pos] = j;
+      }
+    } else if (j > m)
+      m = j;
+  }
+  if (m > dep[k]) atomicMax(&dep[k], m);    // racy read, monotone value: almost every lane skips the atomic
+}
+__global__ void __launch_bounds__(BLOCK) aeam_strag_scatter_kernel(const double *__restrict__ buf,
+                                                                   const int *__restrict__ list, int n,
+                                                                   const int *__restrict__ type, int nel,
+                                                                   double4 *__restrict__ xq)
+{
+  const int q = blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= n) return;
+  const int j = list[q];
+  int t = type[j];
+  if (t < 1 || t > nel) t = 1;    // flagged by the pack kernel of the atom's piece
+  xq[j] = make_double4(buf[3 * (size_t) q], buf[3 * (size_t) q + 1], buf[3 * (size_t) q + 2], w_encode(0.0, t - 1));
+}
+// flags[1] = 2: an atom moved more than margin/2 since the inner rows were derived (they may miss a pair: recompute);
+// 1: more than 80 % of that (the rows are re-derived after this call, before they can miss one)
+__global__ void __launch_bounds__(BLOCK) aeam_check_disp2_kernel(const double4 *__restrict__ xq,
+                                                                 const double4 *__restrict__ xhold, int nall,
+                                                                 double thresh_sq, double soon_sq, int *__restrict__ flags)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= nall) return;
+  const double4 a = xq[i], b = xhold[i];
+  const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  const double d = dx * dx + dy * dy + dz * dz;
+  if (d > soon_sq) atomicMax(&flags[1], d > thresh_sq ? 2 : 1);
+}
+
+static int aeam_prepare_pipeline(b200md_ctx *c)
+{
+  const int inum = c->list_inum;
+  c->aeam_h2d_ready = false;
+  c->aeam_h2d_list = c->n_list_upload;
+  if (c->h2d_chunks <= 1 || c->d2h_chunks <= 1 || inum < c->d2h_min_atoms || inum == 0 || aeam_row_mode(c) != 2) return B200MD_OK;
+  const int K = c->h2d_chunks;
+  AeamChunks cb;
+  cb.K = K;
+  {
+    const double r = c->h2d_ramp > 0 ? (double) c->h2d_ramp : 0.0;
+    double tot = 0.0, acc = 0.0;
+    for (int k = 0; k < K; k++) tot += r > 0.0 ? r + k : 1.0;
+    cb.t[0] = 0;
+    for (int k = 0; k < K; k++) {
+      acc += r > 0.0 ? r + k : 1.0;
+      cb.t[k + 1] = (int) ((double) inum * (acc / tot));
+    }
+    cb.t[K] = inum;
+  }
+  int *dep = c->flags.p + 16;
+  int *pin = (int *) (c->pin_scal.p + 48), *pin_cnt = (int *) (c->pin_scal.p + 60);
+  const int cap = inum / 32 + 1024;
+  c->n_strag = 0;
+  CUDA_TRY(c, c->strag_flag.reserve((size_t) inum + 8));
+  CUDA_TRY(c, c->strag_list.reserve((size_t) cap + 8));
+  for (int pass = 0; pass < 2; pass++) {
+    CUDA_TRY(c, cudaMemsetAsync(dep, 0, K * sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->strag_flag.p, 0, ((size_t) inum + 1) * sizeof(int), c->stream));
+    int *cnt = c->strag_flag.p + inum;
+    {
+      LaunchScope ls(c, "build_inner");
+      aeam_dep_kernel<<<nblocks((long long) inum * 8, BLOCK), BLOCK, 0, c->stream>>>(
+          c->list_off.p, c->list_num.p, c->list_val.p, inum, cb, dep, pass == 0 ? c->strag_flag.p : nullptr, c->strag_list.p,
+          cnt, cap);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(pin, dep, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(pin_cnt, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (pass == 0 && *pin_cnt <= cap) {
+      c->n_strag = *pin_cnt;
+      break;
+    }
+  }
+  if (c->n_strag) {
+    c->strag_host.resize((size_t) c->n_strag);
+    CUDA_TRY(c, cudaMemcpyAsync(c->strag_host.data(), c->strag_list.p, c->n_strag * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, c->strag_pin.reserve(3 * (size_t) c->n_strag + 8));
+    CUDA_TRY(c, c->strag_dev.reserve(3 * (size_t) c->n_strag + 8));
+  }
+  for (int k = 0; k < K; k++) {
+    int p = k;
+    while (p + 1 < K && pin[k] >= cb.t[p + 1]) p++;
+    c->h2d_need[k] = p;
+    c->h2d_t[k] = cb.t[k];
+  }
+  c->h2d_t[K] = inum;
+  c->h2d_K = K;
+  c->aeam_h2d_ready = true;
+  return B200MD_OK;
+}
+
+static int aeam_forces_download_pipelined(b200md_ctx *c, int nlocal, int eflag, int vflag, double *f, double *eng_vdwl,
+                                          double *virial, int *fl);
+
+// One plugin-mode call with upload, kernels and download overlapped.  *redo: the inner rows were stale (an atom beyond
+// margin/2: rare, the rows are re-derived one call ahead of need) -- nothing has been added to the caller's f, the
+// positions are on the device, the caller re-derives and recomputes.
+static int aeam_compute_pipelined(b200md_ctx *c, int nlocal, int nghost, const double *x, int eflag, int vflag, double *f,
+                                  double *eng_vdwl, double *virial, int *fl, bool *redo)
+{
+  *redo = false;
+  const int K = c->h2d_K;
+  const int nall = nlocal + nghost;
+  if (!c->up_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  for (int k = 0; k <= K; k++)
+    if (!c->up_ev[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->up_ev[k], cudaEventDisableTiming));
+  c->nlocal = nlocal;
+  c->nghost = nghost;
+  c->nall = nall;
+  const bool need_check = c->margin < c->skin;
+  int *pin_flag = (int *) (c->pin_scal.p + 56);
+  pin_flag[0] = 0;
+  if (c->tight_derive_pending) {    // a deferred re-derive of the inner rows reads the previous call's positions
+    CUDA_TRY(c, cudaStreamWaitEvent(c->up_stream, c->ev_tight, 0));
+    c->tight_derive_pending = false;
+  }
+  // ---- upload stream
+  cudaStream_t compute_stream = c->stream;
+  c->stream = c->up_stream;
+  int rc = B200MD_OK;
+  auto piece = [&](int lo, int hi) -> int {
+    if (hi <= lo) return B200MD_OK;
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_aos.p + 3 * (size_t) lo, x + 3 * (size_t) lo, 3 * (size_t) (hi - lo) * sizeof(double),
+                                cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long) (3 * (size_t) (hi - lo) * sizeof(double));
+    LaunchScope ls(c, "pack");
+    aeam_pack_kernel<<<nblocks(hi - lo, BLOCK), BLOCK, 0, c->stream>>>(c->x_aos.p, c->type.p, c->ap.nel, hi, c->xq.p,
+                                                                     c->flags.p, lo);
+    return B200MD_OK;
+  };
+  if (c->n_strag) {
+    const int ns = c->n_strag;
+    double *sp = c->strag_pin.p;
+    for (int q = 0; q < ns; q++) {
+      const size_t j = (size_t) c->strag_host[q];
+      sp[3 * (size_t) q] = x[3 * j];
+      sp[3 * (size_t) q + 1] = x[3 * j + 1];
+      sp[3 * (size_t) q + 2] = x[3 * j + 2];
+    }
+    if (cudaMemcpyAsync(c->strag_dev.p, sp, 3 * (size_t) ns * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      rc = B200MD_ERR_CUDA;
+    c->h2d_bytes += (long long) (3 * (size_t) ns * sizeof(double));
+    LaunchScope ls(c, "pack");
+    aeam_strag_scatter_kernel<<<nblocks(ns, BLOCK), BLOCK, 0, c->stream>>>(c->strag_dev.p, c->strag_list.p, ns, c->type.p,
+                                                                          c->ap.nel, c->xq.p);
+  }
+  if (!rc) rc = piece(nlocal, nall);
+  for (int p = 0; p < K && !rc; p++) {
+    rc = piece(c->h2d_t[p], c->h2d_t[p + 1]);
+    if (!rc && cudaEventRecord(c->up_ev[p], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
+  }
+  if (!rc && need_check) {
+    const double half = 0.5 * c->margin, soon = 0.8 * half;
+    if (cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
+    {
+      LaunchScope ls(c, "check_disp");
+      aeam_check_disp2_kernel<<<nblocks(nall, BLOCK), BLOCK, 0, c->stream>>>(c->xq.p, (const double4 *) c->xhold.p, nall,
+                                                                            half * half, soon * soon, c->flags.p);
+    }
+    if (cudaMemcpyAsync(pin_flag, c->flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      rc = B200MD_ERR_CUDA;
+  }
+  if (!rc && cudaEventRecord(c->up_ev[K], c->stream) != cudaSuccess) rc = B200MD_ERR_CUDA;
+  c->stream = compute_stream;
+  if (rc) return rc;
+  // ---- compute stream
+  const size_t n3 = 3 * (size_t) nall;
+  CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+  CUDA_TRY(c, c->rho.reserve((size_t) nall + 32));
+  CUDA_TRY(c, c->fp.reserve((size_t) nall + 32));
+  const double4 *rhor = (const double4 *) c->spl_rhor.p;
+  for (int k = 0; k < K; k++) {
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->up_ev[c->h2d_need[k]], 0));
+    const int lo = c->h2d_t[k], hi = c->h2d_t[k + 1];
+    if (hi <= lo) continue;
+    LaunchScope ls(c, "aeam_density");
+    aeam_density_kernel<true, true><<<nblocks((long long) (hi - lo) * 8, BLOCK), BLOCK, 0, c->stream>>>(
+        c->ap, c->xq.p, c->ea_off.p, c->ea_num.p, c->ea_val.p, rhor, hi, c->rho.p, c->ec_df.p, lo);
+  }
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->up_ev[K - 1], 0));    // the angular centers read anywhere
+  if ((rc = aeam_density_tail(c))) return rc;
+  if (nghost && (rc = b200md_aeam_fill_ghosts_by_tag(c, c->aeam_maxtag))) return rc;
+  // ---- the verdict on the rows arrives while the density kernels are still running
+  CUDA_TRY(c, cudaEventSynchronize(c->up_ev[K]));
+  if (need_check && pin_flag[0] == 2) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    b200md_collect_timers(c);
+    *redo = true;
+    return B200MD_OK;
+  }
+  if ((rc = aeam_forces_download_pipelined(c, nlocal, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+  if (need_check && pin_flag[0] == 1) {
+    // an atom is 80 % of the way to the rows' limit: re-derive them now, after this call's work, from the positions on
+    // the device -- the host integrates in the meantime, the next call's upload waits for the event
+    if ((rc = b200md_aeam_build_inner(c))) return rc;
+    if (!c->ev_tight) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_tight, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventRecord(c->ev_tight, c->stream));
+    c->tight_derive_pending = true;
+  }
+  return B200MD_OK;
+}
+
+// force download pipelined with the pair kernel (force-only or EV calls, default row form): the angular kernel -- the only
+// one that writes ghost forces and forces of other centers -- runs first, the ghost forces leave, then the pair kernel
+// runs over d2h_chunks ranges of centers and every range's forces leave behind its launch
+static int aeam_forces_download_pipelined(b200md_ctx *c, int nlocal, int eflag, int vflag, double *f, double *eng_vdwl,
+                                          double *virial, int *fl)
+{
+  const int KD = c->d2h_chunks;
+  const size_t n3 = 3 * (size_t) c->nall;
+  int rc;
+  if ((rc = b200md_aeam_forces(c, eflag, vflag, 1))) return rc;
+  if ((rc = b200md_d2h_begin(c))) return rc;
+  if ((rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, n3))) return rc;
+  for (int k = 0; k < KD && !rc; k++) {
+    c->aeam_range_lo = (int) ((long long) nlocal * k / KD);
+    c->aeam_range_hi = (int) ((long long) nlocal * (k + 1) / KD);
+    if (c->aeam_range_hi <= c->aeam_range_lo) continue;
+    if (!(rc = b200md_aeam_forces(c, eflag, vflag, 2)))
+      rc = b200md_d2h_range(c, k + 1, f, 3 * (size_t) c->aeam_range_lo, 3 * (size_t) c->aeam_range_hi);
+  }
+  c->aeam_range_lo = c->aeam_range_hi = 0;
+  if (rc) return rc;
+  return b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl);
+}
+
 // one-shot: ghosts are periodic images of owned atoms (single rank); ghost fp via atom IDs
 extern "C" int b200md_aeam_compute(b200md_ctx *c, int nlocal, int nghost, const double *x, const int *type,
                                    const int *tag, int eflag, int vflag, double *f, double *eng_vdwl,
@@ -1815,6 +2095,7 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
   if (!c) return B200MD_ERR_ARG;
   ARG_CHECK(c, f != nullptr || nlocal + nghost == 0, "aeam_compute: f is NULL");
   ARG_CHECK(c, tag != nullptr || nghost == 0, "aeam_compute: atom IDs are needed to give ghosts their fp");
+  CUDA_TRY(c, cudaSetDevice(c->device));
   c->n_compute++;
   if (nlocal + nghost == 0) {    // an empty rank (vacuum brick)
     if (eng_vdwl) *eng_vdwl = 0.0;
@@ -1822,35 +2103,42 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
       for (int k = 0; k < 6; k++) virial[k] = 0.0;
     return B200MD_OK;
   }
-  int rc = aeam_begin(c, nlocal, nghost, x, type, tag);
+  int rc;
+  const bool pipe_ok = !eatom && !vatom && !c->deterministic && c->d2h_chunks > 1 && nlocal >= c->d2h_min_atoms &&
+      aeam_row_mode(c) == 2;
+  if (pipe_ok && c->list_valid && c->aeam_h2d_list != c->n_list_upload) c->aeam_h2d_ready = false;    // a new master list
+  if (pipe_ok && c->inner_valid && c->aeam_h2d_ready && c->type_on_device && c->tag_on_device &&
+      nlocal + nghost == c->ids_nall && c->nlocal == nlocal && c->list_inum == nlocal) {
+    bool redo = false;
+    int fl[16];
+    if ((rc = aeam_compute_pipelined(c, nlocal, nghost, x, eflag, vflag, f, eng_vdwl, virial, fl, &redo))) return rc;
+    c->n_pipelined++;
+    if (!redo) return aeam_check_flags(c, fl);
+    c->n_redo++;
+    // stale rows: the positions are on the device; re-derive and recompute by the plain kernels
+    if ((rc = b200md_aeam_build_inner(c))) return rc;
+    const size_t n3 = 3 * (size_t) c->nall;
+    CUDA_TRY(c, cudaMemsetAsync(c->f.p, 0, (n3 + 8) * sizeof(double), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->stream));
+    if ((rc = b200md_aeam_density(c))) return rc;
+    if (nghost && (rc = b200md_aeam_fill_ghosts_by_tag(c, c->aeam_maxtag))) return rc;
+    if ((rc = aeam_forces_download_pipelined(c, nlocal, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+    return aeam_check_flags(c, fl);
+  }
+  rc = aeam_begin(c, nlocal, nghost, x, type, tag);
   if (rc) return rc;
+  if (pipe_ok && !c->aeam_h2d_ready && (rc = aeam_prepare_pipeline(c))) return rc;
   if ((rc = b200md_peratom_begin(c, eatom != nullptr || vatom != nullptr))) return rc;
   rc = b200md_aeam_density(c);
   if (!rc && nghost) {
     int maxtag = 0;
     for (int i = 0; i < nlocal; i++) maxtag = tag[i] > maxtag ? tag[i] : maxtag;
+    c->aeam_maxtag = maxtag;
     rc = b200md_aeam_fill_ghosts_by_tag(c, maxtag);
   }
-  // force download pipelined with the pair kernel (force-only calls, default row form): the angular kernel -- the only one
-  // that writes ghost forces and forces of other centers -- runs first, the ghost forces leave, then the pair kernel runs
-  // over d2h_chunks ranges of centers and every range's forces leave behind its launch
-  const int KD = c->d2h_chunks;
-  if (!rc && KD > 1 && nlocal >= c->d2h_min_atoms && !eatom && !vatom && !c->deterministic && aeam_row_mode(c) == 2) {
-    const size_t n3 = 3 * (size_t) c->nall;
-    if (!(rc = b200md_aeam_forces(c, eflag, vflag, 1)) && !(rc = b200md_d2h_begin(c)) &&
-        !(rc = b200md_d2h_range(c, 0, f, 3 * (size_t) nlocal, n3))) {
-      for (int k = 0; k < KD && !rc; k++) {
-        c->aeam_range_lo = (int) ((long long) nlocal * k / KD);
-        c->aeam_range_hi = (int) ((long long) nlocal * (k + 1) / KD);
-        if (c->aeam_range_hi <= c->aeam_range_lo) continue;
-        if (!(rc = b200md_aeam_forces(c, eflag, vflag, 2)))
-          rc = b200md_d2h_range(c, k + 1, f, 3 * (size_t) c->aeam_range_lo, 3 * (size_t) c->aeam_range_hi);
-      }
-    }
-    c->aeam_range_lo = c->aeam_range_hi = 0;
-    if (rc) return rc;
+  if (!rc && pipe_ok) {
     int fl[16];
-    if ((rc = b200md_d2h_finish(c, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+    if ((rc = aeam_forces_download_pipelined(c, nlocal, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
     c->n_pipelined++;
     return aeam_check_flags(c, fl);
   }

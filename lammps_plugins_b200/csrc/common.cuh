@@ -292,6 +292,9 @@ struct b200md_ctx {
 
   // ---- AEAM
   bool aeam_ready = false;
+  bool aeam_h2d_ready = false;       // plugin mode: upload pieces and their dependences are set up for the current master list
+  long long aeam_h2d_list = -1;      // ... n_list_upload they belong to
+  int aeam_maxtag = 0;
   int aeam_range_lo = 0, aeam_range_hi = 0;    // plugin mode: the range of centers the next pair-kernel launch takes
   AeamDev ap;
   DevBuf<double> spl_frho, spl_rhor, spl_z2r;    // {c3,c4,c5,c6} per row

@@ -190,6 +190,58 @@ def test_pipelined_force_download_equals_plain_path(ctx, oracle_built, overwrite
     lmp.close()
 
 
+def test_pipelined_upload_equals_plain_path(ctx, oracle_built):
+    """Plugin mode: the position upload is pipelined with the density pass (pieces of x land while the density launches of
+    earlier center ranges run; dependences and stragglers from the master rows), the inner rows are used speculatively,
+    re-derived one call ahead of need ("soon": an atom at 80 % of margin/2) and the call is recomputed when they were
+    stale after all.  Forced on for a small system: every call equals the plain path at the same positions."""
+    lmp = S.make_aeam_system(S.oracle_plugin("aeam"), (5, 5, 5), si_fraction=0.2, displace=0.2)
+    lmp.setup(1, 2)
+    snap = S.snapshot(lmp)
+    f_ref, e_ref, v_ref = oracle_forces(lmp)
+    ctx.aeam_init(aeam_tables())
+    ctx.set_neighbor_csr(snap["inum"], snap["gnum"], snap["off"], snap["val"], snap["skin"])
+    nl, ng = snap["nlocal"], snap["nghost"]
+
+    def run(x):
+        return ctx.aeam_compute(nl, ng, x, snap["type"], snap["tag"], 1, 2)
+
+    try:
+        ctx.set_option("d2h_min_atoms", 0)
+        ctx.set_option("d2h_chunks", 2)
+        ctx.set_option("h2d_chunks", 3)
+        x0 = snap["x"].copy()
+        run(x0)                                     # plain upload: derives the inner rows, sets the pipeline up
+        p0, r0, i0 = ctx.counter("pipelined_calls"), ctx.counter("pipelined_redos"), ctx.counter("inner_rebuilds")
+        f1, e1, v1 = run(x0)                        # pipelined upload
+        assert ctx.counter("upload_stragglers") > 0    # a cell this small: range 0 names atoms of the last piece
+        assert S.rel_err(S.fold_ghost_forces(f1.copy(), snap["swaps"], nl), f_ref) < FTOL
+        assert abs(e1 - e_ref) < ETOL * abs(e_ref) and S.rel_err(v1, v_ref) < FTOL
+        rng = np.random.default_rng(11)
+        x1 = x0 + rng.uniform(-0.03, 0.03, x0.shape)                   # inside 80 % of margin/2 = 0.2: rows stay
+        f2, e2, v2 = run(x1)
+        assert ctx.counter("inner_rebuilds") == i0 and ctx.counter("pipelined_redos") == r0
+        x2 = x1.copy()
+        x2[5] = x0[5] + (0.156, 0.156, 0.0)         # |d| = 0.2206: "soon" (> 0.8 x 0.25), not stale (< margin/2 = 0.25)
+        f3, e3, v3 = run(x2)
+        assert ctx.counter("pipelined_redos") == r0 and ctx.counter("inner_rebuilds") == i0 + 1     # deferred re-derive
+        x3 = x2.copy()
+        x3[9] += (0.3, 0.3, 0.0)                    # |d| = 0.42 > margin/2 (< skin/2: the master list is still good)
+        f4, e4, v4 = run(x3)
+        assert ctx.counter("pipelined_redos") == r0 + 1
+        assert ctx.counter("pipelined_calls") == p0 + 4
+        ctx.set_option("h2d_chunks", 1)             # plain upload again
+        ctx.set_option("d2h_chunks", 1)
+        for x, (fp, ep, vp) in ((x1, (f2, e2, v2)), (x2, (f3, e3, v3)), (x3, (f4, e4, v4))):
+            fq, eq, vq = run(x)
+            assert S.rel_err(fp, fq) < 1e-12 and abs(ep - eq) < 1e-12 * abs(eq) and S.rel_err(vp, vq) < 1e-11
+    finally:
+        ctx.set_option("d2h_min_atoms", 65536)
+        ctx.set_option("d2h_chunks", 4)
+        ctx.set_option("h2d_chunks", 6)
+    lmp.close()
+
+
 def fold_ghost_rows(a, swaps, nlocal):
     a = np.array(a, dtype=np.float64, copy=True)
     for s in reversed(swaps):

@@ -228,6 +228,9 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *  "fuse_integrate"  0/1 (default 1), resident loop: the second half kick of a step that is followed by another step (no
  *                    thermo output, no thermostat in between) is applied by the next step's first integrate launch
  *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)
+ *  "fp_gated"        0/1, AEAM two-phase API: the density phase hands out (rho > minrho ? fp : 0) per owned atom, what a
+ *                    neighbor needs from it (pair_aeam.cpp:329-332), and rho_out / rho_all may be NULL: the host ships one
+ *                    double per ghost and tests nothing itself
  *  "peratom"         0/1, AEAM two-phase API only;  "sync_timing" 0/1: per-launch CUDA events for b200md_kernel_stats */
 int b200md_set_option(b200md_ctx *ctx, const char *name, long long value);
 /* counters: "kernel_launches", "list_uploads" (master lists received: handed over or built on the device), "compute_calls", "inner_rebuilds", "tight_refreshes", "h2d_bytes", "d2h_bytes",

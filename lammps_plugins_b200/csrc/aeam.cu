@@ -2151,6 +2151,20 @@ extern "C" int b200md_aeam_compute_peratom(b200md_ctx *c, int nlocal, int nghost
   return aeam_finish(c, eflag, vflag, f, eng_vdwl, virial);
 }
 
+// option "fp_gated": the density phase hands out (rho > minrho ? fp : 0) -- what a neighbor needs from an atom
+// (pair_aeam.cpp:329-332) -- so that the host ships one double per ghost and tests nothing itself
+__global__ void __launch_bounds__(BLOCK) aeam_fill_kernel(double *__restrict__ a, int n, double v)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void __launch_bounds__(BLOCK) aeam_fp_gated_kernel(const double *__restrict__ rho, const double *__restrict__ fp,
+                                                              int n, double *__restrict__ out)
+{
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i < n) out[i] = rho[i] > 0.0000000000001 ? fp[i] : 0.0;
+}
+
 // two-phase API for hosts that own the halo exchange (LAMMPS: comm->forward_comm(this) in between)
 extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, const double *x,
                                          const int *type, double *rho_out, double *fp_out)
@@ -2164,12 +2178,19 @@ extern "C" int b200md_aeam_density_phase(b200md_ctx *c, int nlocal, int nghost, 
   if ((rc = b200md_aeam_density(c))) return rc;
   if (nlocal) {
     if (rho_out) CUDA_TRY(c, cudaMemcpyAsync(rho_out, c->rho.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (fp_out) CUDA_TRY(c, cudaMemcpyAsync(fp_out, c->fp.p, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    const double *fp_src = c->fp.p;
+    if (fp_out && c->fp_gated) {
+      CUDA_TRY(c, c->fp_tmp.reserve((size_t) nlocal + 8));
+      LaunchScope ls(c, "aeam_gate");
+      aeam_fp_gated_kernel<<<nblocks(nlocal, BLOCK), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, nlocal, c->fp_tmp.p);
+      fp_src = c->fp_tmp.p;
+    }
+    if (fp_out) CUDA_TRY(c, cudaMemcpyAsync(fp_out, fp_src, nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   int fl[16];
   CUDA_TRY(c, cudaMemcpyAsync(fl, c->flags.p, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  c->d2h_bytes += 2LL * nlocal * sizeof(double);
+  c->d2h_bytes += (long long) ((rho_out ? 1 : 0) + (fp_out ? 1 : 0)) * nlocal * sizeof(double);
   return aeam_check_flags(c, fl);
 }
 
@@ -2184,18 +2205,33 @@ extern "C" int b200md_aeam_force_phase_peratom(b200md_ctx *c, const double *rho_
                                                double *vatom)
 {
   if (!c) return B200MD_ERR_ARG;
-  ARG_CHECK(c, c->aeam_ready && c->inner_valid && f && rho_all && fp_all, "aeam_force_phase: call the density phase first");
+  ARG_CHECK(c, c->aeam_ready && c->inner_valid && f && fp_all && (rho_all || c->fp_gated),
+            "aeam_force_phase: call the density phase first (rho_all may be NULL only with option fp_gated)");
   ARG_CHECK(c, !(eatom || vatom) || c->pa_e,
             "aeam_force_phase: per-atom output needs option \"peratom\" = 1 before the density phase");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int ng = c->nghost;
   if (ng) {
     // owned entries are already on the device; ghosts come from the host's halo exchange
-    CUDA_TRY(c, cudaMemcpyAsync(c->rho.p + c->nlocal, rho_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (rho_all) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->rho.p + c->nlocal, rho_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      c->h2d_bytes += (long long) ng * sizeof(double);
+    } else {    // gated fp: the ghosts' rho only has to pass the minrho test
+      LaunchScope ls(c, "aeam_gate");
+      aeam_fill_kernel<<<nblocks(ng, BLOCK), BLOCK, 0, c->stream>>>(c->rho.p + c->nlocal, ng, 1.0);
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->fp.p + c->nlocal, fp_all + c->nlocal, ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += 2LL * ng * sizeof(double);
+    c->h2d_bytes += (long long) ng * sizeof(double);
   }
-  int rc = b200md_aeam_forces(c, eflag, vflag, 0);
+  int rc;
+  if (!eatom && !vatom && !c->pa_e && !c->deterministic && c->d2h_chunks > 1 && c->nlocal >= c->d2h_min_atoms &&
+      aeam_row_mode(c) == 2) {    // force download pipelined with the pair kernel, as in the one-shot call
+    int fl[16];
+    if ((rc = aeam_forces_download_pipelined(c, c->nlocal, eflag, vflag, f, eng_vdwl, virial, fl))) return rc;
+    c->n_pipelined++;
+    return aeam_check_flags(c, fl);
+  }
+  rc = b200md_aeam_forces(c, eflag, vflag, 0);
   if (rc) {
     c->pa_e = c->pa_v = nullptr;
     return rc;

@@ -292,6 +292,8 @@ struct b200md_ctx {
 
   // ---- AEAM
   bool aeam_ready = false;
+  int fp_gated = 0;                  // option "fp_gated" (two-phase API)
+  DevBuf<double> fp_tmp;
   bool aeam_h2d_ready = false;       // plugin mode: upload pieces and their dependences are set up for the current master list
   long long aeam_h2d_list = -1;      // ... n_list_upload they belong to
   int aeam_maxtag = 0;

@@ -109,7 +109,7 @@ extern "C" void b200md_destroy(b200md_ctx *c)
   c->cen_list.release(); c->cen_key.release(); c->cen_scan.release(); c->nM.release(); c->nS.release(); c->det_fb.release(); c->det_j.release();
   c->spl_frho.release(); c->spl_rhor.release(); c->spl_z2r.release(); c->spl_pair.release();
   c->rho.release(); c->fp.release(); c->ea_off.release(); c->ea_num.release(); c->ea_val.release();
-  c->ang_list.release(); c->ang_key.release(); c->ang_scan.release(); c->det_ffix.release(); c->det_part.release();
+  c->ang_list.release(); c->ang_key.release(); c->ang_scan.release(); c->fp_tmp.release(); c->det_ffix.release(); c->det_part.release();
   c->ec_off.release(); c->ec_num.release(); c->ec_val.release(); c->ec_cap.release(); c->ec_df.release();
   c->bin_of.release(); c->bin_count.release(); c->bin_start.release(); c->bin_atoms.release();
   c->stencil_d.release(); c->scan_tmp.release(); c->scan_tmp64.release();
@@ -157,6 +157,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   } else if (n == "sync_timing") c->sync_timing = value ? 1 : 0;
   else if (n == "f_overwrite") c->f_overwrite = value ? 1 : 0;
   else if (n == "peratom") c->peratom_opt = value ? 1 : 0;
+  else if (n == "fp_gated") c->fp_gated = value ? 1 : 0;
   else if (n == "p2p_halo") c->p2p_halo = value ? 1 : 0;
   else if (n == "lj_pairs") {
     c->lj_pairs = value ? 1 : 0;

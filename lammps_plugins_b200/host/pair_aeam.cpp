@@ -24,7 +24,6 @@
 using namespace LAMMPS_NS;
 
 static constexpr int MAXLINE = 1024;
-static constexpr double MINRHO = 0.0000000000001;
 
 /* ---------------------------------------------------------------------- */
 
@@ -53,7 +52,7 @@ PairAEAM::~PairAEAM()
   B200MDHost::write_stats(ctx, "aeam", comm->me);
   if (ctx) b200md_destroy(ctx);
   memory->destroy(rho);
-  memory->destroy(fp);
+  if (fp) b200md_host_free(fp);
   if (allocated) {
     memory->destroy(setflag);
     memory->destroy(cutsq);
@@ -76,11 +75,15 @@ void PairAEAM::compute(int eflag, int vflag)
   }
 
   if (atom->nmax > nmax) {
+    // fp travels between host and device twice per step: page-locked (the class owns it, unlike atom->x / atom->f);
+    // rho stays on the device (the library hands out fp with the minrho test applied, option "fp_gated")
     memory->destroy(rho);
-    memory->destroy(fp);
+    if (fp) b200md_host_free(fp);
     nmax = atom->nmax;
     memory->create(rho, nmax, "pair:rho");
-    memory->create(fp, nmax, "pair:fp");
+    fp = static_cast<double *>(b200md_host_alloc((size_t) nmax * sizeof(double)));
+    if (!fp) error->one(FLERR, "Cannot allocate page-locked memory for the fp halo");
+    for (int i = 0; i < nmax; i++) rho[i] = fp[i] = 0.0;
   }
 
   const int nlocal = atom->nlocal;
@@ -105,19 +108,16 @@ void PairAEAM::compute(int eflag, int vflag)
   B200MDHost::check(error, ctx, b200md_set_option(ctx, "peratom", want_atom), "option");
 
   // phase 1 on the device: density + embedding of owned atoms
-  int rc = b200md_aeam_density_phase(ctx, nlocal, nghost, nall ? &atom->x[0][0] : nullptr, atom->type, rho, fp);
+  // what a neighbor needs from atom j is (rho_j > minrho ? fp_j : 0): the library hands out exactly that (option
+  // "fp_gated", set in init_style), one double per atom, and rho never leaves the device
+  int rc = b200md_aeam_density_phase(ctx, nlocal, nghost, nall ? &atom->x[0][0] : nullptr, atom->type, nullptr, fp);
   B200MDHost::check(error, ctx, rc, "aeam density pass");
-
-  // what a neighbor needs from atom j is (rho_j > minrho ? fp_j : 0): ship exactly that, one double per atom
-  for (int i = 0; i < nlocal; i++)
-    if (!(rho[i] > MINRHO)) fp[i] = 0.0;
   comm->forward_comm(this);
-  for (int i = nlocal; i < nall; i++) rho[i] = 1.0;    // ghosts: the minrho test is already folded into fp
 
   // phase 2 on the device: pair + embedding forces, angular 3-body forces, energy, virial
   double eng = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const int want_virial = (vflag_fdotr || vflag_global) ? B200MD_VIRIAL_FDOTR : 0;
-  rc = b200md_aeam_force_phase_peratom(ctx, rho, fp, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
+  rc = b200md_aeam_force_phase_peratom(ctx, nullptr, fp, eflag_global ? B200MD_ENERGY_GLOBAL : 0, want_virial,
                                        nall ? &atom->f[0][0] : nullptr, &eng, vir, eflag_atom ? eatom : nullptr,
                                        (vflag_atom && vatom) ? &vatom[0][0] : nullptr);
   B200MDHost::check(error, ctx, rc, "aeam force pass");
@@ -208,6 +208,7 @@ void PairAEAM::init_style()
   if (!ctx) {
     int rc = b200md_create(B200MDHost::pick_device(comm->me), &ctx);
     if (rc != B200MD_OK) error->one(FLERR, "Cannot open the B200 device: {}", b200md_last_error(nullptr));
+    B200MDHost::check(error, ctx, b200md_set_option(ctx, "fp_gated", 1), "option");
   }
 
   // hand the raw tables over; the library builds the splines (array2spline) and keeps them on the device

@@ -94,6 +94,20 @@ def test_two_phase_equals_one_shot(ctx, oracle_built):
     assert S.rel_err(f2, f1) < 1e-13
     assert abs(e2 - e1) < 1e-9 * abs(e1)
     assert S.rel_err(v2, v1) < 1e-12
+    try:    # the force phase with its download pipelined (forced on for this small system)
+        ctx.set_option("d2h_min_atoms", 0)
+        ctx.set_option("d2h_chunks", 3)
+        rho, fp = ctx.aeam_density_phase(nl, ng, snap["x"], snap["type"])
+        rho[nl:] = rho[owner[snap["tag"][nl:]]]
+        fp[nl:] = fp[owner[snap["tag"][nl:]]]
+        p0 = ctx.counter("pipelined_calls")
+        f3, e3, v3 = ctx.aeam_force_phase(rho, fp)
+        assert ctx.counter("pipelined_calls") == p0 + 1
+        f3 = S.fold_ghost_forces(f3, snap["swaps"], nl)
+        assert S.rel_err(f3, f1) < 1e-13 and abs(e3 - e1) < 1e-9 * abs(e1) and S.rel_err(v3, v1) < 1e-12
+    finally:
+        ctx.set_option("d2h_min_atoms", 65536)
+        ctx.set_option("d2h_chunks", 4)
     lmp.close()
 
 

@@ -283,6 +283,7 @@ struct b200md_ctx {
   cudaStream_t halo_stream = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_fwd = nullptr, ev_reb = nullptr, ev_rev = nullptr;
   int overlap_halo = 1;              // option "overlap_halo": halos on their own stream beside the interior kernels
+  int flat_halo = 1;                 // option "flat_halo": one rank, the self halos as one gather / one fold
   int peer_vote = 1;                 // option "peer_vote": reneighbor vote through peer memory + a mapped host word
   int neigh_unroll = 1;              // option "neigh_unroll" (tuning)
   int fuse_integrate = 1;            // option "fuse_integrate": final_integrate(k) rides in initial_integrate(k+1)

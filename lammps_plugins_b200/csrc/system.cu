@@ -138,6 +138,11 @@ struct SystemState {
     std::vector<int *> pflag;
     int epoch[3] = {0, 0, 0};      // forward x, forward rho/fp, reverse f
   } p2p;
+  // one rank: every ghost is a periodic image of an owned atom.  flat_src[g] = that atom, flat_code[g] = the swap (1-based,
+  // 8 bits per dimension) whose shift the image received in each dimension: the staged x, y, z copies of a halo (6 swaps,
+  // 3 dependent launches) become ONE gather that applies the same additions in the same order
+  DevBuf<int> flat_src, flat_code;
+  bool flat_ok = false;
   int *vote_host = nullptr;        // mapped pinned word the vote kernel reports to: (epoch << 3) | level
   int vote_epoch = 0;
 };
@@ -473,6 +478,68 @@ __global__ void __launch_bounds__(BLOCK) k_reverse_f2(double *__restrict__ f, co
   atomicAdd(&f[3 * j], f[3 * g]);
   atomicAdd(&f[3 * j + 1], f[3 * g + 1]);
   atomicAdd(&f[3 * j + 2], f[3 * g + 2]);
+}
+
+// ------------------------------------------------------------------ one rank: flat self halo
+struct FlatShifts {
+  double s[6][3];
+  int pbc[6];
+};
+__global__ void __launch_bounds__(BLOCK) k_flat_build(const int *__restrict__ list, int n, int first, int nlocal, int swap,
+                                                      int dim, int *__restrict__ src, int *__restrict__ code)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= n) return;
+  const int j = list[k], g = first + k - nlocal;
+  int sj = j, cj = 0;
+  if (j >= nlocal) {    // the image of an image (a ghost of an earlier dimension)
+    sj = src[j - nlocal];
+    cj = code[j - nlocal];
+  }
+  src[g] = sj;
+  code[g] = cj | ((swap + 1) << (8 * dim));
+}
+__global__ void __launch_bounds__(BLOCK) k_flat_forward_x(double4 *__restrict__ x, const int *__restrict__ src,
+                                                          const int *__restrict__ code, int ng, int nlocal,
+                                                          const __grid_constant__ FlatShifts sh)
+{
+  const int g = blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= ng) return;
+  double4 p = x[src[g]];
+  const int cd = code[g];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {    // the staged halo's additions, dimension by dimension
+    const int sid = ((cd >> (8 * d)) & 255) - 1;
+    if (sid >= 0 && sh.pbc[sid]) {
+      p.x = p.x + sh.s[sid][0];
+      p.y = p.y + sh.s[sid][1];
+      p.z = p.z + sh.s[sid][2];
+    }
+  }
+  double4 q = x[nlocal + g];
+  q.x = p.x;
+  q.y = p.y;
+  q.z = p.z;
+  x[nlocal + g] = q;
+}
+__global__ void __launch_bounds__(BLOCK) k_flat_forward_s2(double *__restrict__ a, double *__restrict__ b,
+                                                           const int *__restrict__ src, int ng, int nlocal)
+{
+  const int g = blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= ng) return;
+  const int j = src[g];
+  a[nlocal + g] = a[j];
+  b[nlocal + g] = b[j];
+}
+__global__ void __launch_bounds__(BLOCK) k_flat_reverse_f(double *__restrict__ f, const int *__restrict__ src, int ng,
+                                                          int nlocal)
+{
+  const int g = blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= ng) return;
+  const size_t j = (size_t) src[g], q = (size_t) nlocal + g;
+  atomicAdd(&f[3 * j], f[3 * q]);
+  atomicAdd(&f[3 * j + 1], f[3 * q + 1]);
+  atomicAdd(&f[3 * j + 2], f[3 * q + 2]);
 }
 
 // ------------------------------------------------------------------ peer-memory halo kernels
@@ -1384,6 +1451,27 @@ static int halo_borders(b200md_ctx *c, SystemState *s)
     }
   }
   CUDA_TRY(c, cudaGetLastError());
+  // one rank, one layer of images per dimension: set the flat halo up (the swaps in order: an image of an image finds
+  // its source's entry already written)
+  s->flat_ok = false;
+  if (c->flat_halo && s->nranks == 1 && s->swaps.size() == 6 && s->maxneed[0] == 1 && s->maxneed[1] == 1 && s->maxneed[2] == 1 &&
+      s->nghost > 0) {
+    bool all_self = true;
+    for (const Swap &sw : s->swaps) all_self = all_self && sw.sendproc == s->me && sw.nrecv == sw.nsend;
+    if (all_self) {
+      CUDA_TRY(c, s->flat_src.reserve((size_t) s->nghost + 8));
+      CUDA_TRY(c, s->flat_code.reserve((size_t) s->nghost + 8));
+      for (size_t k = 0; k < s->swaps.size(); k++) {
+        const Swap &sw = s->swaps[k];
+        if (!sw.nrecv) continue;
+        LaunchScope ls(c, "border_copy");
+        k_flat_build<<<nblk(sw.nrecv), BLOCK, 0, c->stream>>>(sw.sendlist.p, sw.nrecv, sw.firstrecv, s->nlocal, (int) k, sw.dim,
+                                                             s->flat_src.p, s->flat_code.p);
+      }
+      CUDA_TRY(c, cudaGetLastError());
+      s->flat_ok = true;
+    }
+  }
   return p2p_setup(c, s);
 }
 
@@ -1532,8 +1620,25 @@ static int forward_x_one(b200md_ctx *c, SystemState *s, Swap &sw)
   return B200MD_OK;
 }
 
+static FlatShifts flat_shifts(const SystemState *s)
+{
+  FlatShifts sh;
+  for (int k = 0; k < 6; k++) {
+    for (int d = 0; d < 3; d++) sh.s[k][d] = s->swaps[k].fshift[d];
+    sh.pbc[k] = s->swaps[k].pbc_flag;
+  }
+  return sh;
+}
+
 static int halo_forward_x(b200md_ctx *c, SystemState *s)
 {
+  if (s->flat_ok) {
+    LaunchScope ls(c, "forward_x");
+    k_flat_forward_x<<<nblk(s->nghost), BLOCK, 0, c->stream>>>(c->xq.p, s->flat_src.p, s->flat_code.p, s->nghost, s->nlocal,
+                                                              flat_shifts(s));
+    CUDA_TRY(c, cudaGetLastError());
+    return B200MD_OK;
+  }
   s->p2p.epoch[0]++;    // one epoch per halo call, whichever dimensions take the peer path
   for (int dim = 0; dim < 3; dim++) {
     const DimSwaps d = dim_swaps(s, dim);
@@ -1643,6 +1748,12 @@ static int forward_rho_fp_one(b200md_ctx *c, SystemState *s, Swap &sw)
 
 static int halo_forward_rho_fp(b200md_ctx *c, SystemState *s)
 {
+  if (s->flat_ok) {
+    LaunchScope ls(c, "forward_fp");
+    k_flat_forward_s2<<<nblk(s->nghost), BLOCK, 0, c->stream>>>(c->rho.p, c->fp.p, s->flat_src.p, s->nghost, s->nlocal);
+    CUDA_TRY(c, cudaGetLastError());
+    return B200MD_OK;
+  }
   s->p2p.epoch[1]++;
   for (int dim = 0; dim < 3; dim++) {
     const DimSwaps d = dim_swaps(s, dim);
@@ -1734,6 +1845,12 @@ static int reverse_f_one(b200md_ctx *c, SystemState *s, Swap &sw)
 
 static int halo_reverse_f(b200md_ctx *c, SystemState *s)
 {
+  if (s->flat_ok && !c->deterministic) {    // every image's force straight to its owned atom (atomic folds, as the staged ones)
+    LaunchScope ls(c, "reverse_f");
+    k_flat_reverse_f<<<nblk(s->nghost), BLOCK, 0, c->stream>>>(c->f.p, s->flat_src.p, s->nghost, s->nlocal);
+    CUDA_TRY(c, cudaGetLastError());
+    return B200MD_OK;
+  }
   s->p2p.epoch[2]++;
   for (int dim = 2; dim >= 0; dim--) {
     const DimSwaps d = dim_swaps(s, dim);
@@ -2208,6 +2325,8 @@ void b200md_system_free(b200md_ctx *c)
   s->v.release(); s->xhold.release(); s->xt.release(); s->dmass.release(); s->itmp.release(); s->itmp2.release();
   s->x4tmp.release(); s->dtmp.release(); s->scan64.release(); s->sendbuf.release(); s->recvbuf.release();
   s->xbuf.release();
+  s->flat_src.release();
+  s->flat_code.release();
   p2p_release(s);
   if (s->vote_host) cudaFreeHost(s->vote_host);
   if (s->nccl) ncclCommDestroy(s->nccl);
@@ -2247,6 +2366,8 @@ extern "C" int b200md_system_create(b200md_ctx *c, const b200md_system_desc *d, 
     old->itmp2.release(); old->x4tmp.release(); old->dtmp.release(); old->scan64.release(); old->sendbuf.release();
     old->recvbuf.release();
     old->xbuf.release();
+    old->flat_src.release();
+    old->flat_code.release();
     p2p_release(old);
     if (old->vote_host) cudaFreeHost(old->vote_host);
     delete old;

@@ -172,7 +172,8 @@ def test_three_level_list_matches_two_level(ctx, oracle_built):
 def test_run_loop_options_do_not_change_the_trajectory(ctx, oracle_built, style):
     """round-2 run-loop changes -- the second half kick riding in the next step's integrate launch ("fuse_integrate"),
     the reneighbor vote through a mapped host word instead of copy + synchronise ("peer_vote"), master rebuilds in one
-    stencil walk over clipped, bin-sorted candidates ("one_pass_neigh") -- reorder no arithmetic: in deterministic mode
+    stencil walk over clipped, bin-sorted candidates ("one_pass_neigh"), the self halos as one gather through a ghost ->
+    owned-atom map ("flat_halo"; the forward halos -- the reverse fold stays staged in deterministic mode) -- reorder no arithmetic: in deterministic mode
     (no atomics anywhere) a hot run with rebuilds is BITWISE the same with each of them off."""
     if style == "rebomos":
         lmp = S.make_rebomos_system(S.oracle_plugin("rebomos"), (2, 2, 1),
@@ -185,14 +186,14 @@ def test_run_loop_options_do_not_change_the_trajectory(ctx, oracle_built, style)
     ctx.set_option("deterministic", 1)
     runs = {}
     try:
-        for label, opts in (("default", {}), ("plain", {"fuse_integrate": 0, "peer_vote": 0, "one_pass_neigh": 0})):
+        for label, opts in (("default", {}), ("plain", {"fuse_integrate": 0, "peer_vote": 0, "one_pass_neigh": 0, "flat_halo": 0})):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             start_system(ctx, lmp, style)
             ctx.system_run(90, 15)
             runs[label] = (ctx.system_thermo_rows(), ctx.system_sizes(), ctx.system_download())
     finally:
-        for k in ("fuse_integrate", "peer_vote", "one_pass_neigh"):
+        for k in ("fuse_integrate", "peer_vote", "one_pass_neigh", "flat_halo"):
             ctx.set_option(k, 1)
         ctx.set_option("deterministic", 0)
     (ra, sa, da), (rb, sb, db) = runs["default"], runs["plain"]

@@ -222,6 +222,8 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *                    every rank; used to time a master rebuild)
  *  "overlap_halo"    0/1 (default 1), resident loop: the owned centers are split into interior and boundary ones and the
  *                    halos run on a stream of their own beside the interior kernels
+ *  "split_elems"     2 (default) / 3, resident loop with halo overlap: only the S pair rows (the larger LJ launch) are
+ *                    launched as interior + boundary parts, the Mo rows in one launch beside the reverse halo / both elements
  *  "flat_halo"       0/1 (default 1), resident loop on one rank: every ghost is a periodic image of an owned atom, so each
  *                    halo is ONE gather (or fold) through a ghost -> owned-atom map instead of three staged launches
  *  "peer_vote"       0/1 (default 1), resident loop: the per-step reneighbor vote is exchanged through the peer-memory

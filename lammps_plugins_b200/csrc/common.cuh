@@ -283,6 +283,7 @@ struct b200md_ctx {
   cudaStream_t halo_stream = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_fwd = nullptr, ev_reb = nullptr, ev_rev = nullptr;
   int overlap_halo = 1;              // option "overlap_halo": halos on their own stream beside the interior kernels
+  int split_elems = 2;               // option "split_elems": 2 = only the S LJ rows are split into interior / boundary launches, 3 = both elements
   int flat_halo = 1;                 // option "flat_halo": one rank, the self halos as one gather / one fold
   int peer_vote = 1;                 // option "peer_vote": reneighbor vote through peer memory + a mapped host word
   int neigh_unroll = 1;              // option "neigh_unroll" (tuning)

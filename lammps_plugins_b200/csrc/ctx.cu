@@ -173,6 +173,7 @@ extern "C" int b200md_set_option(b200md_ctx *c, const char *name, long long valu
   else if (n == "neigh_unroll") c->neigh_unroll = (int) value;
   else if (n == "peer_vote") c->peer_vote = value ? 1 : 0;
   else if (n == "flat_halo") c->flat_halo = value ? 1 : 0;
+  else if (n == "split_elems") c->split_elems = value == 2 ? 2 : 3;
   else if (n == "aeam_variant") c->aeam_variant = (int) value;
   else if (n == "force_rebuild") c->force_rebuild = value ? 1 : 0;
   else if (n == "aeam_sort_rows") {

@@ -1943,7 +1943,7 @@ static int rebomos_forces_manybody(b200md_ctx *c, int eflag, int vflag, int t_lo
 }
 
 // tapered LJ for the owned atoms with index in [t_lo, t_hi) on c->stream: completes f of exactly those atoms
-static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi, int part = -1)
+static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int t_hi, int part = -1, int elems = 3)
 {
   const int ncen = c->list_inum;
   if (t_hi <= t_lo) return B200MD_OK;
@@ -1970,13 +1970,13 @@ static int rebomos_forces_lj(b200md_ctx *c, int eflag, int vflag, int t_lo, int 
     // CTAs of 128 threads at 80 registers (6 CTAs/SM): 0.605 ms; 256 threads x 3 CTAs: 0.619; 72 regs x 7 CTAs (spills): 0.683
 #define LJP_FORCE(E) LJP_LAUNCH(false, E, 6, false, 128);
     const bool lj_ev = atom || eflag || vflag;    // thermo steps run the energy/virial instances: their own names
-    {
+    if (elems & 1) {
       LaunchScope ls(c, lj_ev ? "lj_mo_ev" : "lj_mo");
       if (atom) LJP_LAUNCH(true, 0, 1, true, 256);
       else if (eflag || vflag) LJP_LAUNCH(true, 0, 2, false, 256);
       else LJP_FORCE(0)
     }
-    {
+    if (elems & 2) {
       LaunchScope ls(c, lj_ev ? "lj_s_ev" : "lj_s");
       if (atom) LJP_LAUNCH(true, 1, 1, true, 256);
       else if (eflag || vflag) LJP_LAUNCH(true, 1, 2, false, 256);
@@ -2020,6 +2020,14 @@ int b200md_rebomos_forces_part(b200md_ctx *c, int part, int which)
 {
   ARG_CHECK(c, c->split_valid && c->lj_pairs, "rebomos_forces_part: the pair rows are not in split order");
   if (which == 0) return rebomos_forces_manybody(c, 0, 0, 0, c->list_inum, true, true);
+  if (c->split_elems == 2) {
+    // only the S rows are split (the larger launch): the interior S rows hide the forward halo, the Mo rows -- one launch,
+    // all of them -- and the boundary S rows run beside the reverse halo: three LJ launches instead of four
+    if (part == 0) return rebomos_forces_lj(c, 0, 0, 0, c->list_inum, 0, 2);
+    int rc = rebomos_forces_lj(c, 0, 0, 0, c->list_inum, -1, 1);
+    if (rc) return rc;
+    return rebomos_forces_lj(c, 0, 0, 0, c->list_inum, 1, 2);
+  }
   return rebomos_forces_lj(c, 0, 0, 0, c->list_inum, part);
 }
 

@@ -231,6 +231,11 @@ int b200md_aeam_get_rho_fp(b200md_ctx *ctx, int nlocal, double *rho, double *fp)
  *                    0, or no peer windows: ncclAllReduce of one int + copy + cudaStreamSynchronize
  *  "fuse_integrate"  0/1 (default 1), resident loop: the second half kick of a step that is followed by another step (no
  *                    thermo output, no thermostat in between) is applied by the next step's first integrate launch
+ *  "one_pass_neigh"  0/1 (default 1), resident loop: master rebuilds after the first walk the stencil once into rows of a
+ *                    fixed (sticky) stride; a row longer than the stride falls back to count + scan + fill
+ *  "neigh_unroll", "aeam_variant", "aeam_sort_rows"   tuning knobs of measured-and-dropped variants (see profiles/):
+ *                    trips of candidates in flight in the row fill when the list cutoff differs by type pair, lane
+ *                    layouts of the cluster-row kernels, index-sorted cluster rows
  *  "ang_ctas"        AEAM angular launches: CTAs per SM (default 10)
  *  "fp_gated"        0/1, AEAM two-phase API: the density phase hands out (rho > minrho ? fp : 0) per owned atom, what a
  *                    neighbor needs from it (pair_aeam.cpp:329-332), and rho_out / rho_all may be NULL: the host ships one

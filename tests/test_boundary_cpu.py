@@ -45,6 +45,18 @@ def has_gpu():
 
 
 @pytest.mark.skipif(has_gpu(), reason="a GPU is present; the no-device error path cannot be provoked")
+def test_header_documents_every_option_and_counter():
+    """every name b200md_set_option / b200md_get_counter accepts (csrc/ctx.cu) appears, quoted, in include/b200md.h"""
+    src = open(os.path.join(S.REPO, "lammps_plugins_b200", "csrc", "ctx.cu")).read()
+    a, b = src.index('extern "C" int b200md_set_option'), src.index("unknown option")
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', src[a:]))
+    assert len(names) > 30 and "deterministic" in names and "kernel_launches" in names
+    hdr = open(HEADER).read()
+    missing = sorted(n for n in names if '"%s"' % n not in hdr)
+    assert not missing, missing
+    assert b > a
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(b2.B200MDError, match="no CPU fallback"):
         b2.Context(0)
